@@ -1,0 +1,128 @@
+/* rabitq_b200.h -- C ABI of the B200-native IVF-RaBitQ query path (librabitq_b200.so).
+ *
+ * Drop-in boundary for ONE path of kemingy/rabitq v0.2.2: `RaBitQ::load_from_dir` + `RaBitQ::query`
+ * (reference src/rabitq.rs:84-125 and :268-367, callers crates/cli/src/main.rs:55,71,82).  The reference has
+ * no FFI of its own; these entry points are what a Rust `extern "C"` block in src/rabitq.rs would bind
+ * (see INTEGRATION.md for the stub).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Error behaviour: the reference panics (`expect`/`assert!`, abort in release, Cargo.toml:43).  Here every
+ * entry returns 0 on success and a non-zero RABITQ_E* code otherwise; rabitq_last_error() gives the message the
+ * reference would have panicked with.  There is NO CPU fallback: without a CUDA device every compute entry
+ * fails with RABITQ_ECUDA.
+ *
+ * Threading: calls on one handle are serialised internally (one stream per handle); distinct handles are
+ * independent.  Matches `&self` + relaxed atomics in the reference (src/metrics.rs).
+ */
+#ifndef RABITQ_B200_H
+#define RABITQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rabitq_index rabitq_index; /* opaque; owns host + device memory (struct RaBitQ, src/rabitq.rs:57-68) */
+
+enum {
+    RABITQ_OK = 0,
+    RABITQ_EIO = 1,      /* file missing / short read ("open ... error", src/rabitq.rs:85-106)            */
+    RABITQ_EINVAL = 2,   /* assertion of the reference violated (dim % 64, query length, topk == 0, ...)    */
+    RABITQ_ECUDA = 3,    /* CUDA runtime error or no device                                                 */
+    RABITQ_ENOMEM = 4,   /* device or host allocation failed                                                */
+    RABITQ_EUNSUPPORTED = 5
+};
+
+/* ---- construction ------------------------------------------------------------------------------------- */
+
+/* RaBitQ::load_from_dir(path) -- src/rabitq.rs:84-125.  Reads the six-file layout (base.fvecs,
+ * orthogonal.fvecs, centroids.fvecs, offsets_ids.ivecs, factors.fvecs, x_binary_vec.u64vecs) and uploads it
+ * to CUDA device `device`. */
+int rabitq_load_from_dir(const char* dir, int device, rabitq_index** out);
+
+/* Same, keeping only shard `shard_rank` of `shard_count`: a contiguous range of cluster ids balanced by vector
+ * count.  Centroids, P and the offsets table are replicated; other clusters look empty to this handle.
+ * (Multi-GPU data parallelism, one process per GPU; the reference is single-process.) */
+int rabitq_load_from_dir_sharded(const char* dir, int device, int shard_rank, int shard_count, rabitq_index** out);
+
+/* The in-memory equivalent of the `RaBitQ { .. }` struct literal at src/rabitq.rs:114-124 / :254-264: adopt
+ * (copy) already-built arrays.  `ptr_on_device` != 0 means every pointer is a device pointer on `device`.
+ *   base       n x dim f32, cluster-sorted, UNROTATED, row u contiguous          (rabitq.rs:110-112)
+ *   orthogonal dim x dim f32, row r = P[r,:]                                      (orthogonal.fvecs)
+ *   centroids  k x dim f32, ROTATED, centroid c contiguous                        (faer dim x k col-major)
+ *   offsets    k+1 u32;  map_ids n u32;  codes n x dim/64 u64;  factors n x 4 f32 (ip, ppc, err, cds) */
+int rabitq_from_arrays(uint32_t dim, size_t n, size_t k, const float* base, const float* orthogonal,
+                       const float* centroids, const uint32_t* offsets, const uint32_t* map_ids,
+                       const uint64_t* codes, const float* factors, int ptr_on_device, int device,
+                       int shard_rank, int shard_count, rabitq_index** out);
+
+void rabitq_free(rabitq_index* idx);
+
+uint32_t rabitq_dim(const rabitq_index* idx);     /* padded D (multiple of 64)        */
+size_t rabitq_num_vectors(const rabitq_index* idx); /* vectors held by this handle/shard */
+size_t rabitq_num_clusters(const rabitq_index* idx);
+
+/* ---- query ---------------------------------------------------------------------------------------------- */
+
+/* RaBitQ::query(&self, query, probe, topk, heuristic_rank) -> Vec<(f32, u32)> -- src/rabitq.rs:268-333.
+ * `len` must satisfy ceil(len/64)*64 == dim (the assert at :275).  Writes up to `topk` (exact squared L2,
+ * original id) pairs, ascending by distance (the reference returns heap order), and the count. */
+int rabitq_query(rabitq_index* idx, const float* query, size_t len, size_t probe, size_t topk,
+                 int heuristic_rank, float* out_dist, uint32_t* out_ids, uint32_t* out_count);
+
+/* The CLI loop (crates/cli/src/main.rs:69-75) as one call: nq queries, row-major nq x len, HOST pointers.
+ * out_dist / out_ids are nq x topk (unused tail: +inf / 0xFFFFFFFF), out_count is nq. */
+int rabitq_query_batch(rabitq_index* idx, const float* queries, size_t nq, size_t len, size_t probe,
+                       size_t topk, int heuristic_rank, float* out_dist, uint32_t* out_ids, uint32_t* out_count);
+
+/* Same with DEVICE pointers for queries and outputs (inputs already resident in HBM). */
+int rabitq_query_batch_device(rabitq_index* idx, const float* d_queries, size_t nq, size_t len, size_t probe,
+                              size_t topk, int heuristic_rank, float* d_out_dist, uint32_t* d_out_ids,
+                              uint32_t* d_out_count);
+
+/* Merge `n_lists` per-shard results (each nq x topk, device pointers laid out back to back: list s starts at
+ * d_dist + s*nq*topk) into one ascending nq x topk result.  Used after the NCCL all-gather of (dist, id). */
+int rabitq_merge_topk_device(int device, const float* d_dist, const uint32_t* d_ids, int n_lists, size_t nq,
+                             size_t topk, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count);
+
+/* METRICS (src/metrics.rs:30-41): out = {query, rough, precise, cache miss}. */
+void rabitq_metrics(const rabitq_index* idx, uint64_t out[4]);
+void rabitq_metrics_reset(rabitq_index* idx);
+
+const char* rabitq_last_error(void); /* thread-local */
+
+/* ---- tuning / measurement --------------------------------------------------------------------------------- */
+
+/* Probe-rank boundaries of the rerank rounds (DESIGN.md "exact replay"): rounds[0] = 0 < rounds[1] < ... ;
+ * the last round always extends to `probe`.  Default {0, 1}. */
+int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
+
+/* CUDA-event timings (ms) of the stages of the LAST rabitq_query_batch* call on this handle, summed over
+ * sub-batches and rounds: [0] H2D+pad, [1] rotate, [2] centroid distances, [3] probe select, [4] quantize,
+ * [5] bucket/inverted lists, [6] code scan, [7] rerank replay, [8] D2H, [9] total (first to last event).
+ * counts: [0] pairs scanned, [1] survivors emitted by the scan, [2] exact distances computed (incl.
+ * speculative), [3] precise (reference counter), [4] scan kernel launches, [5] total kernel launches. */
+int rabitq_last_timings(const rabitq_index* idx, float ms[10], uint64_t counts[6]);
+
+/* ---- stage-level entries (parity tests against the oracle; host pointers) ----------------------------------- */
+
+/* project (src/utils.rs:237-258): y = q * P, nq x dim. */
+int rabitq_stage_rotate(rabitq_index* idx, const float* queries, size_t nq, size_t len, float* out_y);
+/* centroid scan + select (src/rabitq.rs:283-297): out_centroid_dist nq x k (may be NULL), probe lists nq x P'
+ * with P' = min(probe, k). */
+int rabitq_stage_probe(rabitq_index* idx, const float* queries, size_t nq, size_t len, size_t probe,
+                       float* out_centroid_dist, uint32_t* out_probe_ids, float* out_probe_dist);
+/* min_max_residual + scalar_quantize + vector_binarize_query (src/rabitq.rs:305-317) per (query, probe):
+ * out_lo/out_delta nq x P', out_sum nq x P' (u32), out_planes nq x P' x 4*(dim/64) u64. */
+int rabitq_stage_quantize(rabitq_index* idx, const float* queries, size_t nq, size_t len, size_t probe,
+                          float* out_lo, float* out_delta, uint32_t* out_sum, uint64_t* out_planes);
+/* calculate_rough_distance (src/rabitq.rs:336-367) for every (query, probed cluster, vector) in visit order
+ * with NO filter: out_rough/out_abdp hold pair_capacity entries; out_pair_start is nq+1 prefix offsets. */
+int rabitq_stage_scan(rabitq_index* idx, const float* queries, size_t nq, size_t len, size_t probe,
+                      size_t pair_capacity, float* out_rough, uint32_t* out_abdp, uint64_t* out_pair_start);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RABITQ_B200_H */

@@ -1,0 +1,902 @@
+// kernels.cuh -- sm_100a device code of the IVF-RaBitQ query hot path.
+//
+// Written from scratch for B200; the reference (kemingy/rabitq v0.2.2, Rust + AVX2) is cited per kernel as
+// file:line relative to /root/reference so parity can be checked.  Floating-point work that feeds a comparison
+// or a rounding reproduces the reference's AVX evaluation order exactly (8 partial sums, lane v = elements
+// v, v+8, ... with one fused multiply-add each, then ((s0+s4)+(s1+s5))+((s2+s6)+(s3+s7))); everything else is
+// integer.  Compiled with -fmad=false: an FMA exists only where `fmaf` is written.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rq {
+
+#define RQ_DEV __device__ __forceinline__
+constexpr unsigned FULL = 0xffffffffu;
+
+// f32::total_cmp / Ord32 (src/ord32.rs:12-26) as a monotone UNSIGNED key.
+RQ_DEV uint32_t okey(float x) {
+    uint32_t b = __float_as_uint(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+RQ_DEV float okey_to_float(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(b);
+}
+
+// _mm256_cvtps_epi32 (src/simd.rs:215): round to nearest even; NaN and out-of-range give 0x80000000.
+RQ_DEV int cvtps_epi32(float x) {
+    return (fabsf(x) < 2147483648.0f) ? __float2int_rn(x) : (int)0x80000000;
+}
+
+// reduce_f32_256 (src/simd.rs:52-63, 292-303) for 8 accumulators held by one thread.
+RQ_DEV float reduce8(const float* s) {
+    float c0 = __fadd_rn(s[0], s[4]), c1 = __fadd_rn(s[1], s[5]);
+    float c2 = __fadd_rn(s[2], s[6]), c3 = __fadd_rn(s[3], s[7]);
+    return __fadd_rn(__fadd_rn(c0, c1), __fadd_rn(c2, c3));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K0: zero-pad queries to D (src/rabitq.rs:277-280).
+__global__ void pad_queries_kernel(const float* __restrict__ q, float* __restrict__ qpad, size_t nq, int len, int D) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= nq * (size_t)D) return;
+    size_t r = i / D;
+    int c = (int)(i % D);
+    qpad[i] = c < len ? q[r * len + c] : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: batched rotation y = q * P with the summation order of project -> simd::vector_dot_product
+// (src/utils.rs:237-258, src/simd.rs:257-314).  Thread = one output column for TQ queries; P rows are read
+// coalesced (row r = P[r,:]), the query tile is broadcast from shared memory.
+constexpr int ROT_TQ = 8;
+constexpr int ROT_THREADS = 64;
+constexpr int ROT_RCH = 64;
+
+__global__ void __launch_bounds__(ROT_THREADS) rotate_kernel(const float* __restrict__ qpad, const float* __restrict__ P,
+                                                             float* __restrict__ y, int nq, int D) {
+    __shared__ float4 sq[ROT_TQ][ROT_RCH / 4];
+    const int col = blockIdx.x * ROT_THREADS + threadIdx.x;
+    const int q0 = blockIdx.y * ROT_TQ;
+    float acc[ROT_TQ][8];
+#pragma unroll
+    for (int t = 0; t < ROT_TQ; t++)
+#pragma unroll
+        for (int v = 0; v < 8; v++) acc[t][v] = 0.0f;
+    for (int r0 = 0; r0 < D; r0 += ROT_RCH) {
+        for (int i = threadIdx.x; i < ROT_TQ * ROT_RCH; i += ROT_THREADS) {
+            int t = i / ROT_RCH, r = i % ROT_RCH;
+            reinterpret_cast<float*>(&sq[t][0])[r] = (q0 + t < nq) ? qpad[(size_t)(q0 + t) * D + r0 + r] : 0.0f;
+        }
+        __syncthreads();
+        if (col < D) {
+#pragma unroll 2
+            for (int r = 0; r < ROT_RCH; r += 8) {
+                float pv[8];
+#pragma unroll
+                for (int v = 0; v < 8; v++) pv[v] = __ldg(&P[(size_t)(r0 + r + v) * D + col]);
+#pragma unroll
+                for (int t = 0; t < ROT_TQ; t++) {
+                    float4 a = sq[t][r / 4], b = sq[t][r / 4 + 1];
+                    acc[t][0] = fmaf(a.x, pv[0], acc[t][0]);
+                    acc[t][1] = fmaf(a.y, pv[1], acc[t][1]);
+                    acc[t][2] = fmaf(a.z, pv[2], acc[t][2]);
+                    acc[t][3] = fmaf(a.w, pv[3], acc[t][3]);
+                    acc[t][4] = fmaf(b.x, pv[4], acc[t][4]);
+                    acc[t][5] = fmaf(b.y, pv[5], acc[t][5]);
+                    acc[t][6] = fmaf(b.z, pv[6], acc[t][6]);
+                    acc[t][7] = fmaf(b.w, pv[7], acc[t][7]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (col < D) {
+#pragma unroll
+        for (int t = 0; t < ROT_TQ; t++)
+            if (q0 + t < nq) y[(size_t)(q0 + t) * D + col] = reduce8(acc[t]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: squared L2 of every rotated centroid to every rotated query, order of simd::l2_squared_distance
+// (src/rabitq.rs:283-293, src/simd.rs:14-73: diff = c - y rounded, then sum = fma(diff, diff, sum)).
+// Thread = one centroid (its row streamed straight from L2 as 2 x 128-bit loads per 8 dims) x TQ queries
+// (broadcast from shared memory).
+constexpr int CD_TQ = 8;
+constexpr int CD_THREADS = 128;
+constexpr int CD_DCH = 64;
+
+__global__ void __launch_bounds__(CD_THREADS) centroid_dist_kernel(const float* __restrict__ cent, const float* __restrict__ y,
+                                                                   float* __restrict__ out, int nq, int K, int D) {
+    __shared__ float4 sy[CD_TQ][CD_DCH / 4];
+    const int c = blockIdx.x * CD_THREADS + threadIdx.x;
+    const int q0 = blockIdx.y * CD_TQ;
+    float acc[CD_TQ][8];
+#pragma unroll
+    for (int t = 0; t < CD_TQ; t++)
+#pragma unroll
+        for (int v = 0; v < 8; v++) acc[t][v] = 0.0f;
+    const float4* crow = reinterpret_cast<const float4*>(cent + (size_t)(c < K ? c : 0) * D);
+    for (int d0 = 0; d0 < D; d0 += CD_DCH) {
+        for (int i = threadIdx.x; i < CD_TQ * CD_DCH; i += CD_THREADS) {
+            int t = i / CD_DCH, d = i % CD_DCH;
+            reinterpret_cast<float*>(&sy[t][0])[d] = (q0 + t < nq) ? y[(size_t)(q0 + t) * D + d0 + d] : 0.0f;
+        }
+        __syncthreads();
+        if (c < K) {
+#pragma unroll 2
+            for (int d = 0; d < CD_DCH; d += 8) {
+                float4 ca = __ldg(&crow[(d0 + d) / 4]), cb = __ldg(&crow[(d0 + d) / 4 + 1]);
+#pragma unroll
+                for (int t = 0; t < CD_TQ; t++) {
+                    float4 a = sy[t][d / 4], b = sy[t][d / 4 + 1];
+                    float f;
+                    f = __fsub_rn(ca.x, a.x); acc[t][0] = fmaf(f, f, acc[t][0]);
+                    f = __fsub_rn(ca.y, a.y); acc[t][1] = fmaf(f, f, acc[t][1]);
+                    f = __fsub_rn(ca.z, a.z); acc[t][2] = fmaf(f, f, acc[t][2]);
+                    f = __fsub_rn(ca.w, a.w); acc[t][3] = fmaf(f, f, acc[t][3]);
+                    f = __fsub_rn(cb.x, b.x); acc[t][4] = fmaf(f, f, acc[t][4]);
+                    f = __fsub_rn(cb.y, b.y); acc[t][5] = fmaf(f, f, acc[t][5]);
+                    f = __fsub_rn(cb.z, b.z); acc[t][6] = fmaf(f, f, acc[t][6]);
+                    f = __fsub_rn(cb.w, b.w); acc[t][7] = fmaf(f, f, acc[t][7]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (c < K) {
+#pragma unroll
+        for (int t = 0; t < CD_TQ; t++)
+            if (q0 + t < nq) out[(size_t)(q0 + t) * K + c] = reduce8(acc[t]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Block-wide exclusive scan of n u32 values in shared memory (in place); returns the total.
+template <int THREADS>
+RQ_DEV uint32_t block_exclusive_scan(uint32_t* a, int n, uint32_t* warp_tot /* THREADS/32 + 1 */) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + THREADS - 1) / THREADS;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    uint32_t s = 0;
+    for (int i = lo; i < hi; i++) s += a[i];
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < THREADS / 32 ? warp_tot[lane] : 0, winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(FULL, winc, o);
+            if (lane >= o) winc += v;
+        }
+        if (lane < THREADS / 32) warp_tot[lane] = winc - w;
+        if (lane == THREADS / 32 - 1) warp_tot[THREADS / 32] = winc;
+    }
+    __syncthreads();
+    uint32_t run = warp_tot[warp] + inc - s;
+    for (int i = lo; i < hi; i++) {
+        uint32_t v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    uint32_t total = warp_tot[THREADS / 32];
+    __syncthreads();
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2b: top-`P` nearest centroids per query, ascending (src/rabitq.rs:294-297: select_nth_unstable_by +
+// truncate + sort_by(total_cmp)).  Ties between EQUAL distances are unspecified in the reference; here the
+// smaller centroid index wins.  Also emits, per (query, rank), the prefix of 32-vector words of the probed
+// clusters (the survivor-slot layout) and the per-query totals (`rough` counter of src/rerank.rs:105).
+constexpr int SEL_THREADS = 256;
+
+__global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* __restrict__ cdist, int K, int P, int Ppow2,
+                                                                   const uint32_t* __restrict__ offsets,
+                                                                   uint32_t* __restrict__ probe_ids, float* __restrict__ probe_dist,
+                                                                   uint32_t* __restrict__ slot_local, uint32_t* __restrict__ q_words,
+                                                                   uint32_t* __restrict__ q_pairs) {
+    extern __shared__ unsigned long long sel_buf[];  // Ppow2 keys; reused as u32 scratch afterwards
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_bucket, s_need, s_nout;
+    __shared__ uint32_t warp_tot[SEL_THREADS / 32 + 1];
+    __shared__ uint32_t eq_cnt[SEL_THREADS];
+    const int tid = threadIdx.x;
+    const size_t q = blockIdx.x;
+    const float* row = cdist + q * (size_t)K;
+
+    uint32_t prefix = 0, mask = 0, need = (uint32_t)P;
+    for (int pass = 3; pass >= 0; pass--) {
+        hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < K; i += SEL_THREADS) {
+            uint32_t key = okey(row[i]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t cum = 0;
+            int b = 0;
+            for (; b < 256; b++) {
+                if (cum + hist[b] >= need) break;
+                cum += hist[b];
+            }
+            s_bucket = (uint32_t)b;
+            s_need = need - cum;
+            if (pass == 0) s_nout = 0;
+        }
+        __syncthreads();
+        prefix |= s_bucket << (8 * pass);
+        mask |= 0xffu << (8 * pass);
+        need = s_need;
+        __syncthreads();
+    }
+    const uint32_t kth = prefix, need_eq = need, n_less = (uint32_t)P - need_eq;
+    // strictly smaller keys: any order (sorted below)
+    for (int i = tid; i < K; i += SEL_THREADS) {
+        uint32_t key = okey(row[i]);
+        if (key < kth) {
+            uint32_t pos = atomicAdd(&s_nout, 1u);
+            sel_buf[pos] = ((unsigned long long)key << 32) | (uint32_t)i;
+        }
+    }
+    // keys equal to the P-th: the first `need_eq` by index
+    {
+        const int per = (K + SEL_THREADS - 1) / SEL_THREADS;
+        const int lo = min(K, tid * per), hi = min(K, lo + per);
+        uint32_t c = 0;
+        for (int i = lo; i < hi; i++) c += (okey(row[i]) == kth);
+        eq_cnt[tid] = c;
+        __syncthreads();
+        block_exclusive_scan<SEL_THREADS>(eq_cnt, SEL_THREADS, warp_tot);
+        uint32_t base = eq_cnt[tid];
+        for (int i = lo; i < hi && base < need_eq; i++)
+            if (okey(row[i]) == kth) {
+                sel_buf[n_less + base] = ((unsigned long long)kth << 32) | (uint32_t)i;
+                base++;
+            }
+    }
+    for (int i = P + tid; i < Ppow2; i += SEL_THREADS) sel_buf[i] = ~0ull;
+    __syncthreads();
+    // bitonic sort ascending on (key, index)
+    for (int k2 = 2; k2 <= Ppow2; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < Ppow2; i += SEL_THREADS) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = sel_buf[i], b = sel_buf[ixj];
+                    bool up = (i & k2) == 0;
+                    if ((a > b) == up) { sel_buf[i] = b; sel_buf[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // outputs; the words-per-slot array overlays the tail of sel_buf (as u32, after the keys are consumed)
+    uint32_t my_ids[16];  // P <= 4096 -> at most 16 per thread
+    int cnt = 0;
+    uint32_t pairs_local = 0;
+    for (int p = tid; p < P; p += SEL_THREADS) my_ids[cnt++] = (uint32_t)(sel_buf[p] & 0xffffffffu);
+    __syncthreads();
+    uint32_t* words = reinterpret_cast<uint32_t*>(sel_buf);
+    cnt = 0;
+    for (int p = tid; p < P; p += SEL_THREADS) {
+        uint32_t id = my_ids[cnt++];
+        probe_ids[q * P + p] = id;
+        probe_dist[q * P + p] = row[id];
+        uint32_t n_c = offsets[id + 1] - offsets[id];
+        words[p] = (n_c + 31u) >> 5;
+        pairs_local += n_c;
+    }
+    __syncthreads();
+    uint32_t total_words = block_exclusive_scan<SEL_THREADS>(words, P, warp_tot);
+    for (int p = tid; p < P; p += SEL_THREADS) slot_local[q * P + p] = words[p];
+    // per-query pair count
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pairs_local += __shfl_xor_sync(FULL, pairs_local, o);
+    __syncthreads();
+    if ((tid & 31) == 0) warp_tot[tid >> 5] = pairs_local;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < SEL_THREADS / 32; w++) s += warp_tot[w];
+        q_pairs[q] = s;
+        q_words[q] = total_words;
+    }
+}
+
+// Exclusive scan over the per-query word/pair totals (single block).  q_wbase[nq] = total words.
+__global__ void __launch_bounds__(1024) query_base_scan_kernel(const uint32_t* __restrict__ q_words, const uint32_t* __restrict__ q_pairs,
+                                                               int nq, uint32_t* __restrict__ q_wbase,
+                                                               unsigned long long* __restrict__ q_pbase) {
+    __shared__ unsigned long long wtot[33], ptot[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (nq + 1023) / 1024;
+    const int lo = min(nq, tid * per), hi = min(nq, lo + per);
+    unsigned long long sw = 0, sp = 0;
+    for (int i = lo; i < hi; i++) { sw += q_words[i]; sp += q_pairs[i]; }
+    unsigned long long iw = sw, ip = sp;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long a = __shfl_up_sync(FULL, iw, o), b = __shfl_up_sync(FULL, ip, o);
+        if (lane >= o) { iw += a; ip += b; }
+    }
+    if (lane == 31) { wtot[warp] = iw; ptot[warp] = ip; }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long a = wtot[lane], b = ptot[lane], ia = a, ib = b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long x = __shfl_up_sync(FULL, ia, o), z = __shfl_up_sync(FULL, ib, o);
+            if (lane >= o) { ia += x; ib += z; }
+        }
+        wtot[lane] = ia - a; ptot[lane] = ib - b;
+        if (lane == 31) { wtot[32] = ia; ptot[32] = ib; }
+    }
+    __syncthreads();
+    unsigned long long rw = wtot[warp] + iw - sw, rp = ptot[warp] + ip - sp;
+    for (int i = lo; i < hi; i++) {
+        q_wbase[i] = (uint32_t)rw;
+        q_pbase[i] = rp;
+        rw += q_words[i];
+        rp += q_pairs[i];
+    }
+    if (tid == 0) { q_wbase[nq] = (uint32_t)wtot[32]; q_pbase[nq] = ptot[32]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: per (query, probed cluster): residual, min/max, 4-bit scalar quantisation, bit-planes
+// (src/rabitq.rs:305-317 -> src/simd.rs:117-173, 185-247, 83-107).  One warp per (q, p); the movemask of the
+// AVX2 code becomes __ballot_sync.  Output is one packed record per (q, p):
+//   u32[0 .. 4*W32)   planes, plane-major: plane b word w  = bit b of q_u[32w .. 32w+31]
+//   f32[4*W32 + 0..3] lower_bound, delta, (f32) sum q_u, y_c_distance_square
+//   f32[4*W32 + 4]    sqrt(y_c_distance_square)
+//   u32[4*W32 + 5]    sum q_u (raw u32)     u32[+6] first 32-vector word of this slot     u32[+7] cluster id
+constexpr float SCALAR_1_15 = 1.0f / 15.0f;  // src/consts.rs:10
+
+__global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__ y, const float* __restrict__ cent,
+                                                       const uint32_t* __restrict__ probe_ids, const float* __restrict__ probe_dist,
+                                                       const uint32_t* __restrict__ slot_local, const uint32_t* __restrict__ q_wbase,
+                                                       uint32_t* __restrict__ qrec, int nq, int P, int D) {
+    const int lane = threadIdx.x & 31;
+    const size_t gw = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (gw >= (size_t)nq * P) return;
+    const size_t q = gw / P;
+    const uint32_t c = probe_ids[gw];
+    const float* yr = y + q * (size_t)D;
+    const float* cr = cent + (size_t)c * D;
+    const int W32 = D / 32, RS = 4 * W32 + 8;
+    uint32_t* rec = qrec + gw * (size_t)RS;
+    float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+    for (int d = lane; d < D; d += 32) {
+        float r = __fsub_rn(yr[d], cr[d]);
+        mn = fminf(mn, r);
+        mx = fmaxf(mx, r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+    }
+    const float delta = __fmul_rn(__fsub_rn(mx, mn), SCALAR_1_15);  // rabitq.rs:307
+    const float inv = __fdiv_rn(1.0f, delta);                       // :308 recip()
+    int sum = 0;
+    for (int g = 0; g < W32; g++) {
+        int d = g * 32 + lane;
+        float r = __fsub_rn(yr[d], cr[d]);
+        int qi = cvtps_epi32(__fmul_rn(__fsub_rn(r, mn), inv));
+        sum += qi;  // i32 lanes wrap like _mm256_add_epi32
+        uint32_t b0 = __ballot_sync(FULL, qi & 1), b1 = __ballot_sync(FULL, qi & 2);
+        uint32_t b2 = __ballot_sync(FULL, qi & 4), b3 = __ballot_sync(FULL, qi & 8);
+        if (lane == 0) {
+            rec[0 * W32 + g] = b0;
+            rec[1 * W32 + g] = b1;
+            rec[2 * W32 + g] = b2;
+            rec[3 * W32 + g] = b3;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    if (lane == 0) {
+        const float ycd = probe_dist[gw];
+        float* rf = reinterpret_cast<float*>(rec + 4 * W32);
+        rf[0] = mn;
+        rf[1] = delta;
+        rf[2] = __uint2float_rn((uint32_t)sum);  // `scalar_sum as f32`, rabitq.rs:322
+        rf[3] = ycd;
+        rf[4] = __fsqrt_rn(ycd);                 // rabitq.rs:346
+        rec[4 * W32 + 5] = (uint32_t)sum;
+        rec[4 * W32 + 6] = q_wbase[q] + slot_local[gw];
+        rec[4 * W32 + 7] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Inverted probe lists for one round of probe ranks [p_lo, p_hi): cluster -> the (q, p) items probing it, and
+// the scan work list (cluster, chunk of VT vectors).
+__global__ void bucket_count_kernel(const uint32_t* __restrict__ probe_ids, size_t nq, int P, int p_lo, int p_hi,
+                                    uint32_t* __restrict__ cl_count) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    int R = p_hi - p_lo;
+    if (i >= nq * (size_t)R) return;
+    size_t q = i / R;
+    int p = p_lo + (int)(i % R);
+    atomicAdd(&cl_count[probe_ids[q * P + p]], 1u);
+}
+
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __restrict__ cl_count, const uint32_t* __restrict__ offsets,
+                                                           int K, int VT, uint32_t* __restrict__ cl_start,
+                                                           uint32_t* __restrict__ item_start, uint32_t* __restrict__ cl_cursor,
+                                                           uint32_t* __restrict__ work_ctl /* [0] counter, [1] n_work */) {
+    __shared__ uint32_t wa[33], wb[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (K + 1023) / 1024;
+    const int lo = min(K, tid * per), hi = min(K, lo + per);
+    uint32_t sa = 0, sb = 0;
+    for (int c = lo; c < hi; c++) {
+        uint32_t m = cl_count[c], n_c = offsets[c + 1] - offsets[c];
+        sa += m;
+        sb += m ? (n_c + VT - 1) / VT : 0;
+    }
+    uint32_t ia = sa, ib = sb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t x = __shfl_up_sync(FULL, ia, o), z = __shfl_up_sync(FULL, ib, o);
+        if (lane >= o) { ia += x; ib += z; }
+    }
+    if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t a = wa[lane], b = wb[lane], xa = a, xb = b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t x = __shfl_up_sync(FULL, xa, o), z = __shfl_up_sync(FULL, xb, o);
+            if (lane >= o) { xa += x; xb += z; }
+        }
+        wa[lane] = xa - a; wb[lane] = xb - b;
+        if (lane == 31) { wa[32] = xa; wb[32] = xb; }
+    }
+    __syncthreads();
+    uint32_t ra = wa[warp] + ia - sa, rb = wb[warp] + ib - sb;
+    for (int c = lo; c < hi; c++) {
+        uint32_t m = cl_count[c], n_c = offsets[c + 1] - offsets[c];
+        cl_start[c] = ra;
+        item_start[c] = rb;
+        cl_cursor[c] = 0;
+        ra += m;
+        rb += m ? (n_c + VT - 1) / VT : 0;
+    }
+    if (tid == 0) {
+        cl_start[K] = wa[32];
+        item_start[K] = wb[32];
+        work_ctl[0] = 0;
+        work_ctl[1] = wb[32];
+    }
+}
+
+__global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, size_t nq, int P, int p_lo, int p_hi,
+                                   const uint32_t* __restrict__ cl_start, uint32_t* __restrict__ cl_cursor,
+                                   uint32_t* __restrict__ cl_items) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    int R = p_hi - p_lo;
+    if (i >= nq * (size_t)R) return;
+    size_t q = i / R;
+    int p = p_lo + (int)(i % R);
+    uint32_t c = probe_ids[q * P + p];
+    uint32_t pos = atomicAdd(&cl_cursor[c], 1u);
+    cl_items[cl_start[c] + pos] = (uint32_t)(q * P + p);
+}
+
+__global__ void work_items_kernel(const uint32_t* __restrict__ item_start, int K, uint2* __restrict__ work) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    uint32_t s = item_start[c], e = item_start[c + 1];
+    for (uint32_t i = s; i < e; i++) work[i] = make_uint2((uint32_t)c, i - s);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4: the code scan.  calculate_rough_distance + asymmetric_binary_dot_product + binary_dot_product
+// (src/rabitq.rs:336-367, src/utils.rs:113-135, src/simd.rs:326-384) fused with the threshold filter of
+// HeapReRanker::rank_batch (src/rerank.rs:84) and an ORDER-PRESERVING compaction.
+//
+// Cluster-major: a CTA takes a work item (cluster, chunk of VT vectors), loads each vector's packed code
+// (128-bit coalesced loads) and Factor (one float4) into REGISTERS once, then streams the records of every
+// (query, probe) item that probes this cluster through shared memory; each thread does AND+__popc over the 4
+// bit-planes, evaluates the estimator in the reference's association without contraction and tests
+// `rough < thr[q]`.  Per warp and query: one ballot word -> bitmap[slot word], survivors' (rough, j) packed at
+// the start of the word's 32-entry block.  No atomics, deterministic layout, visit order preserved.
+struct ScanArgs {
+    const uint32_t* codes;      // n x W32
+    const float4* factors;      // n
+    const uint32_t* offsets;    // K+1 (local to this shard)
+    const uint32_t* cl_start;   // K+1
+    const uint32_t* cl_items;   // (q*P+p) per cluster
+    const uint2* work;          // (cluster, chunk)
+    uint32_t* work_ctl;         // [0] counter [1] n_work
+    const uint32_t* qrec;       // records
+    const float* thr;           // per query
+    uint32_t* bitmap;           // per slot word
+    float2* entries;            // per slot word: 32 x (rough, j as bits)
+    unsigned long long* counters;  // [0] survivors
+    int P;
+    int QS;                     // records per shared-memory slice
+};
+
+constexpr int SCAN_THREADS = 128;
+
+template <int W32, int VPT, bool DENSE>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
+    constexpr int RS = 4 * W32 + 8;   // record words
+    constexpr int RS4 = RS / 4;       // record uint4s
+    constexpr int VT = SCAN_THREADS * VPT;
+    extern __shared__ uint4 s_rec[];  // QS records, then QS thresholds
+    __shared__ uint32_t s_item;
+    float* s_thr = reinterpret_cast<float*>(s_rec + (size_t)a.QS * RS4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned long long n_surv = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&a.work_ctl[0], 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= a.work_ctl[1]) break;
+        const uint2 wk = a.work[item];
+        const uint32_t c = wk.x, chunk = wk.y;
+        const uint32_t off = a.offsets[c], n_c = a.offsets[c + 1] - off;
+        const uint32_t nwords = (n_c + 31u) >> 5;
+        const uint32_t it0 = a.cl_start[c], m = a.cl_start[c + 1] - it0;
+
+        uint32_t code[VPT][W32];
+        float4 fac[VPT];
+        uint32_t jpos[VPT], wloc[VPT];
+        bool valid[VPT];
+#pragma unroll
+        for (int i = 0; i < VPT; i++) {
+            wloc[i] = chunk * (VT / 32) + warp * VPT + i;
+            uint32_t vloc = wloc[i] * 32 + lane;
+            valid[i] = vloc < n_c;
+            jpos[i] = off + vloc;
+            if (valid[i]) {
+                const uint32_t* cp = a.codes + (size_t)jpos[i] * W32;
+                if constexpr (W32 % 4 == 0) {
+#pragma unroll
+                    for (int w = 0; w < W32; w += 4) {
+                        uint4 v = __ldg(reinterpret_cast<const uint4*>(cp + w));
+                        code[i][w] = v.x; code[i][w + 1] = v.y; code[i][w + 2] = v.z; code[i][w + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < W32; w += 2) {
+                        uint2 v = __ldg(reinterpret_cast<const uint2*>(cp + w));
+                        code[i][w] = v.x; code[i][w + 1] = v.y;
+                    }
+                }
+                fac[i] = __ldg(&a.factors[jpos[i]]);
+            } else {
+#pragma unroll
+                for (int w = 0; w < W32; w++) code[i][w] = 0;
+                fac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+
+        for (uint32_t s0 = 0; s0 < m; s0 += a.QS) {
+            const int ns = min((uint32_t)a.QS, m - s0);
+            __syncthreads();
+            for (int i = tid; i < ns * RS4; i += SCAN_THREADS) {
+                int r = i / RS4, w4 = i % RS4;
+                uint32_t it = a.cl_items[it0 + s0 + r];
+                s_rec[r * RS4 + w4] = __ldg(reinterpret_cast<const uint4*>(a.qrec + (size_t)it * RS) + w4);
+            }
+            if (tid < ns) s_thr[tid] = a.thr[a.cl_items[it0 + s0 + tid] / a.P];
+            __syncthreads();
+            for (int r = 0; r < ns; r++) {
+                const uint32_t* rec = reinterpret_cast<const uint32_t*>(s_rec + r * RS4);
+                const float4 sc = *reinterpret_cast<const float4*>(rec + 4 * W32);      // lo, delta, sum, ycd
+                const float sq = *reinterpret_cast<const float*>(rec + 4 * W32 + 4);    // sqrt(ycd)
+                const uint32_t wbase = rec[4 * W32 + 6];
+                const float thr = s_thr[r];
+#pragma unroll
+                for (int i = 0; i < VPT; i++) {
+                    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                    if constexpr (W32 % 4 == 0) {
+#pragma unroll
+                        for (int w = 0; w < W32; w += 4) {
+                            const uint4 p0 = *reinterpret_cast<const uint4*>(rec + 0 * W32 + w);
+                            const uint4 p1 = *reinterpret_cast<const uint4*>(rec + 1 * W32 + w);
+                            const uint4 p2 = *reinterpret_cast<const uint4*>(rec + 2 * W32 + w);
+                            const uint4 p3 = *reinterpret_cast<const uint4*>(rec + 3 * W32 + w);
+                            a0 += __popc(code[i][w] & p0.x) + __popc(code[i][w + 1] & p0.y) + __popc(code[i][w + 2] & p0.z) + __popc(code[i][w + 3] & p0.w);
+                            a1 += __popc(code[i][w] & p1.x) + __popc(code[i][w + 1] & p1.y) + __popc(code[i][w + 2] & p1.z) + __popc(code[i][w + 3] & p1.w);
+                            a2 += __popc(code[i][w] & p2.x) + __popc(code[i][w + 1] & p2.y) + __popc(code[i][w + 2] & p2.z) + __popc(code[i][w + 3] & p2.w);
+                            a3 += __popc(code[i][w] & p3.x) + __popc(code[i][w + 1] & p3.y) + __popc(code[i][w + 2] & p3.z) + __popc(code[i][w + 3] & p3.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < W32; w += 2) {
+                            const uint2 p0 = *reinterpret_cast<const uint2*>(rec + 0 * W32 + w);
+                            const uint2 p1 = *reinterpret_cast<const uint2*>(rec + 1 * W32 + w);
+                            const uint2 p2 = *reinterpret_cast<const uint2*>(rec + 2 * W32 + w);
+                            const uint2 p3 = *reinterpret_cast<const uint2*>(rec + 3 * W32 + w);
+                            a0 += __popc(code[i][w] & p0.x) + __popc(code[i][w + 1] & p0.y);
+                            a1 += __popc(code[i][w] & p1.x) + __popc(code[i][w + 1] & p1.y);
+                            a2 += __popc(code[i][w] & p2.x) + __popc(code[i][w + 1] & p2.y);
+                            a3 += __popc(code[i][w] & p3.x) + __popc(code[i][w + 1] & p3.y);
+                        }
+                    }
+                    const uint32_t abdp = a0 + (a1 << 1) + (a2 << 2) + (a3 << 3);  // utils.rs:113-135
+                    // rabitq.rs:352-363, left-to-right, no contraction:
+                    //   ((((cds + ycd) + lo*ppc) + ((2*abdp - sum) * ip) * delta) - err * sqrt(ycd))
+                    const float t1 = __fadd_rn(fac[i].w, sc.w);
+                    const float t3 = __fadd_rn(t1, __fmul_rn(sc.x, fac[i].y));
+                    const float t4 = __fsub_rn(__fmul_rn(2.0f, __uint2float_rn(abdp)), sc.z);
+                    const float t6 = __fmul_rn(__fmul_rn(t4, fac[i].x), sc.y);
+                    const float rough = __fsub_rn(__fadd_rn(t3, t6), __fmul_rn(fac[i].z, sq));
+                    if (wloc[i] < nwords) {  // warp-uniform
+                        const size_t word = (size_t)wbase + wloc[i];
+                        if constexpr (DENSE) {
+                            if (valid[i]) a.entries[word * 32 + lane] = make_float2(rough, __uint_as_float(abdp));
+                        } else {
+                            const bool pass = valid[i] && (rough < thr);  // rerank.rs:84
+                            const uint32_t mask = __ballot_sync(FULL, pass);
+                            if (lane == 0) a.bitmap[word] = mask;
+                            if (pass) a.entries[word * 32 + __popc(mask & lt_mask)] = make_float2(rough, __uint_as_float(jpos[i]));
+                            n_surv += pass;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if constexpr (!DENSE) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_surv += __shfl_xor_sync(FULL, n_surv, o);
+        if (lane == 0 && n_surv) atomicAdd(&a.counters[0], n_surv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: exact rerank with the reference's SEQUENTIAL threshold semantics (HeapReRanker, src/rerank.rs:61-114).
+// One warp per query walks the query's survivor words in visit order (probe rank ascending, position inside
+// the cluster ascending).  Per chunk of <= 32 survivors: candidates still below the current threshold get their
+// exact squared L2 computed speculatively in parallel (8 lanes per candidate = the 8 AVX lanes of
+// simd::l2_squared_distance, src/simd.rs:14-73, same per-lane order and the same final reduction), then the
+// chunk is replayed in order with the reference's two strict tests, so the heap contents, the threshold
+// trajectory and the `precise` counter are those of the sequential loop.
+struct RerankArgs {
+    const float* qpad;            // nq x D, unrotated padded queries (rabitq.rs:299)
+    const float* base;            // n x D
+    const uint32_t* map_ids;      // n
+    const uint32_t* q_wbase;      // nq+1
+    const uint32_t* slot_local;   // nq x P
+    const uint32_t* bitmap;
+    const float2* entries;
+    float* heap_dist;             // nq x topk   state between rounds, final output when finalize
+    uint32_t* heap_ids;           // nq x topk
+    uint32_t* heap_cnt;           // nq
+    float* thr;                   // nq
+    uint32_t* q_precise;          // nq (accumulated over rounds)
+    unsigned long long* counters; // [1] exact computed (speculative) [2] precise
+    float* out_dist;              // nq x topk (finalize)
+    uint32_t* out_ids;
+    uint32_t* out_count;
+    int nq, P, D, topk;
+};
+
+constexpr int RR_WARPS = 4;
+
+RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, float& thr) {
+    uint32_t bk = 0;
+    int bp = 0x7fffffff;
+    for (int s = lane; s < k; s += 32) {
+        uint32_t key = okey(hd[s]);
+        if (key > bk || (key == bk && s < bp)) { bk = key; bp = s; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        uint32_t ok = __shfl_xor_sync(FULL, bk, o);
+        int op = __shfl_xor_sync(FULL, bp, o);
+        if (ok > bk || (ok == bk && op < bp)) { bk = ok; bp = op; }
+    }
+    maxpos = bp;
+    thr = okey_to_float(bk);
+}
+
+__global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(RerankArgs a, int p_lo, int p_hi, int first, int finalize) {
+    extern __shared__ float rr_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * RR_WARPS + warp;
+    const int D = a.D, k = a.topk;
+    float* qv = rr_smem + (size_t)warp * (D + 2 * k);
+    float* hd = qv + D;
+    uint32_t* hid = reinterpret_cast<uint32_t*>(hd + k);
+    if (q >= a.nq) return;
+
+    for (int d = lane; d < D; d += 32) qv[d] = a.qpad[(size_t)q * D + d];
+    int cnt = first ? 0 : (int)a.heap_cnt[q];
+    float thr = first ? 3.402823466e+38f : a.thr[q];
+    int maxpos = 0;
+    for (int s = lane; s < cnt; s += 32) {
+        hd[s] = a.heap_dist[(size_t)q * k + s];
+        hid[s] = a.heap_ids[(size_t)q * k + s];
+    }
+    __syncwarp();
+    if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);
+    uint32_t precise = 0, computed = 0;
+
+    const uint32_t wb = a.q_wbase[q];
+    const uint32_t wlo = wb + a.slot_local[(size_t)q * a.P + p_lo];
+    const uint32_t whi = (p_hi >= a.P) ? a.q_wbase[q + 1] : wb + a.slot_local[(size_t)q * a.P + p_hi];
+    const int sub = lane >> 3, v = lane & 7;
+
+    for (uint32_t w0 = wlo; w0 < whi; w0 += 32) {
+        const uint32_t m = (w0 + lane < whi) ? a.bitmap[w0 + lane] : 0u;
+        uint32_t incl = __popc(m);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t T = __shfl_sync(FULL, incl, 31);
+        const uint32_t excl = incl - __popc(m);
+        for (uint32_t e0 = 0; e0 < T; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            const bool have = e < T;
+            // source word = first lane whose inclusive prefix exceeds e
+            int pos = 0;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                uint32_t pv = __shfl_sync(FULL, incl, pos + s - 1);
+                if (pv <= e) pos += s;
+            }
+            pos = min(pos, 31);
+            const uint32_t src_excl = __shfl_sync(FULL, excl, pos);
+            float rough = 3.402823466e+38f;
+            uint32_t j = 0;
+            if (have) {
+                float2 en = a.entries[(size_t)(w0 + pos) * 32 + (e - src_excl)];
+                rough = en.x;
+                j = __float_as_uint(en.y);
+            }
+            // speculative exact distances for everything still below the current threshold
+            const uint32_t act = __ballot_sync(FULL, have && rough < thr);
+            const int nact = __popc(act);
+            const int myrank = __popc(act & ((1u << lane) - 1u));
+            float exact = 0.0f;
+            for (int g = 0; g < nact; g += 4) {
+                const int want = g + sub;  // rank of the candidate this 8-lane group computes
+                const uint32_t srcl = __fns(act, 0, want + 1);
+                const uint32_t ju = __shfl_sync(FULL, j, srcl & 31);
+                const bool on = want < nact;
+                float acc = 0.0f;
+                if (on) {
+                    const float* row = a.base + (size_t)ju * D;
+#pragma unroll 8
+                    for (int d = v; d < D; d += 8) {
+                        float diff = __fsub_rn(__ldg(&row[d]), qv[d]);
+                        acc = fmaf(diff, diff, acc);
+                    }
+                }
+                acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
+                acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
+                acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
+                // hand the result to the lane that owns the candidate
+                const int owner_grp = myrank - g;
+                const float res = __shfl_sync(FULL, acc, (owner_grp & 3) * 8);
+                if (((act >> lane) & 1u) && owner_grp >= 0 && owner_grp < 4) exact = res;
+            }
+            computed += nact;
+            // in-order replay (rerank.rs:83-101)
+            uint32_t rem = act;
+            while (rem) {
+                const int t = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const float r = __shfl_sync(FULL, rough, t);
+                const float ex = __shfl_sync(FULL, exact, t);
+                const uint32_t ju = __shfl_sync(FULL, j, t);
+                if (r < thr) {
+                    precise++;
+                    if (ex < thr) {
+                        if (cnt < k) {
+                            if (lane == 0) { hd[cnt] = ex; hid[cnt] = a.map_ids[ju]; }
+                            cnt++;
+                            __syncwarp();
+                            if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);
+                        } else {
+                            if (lane == 0) { hd[maxpos] = ex; hid[maxpos] = a.map_ids[ju]; }
+                            __syncwarp();
+                            heap_recompute_max(hd, k, lane, maxpos, thr);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    if (lane == 0) {
+        a.q_precise[q] = (first ? 0u : a.q_precise[q]) + precise;
+        atomicAdd(&a.counters[1], (unsigned long long)computed);
+        atomicAdd(&a.counters[2], (unsigned long long)precise);
+    }
+    if (!finalize) {
+        for (int s = lane; s < cnt; s += 32) {
+            a.heap_dist[(size_t)q * k + s] = hd[s];
+            a.heap_ids[(size_t)q * k + s] = hid[s];
+        }
+        if (lane == 0) { a.heap_cnt[q] = (uint32_t)cnt; a.thr[q] = thr; }
+    } else {
+        // ascending by (distance, id): rank by counting
+        __syncwarp();
+        for (int s = lane; s < k; s += 32) {
+            if (s < cnt) {
+                const uint32_t ks = okey(hd[s]), is = hid[s];
+                int rank = 0;
+                for (int t = 0; t < cnt; t++) {
+                    const uint32_t kt = okey(hd[t]), itt = hid[t];
+                    rank += (kt < ks) || (kt == ks && (itt < is || (itt == is && t < s)));
+                }
+                a.out_dist[(size_t)q * k + rank] = hd[s];
+                a.out_ids[(size_t)q * k + rank] = is;
+            } else {
+                a.out_dist[(size_t)q * k + s] = __int_as_float(0x7f800000);
+                a.out_ids[(size_t)q * k + s] = 0xffffffffu;
+            }
+        }
+        if (lane == 0) a.out_count[q] = (uint32_t)cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6 (after the NCCL all-gather of per-shard results): k smallest of n_lists x topk candidates per query.
+__global__ void merge_topk_kernel(const float* __restrict__ dist, const uint32_t* __restrict__ ids, int n_lists, size_t nq, int topk,
+                                  float* __restrict__ out_dist, uint32_t* __restrict__ out_ids, uint32_t* __restrict__ out_count) {
+    const int lane = threadIdx.x & 31;
+    const size_t q = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int total = n_lists * topk;
+    uint32_t cnt = 0;
+    for (int s = lane; s < total; s += 32) {
+        const int l = s / topk, i = s % topk;
+        const size_t src = ((size_t)l * nq + q) * topk + i;
+        const uint32_t is = ids[src];
+        if (is == 0xffffffffu) continue;  // unused tail of a shard's list
+        const uint32_t ks = okey(dist[src]);
+        int rank = 0;
+        for (int t = 0; t < total; t++) {
+            const size_t o = ((size_t)(t / topk) * nq + q) * topk + (t % topk);
+            const uint32_t it = ids[o];
+            if (it == 0xffffffffu) continue;
+            const uint32_t kt = okey(dist[o]);
+            rank += (kt < ks) || (kt == ks && (it < is || (it == is && t < s)));
+        }
+        if (rank < topk) {
+            out_dist[q * topk + rank] = dist[src];
+            out_ids[q * topk + rank] = is;
+        }
+        cnt++;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+    const uint32_t have = min(cnt, (uint32_t)topk);
+    for (int s = have + lane; s < topk; s += 32) {
+        out_dist[q * topk + s] = __int_as_float(0x7f800000);
+        out_ids[q * topk + s] = 0xffffffffu;
+    }
+    if (lane == 0) out_count[q] = have;
+}
+
+__global__ void fill_f32_kernel(float* p, size_t n, float v) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace rq

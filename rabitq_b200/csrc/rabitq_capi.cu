@@ -1,0 +1,751 @@
+// rabitq_capi.cu -- host side of librabitq_b200.so: the C ABI declared in include/rabitq_b200.h, the on-disk
+// loader (six-file layout of RaBitQ::dump_to_dir, src/rabitq.rs:128-156) and the batch pipeline that strings
+// the sm_100a kernels of kernels.cuh together on one CUDA stream.  No CPU fallback exists: every compute
+// entry fails with RABITQ_ECUDA when no device is present.
+#include "../../include/rabitq_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(e_ == cudaErrorMemoryAllocation ? RABITQ_ENOMEM : RABITQ_ECUDA,                      \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+// ---- vecs files (src/utils.rs:280-330): record = u32 count, then count elements -------------------------------
+template <typename T>
+bool read_vecs(const std::string& path, std::vector<T>& flat, std::vector<size_t>& rec_len) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    flat.clear();
+    rec_len.clear();
+    flat.reserve(size_t(sz) / sizeof(T));
+    uint32_t cnt;
+    while (std::fread(&cnt, 4, 1, f) == 1) {
+        size_t old = flat.size();
+        flat.resize(old + cnt);
+        if (cnt && std::fread(flat.data() + old, sizeof(T), cnt, f) != cnt) {
+            std::fclose(f);
+            return false;
+        }
+        rec_len.push_back(cnt);
+    }
+    std::fclose(f);
+    return true;
+}
+
+enum Stage { ST_H2D = 0, ST_ROTATE, ST_CDIST, ST_SELECT, ST_QUANT, ST_BUCKET, ST_SCAN, ST_RERANK, ST_D2H, ST_TOTAL, ST_N };
+
+}  // namespace
+
+struct rabitq_index {
+    int device = 0;
+    uint32_t D = 0;
+    size_t n = 0, K = 0;  // vectors held by this shard, clusters (all)
+    int shard_rank = 0, shard_count = 1;
+    int sm_count = 148;
+    uint32_t max_cluster = 0;
+    // resident index (HBM)
+    float* base = nullptr;        // n x D
+    float* P = nullptr;           // D x D rows
+    float* cent = nullptr;        // K x D
+    uint32_t* offsets = nullptr;  // K+1, local rows
+    uint32_t* map_ids = nullptr;  // n
+    uint32_t* codes = nullptr;    // n x D/32
+    float4* factors = nullptr;    // n
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::vector<uint32_t> rounds{0, 1};
+    // work buffers
+    DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_wbase, q_pbase, qrec, cl_count,
+        cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, bitmap,
+        entries, counters, out_dist, out_ids, out_count;
+    uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
+    // metrics (src/metrics.rs)
+    uint64_t m_query = 0, m_rough = 0, m_precise = 0;
+    // last-call measurements
+    float ms[ST_N] = {0};
+    uint64_t counts[6] = {0};
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_stage;
+    size_t ev_used = 0;
+    int scan_blocks_per_sm = 0;
+
+    ~rabitq_index() {
+        cudaSetDevice(device);
+        for (void* p : {(void*)base, (void*)P, (void*)cent, (void*)offsets, (void*)map_ids, (void*)codes, (void*)factors})
+            if (p) cudaFree(p);
+        for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_wbase, &q_pbase,
+                          &qrec, &cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &thr, &heap_dist,
+                          &heap_ids, &heap_cnt, &q_precise, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count})
+            b->release();
+        if (h_pin) cudaFreeHost(h_pin);
+        for (auto e : ev_pool) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+using namespace rq;
+
+int tick(rabitq_index* ix, int stage) {
+    if (ix->ev_used == ix->ev_pool.size()) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        ix->ev_pool.push_back(e);
+        ix->ev_stage.push_back(0);
+    }
+    ix->ev_stage[ix->ev_used] = stage;
+    CU(cudaEventRecord(ix->ev_pool[ix->ev_used], ix->stream));
+    ix->ev_used++;
+    return 0;
+}
+
+int collect_timings(rabitq_index* ix) {
+    CU(cudaStreamSynchronize(ix->stream));
+    for (size_t i = 1; i < ix->ev_used; i++) {
+        if (ix->ev_stage[i] < 0) continue;  // a restart marker
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, ix->ev_pool[i - 1], ix->ev_pool[i]));
+        ix->ms[ix->ev_stage[i]] += t;
+    }
+    if (ix->ev_used >= 2) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, ix->ev_pool[0], ix->ev_pool[ix->ev_used - 1]));
+        ix->ms[ST_TOTAL] = t;
+    }
+    return 0;
+}
+
+// ---- shard geometry: contiguous cluster-id ranges balanced by vector count --------------------------------------
+void shard_rows(const uint32_t* offsets, size_t K, int rank, int count, size_t* row_lo, size_t* row_hi) {
+    size_t N = offsets[K];
+    auto bound = [&](int r) -> size_t {
+        if (r <= 0) return 0;
+        if (r >= count) return N;
+        size_t target = N * size_t(r) / size_t(count);
+        const uint32_t* it = std::lower_bound(offsets, offsets + K + 1, (uint32_t)target);
+        return *it;
+    };
+    *row_lo = bound(rank);
+    *row_hi = bound(rank + 1);
+}
+
+// Build a handle from host or device arrays (full index); keeps only this shard's rows.
+int make_index(uint32_t dim, size_t n_total, size_t K, const float* base, const float* orth, const float* cent,
+               const uint32_t* offsets_h /* host copy, always */, const uint32_t* map_ids, const uint64_t* codes,
+               const float* factors, bool on_device, int device, int shard_rank, int shard_count, rabitq_index** out) {
+    if (dim == 0 || dim % 64 != 0) return fail(RABITQ_EINVAL, "assertion failed: dim % 64 == 0");
+    if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return fail(RABITQ_EINVAL, "bad shard rank/count");
+    if (K == 0) return fail(RABITQ_EINVAL, "offsets is empty");
+    if (offsets_h[K] != n_total) return fail(RABITQ_EINVAL, "offsets[k] != number of vectors");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RABITQ_ECUDA, "no CUDA device: rabitq_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(RABITQ_EINVAL, "bad device ordinal");
+    CU(cudaSetDevice(device));
+    auto ix = new rabitq_index();
+    ix->device = device;
+    ix->D = dim;
+    ix->K = K;
+    ix->shard_rank = shard_rank;
+    ix->shard_count = shard_count;
+    size_t row_lo, row_hi;
+    shard_rows(offsets_h, K, shard_rank, shard_count, &row_lo, &row_hi);
+    ix->n = row_hi - row_lo;
+    std::vector<uint32_t> loc(K + 1);
+    uint32_t mx = 0;
+    for (size_t c = 0; c <= K; c++) {
+        size_t o = std::min(std::max((size_t)offsets_h[c], row_lo), row_hi) - row_lo;
+        loc[c] = (uint32_t)o;
+        if (c) mx = std::max(mx, loc[c] - loc[c - 1]);
+    }
+    ix->max_cluster = mx;
+    const size_t D = dim, W32 = D / 32, n = ix->n;
+    cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+#define ALLOC_COPY(dst, type, count, src)                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = cudaMalloc((void**)&(dst), std::max<size_t>((count) * sizeof(type), 16)); \
+        if (e_ != cudaSuccess) { delete ix; return fail(RABITQ_ENOMEM, std::string("cudaMalloc ") + #dst + ": " + cudaGetErrorString(e_)); } \
+        if ((count) > 0) {                                                                         \
+            e_ = cudaMemcpy((dst), (src), (count) * sizeof(type), kind);                           \
+            if (e_ != cudaSuccess) { delete ix; return fail(RABITQ_ECUDA, std::string("cudaMemcpy ") + #dst + ": " + cudaGetErrorString(e_)); } \
+        }                                                                                          \
+    } while (0)
+    ALLOC_COPY(ix->base, float, n * D, base + row_lo * D);
+    ALLOC_COPY(ix->P, float, D * D, orth);
+    ALLOC_COPY(ix->cent, float, K * D, cent);
+    ALLOC_COPY(ix->map_ids, uint32_t, n, map_ids + row_lo);
+    ALLOC_COPY(ix->codes, uint32_t, n * W32, reinterpret_cast<const uint32_t*>(codes) + row_lo * W32);
+    ALLOC_COPY(ix->factors, float4, n, reinterpret_cast<const float4*>(factors) + row_lo);
+#undef ALLOC_COPY
+    {
+        cudaError_t e_ = cudaMalloc((void**)&ix->offsets, (K + 1) * 4);
+        if (e_ == cudaSuccess) e_ = cudaMemcpy(ix->offsets, loc.data(), (K + 1) * 4, cudaMemcpyHostToDevice);
+        if (e_ != cudaSuccess) { delete ix; return fail(RABITQ_ECUDA, std::string("offsets upload: ") + cudaGetErrorString(e_)); }
+    }
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    ix->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CU(cudaMallocHost((void**)&ix->h_pin, 256));
+    CU(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    *out = ix;
+    return RABITQ_OK;
+}
+
+int load_dir(const char* dir, int device, int shard_rank, int shard_count, rabitq_index** out) {
+    if (!dir || !out) return fail(RABITQ_EINVAL, "null argument");
+    std::string d(dir);
+    std::vector<float> orth, cent_dk, fac, base;
+    std::vector<uint32_t> offs;
+    std::vector<uint64_t> xb;
+    std::vector<size_t> rl_orth, rl_cent, rl_fac, rl_base, rl_offs, rl_xb;
+    if (!read_vecs(d + "/orthogonal.fvecs", orth, rl_orth) || rl_orth.empty()) return fail(RABITQ_EIO, "read vecs error: orthogonal.fvecs");
+    if (!read_vecs(d + "/centroids.fvecs", cent_dk, rl_cent) || rl_cent.empty()) return fail(RABITQ_EIO, "read vecs error: centroids.fvecs");
+    if (!read_vecs(d + "/offsets_ids.ivecs", offs, rl_offs)) return fail(RABITQ_EIO, "open offsets_ids error");
+    if (rl_offs.empty()) return fail(RABITQ_EINVAL, "offsets is empty");
+    if (!read_vecs(d + "/factors.fvecs", fac, rl_fac)) return fail(RABITQ_EIO, "open factors error");
+    if (!read_vecs(d + "/x_binary_vec.u64vecs", xb, rl_xb)) return fail(RABITQ_EIO, "open x_binary_vec error");
+    if (!read_vecs(d + "/base.fvecs", base, rl_base)) return fail(RABITQ_EIO, "read vecs error: base.fvecs");
+    const size_t D = rl_orth.size();  // orthogonal.nrows(), rabitq.rs:108
+    if (D % 64 != 0) return fail(RABITQ_EINVAL, "assertion failed: dim % 64 == 0");
+    if (orth.size() != D * D) return fail(RABITQ_EINVAL, "orthogonal.fvecs is not square");
+    if (rl_cent.size() != D) return fail(RABITQ_EINVAL, "centroids.fvecs must hold dim records (matrix is dim x k)");
+    const size_t K = rl_cent[0];
+    if (cent_dk.size() != D * K) return fail(RABITQ_EINVAL, "centroids.fvecs records differ in length");
+    // offsets = first record, map_ids = last record (rabitq.rs:90-91)
+    const size_t off_len = rl_offs.front(), ids_len = rl_offs.back();
+    if (off_len != K + 1) return fail(RABITQ_EINVAL, "offsets length != k + 1");
+    const uint32_t* offsets = offs.data();
+    const uint32_t* map_ids = offs.data() + (offs.size() - ids_len);
+    const size_t N = ids_len;
+    if (base.size() != N * D) return fail(RABITQ_EINVAL, "base.fvecs size != n * dim");
+    if (fac.size() != N * 4) return fail(RABITQ_EINVAL, "factors.fvecs size != 4 * n");
+    if (xb.size() != N * (D / 64)) return fail(RABITQ_EINVAL, "x_binary_vec.u64vecs size != n * dim / 64");
+    // file rows are components (dim x k); the device wants each rotated centroid contiguous (k x dim)
+    std::vector<float> cent(K * D);
+    for (size_t dd = 0; dd < D; dd++)
+        for (size_t c = 0; c < K; c++) cent[c * D + dd] = cent_dk[dd * K + c];
+    return make_index((uint32_t)D, N, K, base.data(), orth.data(), cent.data(), offsets, map_ids, xb.data(), fac.data(), false,
+                      device, shard_rank, shard_count, out);
+}
+
+// ---- scan launch ------------------------------------------------------------------------------------------------
+template <int W32, bool DENSE>
+int launch_scan_t(rabitq_index* ix, ScanArgs& a) {
+    constexpr int RS = 4 * W32 + 8;
+    int qs = 24576 / (RS * 4);
+    qs = std::max(8, std::min(qs, SCAN_THREADS));
+    a.QS = qs;
+    size_t smem = (size_t)qs * (RS * 4 + 4);
+    auto kern = scan_kernel<W32, 1, DENSE>;
+    int bps = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SCAN_THREADS, smem));
+    bps = std::max(1, bps);
+    ix->scan_blocks_per_sm = bps;
+    kern<<<ix->sm_count * bps, SCAN_THREADS, smem, ix->stream>>>(a);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <bool DENSE>
+int launch_scan(rabitq_index* ix, ScanArgs& a) {
+    switch (ix->D / 32) {
+#define C(w) case w: return launch_scan_t<w, DENSE>(ix, a);
+        C(2) C(4) C(6) C(8) C(10) C(12) C(14) C(16) C(18) C(20) C(24) C(28) C(30) C(32) C(40) C(48) C(64)
+#undef C
+        default:
+            return fail(RABITQ_EUNSUPPORTED, "code scan is instantiated for dim in {64..640 step 64, 768, 896, 960, 1024, 1280, 1536, 2048}");
+    }
+}
+
+enum StopAfter { STOP_ROTATE, STOP_PROBE, STOP_QUANT, STOP_SCAN_DENSE, STOP_NONE };
+
+struct BatchOut {  // device pointers of the sub-batch products
+    uint32_t P = 0;
+    uint32_t total_words = 0;
+    uint64_t total_pairs = 0;
+};
+
+// One sub-batch of nb queries, already on the device in ix->qraw (nb x len).  Runs up to `stop`.
+int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t topk, StopAfter stop, BatchOut* bo) {
+    const int D = (int)ix->D, K = (int)ix->K;
+    const int P = (int)std::min(probe, ix->K);
+    const int W32 = D / 32, RS = 4 * W32 + 8;
+    cudaStream_t st = ix->stream;
+    bo->P = P;
+    CU(ix->qpad.ensure(nb * D * 4));
+    CU(ix->y.ensure(nb * D * 4));
+    {
+        size_t tot = nb * (size_t)D;
+        pad_queries_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ix->qraw.as<float>(), ix->qpad.as<float>(), nb, (int)len, D);
+        CU(cudaGetLastError());
+    }
+    if (tick(ix, ST_H2D)) return RABITQ_ECUDA;
+    {
+        dim3 grid((D + ROT_THREADS - 1) / ROT_THREADS, (unsigned)((nb + ROT_TQ - 1) / ROT_TQ));
+        rotate_kernel<<<grid, ROT_THREADS, 0, st>>>(ix->qpad.as<float>(), ix->P, ix->y.as<float>(), (int)nb, D);
+        CU(cudaGetLastError());
+    }
+    if (tick(ix, ST_ROTATE)) return RABITQ_ECUDA;
+    if (stop == STOP_ROTATE) return 0;
+
+    CU(ix->cdist.ensure(nb * (size_t)K * 4));
+    {
+        dim3 grid((K + CD_THREADS - 1) / CD_THREADS, (unsigned)((nb + CD_TQ - 1) / CD_TQ));
+        centroid_dist_kernel<<<grid, CD_THREADS, 0, st>>>(ix->cent, ix->y.as<float>(), ix->cdist.as<float>(), (int)nb, K, D);
+        CU(cudaGetLastError());
+    }
+    if (tick(ix, ST_CDIST)) return RABITQ_ECUDA;
+    CU(ix->probe_ids.ensure(nb * P * 4));
+    CU(ix->probe_dist.ensure(nb * P * 4));
+    CU(ix->slot_local.ensure(nb * P * 4));
+    CU(ix->q_words.ensure(nb * 4));
+    CU(ix->q_pairs.ensure(nb * 4));
+    CU(ix->q_wbase.ensure((nb + 1) * 4));
+    CU(ix->q_pbase.ensure((nb + 1) * 8));
+    {
+        int Ppow2 = 1;
+        while (Ppow2 < P) Ppow2 <<= 1;
+        select_probe_kernel<<<(unsigned)nb, SEL_THREADS, (size_t)Ppow2 * 8, st>>>(
+            ix->cdist.as<float>(), K, P, Ppow2, ix->offsets, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(),
+            ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>());
+        CU(cudaGetLastError());
+        query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nb,
+                                                   ix->q_wbase.as<uint32_t>(), ix->q_pbase.as<unsigned long long>());
+        CU(cudaGetLastError());
+    }
+    // totals to the host: sizes the survivor slots
+    CU(cudaMemcpyAsync(ix->h_pin, ix->q_wbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ix->h_pin + 2, ix->q_pbase.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
+    if (tick(ix, ST_SELECT)) return RABITQ_ECUDA;
+    CU(cudaStreamSynchronize(st));
+    bo->total_words = ix->h_pin[0];
+    std::memcpy(&bo->total_pairs, ix->h_pin + 2, 8);
+    if (stop == STOP_PROBE) return 0;
+
+    CU(ix->qrec.ensure(nb * (size_t)P * RS * 4));
+    {
+        size_t warps = nb * (size_t)P;
+        quantize_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(ix->y.as<float>(), ix->cent, ix->probe_ids.as<uint32_t>(),
+                                                                       ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(),
+                                                                       ix->q_wbase.as<uint32_t>(), ix->qrec.as<uint32_t>(), (int)nb, P, D);
+        CU(cudaGetLastError());
+    }
+    if (tick(ix, ST_QUANT)) return RABITQ_ECUDA;
+    if (stop == STOP_QUANT) return 0;
+
+    // survivor slots: one bitmap word + 32 (rough, j) entries per 32 vectors of every probed cluster
+    const size_t words = std::max<uint32_t>(bo->total_words, 1);
+    CU(ix->bitmap.ensure(words * 4));
+    CU(ix->entries.ensure(words * 32 * 8));
+    CU(ix->cl_count.ensure((size_t)K * 4));
+    CU(ix->cl_start.ensure((size_t)(K + 1) * 4));
+    CU(ix->item_start.ensure((size_t)(K + 1) * 4));
+    CU(ix->cl_cursor.ensure((size_t)K * 4));
+    CU(ix->cl_items.ensure(nb * (size_t)P * 4));
+    const size_t max_items = ix->n / SCAN_THREADS + (size_t)K + 1;
+    CU(ix->work.ensure(max_items * 8));
+    CU(ix->work_ctl.ensure(16));
+    CU(ix->thr.ensure(nb * 4));
+    CU(ix->heap_dist.ensure(nb * topk * 4));
+    CU(ix->heap_ids.ensure(nb * topk * 4));
+    CU(ix->heap_cnt.ensure(nb * 4));
+    CU(ix->q_precise.ensure(nb * 4));
+    CU(ix->counters.ensure(64));
+    CU(ix->out_dist.ensure(nb * topk * 4));
+    CU(ix->out_ids.ensure(nb * topk * 4));
+    CU(ix->out_count.ensure(nb * 4));
+    CU(cudaMemsetAsync(ix->counters.p, 0, 64, st));
+    fill_f32_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(ix->thr.as<float>(), nb, 3.402823466e+38f);
+    CU(cudaGetLastError());
+
+    ScanArgs sa;
+    sa.codes = ix->codes;
+    sa.factors = ix->factors;
+    sa.offsets = ix->offsets;
+    sa.cl_start = ix->cl_start.as<uint32_t>();
+    sa.cl_items = ix->cl_items.as<uint32_t>();
+    sa.work = ix->work.as<uint2>();
+    sa.work_ctl = ix->work_ctl.as<uint32_t>();
+    sa.qrec = ix->qrec.as<uint32_t>();
+    sa.thr = ix->thr.as<float>();
+    sa.bitmap = ix->bitmap.as<uint32_t>();
+    sa.entries = ix->entries.as<float2>();
+    sa.counters = ix->counters.as<unsigned long long>();
+    sa.P = P;
+    sa.QS = 0;
+
+    RerankArgs ra;
+    ra.qpad = ix->qpad.as<float>();
+    ra.base = ix->base;
+    ra.map_ids = ix->map_ids;
+    ra.q_wbase = ix->q_wbase.as<uint32_t>();
+    ra.slot_local = ix->slot_local.as<uint32_t>();
+    ra.bitmap = ix->bitmap.as<uint32_t>();
+    ra.entries = ix->entries.as<float2>();
+    ra.heap_dist = ix->heap_dist.as<float>();
+    ra.heap_ids = ix->heap_ids.as<uint32_t>();
+    ra.heap_cnt = ix->heap_cnt.as<uint32_t>();
+    ra.thr = ix->thr.as<float>();
+    ra.q_precise = ix->q_precise.as<uint32_t>();
+    ra.counters = ix->counters.as<unsigned long long>();
+    ra.out_dist = ix->out_dist.as<float>();
+    ra.out_ids = ix->out_ids.as<uint32_t>();
+    ra.out_count = ix->out_count.as<uint32_t>();
+    ra.nq = (int)nb;
+    ra.P = P;
+    ra.D = D;
+    ra.topk = (int)topk;
+
+    // rounds of probe ranks
+    std::vector<int> bounds;
+    if (stop == STOP_SCAN_DENSE) bounds = {0, P};
+    else {
+        for (uint32_t r : ix->rounds)
+            if ((int)r < P && (bounds.empty() || (int)r > bounds.back())) bounds.push_back((int)r);
+        if (bounds.empty() || bounds[0] != 0) bounds.insert(bounds.begin(), 0);
+        bounds.push_back(P);
+    }
+    for (size_t r = 0; r + 1 < bounds.size(); r++) {
+        const int p_lo = bounds[r], p_hi = bounds[r + 1];
+        const size_t items = nb * (size_t)(p_hi - p_lo);
+        CU(cudaMemsetAsync(ix->cl_count.p, 0, (size_t)K * 4, st));
+        bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), nb, P, p_lo, p_hi,
+                                                                              ix->cl_count.as<uint32_t>());
+        CU(cudaGetLastError());
+        bucket_scan_kernel<<<1, 1024, 0, st>>>(ix->cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, ix->cl_start.as<uint32_t>(),
+                                               ix->item_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(), ix->work_ctl.as<uint32_t>());
+        CU(cudaGetLastError());
+        bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), nb, P, p_lo, p_hi,
+                                                                             ix->cl_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
+                                                                             ix->cl_items.as<uint32_t>());
+        CU(cudaGetLastError());
+        work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(ix->item_start.as<uint32_t>(), K, ix->work.as<uint2>());
+        CU(cudaGetLastError());
+        if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
+        int rc = (stop == STOP_SCAN_DENSE) ? launch_scan<true>(ix, sa) : launch_scan<false>(ix, sa);
+        if (rc) return rc;
+        if (tick(ix, ST_SCAN)) return RABITQ_ECUDA;
+        ix->counts[4] += 1;
+        ix->counts[5] += 6;
+        if (stop == STOP_SCAN_DENSE) return 0;
+        const size_t smem = (size_t)RR_WARPS * (D + 2 * topk) * 4;
+        rerank_kernel<<<(unsigned)((nb + RR_WARPS - 1) / RR_WARPS), RR_WARPS * 32, smem, st>>>(ra, p_lo, p_hi, r == 0 ? 1 : 0,
+                                                                                                r + 2 == bounds.size() ? 1 : 0);
+        CU(cudaGetLastError());
+        if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
+    }
+    ix->counts[5] += 7;  // pad, rotate, cdist, select, base scan, quantize, fill
+    return 0;
+}
+
+int validate_query_args(const rabitq_index* ix, size_t len, size_t probe, size_t topk, int heuristic) {
+    if (!ix) return fail(RABITQ_EINVAL, "null index");
+    if ((len + 63) / 64 * 64 != ix->D)
+        return fail(RABITQ_EINVAL, "assertion `left == right` failed: dim != query.len().div_ceil(64) * 64");
+    if (probe == 0) return fail(RABITQ_EINVAL, "probe must be >= 1 (the reference underflows on `length - 1`)");
+    if (std::min(probe, ix->K) > 4096) return fail(RABITQ_EUNSUPPORTED, "probe > 4096 is not supported");
+    if (topk == 0) return fail(RABITQ_EINVAL, "topk must be >= 1 (the reference panics on an empty heap peek)");
+    if (topk > 1024) return fail(RABITQ_EUNSUPPORTED, "topk > 1024 is not supported");
+    if (heuristic) return fail(RABITQ_EUNSUPPORTED, "heuristic_rank (HeuristicReRanker) is not built yet");
+    return 0;
+}
+
+size_t pick_sub_batch(const rabitq_index* ix, size_t nq, size_t probe) {
+    const size_t K = ix->K, P = std::min(probe, K);
+    size_t nb = 65536;
+    nb = std::min(nb, ((size_t)1 << 31) / (K * 4) ? ((size_t)1 << 31) / (K * 4) : 1);  // centroid distances <= 2 GiB
+    // survivor slots: 260 B per 32-vector word; budget 12 GiB of slots (2x headroom on the average cluster size)
+    double words_per_q = double(P) * (double(ix->n) / double(K) / 32.0 + 1.0) * 2.0;
+    size_t by_slots = (size_t)std::max(1.0, (12.0 * 1073741824.0 / 260.0) / words_per_q);
+    nb = std::min(nb, by_slots);
+    nb = std::min(nb, (size_t)0xffffffffu / std::max<size_t>(P, 1));
+    return std::max<size_t>(1, std::min(nb, nq));
+}
+
+int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, size_t nq, size_t len, size_t probe, size_t topk,
+                     int heuristic, float* out_dist, uint32_t* out_ids, uint32_t* out_count) {
+    int rc = validate_query_args(ix, len, probe, topk, heuristic);
+    if (rc) return rc;
+    if (nq == 0) return RABITQ_OK;
+    if (!queries || !out_dist || !out_ids) return fail(RABITQ_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    std::memset(ix->ms, 0, sizeof(ix->ms));
+    std::memset(ix->counts, 0, sizeof(ix->counts));
+    ix->ev_used = 0;
+    const size_t nbmax = pick_sub_batch(ix, nq, probe);
+    cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaMemcpyKind kout = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (tick(ix, -1)) return RABITQ_ECUDA;
+    for (size_t q0 = 0; q0 < nq; q0 += nbmax) {
+        const size_t nb = std::min(nbmax, nq - q0);
+        CU(ix->qraw.ensure(nb * len * 4));
+        CU(cudaMemcpyAsync(ix->qraw.p, queries + q0 * len, nb * len * 4, kin, ix->stream));
+        BatchOut bo;
+        rc = run_sub_batch(ix, nb, len, probe, topk, STOP_NONE, &bo);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(out_dist + q0 * topk, ix->out_dist.p, nb * topk * 4, kout, ix->stream));
+        CU(cudaMemcpyAsync(out_ids + q0 * topk, ix->out_ids.p, nb * topk * 4, kout, ix->stream));
+        if (out_count) CU(cudaMemcpyAsync(out_count + q0, ix->out_count.p, nb * 4, kout, ix->stream));
+        CU(cudaMemcpyAsync(ix->h_pin + 8, ix->counters.p, 32, cudaMemcpyDeviceToHost, ix->stream));
+        if (tick(ix, ST_D2H)) return RABITQ_ECUDA;
+        CU(cudaStreamSynchronize(ix->stream));
+        unsigned long long c[4];
+        std::memcpy(c, ix->h_pin + 8, 32);
+        ix->counts[0] += bo.total_pairs;
+        ix->counts[1] += c[0];
+        ix->counts[2] += c[1];
+        ix->counts[3] += c[2];
+        ix->m_rough += bo.total_pairs;
+        ix->m_precise += c[2];
+        ix->m_query += nb;
+    }
+    return collect_timings(ix);
+}
+
+// helper for the stage entries: upload host queries and run the front of the pipeline
+int stage_prefix(rabitq_index* ix, const float* queries, size_t nq, size_t len, size_t probe, StopAfter stop, BatchOut* bo) {
+    int rc = validate_query_args(ix, len, probe, 1, 0);
+    if (rc) return rc;
+    if (!queries || nq == 0) return fail(RABITQ_EINVAL, "null/empty queries");
+    if (nq > 65536 || nq * ix->K > ((size_t)1 << 29)) return fail(RABITQ_EUNSUPPORTED, "stage entries take small batches only");
+    CU(cudaSetDevice(ix->device));
+    ix->ev_used = 0;
+    std::memset(ix->ms, 0, sizeof(ix->ms));
+    std::memset(ix->counts, 0, sizeof(ix->counts));
+    CU(ix->qraw.ensure(nq * len * 4));
+    CU(cudaMemcpyAsync(ix->qraw.p, queries, nq * len * 4, cudaMemcpyHostToDevice, ix->stream));
+    if (tick(ix, -1)) return RABITQ_ECUDA;
+    rc = run_sub_batch(ix, nq, len, probe, 1, stop, bo);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ix->stream));
+    return 0;
+}
+
+}  // namespace
+
+// ===================================================================================================================
+extern "C" {
+
+const char* rabitq_last_error(void) { return g_err.c_str(); }
+
+int rabitq_load_from_dir(const char* dir, int device, rabitq_index** out) { return load_dir(dir, device, 0, 1, out); }
+
+int rabitq_load_from_dir_sharded(const char* dir, int device, int shard_rank, int shard_count, rabitq_index** out) {
+    return load_dir(dir, device, shard_rank, shard_count, out);
+}
+
+int rabitq_from_arrays(uint32_t dim, size_t n, size_t k, const float* base, const float* orthogonal, const float* centroids,
+                       const uint32_t* offsets, const uint32_t* map_ids, const uint64_t* codes, const float* factors,
+                       int ptr_on_device, int device, int shard_rank, int shard_count, rabitq_index** out) {
+    if (!base || !orthogonal || !centroids || !offsets || !map_ids || !codes || !factors || !out)
+        return fail(RABITQ_EINVAL, "null argument");
+    std::vector<uint32_t> off_h(k + 1);
+    if (ptr_on_device) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            return fail(RABITQ_ECUDA, "no CUDA device: rabitq_b200 has no CPU fallback");
+        }
+        CU(cudaSetDevice(device));
+        CU(cudaMemcpy(off_h.data(), offsets, (k + 1) * 4, cudaMemcpyDeviceToHost));
+    } else {
+        std::memcpy(off_h.data(), offsets, (k + 1) * 4);
+    }
+    return make_index(dim, n, k, base, orthogonal, centroids, off_h.data(), map_ids, codes, factors, ptr_on_device != 0, device,
+                      shard_rank, shard_count, out);
+}
+
+void rabitq_free(rabitq_index* idx) { delete idx; }
+
+uint32_t rabitq_dim(const rabitq_index* idx) { return idx ? idx->D : 0; }
+size_t rabitq_num_vectors(const rabitq_index* idx) { return idx ? idx->n : 0; }
+size_t rabitq_num_clusters(const rabitq_index* idx) { return idx ? idx->K : 0; }
+
+int rabitq_query(rabitq_index* idx, const float* query, size_t len, size_t probe, size_t topk, int heuristic_rank,
+                 float* out_dist, uint32_t* out_ids, uint32_t* out_count) {
+    return query_batch_impl(idx, query, false, 1, len, probe, topk, heuristic_rank, out_dist, out_ids, out_count);
+}
+
+int rabitq_query_batch(rabitq_index* idx, const float* queries, size_t nq, size_t len, size_t probe, size_t topk,
+                       int heuristic_rank, float* out_dist, uint32_t* out_ids, uint32_t* out_count) {
+    return query_batch_impl(idx, queries, false, nq, len, probe, topk, heuristic_rank, out_dist, out_ids, out_count);
+}
+
+int rabitq_query_batch_device(rabitq_index* idx, const float* d_queries, size_t nq, size_t len, size_t probe, size_t topk,
+                              int heuristic_rank, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count) {
+    return query_batch_impl(idx, d_queries, true, nq, len, probe, topk, heuristic_rank, d_out_dist, d_out_ids, d_out_count);
+}
+
+int rabitq_merge_topk_device(int device, const float* d_dist, const uint32_t* d_ids, int n_lists, size_t nq, size_t topk,
+                             float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count) {
+    if (!d_dist || !d_ids || !d_out_dist || !d_out_ids || !d_out_count || n_lists < 1 || topk == 0)
+        return fail(RABITQ_EINVAL, "bad argument");
+    if (nq == 0) return RABITQ_OK;
+    CU(cudaSetDevice(device));
+    rq::merge_topk_kernel<<<(unsigned)((nq + 3) / 4), 128>>>(d_dist, d_ids, n_lists, nq, (int)topk, d_out_dist, d_out_ids, d_out_count);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return RABITQ_OK;
+}
+
+void rabitq_metrics(const rabitq_index* idx, uint64_t out[4]) {
+    out[0] = idx ? idx->m_query : 0;
+    out[1] = idx ? idx->m_rough : 0;
+    out[2] = idx ? idx->m_precise : 0;
+    out[3] = 0;  // cache miss: the disk/S3 cache of crates/disk is out of scope; base vectors are HBM-resident
+}
+
+void rabitq_metrics_reset(rabitq_index* idx) {
+    if (idx) idx->m_query = idx->m_rough = idx->m_precise = 0;
+}
+
+int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n) {
+    if (!idx || !rounds || n < 1 || rounds[0] != 0) return fail(RABITQ_EINVAL, "rounds must start at 0");
+    for (int i = 1; i < n; i++)
+        if (rounds[i] <= rounds[i - 1]) return fail(RABITQ_EINVAL, "rounds must be strictly increasing");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    idx->rounds.assign(rounds, rounds + n);
+    return RABITQ_OK;
+}
+
+int rabitq_last_timings(const rabitq_index* idx, float ms[10], uint64_t counts[6]) {
+    if (!idx) return fail(RABITQ_EINVAL, "null index");
+    if (ms) std::memcpy(ms, idx->ms, sizeof(float) * 10);
+    if (counts) std::memcpy(counts, idx->counts, sizeof(uint64_t) * 6);
+    return RABITQ_OK;
+}
+
+// ---- stage entries --------------------------------------------------------------------------------------------------
+int rabitq_stage_rotate(rabitq_index* idx, const float* queries, size_t nq, size_t len, float* out_y) {
+    if (!idx) return fail(RABITQ_EINVAL, "null index");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    BatchOut bo;
+    int rc = stage_prefix(idx, queries, nq, len, 1, STOP_ROTATE, &bo);
+    if (rc) return rc;
+    CU(cudaMemcpy(out_y, idx->y.p, nq * idx->D * 4, cudaMemcpyDeviceToHost));
+    return RABITQ_OK;
+}
+
+int rabitq_stage_probe(rabitq_index* idx, const float* queries, size_t nq, size_t len, size_t probe, float* out_centroid_dist,
+                       uint32_t* out_probe_ids, float* out_probe_dist) {
+    if (!idx) return fail(RABITQ_EINVAL, "null index");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    BatchOut bo;
+    int rc = stage_prefix(idx, queries, nq, len, probe, STOP_PROBE, &bo);
+    if (rc) return rc;
+    if (out_centroid_dist) CU(cudaMemcpy(out_centroid_dist, idx->cdist.p, nq * idx->K * 4, cudaMemcpyDeviceToHost));
+    if (out_probe_ids) CU(cudaMemcpy(out_probe_ids, idx->probe_ids.p, nq * bo.P * 4, cudaMemcpyDeviceToHost));
+    if (out_probe_dist) CU(cudaMemcpy(out_probe_dist, idx->probe_dist.p, nq * bo.P * 4, cudaMemcpyDeviceToHost));
+    return RABITQ_OK;
+}
+
+int rabitq_stage_quantize(rabitq_index* idx, const float* queries, size_t nq, size_t len, size_t probe, float* out_lo,
+                          float* out_delta, uint32_t* out_sum, uint64_t* out_planes) {
+    if (!idx) return fail(RABITQ_EINVAL, "null index");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    BatchOut bo;
+    int rc = stage_prefix(idx, queries, nq, len, probe, STOP_QUANT, &bo);
+    if (rc) return rc;
+    const size_t W32 = idx->D / 32, RS = 4 * W32 + 8, items = nq * bo.P;
+    std::vector<uint32_t> rec(items * RS);
+    CU(cudaMemcpy(rec.data(), idx->qrec.p, items * RS * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < items; i++) {
+        const uint32_t* r = &rec[i * RS];
+        if (out_planes) std::memcpy(out_planes + i * 2 * W32, r, 4 * W32 * 4);  // [4][W64] u64 little-endian == [4][W32] u32
+        if (out_lo) std::memcpy(&out_lo[i], r + 4 * W32 + 0, 4);
+        if (out_delta) std::memcpy(&out_delta[i], r + 4 * W32 + 1, 4);
+        if (out_sum) out_sum[i] = r[4 * W32 + 5];
+    }
+    return RABITQ_OK;
+}
+
+int rabitq_stage_scan(rabitq_index* idx, const float* queries, size_t nq, size_t len, size_t probe, size_t pair_capacity,
+                      float* out_rough, uint32_t* out_abdp, uint64_t* out_pair_start) {
+    if (!idx) return fail(RABITQ_EINVAL, "null index");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    BatchOut bo;
+    int rc = stage_prefix(idx, queries, nq, len, probe, STOP_SCAN_DENSE, &bo);
+    if (rc) return rc;
+    const size_t P = bo.P, K = idx->K;
+    if (bo.total_pairs > pair_capacity) return fail(RABITQ_EINVAL, "pair_capacity too small");
+    std::vector<uint32_t> wbase(nq + 1), slot(nq * P), pids(nq * P), off(K + 1);
+    std::vector<float2> ent((size_t)bo.total_words * 32);
+    CU(cudaMemcpy(wbase.data(), idx->q_wbase.p, (nq + 1) * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(slot.data(), idx->slot_local.p, nq * P * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(pids.data(), idx->probe_ids.p, nq * P * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(off.data(), idx->offsets, (K + 1) * 4, cudaMemcpyDeviceToHost));
+    if (!ent.empty()) CU(cudaMemcpy(ent.data(), idx->entries.p, ent.size() * 8, cudaMemcpyDeviceToHost));
+    size_t t = 0;
+    for (size_t q = 0; q < nq; q++) {
+        if (out_pair_start) out_pair_start[q] = t;
+        for (size_t p = 0; p < P; p++) {
+            uint32_t c = pids[q * P + p], n_c = off[c + 1] - off[c];
+            size_t w = (size_t)wbase[q] + slot[q * P + p];
+            for (uint32_t v = 0; v < n_c; v++, t++) {
+                float2 e = ent[w * 32 + v];
+                if (out_rough) out_rough[t] = e.x;
+                if (out_abdp) std::memcpy(&out_abdp[t], &e.y, 4);
+            }
+        }
+    }
+    if (out_pair_start) out_pair_start[nq] = t;
+    return RABITQ_OK;
+}
+
+}  // extern "C"

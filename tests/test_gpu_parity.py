@@ -1,0 +1,206 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same seeded index and queries.
+
+Bars (BASELINE.json north_star): quantised codes / bit-planes / popcount sums bit-exact; estimated distances
+within 1e-5 relative (we assert bit-exact); final top-k id lists identical up to exact-distance ties; the
+reference's `rough` and `precise` counters equal.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_index(case):
+    import rabitq_b200 as rb
+
+    a = case["arrays"]
+    return rb.RaBitQ.from_arrays(a["dim"], a["base"], a["orthogonal"], a["centroids"], a["offsets"], a["map_ids"], a["codes"],
+                                 a["factors"], device=0)
+
+
+CASES = ["case_d128", "case_d96", "case_d960"]
+
+
+@pytest.fixture(params=CASES)
+def pair(request):
+    case = request.getfixturevalue(request.param)
+    if "gpu" not in case:
+        case["gpu"] = _gpu_index(case)
+    return case
+
+
+def test_rotate_bit_exact(pair):
+    q = pair["queries"]
+    y = pair["gpu"].stage_rotate(q)
+    for i in range(q.shape[0]):
+        tr = pair["oracle"].trace(q[i], 4, 10)
+        assert np.array_equal(y[i].view(np.uint32), tr["y"].view(np.uint32)), f"query {i}"
+
+
+def test_probe_lists_bit_exact(pair):
+    q = pair["queries"]
+    probe = 12
+    cd, pid, pd = pair["gpu"].stage_probe(q, probe)
+    for i in range(q.shape[0]):
+        tr = pair["oracle"].trace(q[i], probe, 10)
+        assert np.array_equal(cd[i].view(np.uint32), tr["centroid_dist"].view(np.uint32))
+        assert np.array_equal(pid[i], tr["probe_ids"])
+        assert np.array_equal(pd[i].view(np.uint32), tr["probe_dist"].view(np.uint32))
+
+
+def test_probe_larger_than_k(pair):
+    q = pair["queries"][:4]
+    K = pair["gpu"].num_clusters
+    _, pid, _ = pair["gpu"].stage_probe(q, K + 50)
+    assert pid.shape[1] == K
+    for i in range(4):
+        assert sorted(pid[i].tolist()) == list(range(K))
+
+
+def test_quantize_planes_bit_exact(pair):
+    q = pair["queries"]
+    probe = 12
+    lo, delta, s, planes = pair["gpu"].stage_quantize(q, probe)
+    for i in range(q.shape[0]):
+        tr = pair["oracle"].trace(q[i], probe, 10)
+        assert np.array_equal(lo[i].view(np.uint32), tr["lo"].view(np.uint32))
+        assert np.array_equal(delta[i].view(np.uint32), tr["delta"].view(np.uint32))
+        assert np.array_equal(s[i], tr["sum"])
+        assert np.array_equal(planes[i], tr["planes"])
+
+
+def test_scan_abdp_and_rough_bit_exact(pair):
+    q = pair["queries"]
+    probe = 12
+    n = pair["arrays"]["base"].shape[0]
+    rough, abdp, start = pair["gpu"].stage_scan(q, probe, pair_capacity=n * q.shape[0])
+    for i in range(q.shape[0]):
+        tr = pair["oracle"].trace(q[i], probe, 10)
+        s, e = int(start[i]), int(start[i + 1])
+        assert e - s == tr["pairs"]
+        assert np.array_equal(abdp[s:e], tr["abdp"])
+        assert np.array_equal(rough[s:e].view(np.uint32), tr["rough"].view(np.uint32))
+
+
+def _same_up_to_ties(gd, gi, od, oi):
+    """identical distance multiset; ids identical except among equal distances"""
+    go = np.lexsort((gi, gd))
+    oo = np.lexsort((oi, od))
+    gd, gi, od, oi = gd[go], gi[go], od[oo], oi[oo]
+    if not np.array_equal(gd.view(np.uint32), od.view(np.uint32)):
+        return False
+    if np.array_equal(gi, oi):
+        return True
+    for d in np.unique(gd):
+        m = gd == d
+        if m.sum() == 1 and gi[m][0] != oi[m][0]:
+            return False
+    return True
+
+
+@pytest.mark.parametrize("probe,topk", [(1, 10), (8, 10), (32, 1), (64, 100)])
+def test_query_batch_identical_topk_and_counters(pair, probe, topk):
+    q = pair["queries"]
+    g = pair["gpu"]
+    g.metrics_reset()
+    gd, gi, gc = g.query_batch(q, probe, topk)
+    o = pair["oracle"].query_batch(q, probe, topk)
+    assert np.array_equal(gc, o["count"])
+    for i in range(q.shape[0]):
+        c = int(gc[i])
+        assert _same_up_to_ties(gd[i, :c], gi[i, :c], o["dist"][i, :c], o["ids"][i, :c]), f"query {i}"
+        assert np.all(np.diff(gd[i, :c]) >= 0)
+    m = g.metrics()
+    assert m["query"] == q.shape[0]
+    assert m["rough"] == o["rough"]
+    assert m["precise"] == o["precise"]
+
+
+@pytest.mark.parametrize("rounds", [[0], [0, 1], [0, 1, 4, 16], [0, 2, 3, 5, 40]])
+def test_rounds_do_not_change_results(pair, rounds):
+    q = pair["queries"]
+    g = pair["gpu"]
+    g.set_rounds(rounds)
+    try:
+        g.metrics_reset()
+        gd, gi, gc = g.query_batch(q, 48, 10)
+        o = pair["oracle"].query_batch(q, 48, 10)
+        for i in range(q.shape[0]):
+            c = int(gc[i])
+            assert _same_up_to_ties(gd[i, :c], gi[i, :c], o["dist"][i, :c], o["ids"][i, :c])
+        assert g.metrics()["precise"] == o["precise"]
+    finally:
+        g.set_rounds([0, 1])
+
+
+def test_single_query_matches_batch(pair):
+    q = pair["queries"]
+    g = pair["gpu"]
+    gd, gi, gc = g.query_batch(q[:5], 16, 10)
+    for i in range(5):
+        r = g.query(q[i], 16, 10)
+        assert [x[1] for x in r] == gi[i, : int(gc[i])].tolist()
+        assert np.array_equal(np.array([x[0] for x in r], np.float32).view(np.uint32), gd[i, : int(gc[i])].view(np.uint32))
+
+
+def test_load_from_dir_round_trip(pair, tmp_path):
+    import rabitq_b200 as rb
+
+    d = tmp_path / "idx"
+    pair["oracle"].dump_to_dir(str(d))
+    g2 = rb.RaBitQ.load_from_dir(str(d), device=0)
+    q = pair["queries"][:8]
+    a = pair["gpu"].query_batch(q, 16, 10)
+    b = g2.query_batch(q, 16, 10)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    g2.close()
+
+
+def test_errors_match_reference_asserts(pair):
+    import rabitq_b200 as rb
+
+    g = pair["gpu"]
+    D = g.dim
+    with pytest.raises(rb.RabitqError):  # rabitq.rs:275
+        g.query(np.zeros(D + 64, np.float32), 4, 10)
+    with pytest.raises(rb.RabitqError):
+        g.query(np.zeros(D, np.float32), 4, 0)
+    with pytest.raises(rb.RabitqError):
+        rb.RaBitQ.load_from_dir("/nonexistent/dir")
+
+
+def test_sharded_union_equals_full(pair):
+    """cluster-range shards: per-shard top-k merged on the device equals the unsharded top-k distances."""
+    import torch
+
+    import rabitq_b200 as rb
+
+    a = pair["arrays"]
+    q = pair["queries"]
+    topk, probe, S = 10, 32, 3
+    full_d, full_i, _ = pair["gpu"].query_batch(q, probe, topk)
+    ds, is_ = [], []
+    tot = 0
+    for r in range(S):
+        g = rb.RaBitQ.from_arrays(a["dim"], a["base"], a["orthogonal"], a["centroids"], a["offsets"], a["map_ids"], a["codes"],
+                                  a["factors"], device=0, shard_rank=r, shard_count=S)
+        tot += g.num_vectors
+        d, i, _ = g.query_batch(q, probe, topk)
+        ds.append(d); is_.append(i)
+        g.close()
+    assert tot == a["base"].shape[0]
+    D = torch.from_numpy(np.stack(ds)).cuda()
+    I = torch.from_numpy(np.stack(is_).astype(np.int32)).cuda()
+    od = torch.empty((q.shape[0], topk), dtype=torch.float32, device="cuda")
+    oi = torch.empty((q.shape[0], topk), dtype=torch.int32, device="cuda")
+    oc = torch.empty((q.shape[0],), dtype=torch.int32, device="cuda")
+    import ctypes as C
+    rc = rb.lib().rabitq_merge_topk_device(0, C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()), S, q.shape[0], topk,
+                                           C.c_void_p(od.data_ptr()), C.c_void_p(oi.data_ptr()), C.c_void_p(oc.data_ptr()))
+    assert rc == 0
+    md = od.cpu().numpy()
+    # Shard-local thresholds are looser than the global one, so the merged list can only be equal or better.
+    assert np.all(md <= full_d + 0)
+    same = np.mean([np.array_equal(md[i].view(np.uint32), full_d[i].view(np.uint32)) for i in range(q.shape[0])])
+    assert same >= 0.9
