@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- QPS of the IVF-RaBitQ query hot path on B200 (BASELINE.json metric), with the roofline of the code scan
+and the reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|...] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic queries (nq of the workload; nq * N when N GPUs share
+a cluster-sharded index).  `value` is QPS with the queries already resident in HBM, timed with CUDA events on the stream
+the kernels are launched on; `e2e` is the same metric through the host-buffer C-ABI call (pinned host queries in,
+results out, copies inside the timed region).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "QPS @ recall@10>=0.95 (IVF-RaBitQ query batch)"
+TOPK = 10
+PROBE_SWEEP = {"c1": [64], "c2": [16, 32, 64, 128, 256], "c3": [16, 32, 64, 128], "c4": [32], "c5": [64]}
+TARGET_RECALL = 0.95
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """Sample SM clocks and throttle reasons with nvidia-smi DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recall_at_k(ids, truth, k):
+    import torch
+
+    hit = (ids[:, :, None].to(torch.int64) == truth[:, None, :k].to(torch.int64)).any(2).sum(1)
+    return float(hit.float().mean().item()) / k
+
+
+def build_workload(args, device, rank, world):
+    """Synthetic data + index on the device; returns dict with torch tensors."""
+    import torch
+    from tools import synth, build_index_torch as bi
+
+    if args.shape:
+        n, dim, nq, k = [int(x) for x in args.shape.split(",")[:4]]
+        flavour = args.shape.split(",")[4] if len(args.shape.split(",")) > 4 else "sift"
+        shape, seed, name = (n, dim, nq, k, flavour), 77, f"custom {args.shape}"
+    else:
+        shape, seed, name = synth.SHAPES[args.workload], synth.SEEDS[args.workload], args.workload
+    n, dim, nq, k, flavour = shape
+    t0 = time.time()
+    mix = synth.Mixture(dim, k, flavour, seed + 2, device)
+    base = mix.draw(n, seed)
+    queries = mix.draw(nq * world, seed + 1)  # weak scaling: the query batch grows with the number of GPUs
+    cent = mix.centroids()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ix = bi.build_index(base, cent, seed=seed + 3)
+    torch.cuda.synchronize()
+    t2 = time.time()
+    truth = synth.brute_force_topk_torch(base, queries, TOPK)
+    torch.cuda.synchronize()
+    if rank == 0:
+        log(f"[bench] {name}: n={n} dim={dim} nq={nq * world} k={k} ({flavour}); gen {t1 - t0:.1f}s build {t2 - t1:.1f}s truth {time.time() - t2:.1f}s")
+    del base
+    return dict(name=name, n=n, dim=dim, nq=nq * world, k=k, flavour=flavour, queries=queries.contiguous(), truth=truth, index=ix)
+
+
+def oracle_from_index(ix):
+    from oracle import oracle as orc
+    from tools import build_index_torch as bi
+
+    orc.build()
+    a = bi.to_numpy(ix)
+    return orc.OracleIndex.from_built(a["dim"], a["base"], a["orthogonal"], a["centroids"], a["offsets"], a["map_ids"], a["codes"], a["factors"])
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import rabitq_b200 as rb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and rank == 0:
+        log(f"[bench] WORLD_SIZE={world} but --gpus {args.gpus}: using WORLD_SIZE")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    rb.lib()  # fail loudly if the CUDA library is missing
+
+    wl = build_workload(args, device, rank, world)
+    ix, queries, truth = wl["index"], wl["queries"], wl["truth"]
+    nq, D = wl["nq"], ix["dim"]
+    g = rb.RaBitQ.from_arrays(ix["dim"], ix["base"], ix["orthogonal"], ix["centroids"], ix["offsets"], ix["map_ids"], ix["codes"],
+                              ix["factors"], device=local, shard_rank=rank, shard_count=world)
+    stream = torch.cuda.Stream(device)  # a non-default stream shared by torch (events, NCCL) and the library's kernels
+    torch.cuda.synchronize(device)
+    torch.cuda.set_stream(stream)
+    g.set_stream(stream.cuda_stream)
+    if args.rounds:
+        g.set_rounds([int(x) for x in args.rounds.split(",")])
+
+    gather_d = torch.empty((world, nq, TOPK), dtype=torch.float32, device=device) if world > 1 else None
+    gather_i = torch.empty((world, nq, TOPK), dtype=torch.int32, device=device) if world > 1 else None
+    m_d = torch.empty((nq, TOPK), dtype=torch.float32, device=device)
+    m_i = torch.empty((nq, TOPK), dtype=torch.int32, device=device)
+    m_c = torch.empty((nq,), dtype=torch.int32, device=device)
+    import ctypes as C
+
+    def one_pass(probe):
+        d, i, c = g.query_batch(queries, probe, TOPK)
+        if world == 1:
+            return d, i
+        # K6: NCCL all-gather of the per-shard (dist, id) lists over NVLink, then the merge kernel
+        dist.all_gather_into_tensor(gather_d.view(-1), d.view(-1))
+        dist.all_gather_into_tensor(gather_i.view(-1), i.view(-1))
+        torch.cuda.synchronize(device)
+        rc = rb.lib().rabitq_merge_topk_device(local, C.c_void_p(gather_d.data_ptr()), C.c_void_p(gather_i.data_ptr()), world, nq, TOPK,
+                                               C.c_void_p(m_d.data_ptr()), C.c_void_p(m_i.data_ptr()), C.c_void_p(m_c.data_ptr()))
+        assert rc == 0
+        return m_d, m_i
+
+    # ---- choose nprobe: the smallest of the sweep reaching the target recall (outside the timed region) -------------
+    sweep = [args.probe] if args.probe else PROBE_SWEEP.get(args.workload, [64])
+    probe, recall, sweep_log = None, 0.0, {}
+    for p in sweep:
+        _, ids = one_pass(p)
+        r = recall_at_k(ids, truth, TOPK)
+        sweep_log[str(p)] = round(r, 4)
+        probe, recall = p, r
+        if r >= TARGET_RECALL:
+            break
+    if rank == 0:
+        log(f"[bench] recall@{TOPK} by nprobe: {sweep_log} -> nprobe={probe}")
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.zero_()  # flush L2 between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            evs.append((e0, e1))
+        torch.cuda.synchronize(device)
+        return [a.elapsed_time(b) for a, b in evs]
+
+    # ---- device-resident leg ------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        one_pass(probe)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stage_ms = {k: 0.0 for k in rb.TIMING_STAGES}
+    counts = {k: 0 for k in rb.COUNT_NAMES}
+
+    def step_dev():
+        one_pass(probe)
+        t = g.last_timings()
+        for k in rb.TIMING_STAGES:
+            stage_ms[k] += t["ms_" + k]
+        for k in rb.COUNT_NAMES:
+            counts[k] += t[k]
+
+    ms_dev = timed(step_dev, args.steps)
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+
+    # ---- end-to-end leg: pinned host queries in, host results out, through the host-pointer C-ABI call ---------------
+    q_lo, q_hi = 0, nq
+    q_host = torch.empty((nq, queries.shape[1]), dtype=torch.float32).pin_memory()
+    q_host.copy_(queries.cpu())
+    o_d = torch.empty((nq, TOPK), dtype=torch.float32).pin_memory()
+    o_i = torch.empty((nq, TOPK), dtype=torch.int32).pin_memory()
+    o_c = torch.empty((nq,), dtype=torch.int32).pin_memory()
+    qh, od, oi, oc = q_host.numpy(), o_d.numpy(), o_i.numpy().view(np.uint32), o_c.numpy().view(np.uint32)
+    hm_d = torch.empty((nq, TOPK), dtype=torch.float32).pin_memory()
+    hm_i = torch.empty((nq, TOPK), dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        g.query_batch_into(qh, probe, TOPK, od, oi, oc)  # H2D of queries + all kernels + D2H of results inside
+        if world > 1:
+            d = o_d.to(device, non_blocking=True)
+            i = o_i.to(device, non_blocking=True)
+            dist.all_gather_into_tensor(gather_d.view(-1), d.view(-1))
+            dist.all_gather_into_tensor(gather_i.view(-1), i.view(-1))
+            torch.cuda.synchronize(device)
+            rb.lib().rabitq_merge_topk_device(local, C.c_void_p(gather_d.data_ptr()), C.c_void_p(gather_i.data_ptr()), world, nq, TOPK,
+                                              C.c_void_p(m_d.data_ptr()), C.c_void_p(m_i.data_ptr()), C.c_void_p(m_c.data_ptr()))
+            hm_d.copy_(m_d, non_blocking=True)
+            hm_i.copy_(m_i, non_blocking=True)
+            torch.cuda.synchronize(device)
+
+    for _ in range(3):
+        step_e2e()
+    if world > 1:
+        dist.barrier()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ids = torch.from_numpy(oi.view(np.int32).copy()).to(device) if world == 1 else m_i
+    recall_e2e = recall_at_k(e2e_ids, truth, TOPK)
+
+    tot_dev, tot_e2e = sum(ms_dev), sum(ms_e2e)
+    if world > 1:
+        t = torch.tensor([tot_dev, tot_e2e], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_dev, tot_e2e = float(t[0]), float(t[1])
+        c = torch.tensor([counts["pairs"], counts["survivors"], counts["exact_computed"], counts["precise"], counts["kernel_launches"]],
+                         dtype=torch.float64, device=device)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        pairs_all = float(c[0])
+    else:
+        pairs_all = float(counts["pairs"])
+
+    if rank == 0:
+        bytes_per_pair = D // 8 + 16  # packed code + Factor
+        scan_ms = stage_ms["scan"]
+        peak, peak_src = measured_peak_hbm()
+        achieved = counts["pairs"] * bytes_per_pair / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        qps = nq * args.steps / (tot_dev * 1e-3)
+        qps_e2e = nq * args.steps / (tot_e2e * 1e-3)
+        out = {
+            "metric": METRIC, "value": round(qps, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(tot_dev / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32 popcount + f32", "data": "synthetic",
+            "config": {"workload": f"{wl['name']}: {wl['n']}x{wl['dim']} base ({wl['flavour']}-shaped mixture), {nq} queries/step, "
+                                   f"{wl['k']} IVF centroids, nprobe={probe}, top-{TOPK}",
+                       "nprobe": probe, "topk": TOPK, "recall_at_10": round(recall, 4), "recall_by_nprobe": sweep_log,
+                       "timing": "CUDA events on the launch stream, L2 flushed (256 MB write) between timed steps",
+                       "parallelism": "single GPU" if world == 1 else f"index sharded by cluster range over {world} GPUs, "
+                                      f"queries replicated ({nq} = {nq // world} x {world}), NCCL all-gather of (dist,id) + merge kernel",
+                       "rerank_rounds": args.rounds or "0,1"},
+            "e2e": {"value": round(qps_e2e, 1), "unit": "queries/s", "h2d_bytes_per_step": int(nq * queries.shape[1] * 4),
+                    "d2h_bytes_per_step": int(nq * TOPK * 8 + nq * 4), "ms_per_step": round(tot_e2e / args.steps, 4),
+                    "recall_at_10": round(recall_e2e, 4)},
+            "gpu_launches": int(counts["kernel_launches"]),
+            "roofline": {"bound": "hbm", "kernel": "rq::scan_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_pair": bytes_per_pair, "pairs_per_step": counts["pairs"] // args.steps,
+                         "scan_ms_per_step": round(scan_ms / args.steps, 4), "scan_launches_per_step": counts["scan_launches"] // args.steps,
+                         "gpairs_per_s": round(counts["pairs"] / (scan_ms * 1e-3) / 1e9, 2) if scan_ms > 0 else 0.0,
+                         "note": "rank-0 shard; achieved = pairs x (D/8+16) B / scan-kernel time; cross-query reuse keeps real DRAM traffic below this"},
+            "stage_ms_per_step": {k: round(v / args.steps, 4) for k, v in stage_ms.items()},
+            "counters_per_step": {"pairs_all_gpus": int(pairs_all // args.steps), "survivors": counts["survivors"] // args.steps,
+                                  "exact_computed": counts["exact_computed"] // args.steps, "precise": counts["precise"] // args.steps},
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world >= 1:
+            out["cpu_baseline"] = cpu_baseline(wl, probe, threads=1, budget_s=args.cpu_seconds)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(wl, probe, threads, budget_s, fixed_sample=None):
+    """Time the oracle (port of the reference's AVX2 path) on a bounded sample of the same workload."""
+    import numpy as np
+
+    o = oracle_from_index(wl["index"])
+    q = wl["queries"].cpu().numpy()
+    # calibrate on a few queries, then size the sample for ~budget_s of CPU work
+    n0 = min(8 * threads, q.shape[0])
+    r0 = o.query_batch(q[:n0], probe, TOPK, nthreads=threads)
+    per_q = max(r0["seconds"] / n0, 1e-6)
+    ns = fixed_sample or int(min(q.shape[0], max(n0, budget_s / per_q)))
+    r = o.query_batch(q[:ns], probe, TOPK, nthreads=threads)
+    truth = wl["truth"][:ns].cpu().numpy()
+    rec = float(np.mean([len(set(r["ids"][i].tolist()) & set(truth[i].tolist())) / TOPK for i in range(ns)]))
+    return {"value": round(ns / r["seconds"], 2), "unit": "queries/s", "cores": threads, "kind": "port",
+            "sample": f"first {ns} of {q.shape[0]} queries of the same workload, nprobe={probe}, top-{TOPK}, {threads} thread(s); "
+                      f"oracle/ (C++ restatement of the reference's AVX2 path; the Rust reference cannot be built here)",
+            "recall_at_10": round(rec, 4), "rough": r["rough"], "precise": r["precise"]}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference", "unavailable": "needs the GPU only to generate the synthetic workload and index"}))
+        return
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    wl = build_workload(args, device, 0, 1)
+    probe = args.probe or {"c1": 64, "c2": 64, "c3": 64, "c4": 32, "c5": 64}.get(args.workload, 64)
+    threads = os.cpu_count() or 1
+    import numpy as np
+
+    o = oracle_from_index(wl["index"])
+    q = wl["queries"].cpu().numpy()
+    n0 = min(4 * threads, q.shape[0])
+    r0 = o.query_batch(q[:n0], probe, TOPK, nthreads=threads)
+    per_q = max(r0["seconds"] / n0, 1e-6)
+    total_steps = args.steps + max(args.warmup, 1)
+    ns = int(min(q.shape[0], max(threads, (args.cpu_seconds * 4 / total_steps) / per_q)))
+    for _ in range(max(args.warmup, 1)):
+        o.query_batch(q[:ns], probe, TOPK, nthreads=threads)
+    secs = 0.0
+    for _ in range(args.steps):
+        r = o.query_batch(q[:ns], probe, TOPK, nthreads=threads)
+        secs += r["seconds"]
+    truth = wl["truth"][:ns].cpu().numpy()
+    rec = float(np.mean([len(set(r["ids"][i].tolist()) & set(truth[i].tolist())) / TOPK for i in range(ns)]))
+    qps = ns * args.steps / secs
+    sample = (f"{ns} of {q.shape[0]} queries per step, nprobe={probe}, top-{TOPK}, {threads} host threads over queries; oracle/ port of the "
+              f"reference's AVX2 path (Rust toolchain absent, reference not buildable here)")
+    out = {"impl": "reference", "metric": METRIC, "value": round(qps, 2), "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": max(args.warmup, 1), "ms_per_step": round(secs / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64 popcount + f32 (AVX2)", "data": "synthetic",
+           "config": {"workload": f"{wl['name']}: {wl['n']}x{wl['dim']} base, {wl['k']} IVF centroids, nprobe={probe}, top-{TOPK}",
+                      "nprobe": probe, "topk": TOPK, "recall_at_10": round(rec, 4)},
+           "cpu_baseline": {"value": round(qps, 2), "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": round(qps, 2), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--shape", default=None, help="custom n,dim,nq,k[,flavour] (debug)")
+    ap.add_argument("--probe", type=int, default=0, help="fix nprobe instead of sweeping to the target recall")
+    ap.add_argument("--rounds", default=None, help="rerank round boundaries, e.g. 0,1,8")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

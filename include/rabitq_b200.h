@@ -98,6 +98,10 @@ const char* rabitq_last_error(void); /* thread-local */
  * the last round always extends to `probe`.  Default {0, 1}. */
 int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
 
+/* Launch everything on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) so
+ * the caller can bracket calls with its own CUDA events; NULL restores the handle's private stream. */
+int rabitq_set_stream(rabitq_index* idx, void* cuda_stream);
+
 /* CUDA-event timings (ms) of the stages of the LAST rabitq_query_batch* call on this handle, summed over
  * sub-batches and rounds: [0] H2D+pad, [1] rotate, [2] centroid distances, [3] probe select, [4] quantize,
  * [5] bucket/inverted lists, [6] code scan, [7] rerank replay, [8] D2H, [9] total (first to last event).

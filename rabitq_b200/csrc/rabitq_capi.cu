@@ -103,6 +103,7 @@ struct rabitq_index {
     uint32_t* codes = nullptr;    // n x D/32
     float4* factors = nullptr;    // n
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     std::mutex mu;
     std::vector<uint32_t> rounds{0, 1};
     // work buffers
@@ -130,7 +131,7 @@ struct rabitq_index {
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         for (auto e : ev_pool) cudaEventDestroy(e);
-        if (stream) cudaStreamDestroy(stream);
+        if (own_stream) cudaStreamDestroy(own_stream);
     }
 };
 
@@ -239,7 +240,8 @@ int make_index(uint32_t dim, size_t n_total, size_t K, const float* base, const 
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     ix->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
+    ix->stream = ix->own_stream;
     CU(cudaMallocHost((void**)&ix->h_pin, 256));
     CU(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     *out = ix;
@@ -297,7 +299,7 @@ int launch_scan_t(rabitq_index* ix, ScanArgs& a) {
     bps = std::max(1, bps);
     ix->scan_blocks_per_sm = bps;
     kern<<<ix->sm_count * bps, SCAN_THREADS, smem, ix->stream>>>(a);
-    CU(cudaGetLastError());
+    CU(cudaGetLastError()); ix->counts[5]++;
     return 0;
 }
 
@@ -332,13 +334,13 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     {
         size_t tot = nb * (size_t)D;
         pad_queries_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ix->qraw.as<float>(), ix->qpad.as<float>(), nb, (int)len, D);
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
     }
     if (tick(ix, ST_H2D)) return RABITQ_ECUDA;
     {
         dim3 grid((D + ROT_THREADS - 1) / ROT_THREADS, (unsigned)((nb + ROT_TQ - 1) / ROT_TQ));
         rotate_kernel<<<grid, ROT_THREADS, 0, st>>>(ix->qpad.as<float>(), ix->P, ix->y.as<float>(), (int)nb, D);
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
     }
     if (tick(ix, ST_ROTATE)) return RABITQ_ECUDA;
     if (stop == STOP_ROTATE) return 0;
@@ -347,7 +349,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     {
         dim3 grid((K + CD_THREADS - 1) / CD_THREADS, (unsigned)((nb + CD_TQ - 1) / CD_TQ));
         centroid_dist_kernel<<<grid, CD_THREADS, 0, st>>>(ix->cent, ix->y.as<float>(), ix->cdist.as<float>(), (int)nb, K, D);
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
     }
     if (tick(ix, ST_CDIST)) return RABITQ_ECUDA;
     CU(ix->probe_ids.ensure(nb * P * 4));
@@ -363,10 +365,10 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
         select_probe_kernel<<<(unsigned)nb, SEL_THREADS, (size_t)Ppow2 * 8, st>>>(
             ix->cdist.as<float>(), K, P, Ppow2, ix->offsets, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(),
             ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>());
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
         query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nb,
                                                    ix->q_wbase.as<uint32_t>(), ix->q_pbase.as<unsigned long long>());
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
     }
     // totals to the host: sizes the survivor slots
     CU(cudaMemcpyAsync(ix->h_pin, ix->q_wbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, st));
@@ -383,7 +385,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
         quantize_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(ix->y.as<float>(), ix->cent, ix->probe_ids.as<uint32_t>(),
                                                                        ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(),
                                                                        ix->q_wbase.as<uint32_t>(), ix->qrec.as<uint32_t>(), (int)nb, P, D);
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
     }
     if (tick(ix, ST_QUANT)) return RABITQ_ECUDA;
     if (stop == STOP_QUANT) return 0;
@@ -411,7 +413,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     CU(ix->out_count.ensure(nb * 4));
     CU(cudaMemsetAsync(ix->counters.p, 0, 64, st));
     fill_f32_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(ix->thr.as<float>(), nb, 3.402823466e+38f);
-    CU(cudaGetLastError());
+    CU(cudaGetLastError()); ix->counts[5]++;
 
     ScanArgs sa;
     sa.codes = ix->codes;
@@ -466,30 +468,28 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
         CU(cudaMemsetAsync(ix->cl_count.p, 0, (size_t)K * 4, st));
         bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), nb, P, p_lo, p_hi,
                                                                               ix->cl_count.as<uint32_t>());
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
         bucket_scan_kernel<<<1, 1024, 0, st>>>(ix->cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, ix->cl_start.as<uint32_t>(),
                                                ix->item_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(), ix->work_ctl.as<uint32_t>());
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
         bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), nb, P, p_lo, p_hi,
                                                                              ix->cl_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
                                                                              ix->cl_items.as<uint32_t>());
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
         work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(ix->item_start.as<uint32_t>(), K, ix->work.as<uint2>());
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
         if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
         int rc = (stop == STOP_SCAN_DENSE) ? launch_scan<true>(ix, sa) : launch_scan<false>(ix, sa);
         if (rc) return rc;
         if (tick(ix, ST_SCAN)) return RABITQ_ECUDA;
         ix->counts[4] += 1;
-        ix->counts[5] += 6;
         if (stop == STOP_SCAN_DENSE) return 0;
         const size_t smem = (size_t)RR_WARPS * (D + 2 * topk) * 4;
         rerank_kernel<<<(unsigned)((nb + RR_WARPS - 1) / RR_WARPS), RR_WARPS * 32, smem, st>>>(ra, p_lo, p_hi, r == 0 ? 1 : 0,
                                                                                                 r + 2 == bounds.size() ? 1 : 0);
-        CU(cudaGetLastError());
+        CU(cudaGetLastError()); ix->counts[5]++;
         if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
     }
-    ix->counts[5] += 7;  // pad, rotate, cdist, select, base scan, quantize, fill
     return 0;
 }
 
@@ -661,6 +661,13 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n) {
         if (rounds[i] <= rounds[i - 1]) return fail(RABITQ_EINVAL, "rounds must be strictly increasing");
     std::lock_guard<std::mutex> lk(idx->mu);
     idx->rounds.assign(rounds, rounds + n);
+    return RABITQ_OK;
+}
+
+int rabitq_set_stream(rabitq_index* idx, void* cuda_stream) {
+    if (!idx) return fail(RABITQ_EINVAL, "null index");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    idx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : idx->own_stream;
     return RABITQ_OK;
 }
 

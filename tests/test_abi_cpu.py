@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads, exports every symbol include/rabitq_b200.h declares, and refuses to compute
+without a CUDA device (no CPU fallback).  No compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import rabitq_b200
+    from rabitq_b200 import build
+
+    build.build()
+    rabitq_b200.lib()
+    return rabitq_b200
+
+
+def test_header_symbols_all_exported(rb):
+    hdr = open(os.path.join(ROOT, "include", "rabitq_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rabitq_[a-z_0-9]+)\s*\(", hdr))
+    declared.discard("rabitq_index")
+    assert declared == set(rb.ABI_SYMBOLS)
+    L = rb.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_no_torch_types_in_header():
+    hdr = open(os.path.join(ROOT, "include", "rabitq_b200.h")).read()
+    assert "torch" not in hdr.lower().replace("no c++/torch types", "") and "std::" not in hdr and "at::" not in hdr
+
+
+def test_io_errors_like_reference(rb, tmp_path):
+    with pytest.raises(rb.RabitqError) as e:
+        rb.RaBitQ.load_from_dir(str(tmp_path / "missing"))
+    assert e.value.code == 1  # RABITQ_EIO
+
+
+def test_product_never_touches_oracle():
+    """The product tree must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "rabitq_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("against the oracle", "").replace("the oracle)", "").lower() or f == "__init__.py" and "import oracle" not in src, f
+
+
+def test_no_gpu_means_loud_failure(rb, case_d128):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    a = case_d128["arrays"]
+    with pytest.raises(rb.RabitqError) as e:
+        rb.RaBitQ.from_arrays(a["dim"], a["base"], a["orthogonal"], a["centroids"], a["offsets"], a["map_ids"], a["codes"], a["factors"])
+    assert e.value.code == 3  # RABITQ_ECUDA
+    assert "no CPU fallback" in str(e.value)

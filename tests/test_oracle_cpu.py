@@ -1,0 +1,261 @@
+"""CPU tests of the oracle (no GPU): the reference's own AVX2-vs-scalar twins, known answers of the
+intrinsics the parity depends on, the float64 model, IO round trips and index-builder invariants."""
+import numpy as np
+import pytest
+
+from tests import model_f64 as m64
+
+import ctypes as C
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+f32p, u32p, u64p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)
+
+
+def test_consts(oracle_lib):
+    # src/consts.rs:10  SCALAR = 1/15 as f32
+    assert np.float32(oracle_lib.lib().orc_scalar_const()) == np.float32(1.0) / np.float32(15.0)
+    assert abs(float(oracle_lib.lib().orc_scalar_const()) - 0.0666666701) < 1e-9
+
+
+@pytest.mark.parametrize("x", [0.0, -0.0, 1.0, -1.0, 3.5e38, -3.5e38, 1e-40, -1e-40, float("inf"), float("-inf")])
+def test_ord32_monotone_roundtrip(oracle_lib, x):
+    L = oracle_lib.lib()
+    k = L.orc_ord32_from_f32(x)
+    assert np.float32(L.orc_ord32_to_f32(k)).view(np.uint32) == np.float32(x).view(np.uint32)
+
+
+def test_ord32_order(oracle_lib):
+    L = oracle_lib.lib()
+    xs = np.array([-np.inf, -3.0, -1e-30, -0.0, 0.0, 1e-30, 2.5, np.inf], np.float32)
+    ks = [L.orc_ord32_from_f32(float(x)) for x in xs]
+    assert ks == sorted(ks) and len(set(ks)) == len(ks)
+
+
+def test_cvtps_round_half_even_known_answers(oracle_lib):
+    """_mm256_cvtps_epi32 gives 0.5->0, 1.5->2, 2.5->2, 14.5->14, 7.5->8; the bias is unused."""
+    L = oracle_lib.lib()
+    v = np.array([0.5, 1.5, 2.5, 14.5, 7.5, 3.49, 3.51, 15.0], np.float32)
+    q = np.zeros(8, np.uint8)
+    s = L.orc_scalar_quantize(_p(q, u8p), _p(v, f32p), 8, 0.0, 1.0)
+    assert q.tolist() == [0, 2, 2, 14, 8, 3, 4, 15]
+    assert s == sum(q.tolist())
+
+
+def test_quantize_degenerate_delta_zero(oracle_lib):
+    """constant residual -> delta = 0 -> inv = inf -> 0*inf = NaN -> cvtps = INT_MIN ->
+    low byte 0 and the i32 sums wrap to 0 because D is a multiple of 64."""
+    L = oracle_lib.lib()
+    D = 128
+    v = np.full(D, 2.5, np.float32)
+    q = np.full(D, 77, np.uint8)
+    with np.errstate(all="ignore"):
+        s = L.orc_scalar_quantize(_p(q, u8p), _p(v, f32p), D, 2.5, float("inf"))
+    assert q.tolist() == [0] * D and s == 0
+
+
+@pytest.mark.parametrize("dim", [64, 128, 192, 256, 960, 1536])
+def test_twin_binarize_and_popcount_bit_exact(oracle_lib, dim):
+    """Integer twins must agree bit-exactly: src/simd.rs:83-107 vs src/utils.rs:90-97, src/simd.rs:326-384 vs
+    src/utils.rs:101-107 (AVX2 LUT path only when dim >= 256)."""
+    L = oracle_lib.lib()
+    rng = np.random.default_rng(dim)
+    W = dim // 64
+    for _ in range(20):
+        q = rng.integers(0, 16, dim).astype(np.uint8)
+        a = np.zeros(4 * W, np.uint64)
+        b = np.zeros(4 * W, np.uint64)
+        L.orc_vector_binarize_query(_p(q, u8p), dim, _p(a, u64p))
+        L.orc_vector_binarize_query_raw(_p(q, u8p), dim, _p(b, u64p))
+        assert np.array_equal(a, b)
+        assert np.array_equal(a, m64.planes_from_q(q, dim))
+        x = rng.integers(0, 2**63, W).astype(np.uint64) | (rng.integers(0, 2, W).astype(np.uint64) << np.uint64(63))
+        assert L.orc_binary_dot_product(_p(x, u64p), _p(a, u64p), W) == L.orc_binary_dot_product_raw(_p(x, u64p), _p(a, u64p), W)
+        ab = L.orc_asymmetric_binary_dot_product(_p(x, u64p), _p(a, u64p), W)
+        assert ab == m64.abdp(m64.unpack_bits(x, dim), q.astype(np.int64))
+
+
+@pytest.mark.parametrize("n", [64, 128, 960, 1536, 100, 7])
+def test_twin_minmax_exact_and_l2_dot_close(oracle_lib, n):
+    L = oracle_lib.lib()
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    r1 = np.zeros(n, np.float32); r2 = np.zeros(n, np.float32)
+    mn1, mx1, mn2, mx2 = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+    L.orc_min_max_residual(_p(r1, f32p), _p(x, f32p), _p(y, f32p), n, C.byref(mn1), C.byref(mx1))
+    L.orc_min_max_raw(_p(r2, f32p), _p(x, f32p), _p(y, f32p), n, C.byref(mn2), C.byref(mx2))
+    assert np.array_equal(r1, r2) and mn1.value == mn2.value and mx1.value == mx2.value
+    assert np.array_equal(r1, x - y)
+    l2 = L.orc_l2_squared_distance(_p(x, f32p), _p(y, f32p), n)
+    dp = L.orc_vector_dot_product(_p(x, f32p), _p(y, f32p), n)
+    assert abs(l2 - float(((x.astype(np.float64) - y) ** 2).sum())) <= 1e-5 * max(1.0, l2)
+    assert abs(dp - float((x.astype(np.float64) * y).sum())) <= 1e-4 * max(1.0, abs(dp))
+
+
+def test_l2_lane_order_is_the_avx_one(oracle_lib):
+    """The 8-lane association: lane v sums elements v, v+8, ... with fma, then ((s0+s4)+(s1+s5))+((s2+s6)+(s3+s7))."""
+    L = oracle_lib.lib()
+    rng = np.random.default_rng(5)
+    n = 128
+    x = (rng.standard_normal(n) * 100).astype(np.float32)
+    y = (rng.standard_normal(n) * 100).astype(np.float32)
+    import math
+
+    s = [np.float32(0)] * 8
+    for i in range(n):
+        d = np.float32(x[i] - y[i])
+        # fma with a single rounding == exact product in float64 (24+24 bits fit) then one rounding of the sum
+        s[i % 8] = np.float32(np.float64(d) * np.float64(d) + np.float64(s[i % 8]))
+    ref = np.float32(np.float32(np.float32(s[0] + s[4]) + np.float32(s[1] + s[5])) + np.float32(np.float32(s[2] + s[6]) + np.float32(s[3] + s[7])))
+    got = np.float32(L.orc_l2_squared_distance(_p(x, f32p), _p(y, f32p), n))
+    assert got.view(np.uint32) == ref.view(np.uint32)
+
+
+def test_heap_replay_is_topk_multiset(oracle_lib):
+    L = oracle_lib.lib()
+    rng = np.random.default_rng(3)
+    for n, k in [(5, 10), (10, 10), (100, 10), (1000, 7), (50, 1)]:
+        a = rng.integers(0, 40, n).astype(np.float32)  # many exact ties
+        ids = np.arange(n, dtype=np.uint32)
+        od = np.zeros(k + 1, np.float32); oi = np.zeros(k + 1, np.uint32)
+        c = L.orc_heap_replay(_p(a, f32p), _p(ids, u32p), n, k, _p(od, f32p), _p(oi, u32p))
+        assert c == min(n, k)
+        assert sorted(od[:c].tolist()) == sorted(a.tolist())[:c]
+        for d, i in zip(od[:c], oi[:c]):
+            assert a[i] == d
+
+
+def test_builder_invariants_and_f64_model(case_d128):
+    a = case_d128["arrays"]
+    D = a["dim"]
+    n = a["base"].shape[0]
+    off = a["offsets"]
+    assert off[0] == 0 and off[-1] == n and np.all(np.diff(off.astype(np.int64)) >= 0)
+    assert sorted(a["map_ids"].tolist()) == list(range(n))
+    P = a["orthogonal"].astype(np.float64)
+    assert np.allclose(P @ P.T, np.eye(D), atol=1e-5)
+    # base is the permuted, unrotated input (src/rabitq.rs:245-247)
+    assert np.array_equal(a["base"], case_d128["base"][a["map_ids"]])
+    # per-vector factors from the definitions (src/rabitq.rs:218-229), cluster order ascending by centroid distance
+    rng = np.random.default_rng(0)
+    cl = np.searchsorted(off, np.arange(n), side="right") - 1
+    for j in rng.integers(0, n, 40):
+        c = cl[j]
+        xr = a["base"][j].astype(np.float64) @ P
+        r = xr - a["centroids"][c].astype(np.float64)
+        bits = m64.unpack_bits(a["codes"][j], D)
+        assert np.array_equal(bits, (r > 0).astype(np.int64)) or np.min(np.abs(r)) < 1e-4
+        s = 2.0 * bits - 1.0
+        nr = np.linalg.norm(r)
+        xdp = (r * s).sum() / (nr * np.sqrt(D))
+        t = nr / xdp
+        ip, ppc, err, cds = a["factors"][j]
+        assert np.isclose(cds, nr * nr, rtol=1e-4)
+        assert np.isclose(ip, -2.0 / np.sqrt(D) * t, rtol=1e-4)
+        assert np.isclose(ppc, ip * s.sum(), rtol=1e-4, atol=1e-3)
+        assert np.isclose(err, 2 * 1.9 / np.sqrt(D - 1) * np.sqrt(max(t * t - nr * nr, 0)), rtol=1e-3)
+    for c in rng.integers(0, len(off) - 1, 10):
+        rows = np.arange(off[c], off[c + 1])
+        if len(rows) > 1:
+            assert np.all(np.diff(a["factors"][rows, 3]) >= -1e-3 * np.abs(a["factors"][rows[1:], 3]))
+
+
+@pytest.mark.parametrize("case_name", ["case_d128", "case_d96", "case_d960"])
+def test_trace_against_f64_model(request, case_name):
+    case = request.getfixturevalue(case_name)
+    a = case["arrays"]
+    D = a["dim"]
+    ix = case["oracle"]
+    q = case["queries"][0]
+    tr = ix.trace(q, 6, 10)
+    qp = np.zeros(D, np.float32); qp[: len(q)] = q
+    y = qp.astype(np.float64) @ a["orthogonal"].astype(np.float64)
+    assert np.allclose(tr["y"], y, rtol=1e-4, atol=1e-3 * np.abs(y).max())
+    cd = ((a["centroids"].astype(np.float64) - y[None, :]) ** 2).sum(1)
+    assert np.allclose(tr["centroid_dist"], cd, rtol=1e-4)
+    assert np.array_equal(np.sort(tr["probe_dist"]), tr["probe_dist"])
+    assert set(tr["probe_ids"].tolist()) == set(np.argsort(cd, kind="stable")[:6].tolist())
+    t = 0
+    for p, c in enumerate(tr["probe_ids"]):
+        r = tr["y"] - a["centroids"][c]
+        lo, delta, qv = m64.quantize_rne(r)
+        assert lo == tr["lo"][p] and delta == tr["delta"][p]
+        assert np.array_equal(qv.astype(np.uint8), tr["quantized"][p])
+        assert int(qv.sum()) == int(tr["sum"][p])
+        assert np.array_equal(m64.planes_from_q(qv, D), tr["planes"][p])
+        for j in range(a["offsets"][c], a["offsets"][c + 1]):
+            if (j - a["offsets"][c]) % 17 == 0:
+                bits = m64.unpack_bits(a["codes"][j], D)
+                ab = m64.abdp(bits, qv)
+                assert ab == tr["abdp"][t]
+                r1 = m64.rough_f64(a["factors"][j], tr["probe_dist"][p], lo, delta, qv.sum(), ab)
+                r2 = m64.rough_identity_f64(a["factors"][j], tr["probe_dist"][p], lo, delta, qv, bits)
+                scale = abs(float(a["factors"][j][3])) + abs(float(tr["probe_dist"][p])) + 1.0
+                assert abs(r1 - float(tr["rough"][t])) <= 2e-5 * scale
+                assert abs(r2 - r1) <= 1e-6 * scale
+            assert tr["pair_pos"][t] == j
+            t += 1
+    assert t == tr["pairs"]
+    # rerank bookkeeping: exact distances are true squared L2 to the unrotated base vectors
+    m = tr["action"] > 0
+    ex = ((a["base"][tr["pair_pos"][m]].astype(np.float64) - qp[None, :]) ** 2).sum(1)
+    assert np.allclose(tr["exact"][m], ex, rtol=1e-5)
+    assert tr["precise"] == int(m.sum())
+    res_ids = sorted(i for _, i in tr["result"])
+    pushed = tr["action"] == 2
+    best = np.argsort(tr["exact"][pushed], kind="stable")[:10]
+    assert sorted(np.sort(tr["exact"][pushed])[:10].tolist()) == sorted(d for d, _ in tr["result"])
+    assert len(res_ids) == min(10, int(pushed.sum()))
+
+
+def test_recall_vs_brute_force(case_d128):
+    from tools import synth
+
+    truth = synth.brute_force_topk_numpy(case_d128["base"], case_d128["queries"], 10)
+    r = case_d128["oracle"].query_batch(case_d128["queries"], 64, 10)  # all 64 clusters probed
+    rec = np.mean([len(set(r["ids"][i].tolist()) & set(truth[i].tolist())) / 10 for i in range(truth.shape[0])])
+    assert rec >= 0.97
+    assert r["rough"] == case_d128["base"].shape[0] * case_d128["queries"].shape[0]
+
+
+def test_dump_load_round_trip_and_layout(case_d96, tmp_path):
+    """Six-file layout (src/rabitq.rs:128-156): record headers, centroids stored dim x k."""
+    from oracle import oracle as orc
+
+    ix = case_d96["oracle"]
+    d = tmp_path / "idx"
+    ix.dump_to_dir(str(d))
+    a = ix.arrays()
+    D, n, k = a["dim"], a["base"].shape[0], a["centroids"].shape[0]
+    import os, struct
+
+    assert os.path.getsize(d / "base.fvecs") == n * (4 + 4 * D)
+    assert os.path.getsize(d / "orthogonal.fvecs") == D * (4 + 4 * D)
+    assert os.path.getsize(d / "centroids.fvecs") == D * (4 + 4 * k)
+    assert os.path.getsize(d / "offsets_ids.ivecs") == 4 + 4 * (k + 1) + 4 + 4 * n
+    assert os.path.getsize(d / "factors.fvecs") == 4 + 16 * n
+    assert os.path.getsize(d / "x_binary_vec.u64vecs") == 4 + 8 * n * (D // 64)
+    with open(d / "centroids.fvecs", "rb") as f:
+        assert struct.unpack("<I", f.read(4))[0] == k
+    ix2 = orc.OracleIndex.load_from_dir(str(d))
+    b = ix2.arrays()
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+    q = case_d96["queries"][:5]
+    r1 = ix.query_batch(q, 8, 10); r2 = ix2.query_batch(q, 8, 10)
+    assert np.array_equal(r1["ids"], r2["ids"]) and np.array_equal(r1["dist"], r2["dist"])
+
+
+def test_query_dim_assert(case_d128):
+    with pytest.raises(RuntimeError):  # src/rabitq.rs:275
+        case_d128["oracle"].query(np.zeros(64, np.float32), 4, 10)
+
+
+def test_heuristic_reranker_runs(case_d128):
+    q = case_d128["queries"][:8]
+    r = case_d128["oracle"].query_batch(q, 16, 10, heuristic_rank=True)
+    assert np.all(r["count"] == 10)

@@ -1,12 +1,16 @@
 """Seeded synthetic datasets of the BASELINE.json shapes (harness, not product).
 
-SURVEY.md section 8(d): the data must be *clustered* (an i.i.d. Gaussian has no IVF structure).  Each dataset is
-a mixture of `k` Gaussians; the mixture means double as the "precomputed IVF centroids" the configs name.
-numpy path for the small CPU/GPU-parity cases, torch path (device-resident, chunked) for the bench sizes.
+SURVEY.md section 8(d): the data must be *clustered*; an i.i.d. Gaussian has no IVF structure.  Real embedding sets have a
+low intrinsic dimension and overlapping clusters, so that recall grows gradually with nprobe.  We emulate that with a
+mixture of `k` Gaussians in a LATENT space of `latent` dims, pushed to `dim` dims by a fixed random linear map plus
+small isotropic noise, then given the flavour of the named dataset (non-negative integers for SIFT, small non-negative
+floats for GIST, unit rows for DEEP / embeddings).  The mixture means (mapped the same way) are the "precomputed IVF
+centroids" the configs name.  Everything runs in torch on the given device (CPU for tests, CUDA for the bench).
 """
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 # name -> (n, dim, n_queries, k, flavour)
 SHAPES = {
@@ -18,99 +22,86 @@ SHAPES = {
 }
 SEEDS = {"c1": 1001, "c2": 2001, "c3": 3001, "c4": 4001, "c5": 5001}
 
-
-def _flavour_params(flavour: str):
-    # (mean_lo, mean_hi, sigma_lo, sigma_hi, clip_nonneg, round_int, normalise)
-    return {
-        "sift": (0.0, 128.0, 18.0, 36.0, True, True, False),
-        "gist": (0.0, 0.3, 0.04, 0.08, True, False, False),
-        "deep": (-1.0, 1.0, 0.35, 0.7, False, False, True),
-        "embed": (-1.0, 1.0, 0.35, 0.7, False, False, True),
-    }[flavour]
+# flavour -> (latent dims, component sigma range in latent units, ambient noise, post-transform)
+_FLAVOUR = {
+    "sift": dict(latent=24, sig=(0.55, 0.95), noise=0.10, post="sift"),
+    "gist": dict(latent=32, sig=(0.55, 0.95), noise=0.10, post="gist"),
+    "deep": dict(latent=24, sig=(0.55, 0.95), noise=0.10, post="unit"),
+    "embed": dict(latent=48, sig=(0.55, 0.95), noise=0.10, post="unit"),
+}
 
 
-def make_numpy(n: int, dim: int, nq: int, k: int, flavour: str = "sift", seed: int = 1):
-    """Small datasets on the CPU: returns (base[n,dim], queries[nq,dim], centroids[k,dim]) float32."""
-    lo, hi, slo, shi, clip, rnd, norm = _flavour_params(flavour)
-    rng = np.random.default_rng(seed)
-    means = rng.uniform(lo, hi, size=(k, dim)).astype(np.float32)
-    sig = rng.uniform(slo, shi, size=(k, 1)).astype(np.float32)
+class Mixture:
+    """Frozen mixture parameters (so base and queries come from the same distribution)."""
 
-    def draw(m, r):
-        comp = r.integers(0, k, size=m)
-        x = means[comp] + sig[comp] * r.standard_normal((m, dim)).astype(np.float32)
-        if clip:
-            x = np.maximum(x, 0)
-        if rnd:
-            x = np.round(x)
-        if norm:
-            x = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)
-        return x.astype(np.float32)
+    def __init__(self, dim: int, k: int, flavour: str, seed: int, device):
+        f = _FLAVOUR[flavour]
+        self.dim, self.k, self.flavour, self.device = dim, k, flavour, torch.device(device)
+        self.post, self.noise = f["post"], f["noise"]
+        g = torch.Generator(device=self.device)
+        g.manual_seed(seed)
+        L = f["latent"]
+        self.means_z = torch.randn(k, L, device=self.device, generator=g)
+        self.sig = torch.empty(k, 1, device=self.device).uniform_(f["sig"][0], f["sig"][1], generator=g)
+        self.A = torch.randn(L, dim, device=self.device, generator=g) / float(L) ** 0.5
+        # skewed component weights: real IVF lists are far from equal-sized
+        self.weights = torch.exp(0.7 * torch.randn(k, device=self.device, generator=g))
+        self.shift = torch.empty(1, dim, device=self.device).uniform_(-0.5, 0.5, generator=g)
 
-    base = draw(n, np.random.default_rng(seed + 1))
-    queries = draw(nq, np.random.default_rng(seed + 2))
-    cent = means.copy()
-    if norm:
-        cent = cent / np.maximum(np.linalg.norm(cent, axis=1, keepdims=True), 1e-12)
-    return base, queries, cent.astype(np.float32)
+    def _post(self, x: torch.Tensor) -> torch.Tensor:
+        if self.post == "sift":      # non-negative integers, SIFT-like range
+            return (x * 24.0 + 48.0).clamp_(min=0).round_()
+        if self.post == "gist":      # small non-negative floats
+            return (x * 0.05 + 0.12).clamp_(min=0)
+        return x / x.norm(dim=1, keepdim=True).clamp_(min=1e-12)
+
+    def draw(self, m: int, seed: int, chunk: int = 1 << 18) -> torch.Tensor:
+        g = torch.Generator(device=self.device)
+        g.manual_seed(seed)
+        out = torch.empty(m, self.dim, device=self.device)
+        for s in range(0, m, chunk):
+            e = min(m, s + chunk)
+            comp = torch.multinomial(self.weights, e - s, replacement=True, generator=g)
+            z = self.means_z[comp] + self.sig[comp] * torch.randn(e - s, self.means_z.shape[1], device=self.device, generator=g)
+            x = z @ self.A + self.shift + self.noise * torch.randn(e - s, self.dim, device=self.device, generator=g)
+            out[s:e] = self._post(x)
+        return out
+
+    def centroids(self) -> torch.Tensor:
+        return self._post(self.means_z @ self.A + self.shift)
 
 
-def brute_force_topk_numpy(base: np.ndarray, queries: np.ndarray, topk: int) -> np.ndarray:
-    b2 = (base.astype(np.float64) ** 2).sum(1)
-    out = np.empty((queries.shape[0], topk), np.int32)
-    for i in range(0, queries.shape[0], 256):
-        q = queries[i:i + 256].astype(np.float64)
-        d = b2[None, :] - 2.0 * q @ base.astype(np.float64).T
-        out[i:i + 256] = np.argsort(d, axis=1, kind="stable")[:, :topk]
-    return out
-
-
-def make_torch(name_or_shape, device, seed: int | None = None, chunk: int = 1 << 18):
-    """Bench-size datasets generated on `device` with torch.  Returns (base, queries, centroids) tensors
-    (float32, base is [n, dim]).  `name_or_shape` is a key of SHAPES or a tuple (n, dim, nq, k, flavour)."""
-    import torch
-
+def make_torch(name_or_shape, device="cpu", seed: int | None = None):
+    """(base [n, dim], queries [nq, dim], centroids [k, dim]) float32 tensors on `device`."""
     if isinstance(name_or_shape, str):
         n, dim, nq, k, flavour = SHAPES[name_or_shape]
         seed = SEEDS[name_or_shape] if seed is None else seed
     else:
         n, dim, nq, k, flavour = name_or_shape
         seed = 1 if seed is None else seed
-    lo, hi, slo, shi, clip, rnd, norm = _flavour_params(flavour)
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    means = torch.empty(k, dim, device=device).uniform_(lo, hi, generator=g)
-    sig = torch.empty(k, 1, device=device).uniform_(slo, shi, generator=g)
-
-    def draw(m, gen):
-        out = torch.empty(m, dim, device=device)
-        for s in range(0, m, chunk):
-            e = min(m, s + chunk)
-            comp = torch.randint(0, k, (e - s,), device=device, generator=gen)
-            x = means[comp] + sig[comp] * torch.randn(e - s, dim, device=device, generator=gen)
-            if clip:
-                x.clamp_(min=0)
-            if rnd:
-                x.round_()
-            if norm:
-                x = x / x.norm(dim=1, keepdim=True).clamp_(min=1e-12)
-            out[s:e] = x
-        return out
-
-    g1 = torch.Generator(device=device); g1.manual_seed(seed + 1)
-    g2 = torch.Generator(device=device); g2.manual_seed(seed + 2)
-    base = draw(n, g1)
-    queries = draw(nq, g2)
-    cent = means.clone()
-    if norm:
-        cent = cent / cent.norm(dim=1, keepdim=True).clamp_(min=1e-12)
-    return base, queries, cent
+    mix = Mixture(dim, k, flavour, seed + 2, device)
+    return mix.draw(n, seed), mix.draw(nq, seed + 1), mix.centroids()
 
 
-def brute_force_topk_torch(base, queries, topk: int, chunk: int = 1 << 20):
+def make_numpy(n: int, dim: int, nq: int, k: int, flavour: str = "sift", seed: int = 1):
+    """Small datasets for the tests (generated with torch on the CPU, returned as numpy)."""
+    b, q, c = make_torch((n, dim, nq, k, flavour), "cpu", seed)
+    return b.numpy(), q.numpy(), c.numpy()
+
+
+def brute_force_topk_numpy(base: np.ndarray, queries: np.ndarray, topk: int) -> np.ndarray:
+    b = base.astype(np.float64)
+    b2 = (b ** 2).sum(1)
+    out = np.empty((queries.shape[0], topk), np.int32)
+    for i in range(0, queries.shape[0], 256):
+        q = queries[i:i + 256].astype(np.float64)
+        d = b2[None, :] - 2.0 * q @ b.T
+        out[i:i + 256] = np.argsort(d, axis=1, kind="stable")[:, :topk]
+    return out
+
+
+def brute_force_topk_torch(base: torch.Tensor, queries: torch.Tensor, topk: int, chunk: int = 1 << 19) -> torch.Tensor:
     """Exact fp32 top-k ids by squared L2 on the device (ground truth for recall)."""
-    import torch
-
     nq = queries.shape[0]
     best_d = torch.full((nq, topk), float("inf"), device=base.device)
     best_i = torch.zeros((nq, topk), dtype=torch.int64, device=base.device)
