@@ -666,12 +666,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
 
 // ---------------------------------------------------------------------------------------------------------
 // K5: exact rerank with the reference's SEQUENTIAL threshold semantics (HeapReRanker, src/rerank.rs:61-114).
-// One warp per query walks the query's survivor words in visit order (probe rank ascending, position inside
-// the cluster ascending).  Per chunk of <= 32 survivors: candidates still below the current threshold get their
-// exact squared L2 computed speculatively in parallel (8 lanes per candidate = the 8 AVX lanes of
-// simd::l2_squared_distance, src/simd.rs:14-73, same per-lane order and the same final reduction), then the
-// chunk is replayed in order with the reference's two strict tests, so the heap contents, the threshold
-// trajectory and the `precise` counter are those of the sequential loop.
+//
+// One warp per query streams the query's survivor words in visit order (probe rank ascending, position inside
+// the cluster ascending) and queues the candidates whose estimate is still below the current threshold.  A full
+// queue is a WAVE: the raw base rows of the wave are gathered into shared memory with one TMA bulk copy per row
+// (cp.async.bulk, completion on an mbarrier), every exact squared L2 of the wave is computed in parallel --
+// 8 lanes per candidate = the 8 AVX lanes of simd::l2_squared_distance (src/simd.rs:14-73), same per-lane
+// order, same final reduction -- and the wave is then replayed in order with the reference's two strict tests.
+// Heap contents, the threshold trajectory and the `precise` counter are exactly those of the sequential loop;
+// speculation only costs extra gathers.
 struct RerankArgs {
     const float* qpad;            // nq x D, unrotated padded queries (rabitq.rs:299)
     const float* base;            // n x D
@@ -680,7 +683,7 @@ struct RerankArgs {
     const uint32_t* slot_local;   // nq x P
     const uint32_t* bitmap;
     const float2* entries;
-    float* heap_dist;             // nq x topk   state between rounds, final output when finalize
+    float* heap_dist;             // nq x topk   state between rounds
     uint32_t* heap_ids;           // nq x topk
     uint32_t* heap_cnt;           // nq
     float* thr;                   // nq
@@ -690,9 +693,34 @@ struct RerankArgs {
     uint32_t* out_ids;
     uint32_t* out_count;
     int nq, P, D, topk;
+    int R;                        // rows per wave (<= 32)
+    int smem_per_warp;            // bytes
 };
 
-constexpr int RR_WARPS = 4;
+RQ_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+RQ_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+RQ_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+RQ_DEV void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+RQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; spin++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (spin > (1u << 24)) __trap();  // a lost transaction must fail loudly, never hang the GPU
+    }
+}
 
 RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, float& thr) {
     uint32_t bk = 0;
@@ -711,16 +739,23 @@ RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, fl
     thr = okey_to_float(bk);
 }
 
-__global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(RerankArgs a, int p_lo, int p_hi, int first, int finalize) {
-    extern __shared__ float rr_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = blockIdx.x * RR_WARPS + warp;
-    const int D = a.D, k = a.topk;
-    float* qv = rr_smem + (size_t)warp * (D + 2 * k);
-    float* hd = qv + D;
-    uint32_t* hid = reinterpret_cast<uint32_t*>(hd + k);
+__global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int p_hi, int first, int finalize) {
+    extern __shared__ __align__(16) unsigned char rr_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int q = blockIdx.x * wpb + warp;
     if (q >= a.nq) return;
+    const int D = a.D, k = a.topk, R = a.R, pitch = D + 8;  // +8 floats: the 4 candidates of a group hit disjoint banks
+    unsigned char* wbase = rr_smem_raw + (size_t)warp * a.smem_per_warp;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase);
+    float* qv = reinterpret_cast<float*>(wbase + 16);
+    float* rows = qv + D;
+    float* hd = rows + (size_t)R * pitch;
+    uint32_t* hid = reinterpret_cast<uint32_t*>(hd + k);
+    float* qr = reinterpret_cast<float*>(hid + k);
+    uint32_t* qj = reinterpret_cast<uint32_t*>(qr + R + 32);
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
+    if (lane == 0) mbar_init(mbar, 1);
     for (int d = lane; d < D; d += 32) qv[d] = a.qpad[(size_t)q * D + d];
     int cnt = first ? 0 : (int)a.heap_cnt[q];
     float thr = first ? 3.402823466e+38f : a.thr[q];
@@ -731,12 +766,74 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(RerankArgs a, int
     }
     __syncwarp();
     if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);
-    uint32_t precise = 0, computed = 0;
+    uint32_t precise = 0, computed = 0, phase = 0;
+    int qn = 0;  // queued candidates (qr/qj[0..qn))
+    const int sub = lane >> 3, v = lane & 7;
+
+    // one wave: the first n (<= R) queued candidates
+    auto wave = [&](int n) {
+        const bool mine = lane < n;
+        const float rough = mine ? qr[lane] : 0.0f;
+        const uint32_t j = mine ? qj[lane] : 0u;
+        const uint32_t act = __ballot_sync(FULL, mine && rough < thr);
+        const int nact = __popc(act);
+        if (nact == 0) return;
+        const int myrank = __popc(act & lt_mask);
+        const bool active = (act >> lane) & 1u;
+        // gather: one bulk copy per active row into slot `myrank`
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) mbar_expect_tx(mbar, (uint32_t)nact * (uint32_t)D * 4u);
+        __syncwarp();
+        if (active) tma_bulk_g2s(rows + (size_t)myrank * pitch, a.base + (size_t)j * D, (uint32_t)D * 4u, mbar);
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+        float exact = 0.0f;
+        for (int g = 0; g < nact; g += 8) {
+            const float* r0 = rows + (size_t)min(g + sub, R - 1) * pitch;
+            const float* r1 = rows + (size_t)min(g + 4 + sub, R - 1) * pitch;
+            float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 4
+            for (int d = v; d < D; d += 8) {
+                const float qd = qv[d];
+                const float f0 = __fsub_rn(r0[d], qd), f1 = __fsub_rn(r1[d], qd);
+                acc0 = fmaf(f0, f0, acc0);
+                acc1 = fmaf(f1, f1, acc1);
+            }
+            acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 4));
+            acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 4));
+            acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 1));
+            acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 1));
+            acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 2));
+            acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 2));
+            const int src = (myrank & 3) * 8;
+            const float res0 = __shfl_sync(FULL, acc0, src), res1 = __shfl_sync(FULL, acc1, src);
+            if (active && (myrank >> 3) == (g >> 3)) exact = ((myrank >> 2) & 1) ? res1 : res0;
+        }
+        computed += nact;
+        // in-order replay (rerank.rs:83-101)
+        uint32_t rem = act;
+        while (rem) {
+            const int t = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const float r = __shfl_sync(FULL, rough, t);
+            const float ex = __shfl_sync(FULL, exact, t);
+            const uint32_t ju = __shfl_sync(FULL, j, t);
+            if (r < thr) {
+                precise++;
+                if (ex < thr) {
+                    const int slot = cnt < k ? cnt : maxpos;
+                    if (lane == 0) { hd[slot] = ex; hid[slot] = a.map_ids[ju]; }
+                    if (cnt < k) cnt++;
+                    __syncwarp();
+                    if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);
+                }
+            }
+        }
+    };
 
     const uint32_t wb = a.q_wbase[q];
     const uint32_t wlo = wb + a.slot_local[(size_t)q * a.P + p_lo];
     const uint32_t whi = (p_hi >= a.P) ? a.q_wbase[q + 1] : wb + a.slot_local[(size_t)q * a.P + p_hi];
-    const int sub = lane >> 3, v = lane & 7;
 
     for (uint32_t w0 = wlo; w0 < whi; w0 += 32) {
         const uint32_t m = (w0 + lane < whi) ? a.bitmap[w0 + lane] : 0u;
@@ -751,8 +848,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(RerankArgs a, int
         for (uint32_t e0 = 0; e0 < T; e0 += 32) {
             const uint32_t e = e0 + lane;
             const bool have = e < T;
-            // source word = first lane whose inclusive prefix exceeds e
-            int pos = 0;
+            int pos = 0;  // source word = first lane whose inclusive prefix exceeds e
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) {
                 uint32_t pv = __shfl_sync(FULL, incl, pos + s - 1);
@@ -767,60 +863,30 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(RerankArgs a, int
                 rough = en.x;
                 j = __float_as_uint(en.y);
             }
-            // speculative exact distances for everything still below the current threshold
-            const uint32_t act = __ballot_sync(FULL, have && rough < thr);
-            const int nact = __popc(act);
-            const int myrank = __popc(act & ((1u << lane) - 1u));
-            float exact = 0.0f;
-            for (int g = 0; g < nact; g += 4) {
-                const int want = g + sub;  // rank of the candidate this 8-lane group computes
-                const uint32_t srcl = __fns(act, 0, want + 1);
-                const uint32_t ju = __shfl_sync(FULL, j, srcl & 31);
-                const bool on = want < nact;
-                float acc = 0.0f;
-                if (on) {
-                    const float* row = a.base + (size_t)ju * D;
-#pragma unroll 8
-                    for (int d = v; d < D; d += 8) {
-                        float diff = __fsub_rn(__ldg(&row[d]), qv[d]);
-                        acc = fmaf(diff, diff, acc);
-                    }
-                }
-                acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
-                acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
-                acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
-                // hand the result to the lane that owns the candidate
-                const int owner_grp = myrank - g;
-                const float res = __shfl_sync(FULL, acc, (owner_grp & 3) * 8);
-                if (((act >> lane) & 1u) && owner_grp >= 0 && owner_grp < 4) exact = res;
+            // queue what is still below the threshold (order preserved)
+            const bool pass = have && rough < thr;
+            const uint32_t pm = __ballot_sync(FULL, pass);
+            if (pass) {
+                const int at = qn + __popc(pm & lt_mask);
+                qr[at] = rough;
+                qj[at] = j;
             }
-            computed += nact;
-            // in-order replay (rerank.rs:83-101)
-            uint32_t rem = act;
-            while (rem) {
-                const int t = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const float r = __shfl_sync(FULL, rough, t);
-                const float ex = __shfl_sync(FULL, exact, t);
-                const uint32_t ju = __shfl_sync(FULL, j, t);
-                if (r < thr) {
-                    precise++;
-                    if (ex < thr) {
-                        if (cnt < k) {
-                            if (lane == 0) { hd[cnt] = ex; hid[cnt] = a.map_ids[ju]; }
-                            cnt++;
-                            __syncwarp();
-                            if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);
-                        } else {
-                            if (lane == 0) { hd[maxpos] = ex; hid[maxpos] = a.map_ids[ju]; }
-                            __syncwarp();
-                            heap_recompute_max(hd, k, lane, maxpos, thr);
-                        }
-                    }
-                }
+            qn += __popc(pm);
+            __syncwarp();
+            while (qn >= R) {
+                wave(R);
+                const int left = qn - R;  // < 32
+                float tr = 0.0f;
+                uint32_t tj = 0;
+                if (lane < left) { tr = qr[R + lane]; tj = qj[R + lane]; }
+                __syncwarp();
+                if (lane < left) { qr[lane] = tr; qj[lane] = tj; }
+                __syncwarp();
+                qn = left;
             }
         }
     }
+    if (qn > 0) wave(qn);
 
     if (lane == 0) {
         a.q_precise[q] = (first ? 0u : a.q_precise[q]) + precise;

@@ -243,7 +243,7 @@ int make_index(uint32_t dim, size_t n_total, size_t K, const float* base, const 
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     CU(cudaMallocHost((void**)&ix->h_pin, 256));
-    CU(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     *out = ix;
     return RABITQ_OK;
 }
@@ -452,6 +452,10 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     ra.P = P;
     ra.D = D;
     ra.topk = (int)topk;
+    // rows gathered per wave: what fits in ~32 KB of shared memory per warp, at most one per lane
+    ra.R = (int)std::max<size_t>(2, std::min<size_t>(32, 32768 / ((size_t)D * 4)));
+    ra.smem_per_warp = (int)((16 + (size_t)D * 4 + (size_t)ra.R * (D + 8) * 4 + 2 * topk * 4 + 2 * (size_t)(ra.R + 32) * 4 + 15) / 16 * 16);
+    const int rr_wpb = ra.smem_per_warp > 24 * 1024 ? 2 : 4;
 
     // rounds of probe ranks
     std::vector<int> bounds;
@@ -484,9 +488,8 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
         if (tick(ix, ST_SCAN)) return RABITQ_ECUDA;
         ix->counts[4] += 1;
         if (stop == STOP_SCAN_DENSE) return 0;
-        const size_t smem = (size_t)RR_WARPS * (D + 2 * topk) * 4;
-        rerank_kernel<<<(unsigned)((nb + RR_WARPS - 1) / RR_WARPS), RR_WARPS * 32, smem, st>>>(ra, p_lo, p_hi, r == 0 ? 1 : 0,
-                                                                                                r + 2 == bounds.size() ? 1 : 0);
+        rerank_kernel<<<(unsigned)((nb + rr_wpb - 1) / rr_wpb), rr_wpb * 32, (size_t)rr_wpb * ra.smem_per_warp, st>>>(
+            ra, p_lo, p_hi, r == 0 ? 1 : 0, r + 2 == bounds.size() ? 1 : 0);
         CU(cudaGetLastError()); ix->counts[5]++;
         if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
     }
