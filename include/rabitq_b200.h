@@ -81,6 +81,10 @@ int rabitq_query_batch_device(rabitq_index* idx, const float* d_queries, size_t 
                               size_t topk, int heuristic_rank, float* d_out_dist, uint32_t* d_out_ids,
                               uint32_t* d_out_count);
 
+/* Shard geometry used by the sharded constructors (host-only, no device needed): rows [row_lo, row_hi) of the
+ * cluster-sorted arrays belong to shard `shard_rank`; boundaries fall on cluster boundaries. */
+int rabitq_shard_range(const uint32_t* offsets, size_t k, int shard_rank, int shard_count, size_t* row_lo, size_t* row_hi);
+
 /* Merge `n_lists` per-shard results (each nq x topk, device pointers laid out back to back: list s starts at
  * d_dist + s*nq*topk) into one ascending nq x topk result.  Used after the NCCL all-gather of (dist, id). */
 int rabitq_merge_topk_device(int device, const float* d_dist, const uint32_t* d_ids, int n_lists, size_t nq,
@@ -97,6 +101,11 @@ const char* rabitq_last_error(void); /* thread-local */
 /* Probe-rank boundaries of the rerank rounds (DESIGN.md "exact replay"): rounds[0] = 0 < rounds[1] < ... ;
  * the last round always extends to `probe`.  Default {0, 1}. */
 int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
+
+/* Integer tuning knobs (results never depend on them; tests sweep them): "first_chunks" = 128-vector chunks of the nearest
+ * cluster that form the first rerank round (default 1, 0 = whole cluster); "scan_mode" = carry-save depth of the scan's
+ * popcount (0 plain, 1 = 3->2, 2 = 7->3 compressors, -1 = by dimension); "rerank_rows" = rows per rerank wave (0 = auto). */
+int rabitq_set_option(rabitq_index* idx, const char* name, long value);
 
 /* Launch everything on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) so
  * the caller can bracket calls with its own CUDA events; NULL restores the handle's private stream. */

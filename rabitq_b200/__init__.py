@@ -23,8 +23,8 @@ c_u64p = C.POINTER(C.c_uint64)
 ABI_SYMBOLS = [
     "rabitq_load_from_dir", "rabitq_load_from_dir_sharded", "rabitq_from_arrays", "rabitq_free", "rabitq_dim",
     "rabitq_num_vectors", "rabitq_num_clusters", "rabitq_query", "rabitq_query_batch", "rabitq_query_batch_device",
-    "rabitq_merge_topk_device", "rabitq_metrics", "rabitq_metrics_reset", "rabitq_last_error", "rabitq_set_rounds",
-    "rabitq_set_stream", "rabitq_last_timings", "rabitq_stage_rotate", "rabitq_stage_probe", "rabitq_stage_quantize", "rabitq_stage_scan",
+    "rabitq_shard_range", "rabitq_merge_topk_device", "rabitq_metrics", "rabitq_metrics_reset", "rabitq_last_error", "rabitq_set_rounds",
+    "rabitq_set_option", "rabitq_set_stream", "rabitq_last_timings", "rabitq_stage_rotate", "rabitq_stage_probe", "rabitq_stage_quantize", "rabitq_stage_scan",
 ]
 
 TIMING_STAGES = ["h2d_pad", "rotate", "centroid_dist", "select", "quantize", "bucket", "scan", "rerank", "d2h", "total"]
@@ -67,6 +67,7 @@ def lib():
     L.rabitq_query_batch.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp, vp]
     L.rabitq_query_batch_device.argtypes = L.rabitq_query_batch.argtypes
     L.rabitq_merge_topk_device.argtypes = [C.c_int, vp, vp, C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp]
+    L.rabitq_shard_range.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.rabitq_metrics.argtypes = [vp, c_u64p]
     L.rabitq_metrics.restype = None
     L.rabitq_metrics_reset.argtypes = [vp]
@@ -74,6 +75,7 @@ def lib():
     L.rabitq_set_rounds.argtypes = [vp, c_u32p, C.c_int]
     L.rabitq_last_timings.argtypes = [vp, c_f32p, c_u64p]
     L.rabitq_set_stream.argtypes = [vp, vp]
+    L.rabitq_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.rabitq_stage_rotate.argtypes = [vp, vp, C.c_size_t, C.c_size_t, vp]
     L.rabitq_stage_probe.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp]
     L.rabitq_stage_quantize.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp, vp]
@@ -219,6 +221,9 @@ class RaBitQ:
     def set_rounds(self, rounds) -> None:
         r = _np(rounds, np.uint32)
         _check(lib().rabitq_set_rounds(self._h, r.ctypes.data_as(c_u32p), len(r)))
+
+    def set_option(self, name: str, value: int) -> None:
+        _check(lib().rabitq_set_option(self._h, name.encode(), int(value)))
 
     def set_stream(self, cuda_stream: int | None) -> None:
         """Run on the caller's stream (e.g. `torch.cuda.current_stream().cuda_stream`); None = private stream."""

@@ -103,46 +103,60 @@ __global__ void __launch_bounds__(ROT_THREADS) rotate_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------------------
 // K2: squared L2 of every rotated centroid to every rotated query, order of simd::l2_squared_distance
 // (src/rabitq.rs:283-293, src/simd.rs:14-73: diff = c - y rounded, then sum = fma(diff, diff, sum)).
-// Thread = one centroid (its row streamed straight from L2 as 2 x 128-bit loads per 8 dims) x TQ queries
-// (broadcast from shared memory).
-constexpr int CD_TQ = 8;
-constexpr int CD_THREADS = 128;
+// CTA tile = 64 centroids x 32 queries; both operand tiles are staged in shared memory with coalesced 128-bit
+// loads (the centroid tile padded to a 68-float pitch so that 32 threads reading 32 different rows with LDS.128
+// hit disjoint banks).  Thread = one centroid x 8 queries, 8 AVX-lane accumulators each (64 registers).
+constexpr int CD_TQ = 8;        // queries per thread
+constexpr int CD_QG = 4;        // query groups per CTA
+constexpr int CD_TC = 64;       // centroids per CTA
+constexpr int CD_THREADS = CD_TC * CD_QG;
 constexpr int CD_DCH = 64;
+constexpr int CD_PITCH = CD_DCH + 4;
 
-__global__ void __launch_bounds__(CD_THREADS) centroid_dist_kernel(const float* __restrict__ cent, const float* __restrict__ y,
-                                                                   float* __restrict__ out, int nq, int K, int D) {
-    __shared__ float4 sy[CD_TQ][CD_DCH / 4];
-    const int c = blockIdx.x * CD_THREADS + threadIdx.x;
-    const int q0 = blockIdx.y * CD_TQ;
+__global__ void __launch_bounds__(CD_THREADS, 2) centroid_dist_kernel(const float* __restrict__ cent, const float* __restrict__ y,
+                                                                      float* __restrict__ out, int nq, int K, int D) {
+    __shared__ __align__(16) float sc[CD_TC][CD_PITCH];
+    __shared__ float4 sy[CD_QG * CD_TQ][CD_DCH / 4];
+    const int tid = threadIdx.x;
+    const int cl = tid & (CD_TC - 1), qg = tid / CD_TC;
+    const int c0 = blockIdx.x * CD_TC, c = c0 + cl;
+    const int qb = blockIdx.y * (CD_QG * CD_TQ), q0 = qb + qg * CD_TQ;
     float acc[CD_TQ][8];
 #pragma unroll
     for (int t = 0; t < CD_TQ; t++)
 #pragma unroll
         for (int v = 0; v < 8; v++) acc[t][v] = 0.0f;
-    const float4* crow = reinterpret_cast<const float4*>(cent + (size_t)(c < K ? c : 0) * D);
     for (int d0 = 0; d0 < D; d0 += CD_DCH) {
-        for (int i = threadIdx.x; i < CD_TQ * CD_DCH; i += CD_THREADS) {
-            int t = i / CD_DCH, d = i % CD_DCH;
-            reinterpret_cast<float*>(&sy[t][0])[d] = (q0 + t < nq) ? y[(size_t)(q0 + t) * D + d0 + d] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < (CD_TC * CD_DCH / 4) / CD_THREADS; i++) {
+            const int idx = tid + i * CD_THREADS, row = idx / (CD_DCH / 4), c4 = idx % (CD_DCH / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + row < K) v = __ldg(reinterpret_cast<const float4*>(cent + (size_t)(c0 + row) * D + d0) + c4);
+            *reinterpret_cast<float4*>(&sc[row][c4 * 4]) = v;
+        }
+#pragma unroll
+        for (int i = 0; i < (CD_QG * CD_TQ * CD_DCH / 4) / CD_THREADS; i++) {
+            const int idx = tid + i * CD_THREADS, row = idx / (CD_DCH / 4), c4 = idx % (CD_DCH / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (qb + row < nq) v = __ldg(reinterpret_cast<const float4*>(y + (size_t)(qb + row) * D + d0) + c4);
+            sy[row][c4] = v;
         }
         __syncthreads();
-        if (c < K) {
 #pragma unroll 2
-            for (int d = 0; d < CD_DCH; d += 8) {
-                float4 ca = __ldg(&crow[(d0 + d) / 4]), cb = __ldg(&crow[(d0 + d) / 4 + 1]);
+        for (int d = 0; d < CD_DCH; d += 8) {
+            const float4 ca = *reinterpret_cast<const float4*>(&sc[cl][d]), cb = *reinterpret_cast<const float4*>(&sc[cl][d + 4]);
 #pragma unroll
-                for (int t = 0; t < CD_TQ; t++) {
-                    float4 a = sy[t][d / 4], b = sy[t][d / 4 + 1];
-                    float f;
-                    f = __fsub_rn(ca.x, a.x); acc[t][0] = fmaf(f, f, acc[t][0]);
-                    f = __fsub_rn(ca.y, a.y); acc[t][1] = fmaf(f, f, acc[t][1]);
-                    f = __fsub_rn(ca.z, a.z); acc[t][2] = fmaf(f, f, acc[t][2]);
-                    f = __fsub_rn(ca.w, a.w); acc[t][3] = fmaf(f, f, acc[t][3]);
-                    f = __fsub_rn(cb.x, b.x); acc[t][4] = fmaf(f, f, acc[t][4]);
-                    f = __fsub_rn(cb.y, b.y); acc[t][5] = fmaf(f, f, acc[t][5]);
-                    f = __fsub_rn(cb.z, b.z); acc[t][6] = fmaf(f, f, acc[t][6]);
-                    f = __fsub_rn(cb.w, b.w); acc[t][7] = fmaf(f, f, acc[t][7]);
-                }
+            for (int t = 0; t < CD_TQ; t++) {
+                const float4 a = sy[qg * CD_TQ + t][d / 4], b = sy[qg * CD_TQ + t][d / 4 + 1];
+                float f;
+                f = __fsub_rn(ca.x, a.x); acc[t][0] = fmaf(f, f, acc[t][0]);
+                f = __fsub_rn(ca.y, a.y); acc[t][1] = fmaf(f, f, acc[t][1]);
+                f = __fsub_rn(ca.z, a.z); acc[t][2] = fmaf(f, f, acc[t][2]);
+                f = __fsub_rn(ca.w, a.w); acc[t][3] = fmaf(f, f, acc[t][3]);
+                f = __fsub_rn(cb.x, b.x); acc[t][4] = fmaf(f, f, acc[t][4]);
+                f = __fsub_rn(cb.y, b.y); acc[t][5] = fmaf(f, f, acc[t][5]);
+                f = __fsub_rn(cb.z, b.z); acc[t][6] = fmaf(f, f, acc[t][6]);
+                f = __fsub_rn(cb.w, b.w); acc[t][7] = fmaf(f, f, acc[t][7]);
             }
         }
         __syncthreads();
@@ -200,26 +214,51 @@ RQ_DEV uint32_t block_exclusive_scan(uint32_t* a, int n, uint32_t* warp_tot /* T
 // clusters (the survivor-slot layout) and the per-query totals (`rough` counter of src/rerank.rs:105).
 constexpr int SEL_THREADS = 256;
 
-__global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* __restrict__ cdist, int K, int P, int Ppow2,
+__global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* __restrict__ cdist, int K, int P, int Ppow2, int cache_keys,
                                                                    const uint32_t* __restrict__ offsets,
                                                                    uint32_t* __restrict__ probe_ids, float* __restrict__ probe_dist,
                                                                    uint32_t* __restrict__ slot_local, uint32_t* __restrict__ q_words,
                                                                    uint32_t* __restrict__ q_pairs) {
-    extern __shared__ unsigned long long sel_buf[];  // Ppow2 keys; reused as u32 scratch afterwards
+    extern __shared__ unsigned long long sel_buf[];  // Ppow2 (key,index) pairs, then (optionally) the K keys of this query
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_bucket, s_need, s_nout;
     __shared__ uint32_t warp_tot[SEL_THREADS / 32 + 1];
     __shared__ uint32_t eq_cnt[SEL_THREADS];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const size_t q = blockIdx.x;
     const float* row = cdist + q * (size_t)K;
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(sel_buf + Ppow2);
+    // Keys are taken relative to the smallest one: squared distances share their high bits, and a radix digit that is
+    // identical for every key would serialise all histogram updates on one shared-memory bin.
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    for (int i = tid; i < K; i += SEL_THREADS) {
+        const uint32_t key = okey(row[i]);
+        if (cache_keys) skeys[i] = key;
+        kmin = min(kmin, key);
+        kmax = max(kmax, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(FULL, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(FULL, kmax, o));
+    }
+    if (lane == 0) { hist[tid >> 5] = kmin; hist[8 + (tid >> 5)] = kmax; }
+    __syncthreads();
+    kmin = hist[0]; kmax = hist[8];
+#pragma unroll
+    for (int w = 1; w < SEL_THREADS / 32; w++) { kmin = min(kmin, hist[w]); kmax = max(kmax, hist[8 + w]); }
+    __syncthreads();
+    auto getkey = [&](int i) -> uint32_t { return (cache_keys ? skeys[i] : okey(row[i])) - kmin; };
+    const uint32_t range = kmax - kmin;
+    const int passes = range ? (32 - __clz(range) + 7) / 8 : 0;
 
     uint32_t prefix = 0, mask = 0, need = (uint32_t)P;
-    for (int pass = 3; pass >= 0; pass--) {
+    if (tid == 0) s_nout = 0;
+    for (int pass = passes - 1; pass >= 0; pass--) {
         hist[tid] = 0;
         __syncthreads();
         for (int i = tid; i < K; i += SEL_THREADS) {
-            uint32_t key = okey(row[i]);
+            const uint32_t key = getkey(i);
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
         }
         __syncthreads();
@@ -232,7 +271,6 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
             }
             s_bucket = (uint32_t)b;
             s_need = need - cum;
-            if (pass == 0) s_nout = 0;
         }
         __syncthreads();
         prefix |= s_bucket << (8 * pass);
@@ -240,10 +278,11 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
         need = s_need;
         __syncthreads();
     }
+    __syncthreads();
     const uint32_t kth = prefix, need_eq = need, n_less = (uint32_t)P - need_eq;
     // strictly smaller keys: any order (sorted below)
     for (int i = tid; i < K; i += SEL_THREADS) {
-        uint32_t key = okey(row[i]);
+        uint32_t key = getkey(i);
         if (key < kth) {
             uint32_t pos = atomicAdd(&s_nout, 1u);
             sel_buf[pos] = ((unsigned long long)key << 32) | (uint32_t)i;
@@ -254,13 +293,13 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
         const int per = (K + SEL_THREADS - 1) / SEL_THREADS;
         const int lo = min(K, tid * per), hi = min(K, lo + per);
         uint32_t c = 0;
-        for (int i = lo; i < hi; i++) c += (okey(row[i]) == kth);
+        for (int i = lo; i < hi; i++) c += (getkey(i) == kth);
         eq_cnt[tid] = c;
         __syncthreads();
         block_exclusive_scan<SEL_THREADS>(eq_cnt, SEL_THREADS, warp_tot);
         uint32_t base = eq_cnt[tid];
         for (int i = lo; i < hi && base < need_eq; i++)
-            if (okey(row[i]) == kth) {
+            if (getkey(i) == kth) {
                 sel_buf[n_less + base] = ((unsigned long long)kth << 32) | (uint32_t)i;
                 base++;
             }
@@ -280,7 +319,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
             }
             __syncthreads();
         }
-    // outputs; the words-per-slot array overlays the tail of sel_buf (as u32, after the keys are consumed)
+    // outputs; the words-per-slot array overlays the head of sel_buf (as u32, after the keys are consumed)
     uint32_t my_ids[16];  // P <= 4096 -> at most 16 per thread
     int cnt = 0;
     uint32_t pairs_local = 0;
@@ -362,6 +401,7 @@ __global__ void __launch_bounds__(1024) query_base_scan_kernel(const uint32_t* _
 //   u32[4*W32 + 5]    sum q_u (raw u32)     u32[+6] first 32-vector word of this slot     u32[+7] cluster id
 constexpr float SCALAR_1_15 = 1.0f / 15.0f;  // src/consts.rs:10
 
+template <int W32T>  // W32T > 0: D = 32*W32T held in registers (one pass over memory); 0: any D, two passes
 __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__ y, const float* __restrict__ cent,
                                                        const uint32_t* __restrict__ probe_ids, const float* __restrict__ probe_dist,
                                                        const uint32_t* __restrict__ slot_local, const uint32_t* __restrict__ q_wbase,
@@ -373,13 +413,21 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
     const uint32_t c = probe_ids[gw];
     const float* yr = y + q * (size_t)D;
     const float* cr = cent + (size_t)c * D;
-    const int W32 = D / 32, RS = 4 * W32 + 8;
+    const int W32 = W32T > 0 ? W32T : D / 32, RS = 4 * W32 + 8;
     uint32_t* rec = qrec + gw * (size_t)RS;
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
-    for (int d = lane; d < D; d += 32) {
-        float r = __fsub_rn(yr[d], cr[d]);
-        mn = fminf(mn, r);
-        mx = fmaxf(mx, r);
+    float rr[W32T > 0 ? W32T : 1];
+    if constexpr (W32T > 0) {
+#pragma unroll
+        for (int g = 0; g < W32T; g++) rr[g] = __fsub_rn(__ldg(&yr[g * 32 + lane]), __ldg(&cr[g * 32 + lane]));
+#pragma unroll
+        for (int g = 0; g < W32T; g++) { mn = fminf(mn, rr[g]); mx = fmaxf(mx, rr[g]); }
+    } else {
+        for (int d = lane; d < D; d += 32) {
+            float r = __fsub_rn(yr[d], cr[d]);
+            mn = fminf(mn, r);
+            mx = fmaxf(mx, r);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -389,9 +437,7 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
     const float delta = __fmul_rn(__fsub_rn(mx, mn), SCALAR_1_15);  // rabitq.rs:307
     const float inv = __fdiv_rn(1.0f, delta);                       // :308 recip()
     int sum = 0;
-    for (int g = 0; g < W32; g++) {
-        int d = g * 32 + lane;
-        float r = __fsub_rn(yr[d], cr[d]);
+    auto emit = [&](int g, float r) {
         int qi = cvtps_epi32(__fmul_rn(__fsub_rn(r, mn), inv));
         sum += qi;  // i32 lanes wrap like _mm256_add_epi32
         uint32_t b0 = __ballot_sync(FULL, qi & 1), b1 = __ballot_sync(FULL, qi & 2);
@@ -402,6 +448,12 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
             rec[2 * W32 + g] = b2;
             rec[3 * W32 + g] = b3;
         }
+    };
+    if constexpr (W32T > 0) {
+#pragma unroll
+        for (int g = 0; g < W32T; g++) emit(g, rr[g]);
+    } else {
+        for (int g = 0; g < W32; g++) emit(g, __fsub_rn(yr[g * 32 + lane], cr[g * 32 + lane]));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
@@ -432,8 +484,14 @@ __global__ void bucket_count_kernel(const uint32_t* __restrict__ probe_ids, size
     atomicAdd(&cl_count[probe_ids[q * P + p]], 1u);
 }
 
+RQ_DEV uint32_t chunk_count(uint32_t m, uint32_t n_c, int VT, uint32_t ch_min, uint32_t ch_max) {
+    if (!m) return 0;
+    const uint32_t nch = min((n_c + VT - 1) / VT, ch_max);
+    return nch > ch_min ? nch - ch_min : 0;
+}
+
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __restrict__ cl_count, const uint32_t* __restrict__ offsets,
-                                                           int K, int VT, uint32_t* __restrict__ cl_start,
+                                                           int K, int VT, uint32_t ch_min, uint32_t ch_max, uint32_t* __restrict__ cl_start,
                                                            uint32_t* __restrict__ item_start, uint32_t* __restrict__ cl_cursor,
                                                            uint32_t* __restrict__ work_ctl /* [0] counter, [1] n_work */) {
     __shared__ uint32_t wa[33], wb[33];
@@ -444,7 +502,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __res
     for (int c = lo; c < hi; c++) {
         uint32_t m = cl_count[c], n_c = offsets[c + 1] - offsets[c];
         sa += m;
-        sb += m ? (n_c + VT - 1) / VT : 0;
+        sb += chunk_count(m, n_c, VT, ch_min, ch_max);
     }
     uint32_t ia = sa, ib = sb;
 #pragma unroll
@@ -472,7 +530,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __res
         item_start[c] = rb;
         cl_cursor[c] = 0;
         ra += m;
-        rb += m ? (n_c + VT - 1) / VT : 0;
+        rb += chunk_count(m, n_c, VT, ch_min, ch_max);
     }
     if (tid == 0) {
         cl_start[K] = wa[32];
@@ -495,11 +553,11 @@ __global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, size_
     cl_items[cl_start[c] + pos] = (uint32_t)(q * P + p);
 }
 
-__global__ void work_items_kernel(const uint32_t* __restrict__ item_start, int K, uint2* __restrict__ work) {
+__global__ void work_items_kernel(const uint32_t* __restrict__ item_start, int K, uint32_t ch_min, uint2* __restrict__ work) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= K) return;
     uint32_t s = item_start[c], e = item_start[c + 1];
-    for (uint32_t i = s; i < e; i++) work[i] = make_uint2((uint32_t)c, i - s);
+    for (uint32_t i = s; i < e; i++) work[i] = make_uint2((uint32_t)c, ch_min + i - s);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -513,6 +571,63 @@ __global__ void work_items_kernel(const uint32_t* __restrict__ item_start, int K
 // bit-planes, evaluates the estimator in the reference's association without contraction and tests
 // `rough < thr[q]`.  Per warp and query: one ballot word -> bitmap[slot word], survivors' (rough, j) packed at
 // the start of the word's 32-entry block.  No atomics, deterministic layout, visit order preserved.
+// Carry-save popcount: POPC issues on the XU pipe (measured ~28 lane-ops/clk/SM on sm_100a, profiles/pipe_bench_r01.txt)
+// and saturates long before the ALU pipe, so words of equal weight are first compressed 3 -> 2 (or 7 -> 3) with
+// LOP3 full adders.  Integer-exact: popc(a)+popc(b)+popc(c) == popc(a^b^c) + 2*popc(maj(a,b,c)).
+RQ_DEV uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+RQ_DEV uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// sum_w popc(x[w] & pl[w]) over one bit-plane (pl in shared memory, 8-byte aligned; 16-byte when W32 % 4 == 0)
+template <int W32, int MODE>
+RQ_DEV uint32_t plane_sum(const uint32_t (&x)[W32], const uint32_t* pl) {
+    uint32_t a[W32];
+    if constexpr (W32 % 4 == 0) {
+#pragma unroll
+        for (int w = 0; w < W32; w += 4) {
+            const uint4 p = *reinterpret_cast<const uint4*>(pl + w);
+            a[w] = x[w] & p.x; a[w + 1] = x[w + 1] & p.y; a[w + 2] = x[w + 2] & p.z; a[w + 3] = x[w + 3] & p.w;
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < W32; w += 2) {
+            const uint2 p = *reinterpret_cast<const uint2*>(pl + w);
+            a[w] = x[w] & p.x; a[w + 1] = x[w + 1] & p.y;
+        }
+    }
+    uint32_t ones = 0, twos = 0, fours = 0;
+    constexpr int G7 = (MODE == 2) ? W32 / 7 : 0;
+    constexpr int R7 = W32 - 7 * G7;
+    constexpr int G3 = (MODE >= 1) ? R7 / 3 : 0;
+    constexpr int R3 = R7 - 3 * G3;
+#pragma unroll
+    for (int g = 0; g < G7; g++) {
+        const int w = 7 * g;
+        const uint32_t s1 = xor3(a[w], a[w + 1], a[w + 2]), c1 = maj3(a[w], a[w + 1], a[w + 2]);
+        const uint32_t s2 = xor3(a[w + 3], a[w + 4], a[w + 5]), c2 = maj3(a[w + 3], a[w + 4], a[w + 5]);
+        const uint32_t s3 = xor3(s1, s2, a[w + 6]), c3 = maj3(s1, s2, a[w + 6]);
+        ones += __popc(s3);
+        twos += __popc(xor3(c1, c2, c3));
+        fours += __popc(maj3(c1, c2, c3));
+    }
+#pragma unroll
+    for (int g = 0; g < G3; g++) {
+        const int w = 7 * G7 + 3 * g;
+        ones += __popc(xor3(a[w], a[w + 1], a[w + 2]));
+        twos += __popc(maj3(a[w], a[w + 1], a[w + 2]));
+    }
+#pragma unroll
+    for (int i = 0; i < R3; i++) ones += __popc(a[7 * G7 + 3 * G3 + i]);
+    return ones + (twos << 1) + (fours << 2);
+}
+
 struct ScanArgs {
     const uint32_t* codes;      // n x W32
     const float4* factors;      // n
@@ -528,11 +643,13 @@ struct ScanArgs {
     unsigned long long* counters;  // [0] survivors
     int P;
     int QS;                     // records per shared-memory slice
+    // this round = visit positions (probe rank, 128-vector chunk) in [lo, hi), lexicographic
+    int p_lo, ch_lo, p_hi, ch_hi;
 };
 
 constexpr int SCAN_THREADS = 128;
 
-template <int W32, int VPT, bool DENSE>
+template <int W32, int VPT, bool DENSE, int MODE>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
     constexpr int RS = 4 * W32 + 8;   // record words
     constexpr int RS4 = RS / 4;       // record uint4s
@@ -540,6 +657,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
     extern __shared__ uint4 s_rec[];  // QS records, then QS thresholds
     __shared__ uint32_t s_item;
     float* s_thr = reinterpret_cast<float*>(s_rec + (size_t)a.QS * RS4);
+    int* s_rank = reinterpret_cast<int*>(s_thr + a.QS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     unsigned long long n_surv = 0;
@@ -597,7 +715,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
                 uint32_t it = a.cl_items[it0 + s0 + r];
                 s_rec[r * RS4 + w4] = __ldg(reinterpret_cast<const uint4*>(a.qrec + (size_t)it * RS) + w4);
             }
-            if (tid < ns) s_thr[tid] = a.thr[a.cl_items[it0 + s0 + tid] / a.P];
+            if (tid < ns) {
+                const uint32_t it = a.cl_items[it0 + s0 + tid];
+                s_thr[tid] = a.thr[it / a.P];
+                s_rank[tid] = (int)(it % a.P);
+            }
             __syncthreads();
             for (int r = 0; r < ns; r++) {
                 const uint32_t* rec = reinterpret_cast<const uint32_t*>(s_rec + r * RS4);
@@ -605,34 +727,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
                 const float sq = *reinterpret_cast<const float*>(rec + 4 * W32 + 4);    // sqrt(ycd)
                 const uint32_t wbase = rec[4 * W32 + 6];
                 const float thr = s_thr[r];
+                {   // is (rank, chunk) inside this round's window?  (uniform over the CTA)
+                    const int pr = s_rank[r], ch = (int)chunk;
+                    const bool ge_lo = pr > a.p_lo || (pr == a.p_lo && ch >= a.ch_lo);
+                    const bool lt_hi = pr < a.p_hi || (pr == a.p_hi && ch < a.ch_hi);
+                    if (!(ge_lo && lt_hi)) continue;
+                }
 #pragma unroll
                 for (int i = 0; i < VPT; i++) {
-                    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                    if constexpr (W32 % 4 == 0) {
-#pragma unroll
-                        for (int w = 0; w < W32; w += 4) {
-                            const uint4 p0 = *reinterpret_cast<const uint4*>(rec + 0 * W32 + w);
-                            const uint4 p1 = *reinterpret_cast<const uint4*>(rec + 1 * W32 + w);
-                            const uint4 p2 = *reinterpret_cast<const uint4*>(rec + 2 * W32 + w);
-                            const uint4 p3 = *reinterpret_cast<const uint4*>(rec + 3 * W32 + w);
-                            a0 += __popc(code[i][w] & p0.x) + __popc(code[i][w + 1] & p0.y) + __popc(code[i][w + 2] & p0.z) + __popc(code[i][w + 3] & p0.w);
-                            a1 += __popc(code[i][w] & p1.x) + __popc(code[i][w + 1] & p1.y) + __popc(code[i][w + 2] & p1.z) + __popc(code[i][w + 3] & p1.w);
-                            a2 += __popc(code[i][w] & p2.x) + __popc(code[i][w + 1] & p2.y) + __popc(code[i][w + 2] & p2.z) + __popc(code[i][w + 3] & p2.w);
-                            a3 += __popc(code[i][w] & p3.x) + __popc(code[i][w + 1] & p3.y) + __popc(code[i][w + 2] & p3.z) + __popc(code[i][w + 3] & p3.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < W32; w += 2) {
-                            const uint2 p0 = *reinterpret_cast<const uint2*>(rec + 0 * W32 + w);
-                            const uint2 p1 = *reinterpret_cast<const uint2*>(rec + 1 * W32 + w);
-                            const uint2 p2 = *reinterpret_cast<const uint2*>(rec + 2 * W32 + w);
-                            const uint2 p3 = *reinterpret_cast<const uint2*>(rec + 3 * W32 + w);
-                            a0 += __popc(code[i][w] & p0.x) + __popc(code[i][w + 1] & p0.y);
-                            a1 += __popc(code[i][w] & p1.x) + __popc(code[i][w + 1] & p1.y);
-                            a2 += __popc(code[i][w] & p2.x) + __popc(code[i][w + 1] & p2.y);
-                            a3 += __popc(code[i][w] & p3.x) + __popc(code[i][w + 1] & p3.y);
-                        }
-                    }
+                    const uint32_t a0 = plane_sum<W32, MODE>(code[i], rec + 0 * W32), a1 = plane_sum<W32, MODE>(code[i], rec + 1 * W32);
+                    const uint32_t a2 = plane_sum<W32, MODE>(code[i], rec + 2 * W32), a3 = plane_sum<W32, MODE>(code[i], rec + 3 * W32);
                     const uint32_t abdp = a0 + (a1 << 1) + (a2 << 2) + (a3 << 3);  // utils.rs:113-135
                     // rabitq.rs:352-363, left-to-right, no contraction:
                     //   ((((cds + ycd) + lo*ppc) + ((2*abdp - sum) * ip) * delta) - err * sqrt(ycd))
@@ -703,8 +807,11 @@ RQ_DEV void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-RQ_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+RQ_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {  // no arrive: only raises the pending transaction count
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+RQ_DEV void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 RQ_DEV void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
@@ -739,23 +846,26 @@ RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, fl
     thr = okey_to_float(bk);
 }
 
-__global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int p_hi, int first, int finalize) {
+__global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int ch_lo, int p_hi, int ch_hi, int first, int finalize) {
     extern __shared__ __align__(16) unsigned char rr_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int q = blockIdx.x * wpb + warp;
     if (q >= a.nq) return;
     const int D = a.D, k = a.topk, R = a.R, pitch = D + 8;  // +8 floats: the 4 candidates of a group hit disjoint banks
+    const uint32_t rowbytes = (uint32_t)D * 4u;
     unsigned char* wbase = rr_smem_raw + (size_t)warp * a.smem_per_warp;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase);  // two barriers, one per wave buffer
     float* qv = reinterpret_cast<float*>(wbase + 16);
-    float* rows = qv + D;
-    float* hd = rows + (size_t)R * pitch;
+    float* rows = qv + D;                                   // [2][R][pitch]
+    float* hd = rows + (size_t)2 * R * pitch;
     uint32_t* hid = reinterpret_cast<uint32_t*>(hd + k);
-    float* qr = reinterpret_cast<float*>(hid + k);
-    uint32_t* qj = reinterpret_cast<uint32_t*>(qr + R + 32);
+    float* qr = reinterpret_cast<float*>(hid + k);          // [2][32]
+    uint32_t* qj = reinterpret_cast<uint32_t*>(qr + 64);    // [2][32]
+    float2* sent = reinterpret_cast<float2*>(qj + 64);      // [4][32] staged survivors
+    uint32_t* stot = reinterpret_cast<uint32_t*>(sent + 128);  // [4]
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    if (lane == 0) mbar_init(mbar, 1);
+    if (lane == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
     for (int d = lane; d < D; d += 32) qv[d] = a.qpad[(size_t)q * D + d];
     int cnt = first ? 0 : (int)a.heap_cnt[q];
     float thr = first ? 3.402823466e+38f : a.thr[q];
@@ -766,127 +876,194 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     }
     __syncwarp();
     if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);
-    uint32_t precise = 0, computed = 0, phase = 0;
-    int qn = 0;  // queued candidates (qr/qj[0..qn))
+    uint32_t precise = 0, computed = 0, par = 0;
+    int fill = 0, f = 0, pend_n = 0;  // wave being filled, its fill level, size of the closed-but-unprocessed wave (buffer f^1)
     const int sub = lane >> 3, v = lane & 7;
 
-    // one wave: the first n (<= R) queued candidates
-    auto wave = [&](int n) {
+    // process one closed wave: wait for its rows, all exact distances in parallel, in-order replay
+    auto process = [&](int w, int n) {
+        if (lane == 0) mbar_arrive(&mbar[w]);
+        mbar_wait(&mbar[w], (par >> w) & 1u);
+        par ^= 1u << w;
         const bool mine = lane < n;
-        const float rough = mine ? qr[lane] : 0.0f;
-        const uint32_t j = mine ? qj[lane] : 0u;
+        const float rough = mine ? qr[w * 32 + lane] : 0.0f;
+        const uint32_t j = mine ? qj[w * 32 + lane] : 0u;
         const uint32_t act = __ballot_sync(FULL, mine && rough < thr);
-        const int nact = __popc(act);
-        if (nact == 0) return;
-        const int myrank = __popc(act & lt_mask);
-        const bool active = (act >> lane) & 1u;
-        // gather: one bulk copy per active row into slot `myrank`
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (lane == 0) mbar_expect_tx(mbar, (uint32_t)nact * (uint32_t)D * 4u);
-        __syncwarp();
-        if (active) tma_bulk_g2s(rows + (size_t)myrank * pitch, a.base + (size_t)j * D, (uint32_t)D * 4u, mbar);
-        mbar_wait(mbar, phase);
-        phase ^= 1u;
-        float exact = 0.0f;
-        for (int g = 0; g < nact; g += 8) {
-            const float* r0 = rows + (size_t)min(g + sub, R - 1) * pitch;
-            const float* r1 = rows + (size_t)min(g + 4 + sub, R - 1) * pitch;
-            float acc0 = 0.0f, acc1 = 0.0f;
+        computed += n;
+        if (act) {
+            const float* rw = rows + (size_t)w * R * pitch;
+            float exact = 0.0f;
+            for (int g = 0; g < n; g += 8) {
+                const float* r0 = rw + (size_t)min(g + sub, R - 1) * pitch;
+                const float* r1 = rw + (size_t)min(g + 4 + sub, R - 1) * pitch;
+                float acc0 = 0.0f, acc1 = 0.0f;
+                if (g + 4 < n) {
 #pragma unroll 4
-            for (int d = v; d < D; d += 8) {
-                const float qd = qv[d];
-                const float f0 = __fsub_rn(r0[d], qd), f1 = __fsub_rn(r1[d], qd);
-                acc0 = fmaf(f0, f0, acc0);
-                acc1 = fmaf(f1, f1, acc1);
-            }
-            acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 4));
-            acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 4));
-            acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 1));
-            acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 1));
-            acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 2));
-            acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 2));
-            const int src = (myrank & 3) * 8;
-            const float res0 = __shfl_sync(FULL, acc0, src), res1 = __shfl_sync(FULL, acc1, src);
-            if (active && (myrank >> 3) == (g >> 3)) exact = ((myrank >> 2) & 1) ? res1 : res0;
-        }
-        computed += nact;
-        // in-order replay (rerank.rs:83-101)
-        uint32_t rem = act;
-        while (rem) {
-            const int t = __ffs(rem) - 1;
-            rem &= rem - 1;
-            const float r = __shfl_sync(FULL, rough, t);
-            const float ex = __shfl_sync(FULL, exact, t);
-            const uint32_t ju = __shfl_sync(FULL, j, t);
-            if (r < thr) {
-                precise++;
-                if (ex < thr) {
-                    const int slot = cnt < k ? cnt : maxpos;
-                    if (lane == 0) { hd[slot] = ex; hid[slot] = a.map_ids[ju]; }
-                    if (cnt < k) cnt++;
-                    __syncwarp();
-                    if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);
+                    for (int d = v; d < D; d += 8) {
+                        const float qd = qv[d];
+                        const float f0 = __fsub_rn(r0[d], qd), f1 = __fsub_rn(r1[d], qd);
+                        acc0 = fmaf(f0, f0, acc0);
+                        acc1 = fmaf(f1, f1, acc1);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int d = v; d < D; d += 8) {
+                        const float f0 = __fsub_rn(r0[d], qv[d]);
+                        acc0 = fmaf(f0, f0, acc0);
+                    }
                 }
+                acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 4));
+                acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 4));
+                acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 1));
+                acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 1));
+                acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 2));
+                acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 2));
+                const int src = (lane & 3) * 8;
+                const float res0 = __shfl_sync(FULL, acc0, src), res1 = __shfl_sync(FULL, acc1, src);
+                if ((lane >> 3) == (g >> 3)) exact = ((lane >> 2) & 1) ? res1 : res0;
+            }
+            // in-order replay (rerank.rs:83-101)
+            uint32_t rem = act;
+            while (rem) {
+                const int t = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const float r = __shfl_sync(FULL, rough, t);
+                const float ex = __shfl_sync(FULL, exact, t);
+                const uint32_t ju = __shfl_sync(FULL, j, t);
+                if (r < thr) {
+                    precise++;
+                    if (ex < thr) {
+                        const int slot = cnt < k ? cnt : maxpos;
+                        if (lane == 0) { hd[slot] = ex; hid[slot] = a.map_ids[ju]; }
+                        if (cnt < k) cnt++;
+                        __syncwarp();
+                        if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);
+                    }
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // rows of this buffer are rewritten by later bulk copies
+        __syncwarp();
+    };
+
+    // queue candidates in visit order; the row gather of each is issued right here, so it is in flight while the
+    // stream continues and while the previous wave is being replayed
+    auto enqueue = [&](uint32_t pm, float rough, uint32_t j) {
+        while (pm) {
+            const int space = R - fill;
+            const int rank = __popc(pm & lt_mask);
+            const bool take = ((pm >> lane) & 1u) && rank < space;
+            if (take) {
+                const int slot = fill + rank;
+                qr[f * 32 + slot] = rough;
+                qj[f * 32 + slot] = j;
+                mbar_expect_tx(&mbar[f], rowbytes);
+                tma_bulk_g2s(rows + ((size_t)f * R + slot) * pitch, a.base + (size_t)j * D, rowbytes, &mbar[f]);
+            }
+            const uint32_t took = __ballot_sync(FULL, take);
+            pm &= ~took;
+            fill += __popc(took);
+            __syncwarp();
+            if (fill == R) {
+                if (pend_n) process(f ^ 1, pend_n);
+                pend_n = R;
+                f ^= 1;
+                fill = 0;
             }
         }
     };
 
-    const uint32_t wb = a.q_wbase[q];
-    const uint32_t wlo = wb + a.slot_local[(size_t)q * a.P + p_lo];
-    const uint32_t whi = (p_hi >= a.P) ? a.q_wbase[q + 1] : wb + a.slot_local[(size_t)q * a.P + p_hi];
+    // word window of this round: from (p_lo, ch_lo) to (p_hi, ch_hi) in visit order; a chunk is 128 vectors = 4 words
+    const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
+    auto word_at = [&](int p, int ch) -> uint32_t {
+        if (p >= a.P) return wend;
+        const uint32_t s0 = wb + a.slot_local[(size_t)q * a.P + p];
+        const uint32_t s1 = (p + 1 < a.P) ? wb + a.slot_local[(size_t)q * a.P + p + 1] : wend;
+        return min(s0 + (uint32_t)ch * (SCAN_THREADS / 32), s1);
+    };
+    const uint32_t wlo = word_at(p_lo, ch_lo), whi = word_at(p_hi, ch_hi);
 
-    for (uint32_t w0 = wlo; w0 < whi; w0 += 32) {
-        const uint32_t m = (w0 + lane < whi) ? a.bitmap[w0 + lane] : 0u;
-        uint32_t incl = __popc(m);
+    // Super-block of SB x 32 words: SB independent bitmap loads per lane, then the first 32 survivors of every block
+    // loaded back to back and staged in shared memory; the (rolled, single-instance) processing loop follows.
+    constexpr int SB = 4;
+    for (uint32_t w0 = wlo; w0 < whi; w0 += 32 * SB) {
+        {
+            uint32_t m[SB], incl[SB];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const uint32_t T = __shfl_sync(FULL, incl, 31);
-        const uint32_t excl = incl - __popc(m);
-        for (uint32_t e0 = 0; e0 < T; e0 += 32) {
-            const uint32_t e = e0 + lane;
-            const bool have = e < T;
-            int pos = 0;  // source word = first lane whose inclusive prefix exceeds e
+            for (int u = 0; u < SB; u++) {
+                const uint32_t idx = w0 + u * 32 + lane;
+                m[u] = idx < whi ? a.bitmap[idx] : 0u;
+            }
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) {
-                uint32_t pv = __shfl_sync(FULL, incl, pos + s - 1);
-                if (pv <= e) pos += s;
+            for (int u = 0; u < SB; u++) {
+                uint32_t x = __popc(m[u]);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_up_sync(FULL, x, o);
+                    if (lane >= o) x += t;
+                }
+                incl[u] = x;
             }
-            pos = min(pos, 31);
-            const uint32_t src_excl = __shfl_sync(FULL, excl, pos);
-            float rough = 3.402823466e+38f;
-            uint32_t j = 0;
-            if (have) {
-                float2 en = a.entries[(size_t)(w0 + pos) * 32 + (e - src_excl)];
-                rough = en.x;
-                j = __float_as_uint(en.y);
+            float2 ent[SB];
+#pragma unroll
+            for (int u = 0; u < SB; u++) {
+                const uint32_t T = __shfl_sync(FULL, incl[u], 31);
+                int pos = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {
+                    uint32_t pv = __shfl_sync(FULL, incl[u], pos + s - 1);
+                    if (pv <= (uint32_t)lane) pos += s;
+                }
+                pos = min(pos, 31);
+                const uint32_t src_excl = __shfl_sync(FULL, incl[u] - __popc(m[u]), pos);
+                ent[u] = make_float2(3.402823466e+38f, 0.0f);
+                if ((uint32_t)lane < T) ent[u] = a.entries[(size_t)(w0 + u * 32 + pos) * 32 + (lane - src_excl)];
+                if (lane == 0) stot[u] = T;
             }
-            // queue what is still below the threshold (order preserved)
-            const bool pass = have && rough < thr;
-            const uint32_t pm = __ballot_sync(FULL, pass);
-            if (pass) {
-                const int at = qn + __popc(pm & lt_mask);
-                qr[at] = rough;
-                qj[at] = j;
-            }
-            qn += __popc(pm);
+#pragma unroll
+            for (int u = 0; u < SB; u++) sent[u * 32 + lane] = ent[u];
             __syncwarp();
-            while (qn >= R) {
-                wave(R);
-                const int left = qn - R;  // < 32
-                float tr = 0.0f;
-                uint32_t tj = 0;
-                if (lane < left) { tr = qr[R + lane]; tj = qj[R + lane]; }
-                __syncwarp();
-                if (lane < left) { qr[lane] = tr; qj[lane] = tj; }
-                __syncwarp();
-                qn = left;
+        }
+        for (int u = 0; u < SB; u++) {
+            const uint32_t T = stot[u];
+            if (T == 0) continue;  // uniform
+            {
+                const float2 en = sent[u * 32 + lane];
+                const uint32_t pm = __ballot_sync(FULL, (uint32_t)lane < T && en.x < thr);
+                if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
+            }
+            if (T > 32) {  // dense block (loose threshold, e.g. the first probed cluster): further chunks on demand
+                const uint32_t idx = w0 + u * 32 + lane;
+                const uint32_t mm = idx < whi ? a.bitmap[idx] : 0u;
+                uint32_t inc = __popc(mm);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                const uint32_t exc = inc - __popc(mm);
+                for (uint32_t e0 = 32; e0 < T; e0 += 32) {
+                    const uint32_t e = e0 + lane;
+                    const bool have = e < T;
+                    int pos = 0;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) {
+                        uint32_t pv = __shfl_sync(FULL, inc, pos + s - 1);
+                        if (pv <= e) pos += s;
+                    }
+                    pos = min(pos, 31);
+                    const uint32_t src_excl = __shfl_sync(FULL, exc, pos);
+                    float2 en = make_float2(3.402823466e+38f, 0.0f);
+                    if (have) en = a.entries[(size_t)(w0 + u * 32 + pos) * 32 + (e - src_excl)];
+                    const uint32_t pm = __ballot_sync(FULL, have && en.x < thr);
+                    if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
+                }
             }
         }
+        __syncwarp();
     }
-    if (qn > 0) wave(qn);
+    if (pend_n) process(f ^ 1, pend_n);
+    if (fill) process(f, fill);
 
     if (lane == 0) {
         a.q_precise[q] = (first ? 0u : a.q_precise[q]) + precise;

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -106,6 +107,8 @@ struct rabitq_index {
     cudaStream_t own_stream = nullptr;
     std::mutex mu;
     std::vector<uint32_t> rounds{0, 1};
+    int rerank_rows = 0;   // rows per rerank wave; 0 = by dimension
+    int first_chunks = 1;  // 128-vector chunks of the nearest cluster in the first round (0 = the whole cluster)
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_wbase, q_pbase, qrec, cl_count,
         cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, bitmap,
@@ -120,6 +123,7 @@ struct rabitq_index {
     std::vector<int> ev_stage;
     size_t ev_used = 0;
     int scan_blocks_per_sm = 0;
+    int scan_mode = -1;  // -1 = default; RABITQ_SCAN_MODE overrides (tuning)
 
     ~rabitq_index() {
         cudaSetDevice(device);
@@ -240,10 +244,14 @@ int make_index(uint32_t dim, size_t n_total, size_t K, const float* base, const 
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     ix->sm_count = prop.multiProcessorCount;
+    if (const char* e = std::getenv("RABITQ_SCAN_MODE")) ix->scan_mode = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_FIRST_CHUNKS")) ix->first_chunks = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("RABITQ_RR_ROWS")) ix->rerank_rows = std::atoi(e);
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     CU(cudaMallocHost((void**)&ix->h_pin, 256));
     CU(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     *out = ix;
     return RABITQ_OK;
 }
@@ -286,14 +294,14 @@ int load_dir(const char* dir, int device, int shard_rank, int shard_count, rabit
 }
 
 // ---- scan launch ------------------------------------------------------------------------------------------------
-template <int W32, bool DENSE>
-int launch_scan_t(rabitq_index* ix, ScanArgs& a) {
+template <int W32, bool DENSE, int MODE>
+int launch_scan_m(rabitq_index* ix, ScanArgs& a) {
     constexpr int RS = 4 * W32 + 8;
     int qs = 24576 / (RS * 4);
     qs = std::max(8, std::min(qs, SCAN_THREADS));
     a.QS = qs;
-    size_t smem = (size_t)qs * (RS * 4 + 4);
-    auto kern = scan_kernel<W32, 1, DENSE>;
+    size_t smem = (size_t)qs * (RS * 4 + 8);
+    auto kern = scan_kernel<W32, 1, DENSE, MODE>;
     int bps = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SCAN_THREADS, smem));
     bps = std::max(1, bps);
@@ -301,6 +309,24 @@ int launch_scan_t(rabitq_index* ix, ScanArgs& a) {
     kern<<<ix->sm_count * bps, SCAN_THREADS, smem, ix->stream>>>(a);
     CU(cudaGetLastError()); ix->counts[5]++;
     return 0;
+}
+
+// carry-save depth of the popcount (kernels.cuh plane_sum): 0 plain, 1 = 3->2 compressors, 2 = 7->3 compressors
+int scan_mode(const rabitq_index* ix) {
+    if (ix->scan_mode >= 0) return ix->scan_mode;
+    return ix->D / 32 >= 14 ? 2 : 1;  // measured on B200: 7->3 compressors win at D=960, 3->2 at D=128 (profiles/)
+}
+
+template <int W32, bool DENSE>
+int launch_scan_t(rabitq_index* ix, ScanArgs& a) {
+    if constexpr (DENSE) return launch_scan_m<W32, true, 0>(ix, a);
+    else {
+        switch (scan_mode(ix)) {
+            case 0: return launch_scan_m<W32, false, 0>(ix, a);
+            case 2: return launch_scan_m<W32, false, 2>(ix, a);
+            default: return launch_scan_m<W32, false, 1>(ix, a);
+        }
+    }
 }
 
 template <bool DENSE>
@@ -347,7 +373,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
 
     CU(ix->cdist.ensure(nb * (size_t)K * 4));
     {
-        dim3 grid((K + CD_THREADS - 1) / CD_THREADS, (unsigned)((nb + CD_TQ - 1) / CD_TQ));
+        dim3 grid((K + CD_TC - 1) / CD_TC, (unsigned)((nb + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ)));
         centroid_dist_kernel<<<grid, CD_THREADS, 0, st>>>(ix->cent, ix->y.as<float>(), ix->cdist.as<float>(), (int)nb, K, D);
         CU(cudaGetLastError()); ix->counts[5]++;
     }
@@ -362,8 +388,10 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     {
         int Ppow2 = 1;
         while (Ppow2 < P) Ppow2 <<= 1;
-        select_probe_kernel<<<(unsigned)nb, SEL_THREADS, (size_t)Ppow2 * 8, st>>>(
-            ix->cdist.as<float>(), K, P, Ppow2, ix->offsets, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(),
+        const int cache_keys = K <= 16384 ? 1 : 0;  // keys of one query in shared memory (<= 64 KB)
+        const size_t sel_smem = (size_t)Ppow2 * 8 + (cache_keys ? (size_t)K * 4 : 0);
+        select_probe_kernel<<<(unsigned)nb, SEL_THREADS, sel_smem, st>>>(
+            ix->cdist.as<float>(), K, P, Ppow2, cache_keys, ix->offsets, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(),
             ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
         query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nb,
@@ -382,9 +410,17 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     CU(ix->qrec.ensure(nb * (size_t)P * RS * 4));
     {
         size_t warps = nb * (size_t)P;
-        quantize_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(ix->y.as<float>(), ix->cent, ix->probe_ids.as<uint32_t>(),
-                                                                       ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(),
-                                                                       ix->q_wbase.as<uint32_t>(), ix->qrec.as<uint32_t>(), (int)nb, P, D);
+        const unsigned qgrid = (unsigned)((warps + 3) / 4);
+#define QUANT_ARGS ix->y.as<float>(), ix->cent, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), \
+                   ix->q_wbase.as<uint32_t>(), ix->qrec.as<uint32_t>(), (int)nb, P, D
+        switch (W32) {
+            case 2: quantize_kernel<2><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
+            case 4: quantize_kernel<4><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
+            case 6: quantize_kernel<6><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
+            case 8: quantize_kernel<8><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
+            default: quantize_kernel<0><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
+        }
+#undef QUANT_ARGS
         CU(cudaGetLastError()); ix->counts[5]++;
     }
     if (tick(ix, ST_QUANT)) return RABITQ_ECUDA;
@@ -452,44 +488,56 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     ra.P = P;
     ra.D = D;
     ra.topk = (int)topk;
-    // rows gathered per wave: what fits in ~32 KB of shared memory per warp, at most one per lane
-    ra.R = (int)std::max<size_t>(2, std::min<size_t>(32, 32768 / ((size_t)D * 4)));
-    ra.smem_per_warp = (int)((16 + (size_t)D * 4 + (size_t)ra.R * (D + 8) * 4 + 2 * topk * 4 + 2 * (size_t)(ra.R + 32) * 4 + 15) / 16 * 16);
+    // rows per wave (two wave buffers per warp): small waves keep shared memory low and occupancy high; the gathers are
+    // issued at enqueue time, so a wave's rows are usually resident before it is replayed
+    ra.R = (int)std::max<size_t>(2, std::min<size_t>(8, 16384 / ((size_t)D * 4)));
+    if (ix->rerank_rows > 0) ra.R = std::max(1, std::min(32, ix->rerank_rows));
+    ra.R = (int)std::max<size_t>(1, std::min<size_t>(ra.R, (80 * 1024) / (2 * (size_t)(D + 8) * 4)));  // <= 80 KB of row buffers per warp
+    ra.smem_per_warp = (int)((16 + (size_t)D * 4 + (size_t)2 * ra.R * (D + 8) * 4 + 2 * topk * 4 + 2 * 64 * 4 + 128 * 8 + 16 + 15) / 16 * 16);
     const int rr_wpb = ra.smem_per_warp > 24 * 1024 ? 2 : 4;
 
-    // rounds of probe ranks
-    std::vector<int> bounds;
-    if (stop == STOP_SCAN_DENSE) bounds = {0, P};
+    // rounds: windows of visit positions (probe rank, 128-vector chunk).  The first round covers only the first
+    // `first_chunks` chunks of the nearest cluster, so that everything after it is filtered with a real threshold.
+    struct Pos { int p, ch; };
+    std::vector<Pos> bounds;
+    if (stop == STOP_SCAN_DENSE) bounds = {{0, 0}, {P, 0}};
     else {
+        bounds.push_back({0, 0});
+        if (ix->first_chunks > 0) bounds.push_back({0, ix->first_chunks});
         for (uint32_t r : ix->rounds)
-            if ((int)r < P && (bounds.empty() || (int)r > bounds.back())) bounds.push_back((int)r);
-        if (bounds.empty() || bounds[0] != 0) bounds.insert(bounds.begin(), 0);
-        bounds.push_back(P);
+            if ((int)r > 0 && (int)r < P && (int)r > bounds.back().p) bounds.push_back({(int)r, 0});
+        bounds.push_back({P, 0});
     }
     for (size_t r = 0; r + 1 < bounds.size(); r++) {
-        const int p_lo = bounds[r], p_hi = bounds[r + 1];
-        const size_t items = nb * (size_t)(p_hi - p_lo);
+        const Pos lo = bounds[r], hi = bounds[r + 1];
+        const int p_lo = lo.p, p_hi_incl = std::min(P, hi.p + (hi.ch > 0 ? 1 : 0));  // ranks that have items in this round
+        const bool single_rank = p_hi_incl == p_lo + 1;
+        const uint32_t ch_min = single_rank ? (uint32_t)lo.ch : 0u;
+        const uint32_t ch_max = (single_rank && hi.ch > 0) ? (uint32_t)hi.ch : 0xffffffffu;
+        const size_t items = nb * (size_t)(p_hi_incl - p_lo);
         CU(cudaMemsetAsync(ix->cl_count.p, 0, (size_t)K * 4, st));
-        bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), nb, P, p_lo, p_hi,
+        bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
                                                                               ix->cl_count.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
-        bucket_scan_kernel<<<1, 1024, 0, st>>>(ix->cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, ix->cl_start.as<uint32_t>(),
-                                               ix->item_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(), ix->work_ctl.as<uint32_t>());
+        bucket_scan_kernel<<<1, 1024, 0, st>>>(ix->cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, ch_min, ch_max,
+                                               ix->cl_start.as<uint32_t>(), ix->item_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
+                                               ix->work_ctl.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
-        bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), nb, P, p_lo, p_hi,
+        bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
                                                                              ix->cl_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
                                                                              ix->cl_items.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
-        work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(ix->item_start.as<uint32_t>(), K, ix->work.as<uint2>());
+        work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(ix->item_start.as<uint32_t>(), K, ch_min, ix->work.as<uint2>());
         CU(cudaGetLastError()); ix->counts[5]++;
         if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
+        sa.p_lo = lo.p; sa.ch_lo = lo.ch; sa.p_hi = hi.p; sa.ch_hi = hi.ch;
         int rc = (stop == STOP_SCAN_DENSE) ? launch_scan<true>(ix, sa) : launch_scan<false>(ix, sa);
         if (rc) return rc;
         if (tick(ix, ST_SCAN)) return RABITQ_ECUDA;
         ix->counts[4] += 1;
         if (stop == STOP_SCAN_DENSE) return 0;
         rerank_kernel<<<(unsigned)((nb + rr_wpb - 1) / rr_wpb), rr_wpb * 32, (size_t)rr_wpb * ra.smem_per_warp, st>>>(
-            ra, p_lo, p_hi, r == 0 ? 1 : 0, r + 2 == bounds.size() ? 1 : 0);
+            ra, lo.p, lo.ch, hi.p, hi.ch, r == 0 ? 1 : 0, r + 2 == bounds.size() ? 1 : 0);
         CU(cudaGetLastError()); ix->counts[5]++;
         if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
     }
@@ -635,6 +683,13 @@ int rabitq_query_batch_device(rabitq_index* idx, const float* d_queries, size_t 
     return query_batch_impl(idx, d_queries, true, nq, len, probe, topk, heuristic_rank, d_out_dist, d_out_ids, d_out_count);
 }
 
+int rabitq_shard_range(const uint32_t* offsets, size_t k, int shard_rank, int shard_count, size_t* row_lo, size_t* row_hi) {
+    if (!offsets || !row_lo || !row_hi || k == 0 || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count)
+        return fail(RABITQ_EINVAL, "bad argument");
+    shard_rows(offsets, k, shard_rank, shard_count, row_lo, row_hi);
+    return RABITQ_OK;
+}
+
 int rabitq_merge_topk_device(int device, const float* d_dist, const uint32_t* d_ids, int n_lists, size_t nq, size_t topk,
                              float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count) {
     if (!d_dist || !d_ids || !d_out_dist || !d_out_ids || !d_out_count || n_lists < 1 || topk == 0)
@@ -664,6 +719,17 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n) {
         if (rounds[i] <= rounds[i - 1]) return fail(RABITQ_EINVAL, "rounds must be strictly increasing");
     std::lock_guard<std::mutex> lk(idx->mu);
     idx->rounds.assign(rounds, rounds + n);
+    return RABITQ_OK;
+}
+
+int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
+    if (!idx || !name) return fail(RABITQ_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    const std::string n(name);
+    if (n == "first_chunks") idx->first_chunks = (int)std::max(0L, value);
+    else if (n == "scan_mode") idx->scan_mode = (int)value;
+    else if (n == "rerank_rows") idx->rerank_rows = (int)value;
+    else return fail(RABITQ_EINVAL, "unknown option: " + n);
     return RABITQ_OK;
 }
 

@@ -148,6 +148,25 @@ def test_rounds_do_not_change_results(pair, rounds):
         g.set_rounds([0, 1])
 
 
+@pytest.mark.parametrize("opt,val", [("first_chunks", 0), ("first_chunks", 3), ("scan_mode", 0), ("scan_mode", 1), ("scan_mode", 2),
+                                     ("rerank_rows", 1), ("rerank_rows", 3), ("rerank_rows", 32)])
+def test_tuning_knobs_do_not_change_results(pair, opt, val):
+    q = pair["queries"]
+    g = pair["gpu"]
+    default = {"first_chunks": 1, "scan_mode": -1, "rerank_rows": 0}[opt]
+    g.set_option(opt, val)
+    try:
+        g.metrics_reset()
+        gd, gi, gc = g.query_batch(q, 40, 10)
+        o = pair["oracle"].query_batch(q, 40, 10)
+        for i in range(q.shape[0]):
+            c = int(gc[i])
+            assert _same_up_to_ties(pair, i, gd[i, :c], gi[i, :c], o["dist"][i, :c], o["ids"][i, :c])
+        assert g.metrics()["precise"] == o["precise"] and g.metrics()["rough"] == o["rough"]
+    finally:
+        g.set_option(opt, default)
+
+
 def test_single_query_matches_batch(pair):
     q = pair["queries"]
     g = pair["gpu"]
