@@ -29,6 +29,15 @@ PROBE_SWEEP = {"c1": [64], "c2": [16, 32, 64, 128, 256], "c3": [16, 32, 64, 128]
 TARGET_RECALL = 0.95
 
 
+# stdout carries exactly ONE JSON line: anything a library prints to fd 1 (NCCL's version banner, for one) goes to stderr.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_json(obj) -> None:
+    os.write(_JSON_FD, (json.dumps(obj) + "\n").encode())
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -320,7 +329,7 @@ def run_ours(args):
         }
         if not args.no_cpu and world >= 1:
             out["cpu_baseline"] = cpu_baseline(wl, probe, threads=1, budget_s=args.cpu_seconds)
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -354,7 +363,7 @@ def run_reference(args):
     import torch
 
     if not torch.cuda.is_available():
-        print(json.dumps({"impl": "reference", "unavailable": "needs the GPU only to generate the synthetic workload and index"}))
+        emit_json({"impl": "reference", "unavailable": "needs the GPU only to generate the synthetic workload and index"})
         return
     torch.cuda.set_device(0)
     device = torch.device("cuda", 0)
@@ -389,7 +398,7 @@ def run_reference(args):
            "cpu_baseline": {"value": round(qps, 2), "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": round(qps, 2), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 def main():

@@ -49,55 +49,66 @@ __global__ void pad_queries_kernel(const float* __restrict__ q, float* __restric
 
 // ---------------------------------------------------------------------------------------------------------
 // K1: batched rotation y = q * P with the summation order of project -> simd::vector_dot_product
-// (src/utils.rs:237-258, src/simd.rs:257-314).  Thread = one output column for TQ queries; P rows are read
-// coalesced (row r = P[r,:]), the query tile is broadcast from shared memory.
+// (src/utils.rs:237-258, src/simd.rs:257-314).  CTA tile = 64 output columns x 32 queries; the P tile (64 rows x
+// 64 columns, row r = P[r,:] as on disk) and the query tile are staged in shared memory with coalesced 128-bit
+// loads.  Thread = one column x 8 queries, 8 AVX-lane accumulators each.  CUDA cores by necessity: the quantised
+// codes downstream must be bit-exact, so y must be, so the 8-lane FMA association is reproduced (no 3xTF32).
 constexpr int ROT_TQ = 8;
-constexpr int ROT_THREADS = 64;
+constexpr int ROT_QG = 4;
+constexpr int ROT_TC = 64;
+constexpr int ROT_THREADS = ROT_TC * ROT_QG;
 constexpr int ROT_RCH = 64;
 
-__global__ void __launch_bounds__(ROT_THREADS) rotate_kernel(const float* __restrict__ qpad, const float* __restrict__ P,
-                                                             float* __restrict__ y, int nq, int D) {
-    __shared__ float4 sq[ROT_TQ][ROT_RCH / 4];
-    const int col = blockIdx.x * ROT_THREADS + threadIdx.x;
-    const int q0 = blockIdx.y * ROT_TQ;
+__global__ void __launch_bounds__(ROT_THREADS, 2) rotate_kernel(const float* __restrict__ qpad, const float* __restrict__ P,
+                                                                float* __restrict__ y, int nq, int D) {
+    __shared__ __align__(16) float sP[ROT_RCH][ROT_TC];
+    __shared__ float4 sq[ROT_QG * ROT_TQ][ROT_RCH / 4];
+    const int tid = threadIdx.x;
+    const int cl = tid & (ROT_TC - 1), qg = tid / ROT_TC;
+    const int col0 = blockIdx.x * ROT_TC, col = col0 + cl;
+    const int qb = blockIdx.y * (ROT_QG * ROT_TQ), q0 = qb + qg * ROT_TQ;
     float acc[ROT_TQ][8];
 #pragma unroll
     for (int t = 0; t < ROT_TQ; t++)
 #pragma unroll
         for (int v = 0; v < 8; v++) acc[t][v] = 0.0f;
     for (int r0 = 0; r0 < D; r0 += ROT_RCH) {
-        for (int i = threadIdx.x; i < ROT_TQ * ROT_RCH; i += ROT_THREADS) {
-            int t = i / ROT_RCH, r = i % ROT_RCH;
-            reinterpret_cast<float*>(&sq[t][0])[r] = (q0 + t < nq) ? qpad[(size_t)(q0 + t) * D + r0 + r] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < (ROT_RCH * ROT_TC / 4) / ROT_THREADS; i++) {
+            const int idx = tid + i * ROT_THREADS, row = idx / (ROT_TC / 4), c4 = idx % (ROT_TC / 4);
+            *reinterpret_cast<float4*>(&sP[row][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(P + (size_t)(r0 + row) * D + col0) + c4);
+        }
+#pragma unroll
+        for (int i = 0; i < (ROT_QG * ROT_TQ * ROT_RCH / 4) / ROT_THREADS; i++) {
+            const int idx = tid + i * ROT_THREADS, row = idx / (ROT_RCH / 4), c4 = idx % (ROT_RCH / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (qb + row < nq) v = __ldg(reinterpret_cast<const float4*>(qpad + (size_t)(qb + row) * D + r0) + c4);
+            sq[row][c4] = v;
         }
         __syncthreads();
-        if (col < D) {
 #pragma unroll 2
-            for (int r = 0; r < ROT_RCH; r += 8) {
-                float pv[8];
+        for (int r = 0; r < ROT_RCH; r += 8) {
+            float pv[8];
 #pragma unroll
-                for (int v = 0; v < 8; v++) pv[v] = __ldg(&P[(size_t)(r0 + r + v) * D + col]);
+            for (int v = 0; v < 8; v++) pv[v] = sP[r + v][cl];
 #pragma unroll
-                for (int t = 0; t < ROT_TQ; t++) {
-                    float4 a = sq[t][r / 4], b = sq[t][r / 4 + 1];
-                    acc[t][0] = fmaf(a.x, pv[0], acc[t][0]);
-                    acc[t][1] = fmaf(a.y, pv[1], acc[t][1]);
-                    acc[t][2] = fmaf(a.z, pv[2], acc[t][2]);
-                    acc[t][3] = fmaf(a.w, pv[3], acc[t][3]);
-                    acc[t][4] = fmaf(b.x, pv[4], acc[t][4]);
-                    acc[t][5] = fmaf(b.y, pv[5], acc[t][5]);
-                    acc[t][6] = fmaf(b.z, pv[6], acc[t][6]);
-                    acc[t][7] = fmaf(b.w, pv[7], acc[t][7]);
-                }
+            for (int t = 0; t < ROT_TQ; t++) {
+                const float4 a = sq[qg * ROT_TQ + t][r / 4], b = sq[qg * ROT_TQ + t][r / 4 + 1];
+                acc[t][0] = fmaf(a.x, pv[0], acc[t][0]);
+                acc[t][1] = fmaf(a.y, pv[1], acc[t][1]);
+                acc[t][2] = fmaf(a.z, pv[2], acc[t][2]);
+                acc[t][3] = fmaf(a.w, pv[3], acc[t][3]);
+                acc[t][4] = fmaf(b.x, pv[4], acc[t][4]);
+                acc[t][5] = fmaf(b.y, pv[5], acc[t][5]);
+                acc[t][6] = fmaf(b.z, pv[6], acc[t][6]);
+                acc[t][7] = fmaf(b.w, pv[7], acc[t][7]);
             }
         }
         __syncthreads();
     }
-    if (col < D) {
 #pragma unroll
-        for (int t = 0; t < ROT_TQ; t++)
-            if (q0 + t < nq) y[(size_t)(q0 + t) * D + col] = reduce8(acc[t]);
-    }
+    for (int t = 0; t < ROT_TQ; t++)
+        if (q0 + t < nq) y[(size_t)(q0 + t) * D + col] = reduce8(acc[t]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -218,10 +229,10 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
                                                                    const uint32_t* __restrict__ offsets,
                                                                    uint32_t* __restrict__ probe_ids, float* __restrict__ probe_dist,
                                                                    uint32_t* __restrict__ slot_local, uint32_t* __restrict__ q_words,
-                                                                   uint32_t* __restrict__ q_pairs) {
+                                                                   uint32_t* __restrict__ q_pairs, uint32_t* __restrict__ q_p0) {
     extern __shared__ unsigned long long sel_buf[];  // Ppow2 (key,index) pairs, then (optionally) the K keys of this query
     __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_bucket, s_need, s_nout;
+    __shared__ uint32_t s_bucket, s_need, s_nout, s_p0;
     __shared__ uint32_t warp_tot[SEL_THREADS / 32 + 1];
     __shared__ uint32_t eq_cnt[SEL_THREADS];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
     const int passes = range ? (32 - __clz(range) + 7) / 8 : 0;
 
     uint32_t prefix = 0, mask = 0, need = (uint32_t)P;
-    if (tid == 0) s_nout = 0;
+    if (tid == 0) { s_nout = 0; s_p0 = 0xffffffffu; }
     for (int pass = passes - 1; pass >= 0; pass--) {
         hist[tid] = 0;
         __syncthreads();
@@ -334,6 +345,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
         uint32_t n_c = offsets[id + 1] - offsets[id];
         words[p] = (n_c + 31u) >> 5;
         pairs_local += n_c;
+        if (n_c) atomicMin(&s_p0, (uint32_t)p);  // first probe rank that holds vectors on THIS shard
     }
     __syncthreads();
     uint32_t total_words = block_exclusive_scan<SEL_THREADS>(words, P, warp_tot);
@@ -349,6 +361,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
         for (int w = 0; w < SEL_THREADS / 32; w++) s += warp_tot[w];
         q_pairs[q] = s;
         q_words[q] = total_words;
+        q_p0[q] = s_p0 == 0xffffffffu ? 0u : s_p0;
     }
 }
 
@@ -395,10 +408,10 @@ __global__ void __launch_bounds__(1024) query_base_scan_kernel(const uint32_t* _
 // K3: per (query, probed cluster): residual, min/max, 4-bit scalar quantisation, bit-planes
 // (src/rabitq.rs:305-317 -> src/simd.rs:117-173, 185-247, 83-107).  One warp per (q, p); the movemask of the
 // AVX2 code becomes __ballot_sync.  Output is one packed record per (q, p):
-//   u32[0 .. 4*W32)   planes, plane-major: plane b word w  = bit b of q_u[32w .. 32w+31]
-//   f32[4*W32 + 0..3] lower_bound, delta, (f32) sum q_u, y_c_distance_square
-//   f32[4*W32 + 4]    sqrt(y_c_distance_square)
-//   u32[4*W32 + 5]    sum q_u (raw u32)     u32[+6] first 32-vector word of this slot     u32[+7] cluster id
+//   u32[0 .. 4*WP)    planes, plane-major, plane stride WP = W32 rounded up to 4: plane b word w = bit b of q_u[32w .. 32w+31]
+//   f32[4*WP + 0..3]  lower_bound, delta, (f32) sum q_u, y_c_distance_square
+//   f32[4*WP + 4]     sqrt(y_c_distance_square)
+//   u32[4*WP + 5]     sum q_u (raw u32)     u32[+6] first 32-vector word of this slot     u32[+7] cluster id
 constexpr float SCALAR_1_15 = 1.0f / 15.0f;  // src/consts.rs:10
 
 template <int W32T>  // W32T > 0: D = 32*W32T held in registers (one pass over memory); 0: any D, two passes
@@ -413,7 +426,7 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
     const uint32_t c = probe_ids[gw];
     const float* yr = y + q * (size_t)D;
     const float* cr = cent + (size_t)c * D;
-    const int W32 = W32T > 0 ? W32T : D / 32, RS = 4 * W32 + 8;
+    const int W32 = W32T > 0 ? W32T : D / 32, WP = (W32 + 3) & ~3, RS = 4 * WP + 8;  // plane stride padded to 128 bits
     uint32_t* rec = qrec + gw * (size_t)RS;
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
     float rr[W32T > 0 ? W32T : 1];
@@ -443,10 +456,10 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
         uint32_t b0 = __ballot_sync(FULL, qi & 1), b1 = __ballot_sync(FULL, qi & 2);
         uint32_t b2 = __ballot_sync(FULL, qi & 4), b3 = __ballot_sync(FULL, qi & 8);
         if (lane == 0) {
-            rec[0 * W32 + g] = b0;
-            rec[1 * W32 + g] = b1;
-            rec[2 * W32 + g] = b2;
-            rec[3 * W32 + g] = b3;
+            rec[0 * WP + g] = b0;
+            rec[1 * WP + g] = b1;
+            rec[2 * WP + g] = b2;
+            rec[3 * WP + g] = b3;
         }
     };
     if constexpr (W32T > 0) {
@@ -459,28 +472,32 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
     if (lane == 0) {
         const float ycd = probe_dist[gw];
-        float* rf = reinterpret_cast<float*>(rec + 4 * W32);
+        float* rf = reinterpret_cast<float*>(rec + 4 * WP);
         rf[0] = mn;
         rf[1] = delta;
         rf[2] = __uint2float_rn((uint32_t)sum);  // `scalar_sum as f32`, rabitq.rs:322
         rf[3] = ycd;
         rf[4] = __fsqrt_rn(ycd);                 // rabitq.rs:346
-        rec[4 * W32 + 5] = (uint32_t)sum;
-        rec[4 * W32 + 6] = q_wbase[q] + slot_local[gw];
-        rec[4 * W32 + 7] = c;
+        rec[4 * WP + 5] = (uint32_t)sum;
+        rec[4 * WP + 6] = q_wbase[q] + slot_local[gw];
+        rec[4 * WP + 7] = c;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Inverted probe lists for one round of probe ranks [p_lo, p_hi): cluster -> the (q, p) items probing it, and
 // the scan work list (cluster, chunk of VT vectors).
-__global__ void bucket_count_kernel(const uint32_t* __restrict__ probe_ids, size_t nq, int P, int p_lo, int p_hi,
-                                    uint32_t* __restrict__ cl_count) {
+// Rounds are expressed in EFFECTIVE ranks pe = p - p0[q] (p0 = first probe rank with vectors on this shard), so that the
+// first round always sees the first candidates a query really visits here, also on a shard that does not own its
+// nearest cluster.
+__global__ void bucket_count_kernel(const uint32_t* __restrict__ probe_ids, const uint32_t* __restrict__ q_p0, size_t nq, int P,
+                                    int p_lo, int p_hi, uint32_t* __restrict__ cl_count) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     int R = p_hi - p_lo;
     if (i >= nq * (size_t)R) return;
     size_t q = i / R;
-    int p = p_lo + (int)(i % R);
+    int p = p_lo + (int)(i % R) + (int)q_p0[q];
+    if (p >= P) return;
     atomicAdd(&cl_count[probe_ids[q * P + p]], 1u);
 }
 
@@ -540,14 +557,15 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __res
     }
 }
 
-__global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, size_t nq, int P, int p_lo, int p_hi,
-                                   const uint32_t* __restrict__ cl_start, uint32_t* __restrict__ cl_cursor,
+__global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, const uint32_t* __restrict__ q_p0, size_t nq, int P,
+                                   int p_lo, int p_hi, const uint32_t* __restrict__ cl_start, uint32_t* __restrict__ cl_cursor,
                                    uint32_t* __restrict__ cl_items) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     int R = p_hi - p_lo;
     if (i >= nq * (size_t)R) return;
     size_t q = i / R;
-    int p = p_lo + (int)(i % R);
+    int p = p_lo + (int)(i % R) + (int)q_p0[q];
+    if (p >= P) return;
     uint32_t c = probe_ids[q * P + p];
     uint32_t pos = atomicAdd(&cl_cursor[c], 1u);
     cl_items[cl_start[c] + pos] = (uint32_t)(q * P + p);
@@ -585,22 +603,17 @@ RQ_DEV uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
     return r;
 }
 
-// sum_w popc(x[w] & pl[w]) over one bit-plane (pl in shared memory, 8-byte aligned; 16-byte when W32 % 4 == 0)
+// sum_w popc(x[w] & pl[w]) over one bit-plane (pl in shared memory, 16-byte aligned, padded to 4 words)
 template <int W32, int MODE>
 RQ_DEV uint32_t plane_sum(const uint32_t (&x)[W32], const uint32_t* pl) {
     uint32_t a[W32];
-    if constexpr (W32 % 4 == 0) {
 #pragma unroll
-        for (int w = 0; w < W32; w += 4) {
-            const uint4 p = *reinterpret_cast<const uint4*>(pl + w);
-            a[w] = x[w] & p.x; a[w + 1] = x[w + 1] & p.y; a[w + 2] = x[w + 2] & p.z; a[w + 3] = x[w + 3] & p.w;
-        }
-    } else {
-#pragma unroll
-        for (int w = 0; w < W32; w += 2) {
-            const uint2 p = *reinterpret_cast<const uint2*>(pl + w);
-            a[w] = x[w] & p.x; a[w + 1] = x[w + 1] & p.y;
-        }
+    for (int w = 0; w < W32; w += 4) {  // planes are padded to a multiple of 4 words: always 128-bit broadcast loads
+        const uint4 p = *reinterpret_cast<const uint4*>(pl + w);
+        a[w] = x[w] & p.x;
+        if (w + 1 < W32) a[w + 1] = x[w + 1] & p.y;
+        if (w + 2 < W32) a[w + 2] = x[w + 2] & p.z;
+        if (w + 3 < W32) a[w + 3] = x[w + 3] & p.w;
     }
     uint32_t ones = 0, twos = 0, fours = 0;
     constexpr int G7 = (MODE == 2) ? W32 / 7 : 0;
@@ -638,6 +651,7 @@ struct ScanArgs {
     uint32_t* work_ctl;         // [0] counter [1] n_work
     const uint32_t* qrec;       // records
     const float* thr;           // per query
+    const uint32_t* q_p0;       // per query: first probe rank with vectors on this shard
     uint32_t* bitmap;           // per slot word
     float2* entries;            // per slot word: 32 x (rough, j as bits)
     unsigned long long* counters;  // [0] survivors
@@ -651,7 +665,8 @@ constexpr int SCAN_THREADS = 128;
 
 template <int W32, int VPT, bool DENSE, int MODE>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
-    constexpr int RS = 4 * W32 + 8;   // record words
+    constexpr int WP = (W32 + 3) & ~3;  // padded plane stride
+    constexpr int RS = 4 * WP + 8;    // record words
     constexpr int RS4 = RS / 4;       // record uint4s
     constexpr int VT = SCAN_THREADS * VPT;
     extern __shared__ uint4 s_rec[];  // QS records, then QS thresholds
@@ -718,14 +733,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
             if (tid < ns) {
                 const uint32_t it = a.cl_items[it0 + s0 + tid];
                 s_thr[tid] = a.thr[it / a.P];
-                s_rank[tid] = (int)(it % a.P);
+                s_rank[tid] = (int)(it % a.P) - (int)a.q_p0[it / a.P];
             }
             __syncthreads();
             for (int r = 0; r < ns; r++) {
                 const uint32_t* rec = reinterpret_cast<const uint32_t*>(s_rec + r * RS4);
-                const float4 sc = *reinterpret_cast<const float4*>(rec + 4 * W32);      // lo, delta, sum, ycd
-                const float sq = *reinterpret_cast<const float*>(rec + 4 * W32 + 4);    // sqrt(ycd)
-                const uint32_t wbase = rec[4 * W32 + 6];
+                const float4 sc = *reinterpret_cast<const float4*>(rec + 4 * WP);      // lo, delta, sum, ycd
+                const float sq = *reinterpret_cast<const float*>(rec + 4 * WP + 4);    // sqrt(ycd)
+                const uint32_t wbase = rec[4 * WP + 6];
                 const float thr = s_thr[r];
                 {   // is (rank, chunk) inside this round's window?  (uniform over the CTA)
                     const int pr = s_rank[r], ch = (int)chunk;
@@ -735,8 +750,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
                 }
 #pragma unroll
                 for (int i = 0; i < VPT; i++) {
-                    const uint32_t a0 = plane_sum<W32, MODE>(code[i], rec + 0 * W32), a1 = plane_sum<W32, MODE>(code[i], rec + 1 * W32);
-                    const uint32_t a2 = plane_sum<W32, MODE>(code[i], rec + 2 * W32), a3 = plane_sum<W32, MODE>(code[i], rec + 3 * W32);
+                    const uint32_t a0 = plane_sum<W32, MODE>(code[i], rec + 0 * WP), a1 = plane_sum<W32, MODE>(code[i], rec + 1 * WP);
+                    const uint32_t a2 = plane_sum<W32, MODE>(code[i], rec + 2 * WP), a3 = plane_sum<W32, MODE>(code[i], rec + 3 * WP);
                     const uint32_t abdp = a0 + (a1 << 1) + (a2 << 2) + (a3 << 3);  // utils.rs:113-135
                     // rabitq.rs:352-363, left-to-right, no contraction:
                     //   ((((cds + ycd) + lo*ppc) + ((2*abdp - sum) * ip) * delta) - err * sqrt(ycd))
@@ -785,6 +800,7 @@ struct RerankArgs {
     const uint32_t* map_ids;      // n
     const uint32_t* q_wbase;      // nq+1
     const uint32_t* slot_local;   // nq x P
+    const uint32_t* q_p0;         // nq
     const uint32_t* bitmap;
     const float2* entries;
     float* heap_dist;             // nq x topk   state between rounds
@@ -975,7 +991,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
 
     // word window of this round: from (p_lo, ch_lo) to (p_hi, ch_hi) in visit order; a chunk is 128 vectors = 4 words
     const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
-    auto word_at = [&](int p, int ch) -> uint32_t {
+    const int p0 = (int)a.q_p0[q];
+    auto word_at = [&](int pe, int ch) -> uint32_t {  // pe = effective rank
+        const int p = pe + p0;
         if (p >= a.P) return wend;
         const uint32_t s0 = wb + a.slot_local[(size_t)q * a.P + p];
         const uint32_t s1 = (p + 1 < a.P) ? wb + a.slot_local[(size_t)q * a.P + p + 1] : wend;

@@ -110,7 +110,7 @@ struct rabitq_index {
     int rerank_rows = 0;   // rows per rerank wave; 0 = by dimension
     int first_chunks = 1;  // 128-vector chunks of the nearest cluster in the first round (0 = the whole cluster)
     // work buffers
-    DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_wbase, q_pbase, qrec, cl_count,
+    DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, cl_count,
         cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, bitmap,
         entries, counters, out_dist, out_ids, out_count;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
@@ -129,7 +129,7 @@ struct rabitq_index {
         cudaSetDevice(device);
         for (void* p : {(void*)base, (void*)P, (void*)cent, (void*)offsets, (void*)map_ids, (void*)codes, (void*)factors})
             if (p) cudaFree(p);
-        for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_wbase, &q_pbase,
+        for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &qrec, &cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count})
             b->release();
@@ -296,7 +296,7 @@ int load_dir(const char* dir, int device, int shard_rank, int shard_count, rabit
 // ---- scan launch ------------------------------------------------------------------------------------------------
 template <int W32, bool DENSE, int MODE>
 int launch_scan_m(rabitq_index* ix, ScanArgs& a) {
-    constexpr int RS = 4 * W32 + 8;
+    constexpr int RS = 4 * ((W32 + 3) & ~3) + 8;
     int qs = 24576 / (RS * 4);
     qs = std::max(8, std::min(qs, SCAN_THREADS));
     a.QS = qs;
@@ -352,7 +352,7 @@ struct BatchOut {  // device pointers of the sub-batch products
 int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t topk, StopAfter stop, BatchOut* bo) {
     const int D = (int)ix->D, K = (int)ix->K;
     const int P = (int)std::min(probe, ix->K);
-    const int W32 = D / 32, RS = 4 * W32 + 8;
+    const int W32 = D / 32, WP = (W32 + 3) & ~3, RS = 4 * WP + 8;
     cudaStream_t st = ix->stream;
     bo->P = P;
     CU(ix->qpad.ensure(nb * D * 4));
@@ -364,7 +364,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     }
     if (tick(ix, ST_H2D)) return RABITQ_ECUDA;
     {
-        dim3 grid((D + ROT_THREADS - 1) / ROT_THREADS, (unsigned)((nb + ROT_TQ - 1) / ROT_TQ));
+        dim3 grid(D / ROT_TC, (unsigned)((nb + ROT_QG * ROT_TQ - 1) / (ROT_QG * ROT_TQ)));
         rotate_kernel<<<grid, ROT_THREADS, 0, st>>>(ix->qpad.as<float>(), ix->P, ix->y.as<float>(), (int)nb, D);
         CU(cudaGetLastError()); ix->counts[5]++;
     }
@@ -383,6 +383,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     CU(ix->slot_local.ensure(nb * P * 4));
     CU(ix->q_words.ensure(nb * 4));
     CU(ix->q_pairs.ensure(nb * 4));
+    CU(ix->q_p0.ensure(nb * 4));
     CU(ix->q_wbase.ensure((nb + 1) * 4));
     CU(ix->q_pbase.ensure((nb + 1) * 8));
     {
@@ -392,7 +393,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
         const size_t sel_smem = (size_t)Ppow2 * 8 + (cache_keys ? (size_t)K * 4 : 0);
         select_probe_kernel<<<(unsigned)nb, SEL_THREADS, sel_smem, st>>>(
             ix->cdist.as<float>(), K, P, Ppow2, cache_keys, ix->offsets, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(),
-            ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>());
+            ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), ix->q_p0.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
         query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nb,
                                                    ix->q_wbase.as<uint32_t>(), ix->q_pbase.as<unsigned long long>());
@@ -461,6 +462,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     sa.work_ctl = ix->work_ctl.as<uint32_t>();
     sa.qrec = ix->qrec.as<uint32_t>();
     sa.thr = ix->thr.as<float>();
+    sa.q_p0 = ix->q_p0.as<uint32_t>();
     sa.bitmap = ix->bitmap.as<uint32_t>();
     sa.entries = ix->entries.as<float2>();
     sa.counters = ix->counters.as<unsigned long long>();
@@ -473,6 +475,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     ra.map_ids = ix->map_ids;
     ra.q_wbase = ix->q_wbase.as<uint32_t>();
     ra.slot_local = ix->slot_local.as<uint32_t>();
+    ra.q_p0 = ix->q_p0.as<uint32_t>();
     ra.bitmap = ix->bitmap.as<uint32_t>();
     ra.entries = ix->entries.as<float2>();
     ra.heap_dist = ix->heap_dist.as<float>();
@@ -516,14 +519,14 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
         const uint32_t ch_max = (single_rank && hi.ch > 0) ? (uint32_t)hi.ch : 0xffffffffu;
         const size_t items = nb * (size_t)(p_hi_incl - p_lo);
         CU(cudaMemsetAsync(ix->cl_count.p, 0, (size_t)K * 4, st));
-        bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
+        bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
                                                                               ix->cl_count.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
         bucket_scan_kernel<<<1, 1024, 0, st>>>(ix->cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, ch_min, ch_max,
                                                ix->cl_start.as<uint32_t>(), ix->item_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
                                                ix->work_ctl.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
-        bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
+        bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
                                                                              ix->cl_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
                                                                              ix->cl_items.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
@@ -778,15 +781,16 @@ int rabitq_stage_quantize(rabitq_index* idx, const float* queries, size_t nq, si
     BatchOut bo;
     int rc = stage_prefix(idx, queries, nq, len, probe, STOP_QUANT, &bo);
     if (rc) return rc;
-    const size_t W32 = idx->D / 32, RS = 4 * W32 + 8, items = nq * bo.P;
+    const size_t W32 = idx->D / 32, WP = (W32 + 3) & ~(size_t)3, RS = 4 * WP + 8, items = nq * bo.P;
     std::vector<uint32_t> rec(items * RS);
     CU(cudaMemcpy(rec.data(), idx->qrec.p, items * RS * 4, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < items; i++) {
         const uint32_t* r = &rec[i * RS];
-        if (out_planes) std::memcpy(out_planes + i * 2 * W32, r, 4 * W32 * 4);  // [4][W64] u64 little-endian == [4][W32] u32
-        if (out_lo) std::memcpy(&out_lo[i], r + 4 * W32 + 0, 4);
-        if (out_delta) std::memcpy(&out_delta[i], r + 4 * W32 + 1, 4);
-        if (out_sum) out_sum[i] = r[4 * W32 + 5];
+        if (out_planes)  // [4][W64] u64 little-endian == [4][W32] u32
+            for (size_t b = 0; b < 4; b++) std::memcpy(out_planes + i * 2 * W32 + b * (W32 / 2), r + b * WP, W32 * 4);
+        if (out_lo) std::memcpy(&out_lo[i], r + 4 * WP + 0, 4);
+        if (out_delta) std::memcpy(&out_delta[i], r + 4 * WP + 1, 4);
+        if (out_sum) out_sum[i] = r[4 * WP + 5];
     }
     return RABITQ_OK;
 }

@@ -16,7 +16,7 @@ DEFAULT_X_DOT_PRODUCT = 0.8  # src/consts.rs:4
 
 
 @torch.no_grad()
-def build_index(base: torch.Tensor, centroids: torch.Tensor, seed: int = 1, chunk: int = 1 << 17) -> dict:
+def build_index(base: torch.Tensor, centroids: torch.Tensor, seed: int = 1, chunk: int | None = None) -> dict:
     """base [n, len], centroids [k, len] (original space, same device).  Returns the arrays of `struct RaBitQ`
     (src/rabitq.rs:57-68) as device tensors: dim, base (padded, cluster-sorted, UNROTATED), orthogonal [D, D]
     (row r = P[r,:]), centroids [k, D] ROTATED, offsets [k+1] i32, map_ids [n] i32, codes [n, D/64] i64,
@@ -25,6 +25,8 @@ def build_index(base: torch.Tensor, centroids: torch.Tensor, seed: int = 1, chun
     n, ln = base.shape
     k = centroids.shape[0]
     D = (ln + 63) // 64 * 64  # rabitq.rs:167-179
+    if chunk is None:  # keep the chunk x k distance tile around 1 GiB
+        chunk = max(1 << 12, min(1 << 17, (1 << 28) // max(k, 1)))
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     try:

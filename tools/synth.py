@@ -100,9 +100,11 @@ def brute_force_topk_numpy(base: np.ndarray, queries: np.ndarray, topk: int) -> 
     return out
 
 
-def brute_force_topk_torch(base: torch.Tensor, queries: torch.Tensor, topk: int, chunk: int = 1 << 19) -> torch.Tensor:
+def brute_force_topk_torch(base: torch.Tensor, queries: torch.Tensor, topk: int, chunk: int | None = None) -> torch.Tensor:
     """Exact fp32 top-k ids by squared L2 on the device (ground truth for recall)."""
     nq = queries.shape[0]
+    if chunk is None:  # keep the nq x chunk distance tile around 1 GiB
+        chunk = max(1 << 12, min(1 << 19, (1 << 28) // max(nq, 1)))
     best_d = torch.full((nq, topk), float("inf"), device=base.device)
     best_i = torch.zeros((nq, topk), dtype=torch.int64, device=base.device)
     q2 = (queries * queries).sum(1, keepdim=True)
