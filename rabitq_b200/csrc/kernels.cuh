@@ -37,6 +37,31 @@ RQ_DEV float reduce8(const float* s) {
     return __fadd_rn(__fadd_rn(c0, c1), __fadd_rn(c2, c3));
 }
 
+// Packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2): two IEEE round-to-nearest fp32 operations per instruction, each
+// lane rounded exactly like the scalar op, so the AVX evaluation order is kept while the issue slots are halved.
+typedef unsigned long long f32x2;
+RQ_DEV f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+RQ_DEV void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+RQ_DEV f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+RQ_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+RQ_DEV float reduce8p(const f32x2* s) {  // reduce_f32_256 over 8 lanes held as 4 packed pairs (0,1) (2,3) (4,5) (6,7)
+    float v[8];
+    unpack2(s[0], v[0], v[1]); unpack2(s[1], v[2], v[3]); unpack2(s[2], v[4], v[5]); unpack2(s[3], v[6], v[7]);
+    return reduce8(v);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K0: zero-pad queries to D (src/rabitq.rs:277-280).
 __global__ void pad_queries_kernel(const float* __restrict__ q, float* __restrict__ qpad, size_t nq, int len, int D) {
@@ -67,11 +92,11 @@ __global__ void __launch_bounds__(ROT_THREADS, 2) rotate_kernel(const float* __r
     const int cl = tid & (ROT_TC - 1), qg = tid / ROT_TC;
     const int col0 = blockIdx.x * ROT_TC, col = col0 + cl;
     const int qb = blockIdx.y * (ROT_QG * ROT_TQ), q0 = qb + qg * ROT_TQ;
-    float acc[ROT_TQ][8];
+    f32x2 acc[ROT_TQ][4];
 #pragma unroll
     for (int t = 0; t < ROT_TQ; t++)
 #pragma unroll
-        for (int v = 0; v < 8; v++) acc[t][v] = 0.0f;
+        for (int v = 0; v < 4; v++) acc[t][v] = 0ull;
     for (int r0 = 0; r0 < D; r0 += ROT_RCH) {
 #pragma unroll
         for (int i = 0; i < (ROT_RCH * ROT_TC / 4) / ROT_THREADS; i++) {
@@ -88,27 +113,24 @@ __global__ void __launch_bounds__(ROT_THREADS, 2) rotate_kernel(const float* __r
         __syncthreads();
 #pragma unroll 2
         for (int r = 0; r < ROT_RCH; r += 8) {
-            float pv[8];
+            f32x2 pv[4];
 #pragma unroll
-            for (int v = 0; v < 8; v++) pv[v] = sP[r + v][cl];
+            for (int v = 0; v < 4; v++) pv[v] = pack2(sP[r + 2 * v][cl], sP[r + 2 * v + 1][cl]);
 #pragma unroll
             for (int t = 0; t < ROT_TQ; t++) {
-                const float4 a = sq[qg * ROT_TQ + t][r / 4], b = sq[qg * ROT_TQ + t][r / 4 + 1];
-                acc[t][0] = fmaf(a.x, pv[0], acc[t][0]);
-                acc[t][1] = fmaf(a.y, pv[1], acc[t][1]);
-                acc[t][2] = fmaf(a.z, pv[2], acc[t][2]);
-                acc[t][3] = fmaf(a.w, pv[3], acc[t][3]);
-                acc[t][4] = fmaf(b.x, pv[4], acc[t][4]);
-                acc[t][5] = fmaf(b.y, pv[5], acc[t][5]);
-                acc[t][6] = fmaf(b.z, pv[6], acc[t][6]);
-                acc[t][7] = fmaf(b.w, pv[7], acc[t][7]);
+                const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&sq[qg * ROT_TQ + t][r / 4]);
+                const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(&sq[qg * ROT_TQ + t][r / 4 + 1]);
+                acc[t][0] = fma2(a.x, pv[0], acc[t][0]);  // AVX lanes 0,1
+                acc[t][1] = fma2(a.y, pv[1], acc[t][1]);  // 2,3
+                acc[t][2] = fma2(b.x, pv[2], acc[t][2]);  // 4,5
+                acc[t][3] = fma2(b.y, pv[3], acc[t][3]);  // 6,7
             }
         }
         __syncthreads();
     }
 #pragma unroll
     for (int t = 0; t < ROT_TQ; t++)
-        if (q0 + t < nq) y[(size_t)(q0 + t) * D + col] = reduce8(acc[t]);
+        if (q0 + t < nq) y[(size_t)(q0 + t) * D + col] = reduce8p(acc[t]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -132,11 +154,11 @@ __global__ void __launch_bounds__(CD_THREADS, 2) centroid_dist_kernel(const floa
     const int cl = tid & (CD_TC - 1), qg = tid / CD_TC;
     const int c0 = blockIdx.x * CD_TC, c = c0 + cl;
     const int qb = blockIdx.y * (CD_QG * CD_TQ), q0 = qb + qg * CD_TQ;
-    float acc[CD_TQ][8];
+    f32x2 acc[CD_TQ][4];
 #pragma unroll
     for (int t = 0; t < CD_TQ; t++)
 #pragma unroll
-        for (int v = 0; v < 8; v++) acc[t][v] = 0.0f;
+        for (int v = 0; v < 4; v++) acc[t][v] = 0ull;
     for (int d0 = 0; d0 < D; d0 += CD_DCH) {
 #pragma unroll
         for (int i = 0; i < (CD_TC * CD_DCH / 4) / CD_THREADS; i++) {
@@ -155,19 +177,16 @@ __global__ void __launch_bounds__(CD_THREADS, 2) centroid_dist_kernel(const floa
         __syncthreads();
 #pragma unroll 2
         for (int d = 0; d < CD_DCH; d += 8) {
-            const float4 ca = *reinterpret_cast<const float4*>(&sc[cl][d]), cb = *reinterpret_cast<const float4*>(&sc[cl][d + 4]);
+            const ulonglong2 ca = *reinterpret_cast<const ulonglong2*>(&sc[cl][d]), cb = *reinterpret_cast<const ulonglong2*>(&sc[cl][d + 4]);
 #pragma unroll
             for (int t = 0; t < CD_TQ; t++) {
-                const float4 a = sy[qg * CD_TQ + t][d / 4], b = sy[qg * CD_TQ + t][d / 4 + 1];
-                float f;
-                f = __fsub_rn(ca.x, a.x); acc[t][0] = fmaf(f, f, acc[t][0]);
-                f = __fsub_rn(ca.y, a.y); acc[t][1] = fmaf(f, f, acc[t][1]);
-                f = __fsub_rn(ca.z, a.z); acc[t][2] = fmaf(f, f, acc[t][2]);
-                f = __fsub_rn(ca.w, a.w); acc[t][3] = fmaf(f, f, acc[t][3]);
-                f = __fsub_rn(cb.x, b.x); acc[t][4] = fmaf(f, f, acc[t][4]);
-                f = __fsub_rn(cb.y, b.y); acc[t][5] = fmaf(f, f, acc[t][5]);
-                f = __fsub_rn(cb.z, b.z); acc[t][6] = fmaf(f, f, acc[t][6]);
-                f = __fsub_rn(cb.w, b.w); acc[t][7] = fmaf(f, f, acc[t][7]);
+                const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&sy[qg * CD_TQ + t][d / 4]);
+                const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(&sy[qg * CD_TQ + t][d / 4 + 1]);
+                f32x2 f;
+                f = sub2(ca.x, a.x); acc[t][0] = fma2(f, f, acc[t][0]);  // AVX lanes 0,1: diff = c - y, then fma(diff, diff, sum)
+                f = sub2(ca.y, a.y); acc[t][1] = fma2(f, f, acc[t][1]);  // 2,3
+                f = sub2(cb.x, b.x); acc[t][2] = fma2(f, f, acc[t][2]);  // 4,5
+                f = sub2(cb.y, b.y); acc[t][3] = fma2(f, f, acc[t][3]);  // 6,7
             }
         }
         __syncthreads();
@@ -175,7 +194,7 @@ __global__ void __launch_bounds__(CD_THREADS, 2) centroid_dist_kernel(const floa
     if (c < K) {
 #pragma unroll
         for (int t = 0; t < CD_TQ; t++)
-            if (q0 + t < nq) out[(size_t)(q0 + t) * K + c] = reduce8(acc[t]);
+            if (q0 + t < nq) out[(size_t)(q0 + t) * K + c] = reduce8p(acc[t]);
     }
 }
 
@@ -224,6 +243,8 @@ RQ_DEV uint32_t block_exclusive_scan(uint32_t* a, int n, uint32_t* warp_tot /* T
 // smaller centroid index wins.  Also emits, per (query, rank), the prefix of 32-vector words of the probed
 // clusters (the survivor-slot layout) and the per-query totals (`rough` counter of src/rerank.rs:105).
 constexpr int SEL_THREADS = 256;
+constexpr int SEL_SAMPLE = 512;   // pivot path: sample size
+constexpr int SEL_CAND = 1024;    // pivot path: candidate capacity (sel_buf holds max(Ppow2, SEL_CAND) entries)
 
 __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* __restrict__ cdist, int K, int P, int Ppow2, int cache_keys,
                                                                    const uint32_t* __restrict__ offsets,
@@ -238,9 +259,76 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
     const int tid = threadIdx.x, lane = tid & 31;
     const size_t q = blockIdx.x;
     const float* row = cdist + q * (size_t)K;
-    uint32_t* skeys = reinterpret_cast<uint32_t*>(sel_buf + Ppow2);
+    const int buf_n = max(Ppow2, SEL_CAND);
+    uint32_t* samp = reinterpret_cast<uint32_t*>(sel_buf + buf_n);      // SEL_SAMPLE keys
+    uint32_t* skeys = samp + SEL_SAMPLE;                                // K keys when cached
     // Keys are taken relative to the smallest one: squared distances share their high bits, and a radix digit that is
     // identical for every key would serialise all histogram updates on one shared-memory bin.
+    if (tid == 0) s_p0 = 0xffffffffu;
+    // ---- fast path: pivot from a sorted sample, one collecting pass, sort of the few candidates ----------------
+    // Exact: the result is the P smallest (key, index) pairs, same as the radix path, which remains the fallback when
+    // the pivot admits fewer than P or more than SEL_CAND keys.
+    bool have_result = false;
+    if (K >= 16 * P && K >= 4 * SEL_SAMPLE) {
+        const int stride = K / SEL_SAMPLE;
+        for (int i = tid; i < SEL_SAMPLE; i += SEL_THREADS) samp[i] = okey(__ldg(&row[i * stride]));
+        if (tid == 0) s_nout = 0;
+        __syncthreads();
+        for (int k2 = 2; k2 <= SEL_SAMPLE; k2 <<= 1)
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < SEL_SAMPLE; i += SEL_THREADS) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint32_t x = samp[i], z = samp[ixj];
+                        const bool up = (i & k2) == 0;
+                        if ((x > z) == up) { samp[i] = z; samp[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        const int t = min(SEL_SAMPLE - 1, 3 * ((P * SEL_SAMPLE + K - 1) / K) + 8);
+        const uint32_t pivot = samp[t];
+        auto take = [&](float v, int i) {
+            const uint32_t key = okey(v);
+            if (key <= pivot) {
+                const uint32_t pos = atomicAdd(&s_nout, 1u);
+                if (pos < (uint32_t)SEL_CAND) sel_buf[pos] = ((unsigned long long)key << 32) | (uint32_t)i;
+            }
+        };
+        if ((K & 3) == 0) {  // one pass over the keys, 128-bit loads, several in flight per thread
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+#pragma unroll 4
+            for (int i4 = tid; i4 < K / 4; i4 += SEL_THREADS) {
+                const float4 v = __ldg(&row4[i4]);
+                take(v.x, 4 * i4); take(v.y, 4 * i4 + 1); take(v.z, 4 * i4 + 2); take(v.w, 4 * i4 + 3);
+            }
+        } else {
+            for (int i = tid; i < K; i += SEL_THREADS) take(__ldg(&row[i]), i);
+        }
+        __syncthreads();
+        const int cn = (int)s_nout;
+        if (cn >= P && cn <= SEL_CAND) {
+            int cpow2 = 1;
+            while (cpow2 < cn) cpow2 <<= 1;
+            for (int i = cn + tid; i < cpow2; i += SEL_THREADS) sel_buf[i] = ~0ull;
+            __syncthreads();
+            for (int k2 = 2; k2 <= cpow2; k2 <<= 1)
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < cpow2; i += SEL_THREADS) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const unsigned long long x = sel_buf[i], z = sel_buf[ixj];
+                            const bool up = (i & k2) == 0;
+                            if ((x > z) == up) { sel_buf[i] = z; sel_buf[ixj] = x; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            have_result = true;
+        }
+        __syncthreads();
+    }
+    if (!have_result) {
     uint32_t kmin = 0xffffffffu, kmax = 0u;
     for (int i = tid; i < K; i += SEL_THREADS) {
         const uint32_t key = okey(row[i]);
@@ -264,7 +352,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
     const int passes = range ? (32 - __clz(range) + 7) / 8 : 0;
 
     uint32_t prefix = 0, mask = 0, need = (uint32_t)P;
-    if (tid == 0) { s_nout = 0; s_p0 = 0xffffffffu; }
+    if (tid == 0) s_nout = 0;
     for (int pass = passes - 1; pass >= 0; pass--) {
         hist[tid] = 0;
         __syncthreads();
@@ -330,6 +418,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
             }
             __syncthreads();
         }
+    }
     // outputs; the words-per-slot array overlays the head of sel_buf (as u32, after the keys are consumed)
     uint32_t my_ids[16];  // P <= 4096 -> at most 16 per thread
     int cnt = 0;
@@ -808,6 +897,8 @@ struct RerankArgs {
     uint32_t* heap_cnt;           // nq
     float* thr;                   // nq
     uint32_t* q_precise;          // nq (accumulated over rounds)
+    float* h_recent;              // nq  HeuristicReRanker::recent_max_accurate between rounds
+    uint32_t* h_wcount;           // nq  HeuristicReRanker::count between rounds
     unsigned long long* counters; // [1] exact computed (speculative) [2] precise
     float* out_dist;              // nq x topk (finalize)
     uint32_t* out_ids;
@@ -862,6 +953,10 @@ RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, fl
     thr = okey_to_float(bk);
 }
 
+// HEUR = false: HeapReRanker (src/rerank.rs:61-114).  HEUR = true: HeuristicReRanker (src/rerank.rs:117-176): the filter
+// threshold is the largest accepted distance of the last WINDOW_SIZE = 12 accepted candidates (src/consts.rs:12); every
+// accepted candidate is a result candidate and get_result keeps the topk smallest, which is what the k-slot buffer holds.
+template <bool HEUR>
 __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int ch_lo, int p_hi, int ch_hi, int first, int finalize) {
     extern __shared__ __align__(16) unsigned char rr_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -884,14 +979,20 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     if (lane == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
     for (int d = lane; d < D; d += 32) qv[d] = a.qpad[(size_t)q * D + d];
     int cnt = first ? 0 : (int)a.heap_cnt[q];
-    float thr = first ? 3.402823466e+38f : a.thr[q];
+    float thr = first ? 3.402823466e+38f : a.thr[q];   // the filter threshold of the reranker
+    float hmax = 3.402823466e+38f;                      // largest distance among the k kept results (when cnt == k)
+    float recent = first ? -3.402823466e+38f : a.h_recent[q];
+    uint32_t wcount = first ? 0u : a.h_wcount[q];
     int maxpos = 0;
     for (int s = lane; s < cnt; s += 32) {
         hd[s] = a.heap_dist[(size_t)q * k + s];
         hid[s] = a.heap_ids[(size_t)q * k + s];
     }
     __syncwarp();
-    if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);
+    if (cnt == k) {
+        heap_recompute_max(hd, k, lane, maxpos, hmax);
+        if constexpr (!HEUR) thr = hmax;
+    }
     uint32_t precise = 0, computed = 0, par = 0;
     int fill = 0, f = 0, pend_n = 0;  // wave being filled, its fill level, size of the closed-but-unprocessed wave (buffer f^1)
     const int sub = lane >> 3, v = lane & 7;
@@ -949,11 +1050,25 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                 if (r < thr) {
                     precise++;
                     if (ex < thr) {
-                        const int slot = cnt < k ? cnt : maxpos;
-                        if (lane == 0) { hd[slot] = ex; hid[slot] = a.map_ids[ju]; }
-                        if (cnt < k) cnt++;
-                        __syncwarp();
-                        if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);
+                        if (!HEUR || cnt < k || ex < hmax) {
+                            const int slot = cnt < k ? cnt : maxpos;
+                            if (lane == 0) { hd[slot] = ex; hid[slot] = a.map_ids[ju]; }
+                            if (cnt < k) cnt++;
+                            __syncwarp();
+                            if (cnt == k) {
+                                heap_recompute_max(hd, k, lane, maxpos, hmax);
+                                if constexpr (!HEUR) thr = hmax;  // rerank.rs:98-100
+                            }
+                        }
+                        if constexpr (HEUR) {  // rerank.rs:155-162
+                            wcount++;
+                            recent = fmaxf(recent, ex);
+                            if (wcount >= 12u) {
+                                thr = recent;
+                                wcount = 0;
+                                recent = -3.402823466e+38f;
+                            }
+                        }
                     }
                 }
             }
@@ -1093,7 +1208,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
             a.heap_dist[(size_t)q * k + s] = hd[s];
             a.heap_ids[(size_t)q * k + s] = hid[s];
         }
-        if (lane == 0) { a.heap_cnt[q] = (uint32_t)cnt; a.thr[q] = thr; }
+        if (lane == 0) { a.heap_cnt[q] = (uint32_t)cnt; a.thr[q] = thr; a.h_recent[q] = recent; a.h_wcount[q] = wcount; }
     } else {
         // ascending by (distance, id): rank by counting
         __syncwarp();

@@ -111,7 +111,7 @@ struct rabitq_index {
     int first_chunks = 1;  // 128-vector chunks of the nearest cluster in the first round (0 = the whole cluster)
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, cl_count,
-        cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, bitmap,
+        cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
         entries, counters, out_dist, out_ids, out_count;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
     // metrics (src/metrics.rs)
@@ -131,7 +131,7 @@ struct rabitq_index {
             if (p) cudaFree(p);
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &qrec, &cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &thr, &heap_dist,
-                          &heap_ids, &heap_cnt, &q_precise, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count})
+                          &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         for (auto e : ev_pool) cudaEventDestroy(e);
@@ -250,7 +250,8 @@ int make_index(uint32_t dim, size_t n_total, size_t K, const float* base, const 
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     CU(cudaMallocHost((void**)&ix->h_pin, 256));
-    CU(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     *out = ix;
     return RABITQ_OK;
@@ -349,7 +350,7 @@ struct BatchOut {  // device pointers of the sub-batch products
 };
 
 // One sub-batch of nb queries, already on the device in ix->qraw (nb x len).  Runs up to `stop`.
-int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t topk, StopAfter stop, BatchOut* bo) {
+int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t topk, bool heuristic, StopAfter stop, BatchOut* bo) {
     const int D = (int)ix->D, K = (int)ix->K;
     const int P = (int)std::min(probe, ix->K);
     const int W32 = D / 32, WP = (W32 + 3) & ~3, RS = 4 * WP + 8;
@@ -389,8 +390,9 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     {
         int Ppow2 = 1;
         while (Ppow2 < P) Ppow2 <<= 1;
-        const int cache_keys = K <= 16384 ? 1 : 0;  // keys of one query in shared memory (<= 64 KB)
-        const size_t sel_smem = (size_t)Ppow2 * 8 + (cache_keys ? (size_t)K * 4 : 0);
+        const bool pivot_ok = K >= 16 * P && K >= 4 * SEL_SAMPLE;  // kernels.cuh: sampling-pivot path, keys stay in L2/HBM
+        const int cache_keys = (!pivot_ok && K <= 16384) ? 1 : 0;  // radix path: keys of one query in shared memory (<= 64 KB)
+        const size_t sel_smem = (size_t)std::max(Ppow2, SEL_CAND) * 8 + SEL_SAMPLE * 4 + (cache_keys ? (size_t)K * 4 : 0);
         select_probe_kernel<<<(unsigned)nb, SEL_THREADS, sel_smem, st>>>(
             ix->cdist.as<float>(), K, P, Ppow2, cache_keys, ix->offsets, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(),
             ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), ix->q_p0.as<uint32_t>());
@@ -444,6 +446,8 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     CU(ix->heap_ids.ensure(nb * topk * 4));
     CU(ix->heap_cnt.ensure(nb * 4));
     CU(ix->q_precise.ensure(nb * 4));
+    CU(ix->h_recent.ensure(nb * 4));
+    CU(ix->h_wcount.ensure(nb * 4));
     CU(ix->counters.ensure(64));
     CU(ix->out_dist.ensure(nb * topk * 4));
     CU(ix->out_ids.ensure(nb * topk * 4));
@@ -483,6 +487,8 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     ra.heap_cnt = ix->heap_cnt.as<uint32_t>();
     ra.thr = ix->thr.as<float>();
     ra.q_precise = ix->q_precise.as<uint32_t>();
+    ra.h_recent = ix->h_recent.as<float>();
+    ra.h_wcount = ix->h_wcount.as<uint32_t>();
     ra.counters = ix->counters.as<unsigned long long>();
     ra.out_dist = ix->out_dist.as<float>();
     ra.out_ids = ix->out_ids.as<uint32_t>();
@@ -539,8 +545,13 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
         if (tick(ix, ST_SCAN)) return RABITQ_ECUDA;
         ix->counts[4] += 1;
         if (stop == STOP_SCAN_DENSE) return 0;
-        rerank_kernel<<<(unsigned)((nb + rr_wpb - 1) / rr_wpb), rr_wpb * 32, (size_t)rr_wpb * ra.smem_per_warp, st>>>(
-            ra, lo.p, lo.ch, hi.p, hi.ch, r == 0 ? 1 : 0, r + 2 == bounds.size() ? 1 : 0);
+        {
+            const dim3 rgrid((unsigned)((nb + rr_wpb - 1) / rr_wpb)), rblock(rr_wpb * 32);
+            const size_t rsmem = (size_t)rr_wpb * ra.smem_per_warp;
+            const int is_first = r == 0 ? 1 : 0, is_last = r + 2 == bounds.size() ? 1 : 0;
+            if (heuristic) rerank_kernel<true><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, is_first, is_last);
+            else rerank_kernel<false><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, is_first, is_last);
+        }
         CU(cudaGetLastError()); ix->counts[5]++;
         if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
     }
@@ -555,7 +566,6 @@ int validate_query_args(const rabitq_index* ix, size_t len, size_t probe, size_t
     if (std::min(probe, ix->K) > 4096) return fail(RABITQ_EUNSUPPORTED, "probe > 4096 is not supported");
     if (topk == 0) return fail(RABITQ_EINVAL, "topk must be >= 1 (the reference panics on an empty heap peek)");
     if (topk > 1024) return fail(RABITQ_EUNSUPPORTED, "topk > 1024 is not supported");
-    if (heuristic) return fail(RABITQ_EUNSUPPORTED, "heuristic_rank (HeuristicReRanker) is not built yet");
     return 0;
 }
 
@@ -591,7 +601,7 @@ int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, siz
         CU(ix->qraw.ensure(nb * len * 4));
         CU(cudaMemcpyAsync(ix->qraw.p, queries + q0 * len, nb * len * 4, kin, ix->stream));
         BatchOut bo;
-        rc = run_sub_batch(ix, nb, len, probe, topk, STOP_NONE, &bo);
+        rc = run_sub_batch(ix, nb, len, probe, topk, heuristic != 0, STOP_NONE, &bo);
         if (rc) return rc;
         CU(cudaMemcpyAsync(out_dist + q0 * topk, ix->out_dist.p, nb * topk * 4, kout, ix->stream));
         CU(cudaMemcpyAsync(out_ids + q0 * topk, ix->out_ids.p, nb * topk * 4, kout, ix->stream));
@@ -625,7 +635,7 @@ int stage_prefix(rabitq_index* ix, const float* queries, size_t nq, size_t len, 
     CU(ix->qraw.ensure(nq * len * 4));
     CU(cudaMemcpyAsync(ix->qraw.p, queries, nq * len * 4, cudaMemcpyHostToDevice, ix->stream));
     if (tick(ix, -1)) return RABITQ_ECUDA;
-    rc = run_sub_batch(ix, nq, len, probe, 1, stop, bo);
+    rc = run_sub_batch(ix, nq, len, probe, 1, false, stop, bo);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ix->stream));
     return 0;

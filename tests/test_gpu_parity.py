@@ -238,3 +238,47 @@ def test_sharded_union_equals_full(pair):
     assert np.all(md <= full_d + 0)
     same = np.mean([np.array_equal(md[i].view(np.uint32), full_d[i].view(np.uint32)) for i in range(q.shape[0])])
     assert same >= 0.9
+
+
+def test_probe_select_pivot_path_and_ties(oracle_lib):
+    """K >= 2048 and K >= 16 * probe takes the sampling-pivot fast path; duplicated centroids give exactly equal
+    distances, which must resolve to the smaller centroid id exactly as in the oracle."""
+    import rabitq_b200 as rb
+    from tools import synth
+
+    base, queries, cent = synth.make_numpy(6000, 64, 24, 2304, "sift", 41)
+    cent[1000:1200] = cent[0:200]  # exact duplicates -> exact distance ties
+    ix = oracle_lib.OracleIndex.from_arrays(base, cent, seed=7, nthreads=8)
+    a = ix.arrays()
+    g = rb.RaBitQ.from_arrays(a["dim"], a["base"], a["orthogonal"], a["centroids"], a["offsets"], a["map_ids"], a["codes"], a["factors"], device=0)
+    for probe in (1, 7, 64, 144):  # 144 * 16 = 2304 -> still the pivot path; 145+ would fall back to radix
+        cd, pid, pd = g.stage_probe(queries, probe)
+        for i in range(queries.shape[0]):
+            tr = ix.trace(queries[i], probe, 5)
+            assert np.array_equal(pid[i], tr["probe_ids"]), (probe, i)
+            assert np.array_equal(pd[i].view(np.uint32), tr["probe_dist"].view(np.uint32))
+    for probe in (200, 2304):  # radix path
+        cd, pid, pd = g.stage_probe(queries[:6], probe)
+        for i in range(6):
+            tr = ix.trace(queries[i], probe, 5)
+            assert np.array_equal(pid[i], tr["probe_ids"]), (probe, i)
+    gd, gi, gc = g.query_batch(queries, 64, 10)
+    o = ix.query_batch(queries, 64, 10)
+    assert np.array_equal(np.sort(gd, 1).view(np.uint32), np.sort(o["dist"], 1).view(np.uint32))
+    g.close()
+
+
+@pytest.mark.parametrize("probe,topk", [(4, 10), (32, 10), (64, 50)])
+def test_heuristic_reranker_matches_oracle(pair, probe, topk):
+    """-h / heuristic_rank=True: HeuristicReRanker (src/rerank.rs:117-176), same sequential replay, windowed threshold."""
+    q = pair["queries"]
+    g = pair["gpu"]
+    g.metrics_reset()
+    gd, gi, gc = g.query_batch(q, probe, topk, heuristic_rank=True)
+    o = pair["oracle"].query_batch(q, probe, topk, heuristic_rank=True)
+    assert np.array_equal(gc, o["count"])
+    for i in range(q.shape[0]):
+        c = int(gc[i])
+        assert _same_up_to_ties(pair, i, gd[i, :c], gi[i, :c], o["dist"][i, :c], o["ids"][i, :c]), f"query {i}"
+    m = g.metrics()
+    assert m["rough"] == o["rough"] and m["precise"] == o["precise"]
