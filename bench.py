@@ -311,7 +311,7 @@ def run_ours(args):
                        "timing": "CUDA events on the launch stream, L2 flushed (256 MB write) between timed steps",
                        "parallelism": "single GPU" if world == 1 else f"index sharded by cluster range over {world} GPUs, "
                                       f"queries replicated ({nq} = {nq // world} x {world}), NCCL all-gather of (dist,id) + merge kernel",
-                       "rerank_rounds": args.rounds or "0,1"},
+                       "rerank_rounds": args.rounds or "0"},
             "e2e": {"value": round(qps_e2e, 1), "unit": "queries/s", "h2d_bytes_per_step": int(nq * queries.shape[1] * 4),
                     "d2h_bytes_per_step": int(nq * TOPK * 8 + nq * 4), "ms_per_step": round(tot_e2e / args.steps, 4),
                     "recall_at_10": round(recall_e2e, 4)},

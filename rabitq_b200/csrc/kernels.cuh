@@ -977,12 +977,21 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     if (lane == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
-    for (int d = lane; d < D; d += 32) qv[d] = a.qpad[(size_t)q * D + d];
+    // prologue: every independent global load is issued before the first dependent use (the kernel is a chain of
+    // memory latencies; the fewer links the better)
     int cnt = first ? 0 : (int)a.heap_cnt[q];
     float thr = first ? 3.402823466e+38f : a.thr[q];   // the filter threshold of the reranker
     float hmax = 3.402823466e+38f;                      // largest distance among the k kept results (when cnt == k)
     float recent = first ? -3.402823466e+38f : a.h_recent[q];
     uint32_t wcount = first ? 0u : a.h_wcount[q];
+    const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
+    const int p0 = (int)a.q_p0[q];
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.qpad + (size_t)q * D);
+        float4* dst = reinterpret_cast<float4*>(qv);
+#pragma unroll 8
+        for (int d = lane; d < D / 4; d += 32) dst[d] = __ldg(&src[d]);
+    }
     int maxpos = 0;
     for (int s = lane; s < cnt; s += 32) {
         hd[s] = a.heap_dist[(size_t)q * k + s];
@@ -1105,8 +1114,6 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     };
 
     // word window of this round: from (p_lo, ch_lo) to (p_hi, ch_hi) in visit order; a chunk is 128 vectors = 4 words
-    const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
-    const int p0 = (int)a.q_p0[q];
     auto word_at = [&](int pe, int ch) -> uint32_t {  // pe = effective rank
         const int p = pe + p0;
         if (p >= a.P) return wend;

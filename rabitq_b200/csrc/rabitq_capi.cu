@@ -106,7 +106,7 @@ struct rabitq_index {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     std::mutex mu;
-    std::vector<uint32_t> rounds{0, 1};
+    std::vector<uint32_t> rounds{0};
     int rerank_rows = 0;   // rows per rerank wave; 0 = by dimension
     int first_chunks = 1;  // 128-vector chunks of the nearest cluster in the first round (0 = the whole cluster)
     // work buffers
@@ -498,12 +498,25 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     ra.D = D;
     ra.topk = (int)topk;
     // rows per wave (two wave buffers per warp): small waves keep shared memory low and occupancy high; the gathers are
-    // issued at enqueue time, so a wave's rows are usually resident before it is replayed
+    // issued at enqueue time, so a wave's rows are usually resident before it is replayed.  When the batch is small enough
+    // the wave is shrunk further until every query-warp is co-resident (one wave of CTAs instead of two).
+    auto rr_smem = [&](int R) {
+        return (int)((16 + (size_t)D * 4 + (size_t)2 * R * (D + 8) * 4 + 2 * topk * 4 + 2 * 64 * 4 + 128 * 8 + 16 + 15) / 16 * 16);
+    };
+    auto rr_warps_per_block = [&](int smem) { return smem > 12 * 1024 ? 1 : 4; };
+    auto rr_resident = [&](int R) {
+        const int smem = rr_smem(R), wpb = rr_warps_per_block(smem);
+        const int by_smem = (int)((227 * 1024) / ((size_t)wpb * smem + 1024)), by_warps = 32 / wpb;
+        return (size_t)std::max(1, std::min(std::min(by_smem, by_warps), 32)) * wpb * ix->sm_count;
+    };
     ra.R = (int)std::max<size_t>(2, std::min<size_t>(8, 16384 / ((size_t)D * 4)));
     if (ix->rerank_rows > 0) ra.R = std::max(1, std::min(32, ix->rerank_rows));
+    else
+        for (int R = ra.R; R >= 2; R--)
+            if (rr_resident(R) >= nb) { ra.R = R; break; }
     ra.R = (int)std::max<size_t>(1, std::min<size_t>(ra.R, (80 * 1024) / (2 * (size_t)(D + 8) * 4)));  // <= 80 KB of row buffers per warp
-    ra.smem_per_warp = (int)((16 + (size_t)D * 4 + (size_t)2 * ra.R * (D + 8) * 4 + 2 * topk * 4 + 2 * 64 * 4 + 128 * 8 + 16 + 15) / 16 * 16);
-    const int rr_wpb = ra.smem_per_warp > 24 * 1024 ? 2 : 4;
+    ra.smem_per_warp = rr_smem(ra.R);
+    const int rr_wpb = rr_warps_per_block(ra.smem_per_warp);
 
     // rounds: windows of visit positions (probe rank, 128-vector chunk).  The first round covers only the first
     // `first_chunks` chunks of the nearest cluster, so that everything after it is filtered with a real threshold.
