@@ -100,6 +100,11 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the main scan launch, from the committed `ncu --set full` captures
+# (profiles/scan_kernel_full_r01b.txt); a static per-launch figure, not re-measured by this run.
+SCAN_DRAM_TRAFFIC = {"c2": 152.3e6, "c1": 249.9e6}
+
+
 def recall_at_k(ids, truth, k):
     import torch
 
@@ -126,7 +131,14 @@ def build_workload(args, device, rank, world):
     cent = mix.centroids()
     torch.cuda.synchronize()
     t1 = time.time()
-    ix = bi.build_index(base, cent, seed=seed + 3)
+    if getattr(args, "builder", "native") == "torch":
+        ix = bi.build_index(base, cent, seed=seed + 3)
+    else:  # index training by the library itself (rabitq_build = RaBitQ::from_path on the device)
+        import rabitq_b200 as rb
+
+        g0 = rb.RaBitQ.build(base.contiguous(), cent.contiguous(), seed=seed + 3, device=device.index)
+        ix = g0.export_arrays(device_tensors=True)
+        g0.close()
     torch.cuda.synchronize()
     t2 = time.time()
     truth = synth.brute_force_topk_torch(base, queries, TOPK)
@@ -317,7 +329,8 @@ def run_ours(args):
                     "recall_at_10": round(recall_e2e, 4)},
             "gpu_launches": int(counts["kernel_launches"]),
             "roofline": {"bound": "hbm", "kernel": "rq::scan_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": SCAN_DRAM_TRAFFIC.get(args.workload) if not args.shape else None,
+                         "traffic_source": "ncu --set full, profiles/scan_kernel_full_r01b.txt (bytes per main scan launch)", "peak_source": peak_src,
                          "algorithmic_bytes_per_pair": bytes_per_pair, "pairs_per_step": counts["pairs"] // args.steps,
                          "scan_ms_per_step": round(scan_ms / args.steps, 4), "scan_launches_per_step": counts["scan_launches"] // args.steps,
                          "gpairs_per_s": round(counts["pairs"] / (scan_ms * 1e-3) / 1e9, 2) if scan_ms > 0 else 0.0,
@@ -368,12 +381,24 @@ def run_reference(args):
     torch.cuda.set_device(0)
     device = torch.device("cuda", 0)
     wl = build_workload(args, device, 0, 1)
-    probe = args.probe or {"c1": 64, "c2": 64, "c3": 64, "c4": 32, "c5": 64}.get(args.workload, 64)
     threads = os.cpu_count() or 1
     import numpy as np
 
     o = oracle_from_index(wl["index"])
     q = wl["queries"].cpu().numpy()
+    # same rule as our arm: the smallest nprobe of the sweep whose recall@10 reaches the target (measured with this arm)
+    probe, sweep_log = args.probe, {}
+    if not probe:
+        ns0 = min(q.shape[0], 512)
+        tr0 = wl["truth"][:ns0].cpu().numpy()
+        for p in PROBE_SWEEP.get(args.workload, [64]):
+            r0 = o.query_batch(q[:ns0], p, TOPK, nthreads=threads)
+            rec0 = float(np.mean([len(set(r0["ids"][i].tolist()) & set(tr0[i].tolist())) / TOPK for i in range(ns0)]))
+            sweep_log[str(p)] = round(rec0, 4)
+            probe = p
+            if rec0 >= TARGET_RECALL:
+                break
+        log(f"[bench/reference] recall@{TOPK} by nprobe on {ns0} queries: {sweep_log} -> nprobe={probe}")
     n0 = min(4 * threads, q.shape[0])
     r0 = o.query_batch(q[:n0], probe, TOPK, nthreads=threads)
     per_q = max(r0["seconds"] / n0, 1e-6)
@@ -394,7 +419,7 @@ def run_reference(args):
            "warmup": max(args.warmup, 1), "ms_per_step": round(secs / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u64 popcount + f32 (AVX2)", "data": "synthetic",
            "config": {"workload": f"{wl['name']}: {wl['n']}x{wl['dim']} base, {wl['k']} IVF centroids, nprobe={probe}, top-{TOPK}",
-                      "nprobe": probe, "topk": TOPK, "recall_at_10": round(rec, 4)},
+                      "nprobe": probe, "topk": TOPK, "recall_at_10": round(rec, 4), "recall_by_nprobe": sweep_log},
            "cpu_baseline": {"value": round(qps, 2), "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": round(qps, 2), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -404,13 +429,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--shape", default=None, help="custom n,dim,nq,k[,flavour] (debug)")
     ap.add_argument("--probe", type=int, default=0, help="fix nprobe instead of sweeping to the target recall")
     ap.add_argument("--rounds", default=None, help="rerank round boundaries, e.g. 0,1,8")
+    ap.add_argument("--builder", default="native", choices=["native", "torch"], help="index training: rabitq_build (CUDA) or the torch harness")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
     args = ap.parse_args()

@@ -57,6 +57,25 @@ int rabitq_from_arrays(uint32_t dim, size_t n, size_t k, const float* base, cons
                        const uint64_t* codes, const float* factors, int ptr_on_device, int device,
                        int shard_rank, int shard_count, rabitq_index** out);
 
+/* ---- index training (the step before the query path) ------------------------------------- */
+
+/* RaBitQ::from_path(base_path, centroid_path) -- src/rabitq.rs:159-265, on the device.  `seed` makes the random
+ * orthogonal matrix reproducible (the reference draws it from an unseeded RNG, src/utils.rs:16-20). */
+int rabitq_from_path(const char* base_path, const char* centroid_path, uint64_t seed, int device, rabitq_index** out);
+
+/* Same on in-memory arrays: base n x len, centroids k x len (original space, host or device pointers).  `orthogonal`
+ * (dim x dim, row r = P[r,:], dim = len rounded up to 64) may be NULL to generate it from `seed`. */
+int rabitq_build(const float* base, size_t n, size_t len, const float* centroids, size_t k, const float* orthogonal,
+                 uint64_t seed, int ptr_on_device, int device, rabitq_index** out);
+
+/* RaBitQ::dump_to_dir(path) -- src/rabitq.rs:128-156: writes the six-file layout the reference reads back. */
+int rabitq_dump_to_dir(rabitq_index* idx, const char* dir);
+
+/* Copy the arrays of `struct RaBitQ` (src/rabitq.rs:57-68) out of an unsharded handle into caller buffers (host, or
+ * device when ptr_on_device != 0); shapes as in rabitq_from_arrays, any pointer may be NULL. */
+int rabitq_export_arrays(rabitq_index* idx, float* base, float* orthogonal, float* centroids, uint32_t* offsets,
+                         uint32_t* map_ids, uint64_t* codes, float* factors, int ptr_on_device);
+
 void rabitq_free(rabitq_index* idx);
 
 uint32_t rabitq_dim(const rabitq_index* idx);     /* padded D (multiple of 64)        */

@@ -21,7 +21,8 @@ c_u64p = C.POINTER(C.c_uint64)
 
 #: every symbol include/rabitq_b200.h declares
 ABI_SYMBOLS = [
-    "rabitq_load_from_dir", "rabitq_load_from_dir_sharded", "rabitq_from_arrays", "rabitq_free", "rabitq_dim",
+    "rabitq_load_from_dir", "rabitq_load_from_dir_sharded", "rabitq_from_arrays", "rabitq_from_path", "rabitq_build",
+    "rabitq_dump_to_dir", "rabitq_export_arrays", "rabitq_free", "rabitq_dim",
     "rabitq_num_vectors", "rabitq_num_clusters", "rabitq_query", "rabitq_query_batch", "rabitq_query_batch_device",
     "rabitq_shard_range", "rabitq_merge_topk_device", "rabitq_metrics", "rabitq_metrics_reset", "rabitq_last_error", "rabitq_set_rounds",
     "rabitq_set_option", "rabitq_set_stream", "rabitq_last_timings", "rabitq_stage_rotate", "rabitq_stage_probe", "rabitq_stage_quantize", "rabitq_stage_scan",
@@ -55,6 +56,10 @@ def lib():
     L.rabitq_load_from_dir_sharded.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.rabitq_from_arrays.argtypes = [C.c_uint32, C.c_size_t, C.c_size_t, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.POINTER(vp)]
+    L.rabitq_from_path.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(vp)]
+    L.rabitq_build.argtypes = [vp, C.c_size_t, C.c_size_t, vp, C.c_size_t, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]
+    L.rabitq_dump_to_dir.argtypes = [vp, C.c_char_p]
+    L.rabitq_export_arrays.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
     L.rabitq_free.argtypes = [vp]
     L.rabitq_free.restype = None
     L.rabitq_dim.argtypes = [vp]
@@ -138,6 +143,66 @@ class RaBitQ:
         h = C.c_void_p()
         _check(lib().rabitq_from_arrays(dim, n, k, *ptrs, int(on_dev), device, shard_rank, shard_count, C.byref(h)))
         return cls(h, device)
+
+    @classmethod
+    def from_path(cls, base_path, centroid_path, seed: int = 1, device: int = 0) -> "RaBitQ":
+        """`RaBitQ::from_path(base_path, centroid_path)` (src/rabitq.rs:159-265): index training, on the device."""
+        h = C.c_void_p()
+        _check(lib().rabitq_from_path(os.fsencode(str(base_path)), os.fsencode(str(centroid_path)), seed, device, C.byref(h)))
+        return cls(h, device)
+
+    @classmethod
+    def build(cls, base, centroids, orthogonal=None, seed: int = 1, device: int = 0) -> "RaBitQ":
+        """from_path on in-memory arrays: base [n, len], centroids [k, len] (numpy, or torch CUDA tensors on `device`)."""
+        on_dev = hasattr(base, "data_ptr")
+        if on_dev:
+            import torch
+
+            for t in (base, centroids) + ((orthogonal,) if orthogonal is not None else ()):
+                assert t.is_cuda and t.device.index == device and t.dtype == torch.float32 and t.is_contiguous()
+            n, ln = base.shape
+            k = centroids.shape[0]
+            pb, pc = C.c_void_p(base.data_ptr()), C.c_void_p(centroids.data_ptr())
+            po = C.c_void_p(orthogonal.data_ptr()) if orthogonal is not None else None
+            torch.cuda.synchronize(device)
+        else:
+            base = _np(base, np.float32); centroids = _np(centroids, np.float32)
+            orthogonal = None if orthogonal is None else _np(orthogonal, np.float32)
+            n, ln = base.shape
+            k = centroids.shape[0]
+            pb, pc, po = _ptr(base), _ptr(centroids), _ptr(orthogonal)
+        assert centroids.shape[1] == ln
+        h = C.c_void_p()
+        _check(lib().rabitq_build(pb, n, ln, pc, k, po, seed, int(on_dev), device, C.byref(h)))
+        return cls(h, device)
+
+    def dump_to_dir(self, path) -> None:
+        """`RaBitQ::dump_to_dir(path)` (src/rabitq.rs:128-156)."""
+        _check(lib().rabitq_dump_to_dir(self._h, os.fsencode(str(path))))
+
+    def export_arrays(self, device_tensors: bool = False) -> dict:
+        """The arrays of `struct RaBitQ` as numpy arrays (or torch CUDA tensors on this handle's device)."""
+        D, n, k = self.dim, self.num_vectors, self.num_clusters
+        if device_tensors:
+            import torch
+
+            dev = torch.device("cuda", self.device)
+            out = dict(dim=D, base=torch.empty((n, D), dtype=torch.float32, device=dev),
+                       orthogonal=torch.empty((D, D), dtype=torch.float32, device=dev),
+                       centroids=torch.empty((k, D), dtype=torch.float32, device=dev),
+                       offsets=torch.empty((k + 1,), dtype=torch.int32, device=dev),
+                       map_ids=torch.empty((n,), dtype=torch.int32, device=dev),
+                       codes=torch.empty((n, D // 64), dtype=torch.int64, device=dev),
+                       factors=torch.empty((n, 4), dtype=torch.float32, device=dev))
+            ptrs = [C.c_void_p(out[key].data_ptr()) for key in ("base", "orthogonal", "centroids", "offsets", "map_ids", "codes", "factors")]
+            torch.cuda.synchronize(dev)
+        else:
+            out = dict(dim=D, base=np.empty((n, D), np.float32), orthogonal=np.empty((D, D), np.float32),
+                       centroids=np.empty((k, D), np.float32), offsets=np.empty(k + 1, np.uint32), map_ids=np.empty(n, np.uint32),
+                       codes=np.empty((n, D // 64), np.uint64), factors=np.empty((n, 4), np.float32))
+            ptrs = [_ptr(out[key]) for key in ("base", "orthogonal", "centroids", "offsets", "map_ids", "codes", "factors")]
+        _check(lib().rabitq_export_arrays(self._h, *ptrs, int(device_tensors)))
+        return out
 
     def close(self):
         if getattr(self, "_h", None):

@@ -2,9 +2,10 @@
 //
 // Same flags (-b/--base -c/--centroids -q/--query -t/--truth -p/--probe (100) -k/--topk (10) -s/--saved
 // -h/--heuristic-rank), same log lines ("QPS: {}, recall: {}", "Metrics [...]", main.rs:77-82).  The index is
-// loaded from the -s directory (RaBitQ::load_from_dir); building one (RaBitQ::from_path, main.rs:56-61) is the
-// step before this path and is not part of this binary.  Extra flags: --device N, --single (one rabitq_query
-// call per query like the reference's loop, main.rs:69-75; default is one rabitq_query_batch call).
+// loaded from the -s directory (RaBitQ::load_from_dir) or, when that does not exist, trained on the device from -b/-c
+// (RaBitQ::from_path) and saved there (dump_to_dir), main.rs:51-61.  Extra flags: --device N, --seed S (the random
+// rotation), --single (one rabitq_query call per query like the reference's loop, main.rs:69-75; default is one
+// rabitq_query_batch call).
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -68,6 +69,7 @@ int main(int argc, char** argv) {
     size_t probe = 100, topk = 10;
     bool heuristic = false, single = false;
     int device = 0;
+    uint64_t seed = 42;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto val = [&](const char* name) -> std::string {
@@ -84,6 +86,7 @@ int main(int argc, char** argv) {
         else if (a == "-h" || a == "--heuristic-rank") heuristic = true;
         else if (a == "--device") device = std::atoi(val("--device").c_str());
         else if (a == "--single") single = true;
+        else if (a == "--seed") seed = std::strtoull(val("--seed").c_str(), nullptr, 10);
         else if (a == "--help") {
             std::printf("Usage: rabitq_cli -b <base> -c <centroids> -q <query> -t <truth> [-p <probe>] [-k <topk>] -s <saved> [-h]\n\n"
                         "RaBitQ CLI args (B200 twin of crates/cli)\n");
@@ -100,10 +103,15 @@ int main(int argc, char** argv) {
     if (is_dir(saved)) {
         DEBUG("loading from \"%s\"...", saved.c_str());
         if (rabitq_load_from_dir(saved.c_str(), device, &ix)) die("load_from_dir");
-    } else {
-        std::fprintf(stderr, "saved directory %s does not exist: index training (RaBitQ::from_path) is outside this binary; "
-                             "build the index with the reference or tools/build_index_torch.py first\n", saved.c_str());
-        return 101;
+    } else {  // crates/cli/src/main.rs:56-61
+        if (base.empty() || centroids.empty()) {
+            std::fprintf(stderr, "Required options not provided:\n    --base\n    --centroids\n");
+            return 1;
+        }
+        DEBUG("training...");
+        if (rabitq_from_path(base.c_str(), centroids.c_str(), seed, device, &ix)) die("from_path");
+        DEBUG("saving to local file: \"%s\"", saved.c_str());
+        if (rabitq_dump_to_dir(ix, saved.c_str())) die("dump_to_dir");
     }
     std::vector<std::vector<float>> queries;
     std::vector<std::vector<int32_t>> truths;

@@ -14,6 +14,8 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "build_index.cuh"
+#include <sys/stat.h>
 
 namespace {
 
@@ -186,6 +188,23 @@ void shard_rows(const uint32_t* offsets, size_t K, int rank, int count, size_t* 
     *row_hi = bound(rank + 1);
 }
 
+// common tail of every constructor: device properties, stream, pinned staging, kernel attributes, env knobs
+int finish_index(rabitq_index* ix) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ix->device));
+    ix->sm_count = prop.multiProcessorCount;
+    if (const char* e = std::getenv("RABITQ_SCAN_MODE")) ix->scan_mode = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_FIRST_CHUNKS")) ix->first_chunks = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("RABITQ_RR_ROWS")) ix->rerank_rows = std::atoi(e);
+    CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
+    ix->stream = ix->own_stream;
+    CU(cudaMallocHost((void**)&ix->h_pin, 256));
+    CU(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    return 0;
+}
+
 // Build a handle from host or device arrays (full index); keeps only this shard's rows.
 int make_index(uint32_t dim, size_t n_total, size_t K, const float* base, const float* orth, const float* cent,
                const uint32_t* offsets_h /* host copy, always */, const uint32_t* map_ids, const uint64_t* codes,
@@ -241,18 +260,7 @@ int make_index(uint32_t dim, size_t n_total, size_t K, const float* base, const 
         if (e_ == cudaSuccess) e_ = cudaMemcpy(ix->offsets, loc.data(), (K + 1) * 4, cudaMemcpyHostToDevice);
         if (e_ != cudaSuccess) { delete ix; return fail(RABITQ_ECUDA, std::string("offsets upload: ") + cudaGetErrorString(e_)); }
     }
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    ix->sm_count = prop.multiProcessorCount;
-    if (const char* e = std::getenv("RABITQ_SCAN_MODE")) ix->scan_mode = std::atoi(e);
-    if (const char* e = std::getenv("RABITQ_FIRST_CHUNKS")) ix->first_chunks = std::max(0, std::atoi(e));
-    if (const char* e = std::getenv("RABITQ_RR_ROWS")) ix->rerank_rows = std::atoi(e);
-    CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
-    ix->stream = ix->own_stream;
-    CU(cudaMallocHost((void**)&ix->h_pin, 256));
-    CU(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    { int rc_ = finish_index(ix); if (rc_) { delete ix; return rc_; } }
     *out = ix;
     return RABITQ_OK;
 }
@@ -292,6 +300,210 @@ int load_dir(const char* dir, int device, int shard_rank, int shard_count, rabit
         for (size_t c = 0; c < K; c++) cent[c * D + dd] = cent_dk[dd * K + c];
     return make_index((uint32_t)D, N, K, base.data(), orth.data(), cent.data(), offsets, map_ids, xb.data(), fac.data(), false,
                       device, shard_rank, shard_count, out);
+}
+
+// ---- index training on the device: RaBitQ::from_path (src/rabitq.rs:159-265) ----------------------------------------
+struct TmpBufs {  // frees whatever was allocated, on every exit path
+    std::vector<void*> ptrs;
+    ~TmpBufs() { for (void* p : ptrs) if (p) cudaFree(p); }
+    cudaError_t alloc(void** p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16));
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+
+int build_impl(const float* base, size_t n, size_t len, const float* centroids, size_t k, const float* orthogonal, uint64_t seed,
+               bool on_device, int device, rabitq_index** out) {
+    if (!base || !centroids || !out) return fail(RABITQ_EINVAL, "null argument");
+    if (n == 0 || k == 0 || len == 0) return fail(RABITQ_EINVAL, "empty base or centroids");
+    if (n >= ((size_t)1 << 32)) return fail(RABITQ_EUNSUPPORTED, "more than 2^32-1 vectors");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RABITQ_ECUDA, "no CUDA device: rabitq_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(RABITQ_EINVAL, "bad device ordinal");
+    CU(cudaSetDevice(device));
+    const size_t D = (len + 63) / 64 * 64, W32 = D / 32, K = k;  // padding to 64, rabitq.rs:167-179
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    TmpBufs tmp;
+    const float* d_base_in = base;
+    const float* d_cent_in = centroids;
+    if (!on_device) {
+        float *b = nullptr, *c = nullptr;
+        CU(tmp.alloc((void**)&b, n * len * 4));
+        CU(tmp.alloc((void**)&c, K * len * 4));
+        CU(cudaMemcpy(b, base, n * len * 4, kind));
+        CU(cudaMemcpy(c, centroids, K * len * 4, kind));
+        d_base_in = b;
+        d_cent_in = c;
+    }
+    auto ix = new rabitq_index();
+    struct Guard { rabitq_index* p; ~Guard() { delete p; } } guard{ix};
+    ix->device = device;
+    ix->D = (uint32_t)D;
+    ix->K = K;
+    ix->n = n;
+    CU(cudaMalloc((void**)&ix->P, D * D * 4));
+    CU(cudaMalloc((void**)&ix->cent, K * D * 4));
+    CU(cudaMalloc((void**)&ix->offsets, (K + 1) * 4));
+    // --- P: given, or Q of a seeded standard-normal matrix (utils.rs:16-20; fp64 Gram-Schmidt applied twice) ---
+    if (orthogonal) {
+        CU(cudaMemcpy(ix->P, orthogonal, D * D * 4, kind));
+    } else {
+        double *A = nullptr, *dots = nullptr;
+        CU(tmp.alloc((void**)&A, D * D * 8));
+        CU(tmp.alloc((void**)&dots, D * 8));
+        gauss_fill_kernel<<<(unsigned)((D * D + 255) / 256), 256>>>(A, D * D, seed * 0x9e3779b97f4a7c15ull + 12345);
+        for (int j = 0; j < (int)D; j++) {
+            for (int pass = 0; pass < 2 && j > 0; pass++) {
+                gs_dots_kernel<<<(j + 127) / 128, 128>>>(A, (int)D, j, dots);
+                gs_update_kernel<<<((int)D + 127) / 128, 128>>>(A, (int)D, j, dots);
+            }
+            gs_normalize_kernel<<<1, 256>>>(A, (int)D, j);
+        }
+        f64_to_f32_kernel<<<(unsigned)((D * D + 255) / 256), 256>>>(A, ix->P, D * D);
+        CU(cudaGetLastError());
+    }
+    // --- rotated centroids (rabitq.rs:189) ---
+    {
+        float* cpad = nullptr;
+        CU(tmp.alloc((void**)&cpad, K * D * 4));
+        pad_queries_kernel<<<(unsigned)((K * D + 255) / 256), 256>>>(d_cent_in, cpad, K, (int)len, (int)D);
+        dim3 grid((unsigned)(D / ROT_TC), (unsigned)((K + ROT_QG * ROT_TQ - 1) / (ROT_QG * ROT_TQ)));
+        rotate_kernel<<<grid, ROT_THREADS>>>(cpad, ix->P, ix->cent, (int)K, (int)D);
+        CU(cudaGetLastError());
+    }
+    // --- per-vector label, code, Factor; chunks keep the distance tile around 1 GiB ---
+    uint32_t *label = nullptr, *codes_u = nullptr, *vals_in = nullptr, *vals_out = nullptr, *counts = nullptr;
+    float* min_dist = nullptr;
+    float4* fac_u = nullptr;
+    unsigned long long *key_in = nullptr, *key_out = nullptr;
+    CU(tmp.alloc((void**)&label, n * 4));
+    CU(tmp.alloc((void**)&min_dist, n * 4));
+    CU(tmp.alloc((void**)&codes_u, n * W32 * 4));
+    CU(tmp.alloc((void**)&fac_u, n * 16));
+    CU(tmp.alloc((void**)&key_in, n * 8));
+    CU(tmp.alloc((void**)&key_out, n * 8));
+    CU(tmp.alloc((void**)&vals_in, n * 4));
+    CU(tmp.alloc((void**)&vals_out, n * 4));
+    CU(tmp.alloc((void**)&counts, K * 4));
+    {
+        const size_t CH = std::max<size_t>(1024, std::min<size_t>(65536, ((size_t)1 << 28) / K)) / 32 * 32;
+        float *xpad = nullptr, *xp = nullptr, *dist = nullptr;
+        CU(tmp.alloc((void**)&xpad, CH * D * 4));
+        CU(tmp.alloc((void**)&xp, CH * D * 4));
+        CU(tmp.alloc((void**)&dist, CH * K * 4));
+        for (size_t s0 = 0; s0 < n; s0 += CH) {
+            const size_t rows = std::min(CH, n - s0);
+            pad_queries_kernel<<<(unsigned)((rows * D + 255) / 256), 256>>>(d_base_in + s0 * len, xpad, rows, (int)len, (int)D);
+            dim3 g1((unsigned)(D / ROT_TC), (unsigned)((rows + ROT_QG * ROT_TQ - 1) / (ROT_QG * ROT_TQ)));
+            rotate_kernel<<<g1, ROT_THREADS>>>(xpad, ix->P, xp, (int)rows, (int)D);  // rabitq.rs:188
+            dim3 g2((unsigned)((K + CD_TC - 1) / CD_TC), (unsigned)((rows + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ)));
+            centroid_dist_kernel<<<g2, CD_THREADS>>>(ix->cent, xp, dist, (int)rows, (int)K, (int)D);
+            argmin_rows_kernel<<<(unsigned)((rows + 3) / 4), 128>>>(dist, rows, (int)K, label + s0, min_dist + s0);
+            encode_kernel<<<(unsigned)((rows + 3) / 4), 128>>>(xp, ix->cent, label + s0, min_dist + s0, rows, (int)D, codes_u + s0 * W32,
+                                                               fac_u + s0, key_in + s0);
+            CU(cudaGetLastError());
+        }
+    }
+    // --- clusters in id order, ascending distance inside, stable (rabitq.rs:231-252): one stable radix sort ---
+    iota_kernel<<<(unsigned)((n + 255) / 256), 256>>>(vals_in, n);
+    {
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out, vals_in, vals_out, (int64_t)n, 0, 64));
+        void* sort_tmp = nullptr;
+        CU(tmp.alloc(&sort_tmp, tmp_bytes));
+        CU(cub::DeviceRadixSort::SortPairs(sort_tmp, tmp_bytes, key_in, key_out, vals_in, vals_out, (int64_t)n, 0, 64));
+    }
+    CU(cudaMemset(counts, 0, K * 4));
+    label_histogram_kernel<<<(unsigned)((n + 255) / 256), 256>>>(label, n, counts);
+    offsets_scan_kernel<<<1, 1024>>>(counts, (int)K, ix->offsets);
+    CU(cudaMalloc((void**)&ix->base, n * D * 4));
+    CU(cudaMalloc((void**)&ix->codes, n * W32 * 4));
+    CU(cudaMalloc((void**)&ix->factors, n * 16));
+    CU(cudaMalloc((void**)&ix->map_ids, n * 4));
+    permute_kernel<<<(unsigned)((n + 3) / 4), 128>>>(d_base_in, (int)len, (int)D, vals_out, codes_u, fac_u, n, ix->base, ix->codes,
+                                                     ix->factors, ix->map_ids);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    {
+        std::vector<uint32_t> cnt_h(K);
+        CU(cudaMemcpy(cnt_h.data(), counts, K * 4, cudaMemcpyDeviceToHost));
+        ix->max_cluster = *std::max_element(cnt_h.begin(), cnt_h.end());
+    }
+    int rc = finish_index(ix);
+    if (rc) return rc;
+    guard.p = nullptr;
+    *out = ix;
+    return RABITQ_OK;
+}
+
+// RaBitQ::dump_to_dir (src/rabitq.rs:128-156): the six-file layout, byte for byte.
+template <typename T>
+bool write_records(const std::string& path, const T* data, size_t rows, size_t cols) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const uint32_t c = (uint32_t)cols;
+    bool ok = true;
+    for (size_t r = 0; r < rows && ok; r++)
+        ok = std::fwrite(&c, 4, 1, f) == 1 && (cols == 0 || std::fwrite(data + r * cols, sizeof(T), cols, f) == cols);
+    return std::fclose(f) == 0 && ok;
+}
+
+int dump_impl(rabitq_index* ix, const char* dir) {
+    if (!ix || !dir) return fail(RABITQ_EINVAL, "null argument");
+    if (ix->shard_count != 1) return fail(RABITQ_EUNSUPPORTED, "dump_to_dir needs an unsharded handle");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    const std::string d(dir);
+    ::mkdir(d.c_str(), 0777);  // create_dir_all for the leaf; parents are the caller's business
+    const size_t D = ix->D, K = ix->K, n = ix->n, W64 = D / 64;
+    {   // base.fvecs: n records of D floats, streamed in chunks
+        FILE* f = std::fopen((d + "/base.fvecs").c_str(), "wb");
+        if (!f) return fail(RABITQ_EIO, "write base error");
+        const size_t CH = std::max<size_t>(1, ((size_t)64 << 20) / (D * 4));
+        std::vector<float> buf(CH * D);
+        const uint32_t c = (uint32_t)D;
+        for (size_t s0 = 0; s0 < n; s0 += CH) {
+            const size_t rows = std::min(CH, n - s0);
+            CU(cudaMemcpy(buf.data(), ix->base + s0 * D, rows * D * 4, cudaMemcpyDeviceToHost));
+            for (size_t r = 0; r < rows; r++) {
+                std::fwrite(&c, 4, 1, f);
+                std::fwrite(buf.data() + r * D, 4, D, f);
+            }
+        }
+        if (std::fclose(f) != 0) return fail(RABITQ_EIO, "write base error");
+    }
+    std::vector<float> P(D * D), cent(K * D), cdk(D * K);
+    CU(cudaMemcpy(P.data(), ix->P, D * D * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cent.data(), ix->cent, K * D * 4, cudaMemcpyDeviceToHost));
+    for (size_t dd = 0; dd < D; dd++)
+        for (size_t c = 0; c < K; c++) cdk[dd * K + c] = cent[c * D + dd];  // the matrix is D x K, written row-wise (rabitq.rs:133)
+    if (!write_records(d + "/orthogonal.fvecs", P.data(), D, D)) return fail(RABITQ_EIO, "write orthogonal error");
+    if (!write_records(d + "/centroids.fvecs", cdk.data(), D, K)) return fail(RABITQ_EIO, "write centroids error");
+    std::vector<uint32_t> off(K + 1), ids(n);
+    CU(cudaMemcpy(off.data(), ix->offsets, (K + 1) * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ids.data(), ix->map_ids, n * 4, cudaMemcpyDeviceToHost));
+    {
+        FILE* f = std::fopen((d + "/offsets_ids.ivecs").c_str(), "wb");
+        if (!f) return fail(RABITQ_EIO, "write offsets_ids error");
+        uint32_t c = (uint32_t)(K + 1);
+        std::fwrite(&c, 4, 1, f);
+        std::fwrite(off.data(), 4, K + 1, f);
+        c = (uint32_t)n;
+        std::fwrite(&c, 4, 1, f);
+        std::fwrite(ids.data(), 4, n, f);
+        if (std::fclose(f) != 0) return fail(RABITQ_EIO, "write offsets_ids error");
+    }
+    std::vector<float> fac(n * 4);
+    CU(cudaMemcpy(fac.data(), ix->factors, n * 16, cudaMemcpyDeviceToHost));
+    if (!write_records(d + "/factors.fvecs", fac.data(), 1, n * 4)) return fail(RABITQ_EIO, "write factors error");
+    std::vector<uint64_t> codes(n * W64);
+    CU(cudaMemcpy(codes.data(), ix->codes, n * W64 * 8, cudaMemcpyDeviceToHost));
+    if (!write_records(d + "/x_binary_vec.u64vecs", codes.data(), 1, n * W64)) return fail(RABITQ_EIO, "write x_binary_vec error");
+    return RABITQ_OK;
 }
 
 // ---- scan launch ------------------------------------------------------------------------------------------------
@@ -686,6 +898,43 @@ int rabitq_from_arrays(uint32_t dim, size_t n, size_t k, const float* base, cons
     }
     return make_index(dim, n, k, base, orthogonal, centroids, off_h.data(), map_ids, codes, factors, ptr_on_device != 0, device,
                       shard_rank, shard_count, out);
+}
+
+int rabitq_build(const float* base, size_t n, size_t len, const float* centroids, size_t k, const float* orthogonal, uint64_t seed,
+                 int ptr_on_device, int device, rabitq_index** out) {
+    return build_impl(base, n, len, centroids, k, orthogonal, seed, ptr_on_device != 0, device, out);
+}
+
+int rabitq_from_path(const char* base_path, const char* centroid_path, uint64_t seed, int device, rabitq_index** out) {
+    if (!base_path || !centroid_path || !out) return fail(RABITQ_EINVAL, "null argument");
+    std::vector<float> base, cent;
+    std::vector<size_t> rl_b, rl_c;
+    if (!read_vecs(base_path, base, rl_b) || rl_b.empty()) return fail(RABITQ_EIO, "read vecs error: base");
+    if (!read_vecs(centroid_path, cent, rl_c) || rl_c.empty()) return fail(RABITQ_EIO, "read vecs error: centroids");
+    const size_t len = rl_b[0];
+    if (rl_c[0] != len) return fail(RABITQ_EINVAL, "assertion failed: dim == centroids.ncols()");
+    if (base.size() != rl_b.size() * len || cent.size() != rl_c.size() * len) return fail(RABITQ_EINVAL, "ragged fvecs records");
+    return build_impl(base.data(), rl_b.size(), len, cent.data(), rl_c.size(), nullptr, seed, false, device, out);
+}
+
+int rabitq_dump_to_dir(rabitq_index* idx, const char* dir) { return dump_impl(idx, dir); }
+
+int rabitq_export_arrays(rabitq_index* idx, float* base, float* orthogonal, float* centroids, uint32_t* offsets, uint32_t* map_ids,
+                         uint64_t* codes, float* factors, int ptr_on_device) {
+    if (!idx) return fail(RABITQ_EINVAL, "null index");
+    if (idx->shard_count != 1) return fail(RABITQ_EUNSUPPORTED, "export needs an unsharded handle");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CU(cudaSetDevice(idx->device));
+    const cudaMemcpyKind kind = ptr_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const size_t D = idx->D, K = idx->K, n = idx->n;
+    if (base) CU(cudaMemcpy(base, idx->base, n * D * 4, kind));
+    if (orthogonal) CU(cudaMemcpy(orthogonal, idx->P, D * D * 4, kind));
+    if (centroids) CU(cudaMemcpy(centroids, idx->cent, K * D * 4, kind));
+    if (offsets) CU(cudaMemcpy(offsets, idx->offsets, (K + 1) * 4, kind));
+    if (map_ids) CU(cudaMemcpy(map_ids, idx->map_ids, n * 4, kind));
+    if (codes) CU(cudaMemcpy(codes, idx->codes, n * (D / 64) * 8, kind));
+    if (factors) CU(cudaMemcpy(factors, idx->factors, n * 16, kind));
+    return RABITQ_OK;
 }
 
 void rabitq_free(rabitq_index* idx) { delete idx; }

@@ -282,3 +282,86 @@ def test_heuristic_reranker_matches_oracle(pair, probe, topk):
         assert _same_up_to_ties(pair, i, gd[i, :c], gi[i, :c], o["dist"][i, :c], o["ids"][i, :c]), f"query {i}"
     m = g.metrics()
     assert m["rough"] == o["rough"] and m["precise"] == o["precise"]
+
+
+def test_device_index_build_and_dump(case_d96, tmp_path, oracle_lib):
+    """rabitq_build / rabitq_dump_to_dir (RaBitQ::from_path + dump_to_dir on the device): the directory it writes is
+    read back by the oracle's load_from_dir, and both sides then agree on every query; given the same P the device
+    builder reproduces the oracle builder's clustering and codes up to fp32 near-ties."""
+    import rabitq_b200 as rb
+
+    case = case_d96
+    a = case["arrays"]
+    g = rb.RaBitQ.build(case["base"], case["centroids"], orthogonal=a["orthogonal"], device=0)
+    d = tmp_path / "built"
+    g.dump_to_dir(str(d))
+    o = oracle_lib.OracleIndex.load_from_dir(str(d))
+    b = o.arrays()
+    n = case["base"].shape[0]
+    assert b["dim"] == a["dim"] and b["base"].shape == a["base"].shape
+    assert sorted(b["map_ids"].tolist()) == list(range(n))
+    assert np.array_equal(b["base"][:, : case["base"].shape[1]], case["base"][b["map_ids"]])
+    assert b["offsets"][0] == 0 and b["offsets"][-1] == n
+    # same P -> same assignment and codes except for fp32 near-ties
+    assert np.mean(b["offsets"] == a["offsets"]) > 0.95
+    inv_a = np.empty(n, np.int64); inv_a[a["map_ids"]] = np.arange(n)
+    inv_b = np.empty(n, np.int64); inv_b[b["map_ids"]] = np.arange(n)
+    assert np.mean(np.all(a["codes"][inv_a] == b["codes"][inv_b], axis=1)) > 0.999
+    fa, fb = a["factors"][inv_a], b["factors"][inv_b]
+    ok = np.isclose(fa, fb, rtol=1e-3, atol=1e-4).all(axis=1)
+    assert ok.mean() > 0.999
+    # distances sorted inside clusters
+    for c in range(0, len(b["offsets"]) - 1, 5):
+        rows = np.arange(b["offsets"][c], b["offsets"][c + 1])
+        if len(rows) > 1:
+            assert np.all(np.diff(b["factors"][rows, 3]) >= -1e-4 * np.abs(b["factors"][rows[1:], 3]) - 1e-6)
+    # query parity on the device-built index
+    q = case["queries"]
+    gd, gi, gc = g.query_batch(q, 16, 10)
+    r = o.query_batch(q, 16, 10)
+    assert np.array_equal(np.sort(gd, 1).view(np.uint32), np.sort(r["dist"], 1).view(np.uint32))
+    assert g.metrics()["precise"] == r["precise"]
+    # self-generated rotation: orthogonal, and recall holds
+    g2 = rb.RaBitQ.build(case["base"], case["centroids"], seed=5, device=0)
+    d2 = tmp_path / "built2"
+    g2.dump_to_dir(str(d2))
+    P = oracle_lib.OracleIndex.load_from_dir(str(d2)).arrays()["orthogonal"].astype(np.float64)
+    assert np.allclose(P @ P.T, np.eye(P.shape[0]), atol=2e-6)
+    from tools import synth
+    truth = synth.brute_force_topk_numpy(case["base"], q, 10)
+    _, ids, _ = g2.query_batch(q, 48, 10)
+    rec = np.mean([len(set(ids[i].tolist()) & set(truth[i].tolist())) / 10 for i in range(q.shape[0])])
+    assert rec >= 0.95
+    g.close(); g2.close()
+
+
+def test_cli_twin_trains_saves_loads(case_d128, tmp_path):
+    """rabitq_cli with the reference's flags: trains when -s does not exist, then reloads; prints QPS/recall/Metrics."""
+    import os
+    import subprocess
+
+    from rabitq_b200 import build as bld
+    from tools import synth
+
+    case = case_d128
+    def write_vecs(path, arr, dtype):
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        with open(path, "wb") as f:
+            for row in arr:
+                f.write(np.uint32(len(row)).tobytes()); f.write(row.tobytes())
+    write_vecs(tmp_path / "base.fvecs", case["base"], np.float32)
+    write_vecs(tmp_path / "cent.fvecs", case["centroids"], np.float32)
+    write_vecs(tmp_path / "q.fvecs", case["queries"], np.float32)
+    truth = synth.brute_force_topk_numpy(case["base"], case["queries"], 10)
+    write_vecs(tmp_path / "truth.ivecs", truth, np.int32)
+    cmd = [bld.CLI, "-b", str(tmp_path / "base.fvecs"), "-c", str(tmp_path / "cent.fvecs"), "-q", str(tmp_path / "q.fvecs"),
+           "-t", str(tmp_path / "truth.ivecs"), "-p", "32", "-k", "10", "-s", str(tmp_path / "saved")]
+    out1 = subprocess.run(cmd, capture_output=True, text=True)
+    assert out1.returncode == 0, out1.stderr
+    assert "training..." in out1.stderr and "QPS:" in out1.stderr and "Metrics [query: 64," in out1.stderr
+    assert os.path.exists(tmp_path / "saved" / "x_binary_vec.u64vecs")
+    out2 = subprocess.run(cmd + ["--single"], capture_output=True, text=True)
+    assert out2.returncode == 0, out2.stderr
+    assert "loading from" in out2.stderr
+    rec = float(out2.stderr.split("recall: ")[1].split()[0])
+    assert rec >= 0.9
