@@ -107,7 +107,46 @@ int rabitq_shard_range(const uint32_t* offsets, size_t k, int shard_rank, int sh
 /* Merge `n_lists` per-shard results (each nq x topk, device pointers laid out back to back: list s starts at
  * d_dist + s*nq*topk) into one ascending nq x topk result.  Used after the NCCL all-gather of (dist, id). */
 int rabitq_merge_topk_device(int device, const float* d_dist, const uint32_t* d_ids, int n_lists, size_t nq,
-                             size_t topk, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count);
+                             size_t topk, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count,
+                             void* cuda_stream);
+
+/* ---- distributed pipeline: one process per GPU, index sharded by cluster range, results IDENTICAL to the reference --------
+ *
+ * The reference is single-process; its filter threshold is sequential state (src/rerank.rs:83-101).  To keep its results
+ * while the clusters live on different GPUs, the visit order is cut into the same two rounds on every shard and the
+ * survivors of the second round are replayed in order on the query's HOME rank:
+ *
+ *   rabitq_dist_front   home:   pad, rotate, centroid distances, probe selection of this rank's nq_local queries
+ *        -- caller: all-gather of the per-rank chunks (NCCL) --
+ *   rabitq_dist_round1  source: local slots + query records for the whole batch; round 1 = the first 128-vector chunk of
+ *                               the query's nearest non-empty cluster, replayed on the shard that owns it; records of the
+ *                               candidates the reference reranks are written into the home rank's inbox (peer memory)
+ *        -- caller: all-reduce(min) of d_thr (every shard now holds the reference's threshold after round 1) --
+ *   rabitq_dist_round2  source: everything else, filtered with that (frozen) threshold; exact distances of all survivors,
+ *                               shipped to the home inbox by the kernel that computes them (stores over NVLink)
+ *        -- caller: all-reduce(max) of d_status (doubles as the barrier that makes the records visible) --
+ *   rabitq_dist_finish  home:   HeapReRanker::rank_batch replayed over the union, in the reference's visit order
+ *
+ * All pointers are DEVICE pointers; everything is launched on the handle's stream (rabitq_set_stream) so the caller's
+ * collectives on the same stream order the phases.  Every rank passes the same nq_local / probe / topk. */
+int rabitq_dist_init(rabitq_index* idx, int rank, int world, size_t nq_local, size_t probe, size_t topk,
+                     size_t records_per_query, size_t* inbox_bytes);
+/* CUDA IPC handle (64 bytes) of this rank's inbox, to be opened by the other ranks' processes ... */
+int rabitq_dist_ipc_handle(rabitq_index* idx, unsigned char out_handle[64]);
+/* ... or its raw device pointer, when the ranks are handles inside ONE process (tests on a single GPU). */
+int rabitq_dist_inbox_ptr(rabitq_index* idx, void** out);
+/* Register the inbox of rank `peer_rank`: an IPC handle from that rank's process (opened here), or a raw pointer. */
+int rabitq_dist_set_peer(rabitq_index* idx, int peer_rank, const unsigned char* ipc_handle, void* raw_ptr);
+/* 4-byte words one rank contributes to the all-gather: nq_local x (len + dim + 2*probe + 1). */
+size_t rabitq_dist_chunk_words(const rabitq_index* idx, size_t len);
+int rabitq_dist_front(rabitq_index* idx, const float* d_queries, size_t len, void* d_send);
+int rabitq_dist_round1(rabitq_index* idx, const void* d_gathered, float* d_thr /* world*nq_local */);
+int rabitq_dist_round2(rabitq_index* idx, uint32_t* d_status /* 1 word */);
+/* d_status bits after the step: 1 = a (home, source) record region overflowed, 2 = this home saw an overflowed segment;
+ * non-zero on any rank => repeat the step after rabitq_dist_init with a larger records_per_query. */
+int rabitq_dist_finish(rabitq_index* idx, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count, uint32_t* d_status);
+/* dst[i] = min(dst[i], src[i]) on the device: the all-reduce(min) when all ranks live in one process. */
+int rabitq_min_f32_device(int device, float* d_dst, const float* d_src, size_t n, void* cuda_stream);
 
 /* METRICS (src/metrics.rs:30-41): out = {query, rough, precise, cache miss}. */
 void rabitq_metrics(const rabitq_index* idx, uint64_t out[4]);

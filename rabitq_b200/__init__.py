@@ -26,6 +26,8 @@ ABI_SYMBOLS = [
     "rabitq_num_vectors", "rabitq_num_clusters", "rabitq_query", "rabitq_query_batch", "rabitq_query_batch_device",
     "rabitq_shard_range", "rabitq_merge_topk_device", "rabitq_metrics", "rabitq_metrics_reset", "rabitq_last_error", "rabitq_set_rounds",
     "rabitq_set_option", "rabitq_set_stream", "rabitq_last_timings", "rabitq_stage_rotate", "rabitq_stage_probe", "rabitq_stage_quantize", "rabitq_stage_scan",
+    "rabitq_dist_init", "rabitq_dist_ipc_handle", "rabitq_dist_inbox_ptr", "rabitq_dist_set_peer", "rabitq_dist_chunk_words", "rabitq_dist_front",
+    "rabitq_dist_round1", "rabitq_dist_round2", "rabitq_dist_finish", "rabitq_min_f32_device",
 ]
 
 TIMING_STAGES = ["h2d_pad", "rotate", "centroid_dist", "select", "quantize", "bucket", "scan", "rerank", "d2h", "total"]
@@ -71,7 +73,18 @@ def lib():
     L.rabitq_query.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp, vp]
     L.rabitq_query_batch.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp, vp]
     L.rabitq_query_batch_device.argtypes = L.rabitq_query_batch.argtypes
-    L.rabitq_merge_topk_device.argtypes = [C.c_int, vp, vp, C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp]
+    L.rabitq_merge_topk_device.argtypes = [C.c_int, vp, vp, C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp, vp]
+    L.rabitq_dist_init.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.rabitq_dist_ipc_handle.argtypes = [vp, C.c_char_p]
+    L.rabitq_dist_inbox_ptr.argtypes = [vp, C.POINTER(vp)]
+    L.rabitq_dist_set_peer.argtypes = [vp, C.c_int, C.c_char_p, vp]
+    L.rabitq_dist_chunk_words.argtypes = [vp, C.c_size_t]
+    L.rabitq_dist_chunk_words.restype = C.c_size_t
+    L.rabitq_dist_front.argtypes = [vp, vp, C.c_size_t, vp]
+    L.rabitq_dist_round1.argtypes = [vp, vp, vp]
+    L.rabitq_dist_round2.argtypes = [vp, vp]
+    L.rabitq_dist_finish.argtypes = [vp, vp, vp, vp, vp]
+    L.rabitq_min_f32_device.argtypes = [C.c_int, vp, vp, C.c_size_t, vp]
     L.rabitq_shard_range.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.rabitq_metrics.argtypes = [vp, c_u64p]
     L.rabitq_metrics.restype = None

@@ -248,6 +248,7 @@ constexpr int SEL_CAND = 1024;    // pivot path: candidate capacity (sel_buf hol
 
 __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* __restrict__ cdist, int K, int P, int Ppow2, int cache_keys,
                                                                    const uint32_t* __restrict__ offsets,
+                                                                   const uint32_t* __restrict__ offsets_g,
                                                                    uint32_t* __restrict__ probe_ids, float* __restrict__ probe_dist,
                                                                    uint32_t* __restrict__ slot_local, uint32_t* __restrict__ q_words,
                                                                    uint32_t* __restrict__ q_pairs, uint32_t* __restrict__ q_p0) {
@@ -433,8 +434,11 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
         probe_dist[q * P + p] = row[id];
         uint32_t n_c = offsets[id + 1] - offsets[id];
         words[p] = (n_c + 31u) >> 5;
-        pairs_local += n_c;
-        if (n_c) atomicMin(&s_p0, (uint32_t)p);  // first probe rank that holds vectors on THIS shard
+        // offsets_g (distributed pipeline): the pair count and the first non-empty rank refer to the WHOLE index, so that
+        // every shard cuts the visit order into the same rounds; otherwise they refer to this handle's rows
+        const uint32_t n_g = offsets_g ? offsets_g[id + 1] - offsets_g[id] : n_c;
+        pairs_local += n_g;
+        if (n_g) atomicMin(&s_p0, (uint32_t)p);  // first probe rank that holds vectors
     }
     __syncthreads();
     uint32_t total_words = block_exclusive_scan<SEL_THREADS>(words, P, warp_tot);
@@ -507,12 +511,14 @@ template <int W32T>  // W32T > 0: D = 32*W32T held in registers (one pass over m
 __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__ y, const float* __restrict__ cent,
                                                        const uint32_t* __restrict__ probe_ids, const float* __restrict__ probe_dist,
                                                        const uint32_t* __restrict__ slot_local, const uint32_t* __restrict__ q_wbase,
+                                                       const uint32_t* __restrict__ offsets,
                                                        uint32_t* __restrict__ qrec, int nq, int P, int D) {
     const int lane = threadIdx.x & 31;
     const size_t gw = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (gw >= (size_t)nq * P) return;
     const size_t q = gw / P;
     const uint32_t c = probe_ids[gw];
+    if (offsets && offsets[c + 1] == offsets[c]) return;  // cluster held by another shard: its record is never read
     const float* yr = y + q * (size_t)D;
     const float* cr = cent + (size_t)c * D;
     const int W32 = W32T > 0 ? W32T : D / 32, WP = (W32 + 3) & ~3, RS = 4 * WP + 8;  // plane stride padded to 128 bits
@@ -906,6 +912,23 @@ struct RerankArgs {
     int nq, P, D, topk;
     int R;                        // rows per wave (<= 32)
     int smem_per_warp;            // bytes
+    // distributed record sink (template SINK != 0): records go straight into the inbox of the
+    // query's HOME rank -- peer memory over NVLink (one process per GPU) or plain device memory (ranks in one process)
+    unsigned char* const* peers;  // inbox base of every rank
+    size_t off_r1cnt, off_r1rec, off_r2rec;  // byte offsets inside an inbox (same layout on every rank)
+    const uint32_t* r2_off;       // per query: first record inside this shard's region of the home inbox
+    const uint32_t* r2_cnt;       // per query: records this shard will write (0xffffffff = region overflow: skip)
+    int world, rank, nq_local, r1cap;
+    uint32_t cap2;                // records per (home, source) region
+};
+
+// One reranked candidate as shipped to the query's home rank: everything HeapReRanker::rank_batch (src/rerank.rs:83-101)
+// needs to replay its two strict tests (rough < thr, exact < thr) and the heap push, plus the probe rank that orders
+// records of different shards in the reference's visit order.
+struct __align__(16) SurvRec {
+    float rough, exact;
+    uint32_t id;   // original id (map_ids applied, rerank.rs:94)
+    uint32_t p;    // probe rank of the cluster the candidate lives in
 };
 
 RQ_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -956,7 +979,12 @@ RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, fl
 // HEUR = false: HeapReRanker (src/rerank.rs:61-114).  HEUR = true: HeuristicReRanker (src/rerank.rs:117-176): the filter
 // threshold is the largest accepted distance of the last WINDOW_SIZE = 12 accepted candidates (src/consts.rs:12); every
 // accepted candidate is a result candidate and get_result keeps the topk smallest, which is what the k-slot buffer holds.
-template <bool HEUR>
+// SINK = 0: single-GPU replay.  SINK = 1 (distributed round 1, run by the shard that owns the query's nearest non-empty
+// cluster): the same sequential replay, and every candidate the reference computes an exact distance for is also written
+// to the home rank's inbox.  SINK = 2 (distributed round 2): the threshold is FROZEN at the value the reference holds at
+// the end of round 1 (an upper bound of every later threshold), every survivor gets its exact distance and is shipped;
+// no heap, no sequential dependency -- the home rank replays the union in visit order (home_replay_kernel).
+template <bool HEUR, int SINK>
 __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int ch_lo, int p_hi, int ch_hi, int first, int finalize) {
     extern __shared__ __align__(16) unsigned char rr_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -974,24 +1002,47 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     uint32_t* qj = reinterpret_cast<uint32_t*>(qr + 64);    // [2][32]
     float2* sent = reinterpret_cast<float2*>(qj + 64);      // [4][32] staged survivors
     uint32_t* stot = reinterpret_cast<uint32_t*>(sent + 128);  // [4]
+    uint32_t* qp = stot + 4;                                   // [2][32] probe rank of queued candidates (SINK == 2)
+    uint32_t* swd = qp + 64;                                   // [4][32] word of staged survivors (SINK == 2)
     const uint32_t lt_mask = (1u << lane) - 1u;
+    if constexpr (SINK == 2) {
+        const uint32_t c2 = a.r2_cnt[q];
+        if (c2 == 0u || c2 == 0xffffffffu) return;  // nothing to ship / flagged overflow
+    }
 
     if (lane == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
     // prologue: every independent global load is issued before the first dependent use (the kernel is a chain of
     // memory latencies; the fewer links the better)
-    int cnt = first ? 0 : (int)a.heap_cnt[q];
+    int cnt = (first || SINK == 2) ? 0 : (int)a.heap_cnt[q];
     float thr = first ? 3.402823466e+38f : a.thr[q];   // the filter threshold of the reranker
     float hmax = 3.402823466e+38f;                      // largest distance among the k kept results (when cnt == k)
     float recent = first ? -3.402823466e+38f : a.h_recent[q];
     uint32_t wcount = first ? 0u : a.h_wcount[q];
     const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
     const int p0 = (int)a.q_p0[q];
-    {
+    // word window of this round: from (p_lo, ch_lo) to (p_hi, ch_hi) in visit order; a chunk is 128 vectors = 4 words
+    auto word_at = [&](int pe, int ch) -> uint32_t {  // pe = effective rank
+        const int p = pe + p0;
+        if (p >= a.P) return wend;
+        const uint32_t s0 = wb + a.slot_local[(size_t)q * a.P + p];
+        const uint32_t s1 = (p + 1 < a.P) ? wb + a.slot_local[(size_t)q * a.P + p + 1] : wend;
+        return min(s0 + (uint32_t)ch * (SCAN_THREADS / 32), s1);
+    };
+    const uint32_t wlo = word_at(p_lo, ch_lo), whi = word_at(p_hi, ch_hi);
+    if (wlo < whi) {  // a query without candidates in this window (e.g. another shard owns them) skips the row-sized load
         const float4* src = reinterpret_cast<const float4*>(a.qpad + (size_t)q * D);
         float4* dst = reinterpret_cast<float4*>(qv);
 #pragma unroll 8
         for (int d = lane; d < D / 4; d += 32) dst[d] = __ldg(&src[d]);
     }
+    // record sinks
+    const int home = SINK ? q / a.nq_local : 0, ql = SINK ? q - home * a.nq_local : 0;
+    SurvRec* rdst = nullptr;
+    uint32_t nrec = 0;
+    if constexpr (SINK == 1)
+        rdst = reinterpret_cast<SurvRec*>(a.peers[home] + a.off_r1rec) + ((size_t)a.rank * a.nq_local + ql) * a.r1cap;
+    if constexpr (SINK == 2)
+        rdst = reinterpret_cast<SurvRec*>(a.peers[home] + a.off_r2rec) + (size_t)a.rank * a.cap2 + a.r2_off[q];
     int maxpos = 0;
     for (int s = lane; s < cnt; s += 32) {
         hd[s] = a.heap_dist[(size_t)q * k + s];
@@ -1014,7 +1065,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
         const bool mine = lane < n;
         const float rough = mine ? qr[w * 32 + lane] : 0.0f;
         const uint32_t j = mine ? qj[w * 32 + lane] : 0u;
-        const uint32_t act = __ballot_sync(FULL, mine && rough < thr);
+        const uint32_t act = __ballot_sync(FULL, mine && rough < thr);  // SINK == 2: thr is frozen, every queued lane passes
         computed += n;
         if (act) {
             const float* rw = rows + (size_t)w * R * pitch;
@@ -1048,8 +1099,17 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                 const float res0 = __shfl_sync(FULL, acc0, src), res1 = __shfl_sync(FULL, acc1, src);
                 if ((lane >> 3) == (g >> 3)) exact = ((lane >> 2) & 1) ? res1 : res0;
             }
+            if constexpr (SINK == 2) {  // ship (rough, exact, id, rank) of the whole wave, visit order kept
+                if (mine) {
+                    SurvRec rec;
+                    rec.rough = rough; rec.exact = exact; rec.id = a.map_ids[j]; rec.p = qp[w * 32 + lane];
+                    rdst[nrec + lane] = rec;
+                }
+                nrec += n;
+                precise += n;
+            }
             // in-order replay (rerank.rs:83-101)
-            uint32_t rem = act;
+            uint32_t rem = SINK == 2 ? 0u : act;
             while (rem) {
                 const int t = __ffs(rem) - 1;
                 rem &= rem - 1;
@@ -1058,10 +1118,20 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                 const uint32_t ju = __shfl_sync(FULL, j, t);
                 if (r < thr) {
                     precise++;
+                    uint32_t mid = 0;
+                    if (lane == 0) mid = a.map_ids[ju];
+                    if constexpr (SINK == 1) {
+                        if (lane == 0 && nrec < (uint32_t)a.r1cap) {
+                            SurvRec rec;
+                            rec.rough = r; rec.exact = ex; rec.id = mid; rec.p = (uint32_t)(p0 + p_lo);
+                            rdst[nrec] = rec;
+                        }
+                        nrec++;
+                    }
                     if (ex < thr) {
                         if (!HEUR || cnt < k || ex < hmax) {
                             const int slot = cnt < k ? cnt : maxpos;
-                            if (lane == 0) { hd[slot] = ex; hid[slot] = a.map_ids[ju]; }
+                            if (lane == 0) { hd[slot] = ex; hid[slot] = mid; }
                             if (cnt < k) cnt++;
                             __syncwarp();
                             if (cnt == k) {
@@ -1088,7 +1158,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
 
     // queue candidates in visit order; the row gather of each is issued right here, so it is in flight while the
     // stream continues and while the previous wave is being replayed
-    auto enqueue = [&](uint32_t pm, float rough, uint32_t j) {
+    auto enqueue = [&](uint32_t pm, float rough, uint32_t j, uint32_t widx) {
         while (pm) {
             const int space = R - fill;
             const int rank = __popc(pm & lt_mask);
@@ -1097,6 +1167,16 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                 const int slot = fill + rank;
                 qr[f * 32 + slot] = rough;
                 qj[f * 32 + slot] = j;
+                if constexpr (SINK == 2) {  // probe rank of the slot that holds word `widx`: the last p with slot_local[p] <= widx - wb
+                    const uint32_t* sl = a.slot_local + (size_t)q * a.P;
+                    const uint32_t rel = widx - wb;
+                    int lo = 0, hi = a.P;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (sl[mid] <= rel) lo = mid; else hi = mid;
+                    }
+                    qp[f * 32 + slot] = (uint32_t)lo;
+                }
                 mbar_expect_tx(&mbar[f], rowbytes);
                 tma_bulk_g2s(rows + ((size_t)f * R + slot) * pitch, a.base + (size_t)j * D, rowbytes, &mbar[f]);
             }
@@ -1112,16 +1192,6 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
             }
         }
     };
-
-    // word window of this round: from (p_lo, ch_lo) to (p_hi, ch_hi) in visit order; a chunk is 128 vectors = 4 words
-    auto word_at = [&](int pe, int ch) -> uint32_t {  // pe = effective rank
-        const int p = pe + p0;
-        if (p >= a.P) return wend;
-        const uint32_t s0 = wb + a.slot_local[(size_t)q * a.P + p];
-        const uint32_t s1 = (p + 1 < a.P) ? wb + a.slot_local[(size_t)q * a.P + p + 1] : wend;
-        return min(s0 + (uint32_t)ch * (SCAN_THREADS / 32), s1);
-    };
-    const uint32_t wlo = word_at(p_lo, ch_lo), whi = word_at(p_hi, ch_hi);
 
     // Super-block of SB x 32 words: SB independent bitmap loads per lane, then the first 32 survivors of every block
     // loaded back to back and staged in shared memory; the (rolled, single-instance) processing loop follows.
@@ -1159,6 +1229,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                 ent[u] = make_float2(3.402823466e+38f, 0.0f);
                 if ((uint32_t)lane < T) ent[u] = a.entries[(size_t)(w0 + u * 32 + pos) * 32 + (lane - src_excl)];
                 if (lane == 0) stot[u] = T;
+                if constexpr (SINK == 2) swd[u * 32 + lane] = w0 + u * 32 + pos;
             }
 #pragma unroll
             for (int u = 0; u < SB; u++) sent[u * 32 + lane] = ent[u];
@@ -1170,7 +1241,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
             {
                 const float2 en = sent[u * 32 + lane];
                 const uint32_t pm = __ballot_sync(FULL, (uint32_t)lane < T && en.x < thr);
-                if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
+                if (pm) enqueue(pm, en.x, __float_as_uint(en.y), SINK == 2 ? swd[u * 32 + lane] : 0u);
             }
             if (T > 32) {  // dense block (loose threshold, e.g. the first probed cluster): further chunks on demand
                 const uint32_t idx = w0 + u * 32 + lane;
@@ -1196,7 +1267,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                     float2 en = make_float2(3.402823466e+38f, 0.0f);
                     if (have) en = a.entries[(size_t)(w0 + u * 32 + pos) * 32 + (e - src_excl)];
                     const uint32_t pm = __ballot_sync(FULL, have && en.x < thr);
-                    if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
+                    if (pm) enqueue(pm, en.x, __float_as_uint(en.y), w0 + u * 32 + pos);
                 }
             }
         }
@@ -1205,6 +1276,14 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     if (pend_n) process(f ^ 1, pend_n);
     if (fill) process(f, fill);
 
+    if constexpr (SINK == 2) {
+        if (lane == 0) atomicAdd(&a.counters[1], (unsigned long long)computed);
+        return;
+    }
+    if constexpr (SINK == 1) {  // only the owner of the window has words; it tells the home rank how many records to replay
+        if (lane == 0 && wlo < whi)
+            reinterpret_cast<uint32_t*>(a.peers[home] + a.off_r1cnt)[(size_t)a.rank * a.nq_local + ql] = min(nrec, (uint32_t)a.r1cap);
+    }
     if (lane == 0) {
         a.q_precise[q] = (first ? 0u : a.q_precise[q]) + precise;
         atomicAdd(&a.counters[1], (unsigned long long)computed);
@@ -1275,6 +1354,274 @@ __global__ void merge_topk_kernel(const float* __restrict__ dist, const uint32_t
         out_ids[q * topk + s] = 0xffffffffu;
     }
     if (lane == 0) out_count[q] = have;
+}
+
+// =========================================================================================================
+// Distributed pipeline: the index is sharded by cluster range, every rank is the HOME of a
+// contiguous slice of the query batch (front end + final replay) and a SOURCE of survivor records for all queries.
+
+// After the all-gather of the per-rank front-end products.  `gathered` = world chunks, each
+//   [q: nq_l x len][y: nq_l x D][probe ids: nq_l x P][probe dist: nq_l x P][p0: nq_l]   (4-byte units)
+// -> flat per-query arrays over the whole batch (global query gq = rank * nq_l + i), queries zero-padded to D.
+__global__ void dist_unpack_kernel(const uint32_t* __restrict__ gathered, int world, int nq_l, int len, int D, int P,
+                                   float* __restrict__ qpad, float* __restrict__ y, uint32_t* __restrict__ probe_ids,
+                                   float* __restrict__ probe_dist, uint32_t* __restrict__ q_p0) {
+    const size_t per_q = (size_t)D + D + 2 * (size_t)P + 1;  // output words per query
+    const size_t chunk = (size_t)nq_l * ((size_t)len + D + 2 * (size_t)P + 1);
+    const size_t total = (size_t)world * nq_l * per_q;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t gq = i / per_q;
+        const int e = (int)(i % per_q);
+        const int r = (int)(gq / nq_l), ql = (int)(gq % nq_l);
+        const uint32_t* c = gathered + (size_t)r * chunk;
+        const uint32_t* sec_q = c, *sec_y = sec_q + (size_t)nq_l * len, *sec_i = sec_y + (size_t)nq_l * D;
+        const uint32_t* sec_d = sec_i + (size_t)nq_l * P, *sec_p0 = sec_d + (size_t)nq_l * P;
+        if (e < D) qpad[gq * D + e] = e < len ? __uint_as_float(sec_q[(size_t)ql * len + e]) : 0.0f;
+        else if (e < 2 * D) y[gq * D + (e - D)] = __uint_as_float(sec_y[(size_t)ql * D + (e - D)]);
+        else if (e < 2 * D + P) probe_ids[gq * P + (e - 2 * D)] = sec_i[(size_t)ql * P + (e - 2 * D)];
+        else if (e < 2 * D + 2 * P) probe_dist[gq * P + (e - 2 * D - P)] = __uint_as_float(sec_d[(size_t)ql * P + (e - 2 * D - P)]);
+        else q_p0[gq] = sec_p0[ql];
+    }
+}
+
+// Survivor-slot layout of one shard for probe lists that were selected elsewhere: per (query, rank) the exclusive prefix
+// of 32-vector words of the probed clusters THIS shard holds, and the per-query totals (what select_probe_kernel emits
+// when it runs on the shard itself).
+__global__ void __launch_bounds__(SEL_THREADS) slot_layout_kernel(const uint32_t* __restrict__ probe_ids, const uint32_t* __restrict__ offsets,
+                                                                  int P, uint32_t* __restrict__ slot_local, uint32_t* __restrict__ q_words,
+                                                                  uint32_t* __restrict__ q_pairs) {
+    extern __shared__ uint32_t sl_words[];  // P
+    __shared__ uint32_t warp_tot[SEL_THREADS / 32 + 1];
+    __shared__ uint32_t s_pairs;
+    const int tid = threadIdx.x;
+    const size_t q = blockIdx.x;
+    if (tid == 0) s_pairs = 0;
+    __syncthreads();
+    uint32_t pairs = 0;
+    for (int p = tid; p < P; p += SEL_THREADS) {
+        const uint32_t c = probe_ids[q * P + p], n_c = offsets[c + 1] - offsets[c];
+        sl_words[p] = (n_c + 31u) >> 5;
+        pairs += n_c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(FULL, pairs, o);
+    if ((tid & 31) == 0 && pairs) atomicAdd(&s_pairs, pairs);
+    __syncthreads();
+    const uint32_t total = block_exclusive_scan<SEL_THREADS>(sl_words, P, warp_tot);
+    for (int p = tid; p < P; p += SEL_THREADS) slot_local[q * P + p] = sl_words[p];
+    if (tid == 0) { q_words[q] = total; q_pairs[q] = s_pairs; }
+}
+
+// Records this shard will ship per query in the frozen round: the survivors the scan left in the round's word window.
+__global__ void r2_count_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ q_wbase, const uint32_t* __restrict__ slot_local,
+                                const uint32_t* __restrict__ q_p0, int nq, int P, int p_lo, int ch_lo, uint32_t* __restrict__ r2_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const uint32_t wb = q_wbase[q], wend = q_wbase[q + 1];
+    const int p = p_lo + (int)q_p0[q];
+    uint32_t wlo = wend;
+    if (p < P) {
+        const uint32_t s0 = wb + slot_local[(size_t)q * P + p];
+        const uint32_t s1 = (p + 1 < P) ? wb + slot_local[(size_t)q * P + p + 1] : wend;
+        wlo = min(s0 + (uint32_t)ch_lo * (SCAN_THREADS / 32), s1);
+    }
+    uint32_t c = 0;
+    for (uint32_t w = wlo + lane; w < wend; w += 32) c += __popc(bitmap[w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    if (lane == 0) r2_cnt[q] = c;
+}
+
+// One block per home rank: exclusive scan of the counts of the queries homed there = where each query's records start
+// inside this shard's region of that rank's inbox; the (offset, count) table is written into the inbox as well.  A region
+// that would overflow marks the affected queries (count 0xffffffff) and raises the status word: the step is then repeated
+// with larger regions by the host, never silently truncated.
+__global__ void __launch_bounds__(1024) r2_offsets_kernel(uint32_t* __restrict__ r2_cnt, uint32_t* __restrict__ r2_off, int nq_l, uint32_t cap2,
+                                                          unsigned char* const* __restrict__ peers, size_t off_r2tab, int rank,
+                                                          uint32_t* __restrict__ status) {
+    __shared__ uint32_t wtot[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int home = blockIdx.x;
+    uint32_t* cnt = r2_cnt + (size_t)home * nq_l;
+    uint32_t* off = r2_off + (size_t)home * nq_l;
+    uint2* tab = reinterpret_cast<uint2*>(peers[home] + off_r2tab) + (size_t)rank * nq_l;
+    const int per = (nq_l + 1023) / 1024;
+    const int lo = min(nq_l, tid * per), hi = min(nq_l, lo + per);
+    uint32_t s = 0;
+    for (int i = lo; i < hi; i++) s += cnt[i];
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wtot[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(FULL, wi, o);
+            if (lane >= o) wi += v;
+        }
+        wtot[lane] = wi - w;
+        if (lane == 31) wtot[32] = wi;
+    }
+    __syncthreads();
+    uint32_t run = wtot[warp] + inc - s;
+    for (int i = lo; i < hi; i++) {
+        const uint32_t c = cnt[i];
+        off[i] = run;
+        if ((unsigned long long)run + c > cap2) {
+            cnt[i] = 0xffffffffu;
+            tab[i] = make_uint2(run, 0xffffffffu);
+            atomicOr(status, 1u);
+        } else {
+            tab[i] = make_uint2(run, c);
+        }
+        run += c;
+    }
+}
+
+// Final replay on the HOME rank: HeapReRanker::rank_batch (src/rerank.rs:81-106) over the union of the records every shard
+// shipped, in the reference's visit order -- round-1 records first (they are a prefix of the order), then the frozen
+// round's records merged by probe rank (a rank's cluster lives on exactly one shard, and a shard's records are already in
+// its visit order).  The union is a superset of what the reference reranks (frozen threshold >= every later threshold),
+// so the two strict tests below see exactly the candidates, thresholds and heap states of the sequential loop: ids,
+// distances and the `precise` counter are the reference's.
+struct HomeArgs {
+    const unsigned char* inbox;   // this rank's inbox
+    size_t off_r1cnt, off_r1rec, off_r2tab, off_r2rec;
+    const uint32_t* probe_ids;    // whole batch, nq x P
+    const uint32_t* q_p0;         // whole batch
+    const uint32_t* goffsets;     // K+1, global rows
+    const uint32_t* row_bounds;   // world+1, global rows of the shards
+    float* out_dist;              // nq_l x topk
+    uint32_t* out_ids;
+    uint32_t* out_count;
+    unsigned long long* counters; // [2] precise
+    uint32_t* status;
+    int world, rank, nq_l, P, topk, r1cap;
+    uint32_t cap2;
+};
+
+__global__ void __launch_bounds__(128) home_replay_kernel(HomeArgs a) {
+    extern __shared__ __align__(16) unsigned char hr_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int ql = blockIdx.x * wpb + warp;
+    if (ql >= a.nq_l) return;
+    const int k = a.topk;
+    float* hd = reinterpret_cast<float*>(hr_smem) + (size_t)warp * 2 * k;
+    uint32_t* hid = reinterpret_cast<uint32_t*>(hd + k);
+    const size_t gq = (size_t)a.rank * a.nq_l + ql;
+    const int p0 = (int)a.q_p0[gq];
+    int cnt = 0, maxpos = 0;
+    float thr = 3.402823466e+38f;
+    uint32_t precise = 0;
+
+    auto replay = [&](const SurvRec& rec, int n) {  // lanes 0..n-1 hold consecutive records
+        for (int t = 0; t < n; t++) {
+            const float r = __shfl_sync(FULL, rec.rough, t), ex = __shfl_sync(FULL, rec.exact, t);
+            const uint32_t id = __shfl_sync(FULL, rec.id, t);
+            if (r < thr) {            // rerank.rs:84
+                precise++;
+                if (ex < thr) {       // rerank.rs:92
+                    const int slot = cnt < k ? cnt : maxpos;
+                    if (lane == 0) { hd[slot] = ex; hid[slot] = id; }
+                    if (cnt < k) cnt++;
+                    __syncwarp();
+                    if (cnt == k) heap_recompute_max(hd, k, lane, maxpos, thr);  // rerank.rs:98-100
+                }
+            }
+        }
+    };
+    auto owner_of = [&](uint32_t c) -> int {
+        const uint32_t row = a.goffsets[c];
+        int s = 0;
+        while (s + 1 < a.world && row >= a.row_bounds[s + 1]) s++;
+        return s;
+    };
+
+    bool bad = false;
+    if (p0 < a.P) {
+        // ---- round 1: written by the shard that owns the nearest non-empty cluster
+        const uint32_t c0 = a.probe_ids[gq * a.P + p0];
+        if (a.goffsets[c0 + 1] > a.goffsets[c0]) {
+            const int o1 = owner_of(c0);
+            const uint32_t n1 = reinterpret_cast<const uint32_t*>(a.inbox + a.off_r1cnt)[(size_t)o1 * a.nq_l + ql];
+            const SurvRec* r1 = reinterpret_cast<const SurvRec*>(a.inbox + a.off_r1rec) + ((size_t)o1 * a.nq_l + ql) * a.r1cap;
+            for (uint32_t i0 = 0; i0 < n1; i0 += 32) {
+                SurvRec rec = {0.f, 0.f, 0u, 0u};
+                if (i0 + lane < n1) rec = r1[i0 + lane];
+                replay(rec, (int)min(32u, n1 - i0));
+            }
+        }
+        // ---- frozen round: merge the shards' runs by probe rank
+        uint32_t soff = 0, scnt = 0, scur = 0, head = 0xffffffffu;
+        const SurvRec* r2 = reinterpret_cast<const SurvRec*>(a.inbox + a.off_r2rec);
+        if (lane < a.world) {
+            const uint2 t = reinterpret_cast<const uint2*>(a.inbox + a.off_r2tab)[(size_t)lane * a.nq_l + ql];
+            soff = t.x; scnt = t.y;
+            if (scnt == 0xffffffffu) { bad = true; scnt = 0; }
+            if (scnt) head = r2[(size_t)lane * a.cap2 + soff].p;
+        }
+        bad = __any_sync(FULL, bad);
+        while (!bad) {
+            uint32_t pm = head;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pm = min(pm, __shfl_xor_sync(FULL, pm, o));
+            if (pm == 0xffffffffu) break;
+            const int s = __ffs(__ballot_sync(FULL, head == pm)) - 1;
+            const uint32_t o_s = __shfl_sync(FULL, soff, s), c_s = __shfl_sync(FULL, scnt, s);
+            uint32_t cur = __shfl_sync(FULL, scur, s);
+            uint32_t next_head = 0xffffffffu;
+            for (;;) {
+                SurvRec rec = {0.f, 0.f, 0u, 0xffffffffu};
+                if (cur + lane < c_s) rec = r2[(size_t)s * a.cap2 + o_s + cur + lane];
+                const uint32_t same = __ballot_sync(FULL, rec.p == pm);
+                const int n = same == FULL ? 32 : __ffs(~same) - 1;  // records are rank-ordered: a prefix
+                replay(rec, n);
+                cur += n;
+                if (n < 32) {
+                    next_head = __shfl_sync(FULL, rec.p, n);  // 0xffffffff past the end of the segment
+                    break;
+                }
+                if (cur >= c_s) break;
+            }
+            if (lane == s) { scur = cur; head = next_head; }
+        }
+    }
+    if (bad) {
+        if (lane == 0) atomicOr(a.status, 2u);
+        cnt = 0;
+    }
+    __syncwarp();
+    for (int s = lane; s < k; s += 32) {
+        if (s < cnt) {
+            const uint32_t ks = okey(hd[s]), is = hid[s];
+            int rank = 0;
+            for (int t = 0; t < cnt; t++) {
+                const uint32_t kt = okey(hd[t]), itt = hid[t];
+                rank += (kt < ks) || (kt == ks && (itt < is || (itt == is && t < s)));
+            }
+            a.out_dist[(size_t)ql * k + rank] = hd[s];
+            a.out_ids[(size_t)ql * k + rank] = is;
+        } else {
+            a.out_dist[(size_t)ql * k + s] = __int_as_float(0x7f800000);
+            a.out_ids[(size_t)ql * k + s] = 0xffffffffu;
+        }
+    }
+    if (lane == 0) {
+        a.out_count[ql] = (uint32_t)cnt;
+        atomicAdd(&a.counters[2], (unsigned long long)precise);
+    }
+}
+
+// all-reduce(min) of the round-1 thresholds when every rank lives in ONE process (tests on a single GPU): plain device code.
+__global__ void min_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = fminf(dst[i], src[i]);
 }
 
 __global__ void fill_f32_kernel(float* p, size_t n, float v) {

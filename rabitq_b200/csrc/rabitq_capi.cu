@@ -90,6 +90,25 @@ enum Stage { ST_H2D = 0, ST_ROTATE, ST_CDIST, ST_SELECT, ST_QUANT, ST_BUCKET, ST
 
 }  // namespace
 
+// State of the distributed pipeline on one rank.  The inbox is where OTHER ranks' kernels write the
+// survivor records of the queries homed here; it is a plain cudaMalloc block so that it can be exported with CUDA IPC.
+struct DistState {
+    bool ready = false;
+    int world = 0, rank = 0;
+    size_t nq_l = 0, topk = 0, len = 0;
+    int P = 0;
+    uint32_t r1cap = 0, cap2 = 0;
+    unsigned char* inbox = nullptr;
+    size_t inbox_bytes = 0, off_r1cnt = 0, off_r1rec = 0, off_r2tab = 0, off_r2rec = 0;
+    std::vector<unsigned char*> peers_h;
+    std::vector<char> opened;  // peers_h[r] came from cudaIpcOpenMemHandle
+    unsigned char** peers_d = nullptr;
+    int phase = 0;             // 0 idle, 1 front done, 2 round 1 done, 3 round 2 done
+    rq::ScanArgs sa;
+    rq::RerankArgs ra;
+    float* d_thr = nullptr;
+};
+
 struct rabitq_index {
     int device = 0;
     uint32_t D = 0;
@@ -102,6 +121,8 @@ struct rabitq_index {
     float* P = nullptr;           // D x D rows
     float* cent = nullptr;        // K x D
     uint32_t* offsets = nullptr;  // K+1, local rows
+    uint32_t* goffsets = nullptr; // K+1, rows of the WHOLE index (equal to offsets on an unsharded handle)
+    uint32_t* row_bounds = nullptr;  // shard_count+1, global rows where the shards begin
     uint32_t* map_ids = nullptr;  // n
     uint32_t* codes = nullptr;    // n x D/32
     float4* factors = nullptr;    // n
@@ -114,7 +135,8 @@ struct rabitq_index {
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, cl_count,
         cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
-        entries, counters, out_dist, out_ids, out_count;
+        entries, counters, out_dist, out_ids, out_count, r2_cnt, r2_off;
+    DistState dist;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
     // metrics (src/metrics.rs)
     uint64_t m_query = 0, m_rough = 0, m_precise = 0;
@@ -129,11 +151,16 @@ struct rabitq_index {
 
     ~rabitq_index() {
         cudaSetDevice(device);
-        for (void* p : {(void*)base, (void*)P, (void*)cent, (void*)offsets, (void*)map_ids, (void*)codes, (void*)factors})
+        for (void* p : {(void*)base, (void*)P, (void*)cent, (void*)offsets, (void*)goffsets, (void*)row_bounds, (void*)map_ids, (void*)codes,
+                        (void*)factors, (void*)dist.peers_d})
             if (p) cudaFree(p);
+        for (size_t r = 0; r < dist.peers_h.size(); r++)
+            if (dist.opened[r] && dist.peers_h[r]) cudaIpcCloseMemHandle(dist.peers_h[r]);
+        if (dist.inbox) cudaFree(dist.inbox);
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &qrec, &cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &thr, &heap_dist,
-                          &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count})
+                          &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count,
+                          &r2_cnt, &r2_off})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         for (auto e : ev_pool) cudaEventDestroy(e);
@@ -199,8 +226,10 @@ int finish_index(rabitq_index* ix) {
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     CU(cudaMallocHost((void**)&ix->h_pin, 256));
-    CU(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     return 0;
 }
@@ -259,6 +288,19 @@ int make_index(uint32_t dim, size_t n_total, size_t K, const float* base, const 
         cudaError_t e_ = cudaMalloc((void**)&ix->offsets, (K + 1) * 4);
         if (e_ == cudaSuccess) e_ = cudaMemcpy(ix->offsets, loc.data(), (K + 1) * 4, cudaMemcpyHostToDevice);
         if (e_ != cudaSuccess) { delete ix; return fail(RABITQ_ECUDA, std::string("offsets upload: ") + cudaGetErrorString(e_)); }
+    }
+    {
+        std::vector<uint32_t> rb(shard_count + 1);
+        for (int r = 0; r <= shard_count; r++) {
+            size_t lo_r, hi_r;
+            shard_rows(offsets_h, K, std::min(r, shard_count - 1), shard_count, &lo_r, &hi_r);
+            rb[r] = (uint32_t)(r < shard_count ? lo_r : hi_r);
+        }
+        cudaError_t e_ = cudaMalloc((void**)&ix->goffsets, (K + 1) * 4);
+        if (e_ == cudaSuccess) e_ = cudaMemcpy(ix->goffsets, offsets_h, (K + 1) * 4, cudaMemcpyHostToDevice);
+        if (e_ == cudaSuccess) e_ = cudaMalloc((void**)&ix->row_bounds, rb.size() * 4);
+        if (e_ == cudaSuccess) e_ = cudaMemcpy(ix->row_bounds, rb.data(), rb.size() * 4, cudaMemcpyHostToDevice);
+        if (e_ != cudaSuccess) { delete ix; return fail(RABITQ_ECUDA, std::string("global offsets upload: ") + cudaGetErrorString(e_)); }
     }
     { int rc_ = finish_index(ix); if (rc_) { delete ix; return rc_; } }
     *out = ix;
@@ -433,6 +475,13 @@ int build_impl(const float* base, size_t n, size_t len, const float* centroids, 
         CU(cudaMemcpy(cnt_h.data(), counts, K * 4, cudaMemcpyDeviceToHost));
         ix->max_cluster = *std::max_element(cnt_h.begin(), cnt_h.end());
     }
+    {
+        const uint32_t rb[2] = {0u, (uint32_t)n};
+        CU(cudaMalloc((void**)&ix->goffsets, (K + 1) * 4));
+        CU(cudaMemcpy(ix->goffsets, ix->offsets, (K + 1) * 4, cudaMemcpyDeviceToDevice));
+        CU(cudaMalloc((void**)&ix->row_bounds, sizeof(rb)));
+        CU(cudaMemcpy(ix->row_bounds, rb, sizeof(rb), cudaMemcpyHostToDevice));
+    }
     int rc = finish_index(ix);
     if (rc) return rc;
     guard.p = nullptr;
@@ -561,13 +610,14 @@ struct BatchOut {  // device pointers of the sub-batch products
     uint64_t total_pairs = 0;
 };
 
-// One sub-batch of nb queries, already on the device in ix->qraw (nb x len).  Runs up to `stop`.
-int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t topk, bool heuristic, StopAfter stop, BatchOut* bo) {
+// ---- pieces of the batch pipeline (shared by the single-GPU path and the distributed phases) ------------------------------
+struct Pos { int p, ch; };  // a visit position: (effective probe rank, 128-vector chunk)
+
+// K0-K2b for nb queries already in ix->qraw (nb x len): pad, rotate, centroid distances, probe selection.  `global_view`:
+// pair counts and the first non-empty rank refer to the whole index (distributed front end) instead of this shard's rows.
+int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_rotate, bool global_view) {
     const int D = (int)ix->D, K = (int)ix->K;
-    const int P = (int)std::min(probe, ix->K);
-    const int W32 = D / 32, WP = (W32 + 3) & ~3, RS = 4 * WP + 8;
     cudaStream_t st = ix->stream;
-    bo->P = P;
     CU(ix->qpad.ensure(nb * D * 4));
     CU(ix->y.ensure(nb * D * 4));
     {
@@ -582,7 +632,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
         CU(cudaGetLastError()); ix->counts[5]++;
     }
     if (tick(ix, ST_ROTATE)) return RABITQ_ECUDA;
-    if (stop == STOP_ROTATE) return 0;
+    if (stop_after_rotate) return 0;
 
     CU(ix->cdist.ensure(nb * (size_t)K * 4));
     {
@@ -606,41 +656,56 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
         const int cache_keys = (!pivot_ok && K <= 16384) ? 1 : 0;  // radix path: keys of one query in shared memory (<= 64 KB)
         const size_t sel_smem = (size_t)std::max(Ppow2, SEL_CAND) * 8 + SEL_SAMPLE * 4 + (cache_keys ? (size_t)K * 4 : 0);
         select_probe_kernel<<<(unsigned)nb, SEL_THREADS, sel_smem, st>>>(
-            ix->cdist.as<float>(), K, P, Ppow2, cache_keys, ix->offsets, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(),
-            ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), ix->q_p0.as<uint32_t>());
+            ix->cdist.as<float>(), K, P, Ppow2, cache_keys, ix->offsets, global_view ? ix->goffsets : nullptr, ix->probe_ids.as<uint32_t>(),
+            ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(),
+            ix->q_p0.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
         query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nb,
                                                    ix->q_wbase.as<uint32_t>(), ix->q_pbase.as<unsigned long long>());
         CU(cudaGetLastError()); ix->counts[5]++;
     }
-    // totals to the host: sizes the survivor slots
+    return 0;
+}
+
+// totals of the slot layout to the host (sizes the survivor slots); synchronises the stream
+int fetch_totals(rabitq_index* ix, size_t nb, BatchOut* bo) {
+    cudaStream_t st = ix->stream;
     CU(cudaMemcpyAsync(ix->h_pin, ix->q_wbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ix->h_pin + 2, ix->q_pbase.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
     if (tick(ix, ST_SELECT)) return RABITQ_ECUDA;
     CU(cudaStreamSynchronize(st));
     bo->total_words = ix->h_pin[0];
     std::memcpy(&bo->total_pairs, ix->h_pin + 2, 8);
-    if (stop == STOP_PROBE) return 0;
+    return 0;
+}
 
+// K3 for every (query, rank) of the batch; on a shard, pairs whose cluster lives elsewhere are skipped
+int run_quantize(rabitq_index* ix, size_t nb, int P) {
+    const int D = (int)ix->D, W32 = D / 32, WP = (W32 + 3) & ~3, RS = 4 * WP + 8;
+    cudaStream_t st = ix->stream;
     CU(ix->qrec.ensure(nb * (size_t)P * RS * 4));
-    {
-        size_t warps = nb * (size_t)P;
-        const unsigned qgrid = (unsigned)((warps + 3) / 4);
+    size_t warps = nb * (size_t)P;
+    const unsigned qgrid = (unsigned)((warps + 3) / 4);
+    const uint32_t* skip = ix->shard_count > 1 ? ix->offsets : nullptr;
 #define QUANT_ARGS ix->y.as<float>(), ix->cent, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), \
-                   ix->q_wbase.as<uint32_t>(), ix->qrec.as<uint32_t>(), (int)nb, P, D
-        switch (W32) {
-            case 2: quantize_kernel<2><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
-            case 4: quantize_kernel<4><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
-            case 6: quantize_kernel<6><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
-            case 8: quantize_kernel<8><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
-            default: quantize_kernel<0><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
-        }
-#undef QUANT_ARGS
-        CU(cudaGetLastError()); ix->counts[5]++;
+                   ix->q_wbase.as<uint32_t>(), skip, ix->qrec.as<uint32_t>(), (int)nb, P, D
+    switch (W32) {
+        case 2: quantize_kernel<2><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
+        case 4: quantize_kernel<4><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
+        case 6: quantize_kernel<6><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
+        case 8: quantize_kernel<8><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
+        default: quantize_kernel<0><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
     }
+#undef QUANT_ARGS
+    CU(cudaGetLastError()); ix->counts[5]++;
     if (tick(ix, ST_QUANT)) return RABITQ_ECUDA;
-    if (stop == STOP_QUANT) return 0;
+    return 0;
+}
 
+// work buffers + kernel argument blocks of the scan / rerank rounds
+int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut* bo, ScanArgs* sa_out, RerankArgs* ra_out) {
+    const int D = (int)ix->D, K = (int)ix->K;
+    cudaStream_t st = ix->stream;
     // survivor slots: one bitmap word + 32 (rough, j) entries per 32 vectors of every probed cluster
     const size_t words = std::max<uint32_t>(bo->total_words, 1);
     CU(ix->bitmap.ensure(words * 4));
@@ -686,6 +751,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     sa.QS = 0;
 
     RerankArgs ra;
+    std::memset(&ra, 0, sizeof(ra));
     ra.qpad = ix->qpad.as<float>();
     ra.base = ix->base;
     ra.map_ids = ix->map_ids;
@@ -713,7 +779,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     // issued at enqueue time, so a wave's rows are usually resident before it is replayed.  When the batch is small enough
     // the wave is shrunk further until every query-warp is co-resident (one wave of CTAs instead of two).
     auto rr_smem = [&](int R) {
-        return (int)((16 + (size_t)D * 4 + (size_t)2 * R * (D + 8) * 4 + 2 * topk * 4 + 2 * 64 * 4 + 128 * 8 + 16 + 15) / 16 * 16);
+        return (int)((16 + (size_t)D * 4 + (size_t)2 * R * (D + 8) * 4 + 2 * topk * 4 + 2 * 64 * 4 + 128 * 8 + 16 + 64 * 4 + 128 * 4 + 15) / 16 * 16);
     };
     auto rr_warps_per_block = [&](int smem) { return smem > 12 * 1024 ? 1 : 4; };
     auto rr_resident = [&](int R) {
@@ -728,11 +794,75 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
             if (rr_resident(R) >= nb) { ra.R = R; break; }
     ra.R = (int)std::max<size_t>(1, std::min<size_t>(ra.R, (80 * 1024) / (2 * (size_t)(D + 8) * 4)));  // <= 80 KB of row buffers per warp
     ra.smem_per_warp = rr_smem(ra.R);
-    const int rr_wpb = rr_warps_per_block(ra.smem_per_warp);
+    *sa_out = sa;
+    *ra_out = ra;
+    return 0;
+}
 
+enum RoundKind { ROUND_REPLAY, ROUND_DENSE, ROUND_SINK1, ROUND_SINK2 };
+
+// inverted probe lists + work list + scan of one window [lo, hi) of visit positions
+int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos hi, bool dense) {
+    const int K = (int)ix->K;
+    cudaStream_t st = ix->stream;
+    const int p_lo = lo.p, p_hi_incl = std::min(P, hi.p + (hi.ch > 0 ? 1 : 0));  // ranks that have items in this round
+    const bool single_rank = p_hi_incl == p_lo + 1;
+    const uint32_t ch_min = single_rank ? (uint32_t)lo.ch : 0u;
+    const uint32_t ch_max = (single_rank && hi.ch > 0) ? (uint32_t)hi.ch : 0xffffffffu;
+    const size_t items = nb * (size_t)(p_hi_incl - p_lo);
+    CU(cudaMemsetAsync(ix->cl_count.p, 0, (size_t)K * 4, st));
+    bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
+                                                                          ix->cl_count.as<uint32_t>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(ix->cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, ch_min, ch_max,
+                                           ix->cl_start.as<uint32_t>(), ix->item_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
+                                           ix->work_ctl.as<uint32_t>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
+                                                                         ix->cl_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
+                                                                         ix->cl_items.as<uint32_t>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(ix->item_start.as<uint32_t>(), K, ch_min, ix->work.as<uint2>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
+    sa.p_lo = lo.p; sa.ch_lo = lo.ch; sa.p_hi = hi.p; sa.ch_hi = hi.ch;
+    int rc = dense ? launch_scan<true>(ix, sa) : launch_scan<false>(ix, sa);
+    if (rc) return rc;
+    if (tick(ix, ST_SCAN)) return RABITQ_ECUDA;
+    ix->counts[4] += 1;
+    return 0;
+}
+
+int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, Pos hi, bool is_first, bool is_last, bool heuristic,
+                     RoundKind kind) {
+    cudaStream_t st = ix->stream;
+    const int rr_wpb = ra.smem_per_warp > 12 * 1024 ? 1 : 4;
+    const dim3 rgrid((unsigned)((nb + rr_wpb - 1) / rr_wpb)), rblock(rr_wpb * 32);
+    const size_t rsmem = (size_t)rr_wpb * ra.smem_per_warp;
+    const int f = is_first ? 1 : 0, l = is_last ? 1 : 0;
+    if (kind == ROUND_SINK1) rerank_kernel<false, 1><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
+    else if (kind == ROUND_SINK2) rerank_kernel<false, 2><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
+    else if (heuristic) rerank_kernel<true, 0><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
+    else rerank_kernel<false, 0><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
+    CU(cudaGetLastError()); ix->counts[5]++;
+    if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
+    return 0;
+}
+
+// One sub-batch of nb queries, already on the device in ix->qraw (nb x len).  Runs up to `stop`.
+int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t topk, bool heuristic, StopAfter stop, BatchOut* bo) {
+    const int P = (int)std::min(probe, ix->K);
+    bo->P = P;
+    int rc = run_front(ix, nb, len, P, stop == STOP_ROTATE, false);
+    if (rc || stop == STOP_ROTATE) return rc;
+    if ((rc = fetch_totals(ix, nb, bo))) return rc;
+    if (stop == STOP_PROBE) return 0;
+    if ((rc = run_quantize(ix, nb, P)) || stop == STOP_QUANT) return rc;
+    ScanArgs sa;
+    RerankArgs ra;
+    if ((rc = setup_rounds(ix, nb, P, topk, bo, &sa, &ra))) return rc;
     // rounds: windows of visit positions (probe rank, 128-vector chunk).  The first round covers only the first
     // `first_chunks` chunks of the nearest cluster, so that everything after it is filtered with a real threshold.
-    struct Pos { int p, ch; };
     std::vector<Pos> bounds;
     if (stop == STOP_SCAN_DENSE) bounds = {{0, 0}, {P, 0}};
     else {
@@ -743,42 +873,9 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
         bounds.push_back({P, 0});
     }
     for (size_t r = 0; r + 1 < bounds.size(); r++) {
-        const Pos lo = bounds[r], hi = bounds[r + 1];
-        const int p_lo = lo.p, p_hi_incl = std::min(P, hi.p + (hi.ch > 0 ? 1 : 0));  // ranks that have items in this round
-        const bool single_rank = p_hi_incl == p_lo + 1;
-        const uint32_t ch_min = single_rank ? (uint32_t)lo.ch : 0u;
-        const uint32_t ch_max = (single_rank && hi.ch > 0) ? (uint32_t)hi.ch : 0xffffffffu;
-        const size_t items = nb * (size_t)(p_hi_incl - p_lo);
-        CU(cudaMemsetAsync(ix->cl_count.p, 0, (size_t)K * 4, st));
-        bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
-                                                                              ix->cl_count.as<uint32_t>());
-        CU(cudaGetLastError()); ix->counts[5]++;
-        bucket_scan_kernel<<<1, 1024, 0, st>>>(ix->cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, ch_min, ch_max,
-                                               ix->cl_start.as<uint32_t>(), ix->item_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
-                                               ix->work_ctl.as<uint32_t>());
-        CU(cudaGetLastError()); ix->counts[5]++;
-        bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
-                                                                             ix->cl_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
-                                                                             ix->cl_items.as<uint32_t>());
-        CU(cudaGetLastError()); ix->counts[5]++;
-        work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(ix->item_start.as<uint32_t>(), K, ch_min, ix->work.as<uint2>());
-        CU(cudaGetLastError()); ix->counts[5]++;
-        if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
-        sa.p_lo = lo.p; sa.ch_lo = lo.ch; sa.p_hi = hi.p; sa.ch_hi = hi.ch;
-        int rc = (stop == STOP_SCAN_DENSE) ? launch_scan<true>(ix, sa) : launch_scan<false>(ix, sa);
-        if (rc) return rc;
-        if (tick(ix, ST_SCAN)) return RABITQ_ECUDA;
-        ix->counts[4] += 1;
+        if ((rc = run_round_scan(ix, nb, P, sa, bounds[r], bounds[r + 1], stop == STOP_SCAN_DENSE))) return rc;
         if (stop == STOP_SCAN_DENSE) return 0;
-        {
-            const dim3 rgrid((unsigned)((nb + rr_wpb - 1) / rr_wpb)), rblock(rr_wpb * 32);
-            const size_t rsmem = (size_t)rr_wpb * ra.smem_per_warp;
-            const int is_first = r == 0 ? 1 : 0, is_last = r + 2 == bounds.size() ? 1 : 0;
-            if (heuristic) rerank_kernel<true><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, is_first, is_last);
-            else rerank_kernel<false><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, is_first, is_last);
-        }
-        CU(cudaGetLastError()); ix->counts[5]++;
-        if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
+        if ((rc = run_round_rerank(ix, nb, ra, bounds[r], bounds[r + 1], r == 0, r + 2 == bounds.size(), heuristic, ROUND_REPLAY))) return rc;
     }
     return 0;
 }
@@ -866,10 +963,300 @@ int stage_prefix(rabitq_index* ix, const float* queries, size_t nq, size_t len, 
     return 0;
 }
 
+
+// ---- distributed pipeline: phases between the caller's collectives ---------------------------------
+size_t dist_chunk_words(const rabitq_index* ix, size_t nq_l, size_t len, int P) { return nq_l * (len + ix->D + 2 * (size_t)P + 1); }
+
+int dist_init_impl(rabitq_index* ix, int rank, int world, size_t nq_l, size_t probe, size_t topk, size_t records_per_query) {
+    if (!ix) return fail(RABITQ_EINVAL, "null index");
+    if (world < 1 || world > 32 || rank < 0 || rank >= world) return fail(RABITQ_EINVAL, "bad rank/world (world <= 32)");
+    if (world != ix->shard_count || rank != ix->shard_rank) return fail(RABITQ_EINVAL, "rank/world differ from the handle's shard rank/count");
+    if (nq_l == 0) return fail(RABITQ_EINVAL, "nq_local must be >= 1");
+    int rc = validate_query_args(ix, ix->D, probe, topk, 0);
+    if (rc) return rc;
+    if (nq_l * world * std::min(probe, ix->K) > 0xffffffffu) return fail(RABITQ_EUNSUPPORTED, "nq_total * probe exceeds 2^32");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    DistState& d = ix->dist;
+    for (size_t r = 0; r < d.peers_h.size(); r++)
+        if (d.opened[r] && d.peers_h[r]) cudaIpcCloseMemHandle(d.peers_h[r]);
+    if (d.inbox) cudaFree(d.inbox);
+    if (d.peers_d) cudaFree(d.peers_d);
+    d = DistState();
+    d.world = world; d.rank = rank; d.nq_l = nq_l; d.topk = topk;
+    d.P = (int)std::min(probe, ix->K);
+    d.r1cap = (uint32_t)(SCAN_THREADS * std::max(1, ix->first_chunks));
+    const size_t c2 = nq_l * std::max<size_t>(records_per_query, 8);
+    if (c2 > 0x7fffffffu) return fail(RABITQ_EUNSUPPORTED, "records_per_query too large");
+    d.cap2 = (uint32_t)c2;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    d.off_r1cnt = 0;
+    d.off_r1rec = up(d.off_r1cnt + (size_t)world * nq_l * 4);
+    d.off_r2tab = up(d.off_r1rec + (size_t)world * nq_l * d.r1cap * sizeof(SurvRec));
+    d.off_r2rec = up(d.off_r2tab + (size_t)world * nq_l * 8);
+    d.inbox_bytes = up(d.off_r2rec + (size_t)world * d.cap2 * sizeof(SurvRec));
+    CU(cudaMalloc((void**)&d.inbox, d.inbox_bytes));
+    CU(cudaMemset(d.inbox, 0, d.off_r1rec));
+    CU(cudaMalloc((void**)&d.peers_d, sizeof(void*) * world));
+    d.peers_h.assign(world, nullptr);
+    d.opened.assign(world, 0);
+    d.peers_h[rank] = d.inbox;
+    CU(cudaMemcpy(d.peers_d, d.peers_h.data(), sizeof(void*) * world, cudaMemcpyHostToDevice));
+    d.ready = true;
+    return RABITQ_OK;
+}
+
+int dist_set_peer_impl(rabitq_index* ix, int r, const unsigned char* ipc_handle, void* raw) {
+    if (!ix || !ix->dist.ready) return fail(RABITQ_EINVAL, "rabitq_dist_init first");
+    DistState& d = ix->dist;
+    if (r < 0 || r >= d.world) return fail(RABITQ_EINVAL, "bad peer rank");
+    if (r == d.rank) return RABITQ_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    if (d.opened[r] && d.peers_h[r]) { cudaIpcCloseMemHandle(d.peers_h[r]); d.opened[r] = 0; }
+    if (ipc_handle) {
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+        std::memcpy(&h, ipc_handle, sizeof(h));
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        d.peers_h[r] = static_cast<unsigned char*>(ptr);
+        d.opened[r] = 1;
+    } else {
+        if (!raw) return fail(RABITQ_EINVAL, "null peer pointer");
+        d.peers_h[r] = static_cast<unsigned char*>(raw);
+    }
+    CU(cudaMemcpy(d.peers_d, d.peers_h.data(), sizeof(void*) * d.world, cudaMemcpyHostToDevice));
+    return RABITQ_OK;
+}
+
+// Phase 1 (home): front end of this rank's nq_l queries -> its chunk of the all-gather.
+int dist_front_impl(rabitq_index* ix, const float* d_queries, size_t len, void* d_send) {
+    if (!ix || !ix->dist.ready) return fail(RABITQ_EINVAL, "rabitq_dist_init first");
+    if (!d_queries || !d_send) return fail(RABITQ_EINVAL, "null argument");
+    DistState& d = ix->dist;
+    if ((len + 63) / 64 * 64 != ix->D) return fail(RABITQ_EINVAL, "assertion `left == right` failed: dim != query.len().div_ceil(64) * 64");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    std::memset(ix->ms, 0, sizeof(ix->ms));
+    std::memset(ix->counts, 0, sizeof(ix->counts));
+    ix->ev_used = 0;
+    d.len = len;
+    const size_t nq_l = d.nq_l, D = ix->D;
+    const int P = d.P;
+    cudaStream_t st = ix->stream;
+    if (tick(ix, -1)) return RABITQ_ECUDA;
+    CU(cudaMemsetAsync(d.inbox + d.off_r1cnt, 0, (size_t)d.world * nq_l * 4, st));  // before the all-gather = before any owner writes
+    CU(ix->qraw.ensure(nq_l * len * 4));
+    CU(cudaMemcpyAsync(ix->qraw.p, d_queries, nq_l * len * 4, cudaMemcpyDeviceToDevice, st));
+    int rc = run_front(ix, nq_l, len, P, false, true);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ix->h_pin + 4, ix->q_pbase.as<unsigned long long>() + nq_l, 8, cudaMemcpyDeviceToHost, st));  // `rough` of the home queries
+    uint32_t* send = static_cast<uint32_t*>(d_send);
+    CU(cudaMemcpyAsync(send, ix->qraw.p, nq_l * len * 4, cudaMemcpyDeviceToDevice, st));
+    send += nq_l * len;
+    CU(cudaMemcpyAsync(send, ix->y.p, nq_l * D * 4, cudaMemcpyDeviceToDevice, st));
+    send += nq_l * D;
+    CU(cudaMemcpyAsync(send, ix->probe_ids.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
+    send += nq_l * (size_t)P;
+    CU(cudaMemcpyAsync(send, ix->probe_dist.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
+    send += nq_l * (size_t)P;
+    CU(cudaMemcpyAsync(send, ix->q_p0.p, nq_l * 4, cudaMemcpyDeviceToDevice, st));
+    if (tick(ix, ST_SELECT)) return RABITQ_ECUDA;
+    d.phase = 1;
+    return RABITQ_OK;
+}
+
+// Phase 2 (source): the whole batch's products -> local slots, query records, round 1 (first chunk of the nearest non-empty
+// cluster) on the shard that owns it; the round-1 threshold of every owned query lands in d_thr (others keep +FLT_MAX).
+int dist_round1_impl(rabitq_index* ix, const void* d_gathered, float* d_thr) {
+    if (!ix || !ix->dist.ready || ix->dist.phase != 1) return fail(RABITQ_EINVAL, "rabitq_dist_front first");
+    if (!d_gathered || !d_thr) return fail(RABITQ_EINVAL, "null argument");
+    DistState& d = ix->dist;
+    for (int r = 0; r < d.world; r++)
+        if (!d.peers_h[r]) return fail(RABITQ_EINVAL, "peer inbox of rank " + std::to_string(r) + " not set (rabitq_dist_set_peer)");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    const size_t nq = d.nq_l * d.world, D = ix->D;
+    const int P = d.P;
+    CU(ix->qpad.ensure(nq * D * 4));
+    CU(ix->y.ensure(nq * D * 4));
+    CU(ix->probe_ids.ensure(nq * P * 4));
+    CU(ix->probe_dist.ensure(nq * P * 4));
+    CU(ix->slot_local.ensure(nq * P * 4));
+    CU(ix->q_words.ensure(nq * 4));
+    CU(ix->q_pairs.ensure(nq * 4));
+    CU(ix->q_p0.ensure(nq * 4));
+    CU(ix->q_wbase.ensure((nq + 1) * 4));
+    CU(ix->q_pbase.ensure((nq + 1) * 8));
+    CU(ix->r2_cnt.ensure(nq * 4));
+    CU(ix->r2_off.ensure(nq * 4));
+    if (tick(ix, -1)) return RABITQ_ECUDA;  // the all-gather sits between the phases: not ours to time
+    dist_unpack_kernel<<<ix->sm_count * 8, 256, 0, st>>>(static_cast<const uint32_t*>(d_gathered), d.world, (int)d.nq_l, (int)d.len, (int)D, P,
+                                                          ix->qpad.as<float>(), ix->y.as<float>(), ix->probe_ids.as<uint32_t>(),
+                                                          ix->probe_dist.as<float>(), ix->q_p0.as<uint32_t>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    if (tick(ix, ST_H2D)) return RABITQ_ECUDA;
+    slot_layout_kernel<<<(unsigned)nq, SEL_THREADS, (size_t)P * 4, st>>>(ix->probe_ids.as<uint32_t>(), ix->offsets, P, ix->slot_local.as<uint32_t>(),
+                                                                          ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nq, ix->q_wbase.as<uint32_t>(),
+                                               ix->q_pbase.as<unsigned long long>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    BatchOut bo;
+    bo.P = P;
+    int rc = fetch_totals(ix, nq, &bo);
+    if (rc) return rc;
+    ix->counts[0] += bo.total_pairs;
+    if ((rc = run_quantize(ix, nq, P))) return rc;
+    if ((rc = setup_rounds(ix, nq, P, d.topk, &bo, &d.sa, &d.ra))) return rc;
+    fill_f32_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(d_thr, nq, 3.402823466e+38f);
+    CU(cudaGetLastError()); ix->counts[5]++;
+    d.d_thr = d_thr;
+    d.sa.thr = d_thr;
+    d.ra.thr = d_thr;
+    d.ra.peers = d.peers_d;
+    d.ra.off_r1cnt = d.off_r1cnt; d.ra.off_r1rec = d.off_r1rec; d.ra.off_r2rec = d.off_r2rec;
+    d.ra.r2_off = ix->r2_off.as<uint32_t>();
+    d.ra.r2_cnt = ix->r2_cnt.as<uint32_t>();
+    d.ra.world = d.world; d.ra.rank = d.rank; d.ra.nq_local = (int)d.nq_l; d.ra.r1cap = (int)d.r1cap; d.ra.cap2 = d.cap2;
+    const int fc = (int)(d.r1cap / SCAN_THREADS);
+    if ((rc = run_round_scan(ix, nq, P, d.sa, Pos{0, 0}, Pos{0, fc}, false))) return rc;
+    if ((rc = run_round_rerank(ix, nq, d.ra, Pos{0, 0}, Pos{0, fc}, true, false, false, ROUND_SINK1))) return rc;
+    d.phase = 2;
+    return RABITQ_OK;
+}
+
+// Phase 3 (source), after the all-reduce(min) of d_thr: everything after round 1, filtered with the frozen threshold; every
+// survivor's exact distance is computed here, next to its base row, and shipped to the home rank's inbox.
+int dist_round2_impl(rabitq_index* ix, uint32_t* d_status) {
+    if (!ix || !ix->dist.ready || ix->dist.phase != 2) return fail(RABITQ_EINVAL, "rabitq_dist_round1 first");
+    if (!d_status) return fail(RABITQ_EINVAL, "null argument");
+    DistState& d = ix->dist;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    const size_t nq = d.nq_l * d.world;
+    const int P = d.P, fc = (int)(d.r1cap / SCAN_THREADS);
+    if (tick(ix, -1)) return RABITQ_ECUDA;
+    CU(cudaMemsetAsync(d_status, 0, 4, st));
+    int rc = run_round_scan(ix, nq, P, d.sa, Pos{0, fc}, Pos{P, 0}, false);
+    if (rc) return rc;
+    r2_count_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(ix->bitmap.as<uint32_t>(), ix->q_wbase.as<uint32_t>(), ix->slot_local.as<uint32_t>(),
+                                                              ix->q_p0.as<uint32_t>(), (int)nq, P, 0, fc, ix->r2_cnt.as<uint32_t>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    r2_offsets_kernel<<<d.world, 1024, 0, st>>>(ix->r2_cnt.as<uint32_t>(), ix->r2_off.as<uint32_t>(), (int)d.nq_l, d.cap2, d.peers_d, d.off_r2tab,
+                                                 d.rank, d_status);
+    CU(cudaGetLastError()); ix->counts[5]++;
+    if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
+    if ((rc = run_round_rerank(ix, nq, d.ra, Pos{0, fc}, Pos{P, 0}, false, false, false, ROUND_SINK2))) return rc;
+    d.phase = 3;
+    return RABITQ_OK;
+}
+
+// Phase 4 (home), after a barrier that makes every shard's records visible: the sequential replay of the home queries.
+int dist_finish_impl(rabitq_index* ix, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count, uint32_t* d_status) {
+    if (!ix || !ix->dist.ready || ix->dist.phase != 3) return fail(RABITQ_EINVAL, "rabitq_dist_round2 first");
+    if (!d_out_dist || !d_out_ids || !d_out_count || !d_status) return fail(RABITQ_EINVAL, "null argument");
+    DistState& d = ix->dist;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    if (tick(ix, -1)) return RABITQ_ECUDA;
+    HomeArgs h;
+    h.inbox = d.inbox;
+    h.off_r1cnt = d.off_r1cnt; h.off_r1rec = d.off_r1rec; h.off_r2tab = d.off_r2tab; h.off_r2rec = d.off_r2rec;
+    h.probe_ids = ix->probe_ids.as<uint32_t>();
+    h.q_p0 = ix->q_p0.as<uint32_t>();
+    h.goffsets = ix->goffsets;
+    h.row_bounds = ix->row_bounds;
+    h.out_dist = d_out_dist; h.out_ids = d_out_ids; h.out_count = d_out_count;
+    h.counters = ix->counters.as<unsigned long long>();
+    h.status = d_status;
+    h.world = d.world; h.rank = d.rank; h.nq_l = (int)d.nq_l; h.P = d.P; h.topk = (int)d.topk; h.r1cap = (int)d.r1cap; h.cap2 = d.cap2;
+    CU(cudaMemsetAsync(ix->counters.as<unsigned long long>() + 2, 0, 8, st));  // [2] = precise of the HOME queries from here on
+    home_replay_kernel<<<(unsigned)((d.nq_l + 3) / 4), 128, 4 * 2 * d.topk * 4, st>>>(h);
+    CU(cudaGetLastError()); ix->counts[5]++;
+    if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
+    CU(cudaMemcpyAsync(ix->h_pin + 8, ix->counters.p, 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsigned long long c[4], rough_home;
+    std::memcpy(c, ix->h_pin + 8, 32);
+    std::memcpy(&rough_home, ix->h_pin + 4, 8);
+    ix->counts[1] += c[0];
+    ix->counts[2] += c[1];
+    ix->counts[3] += c[2];
+    ix->m_query += d.nq_l;
+    ix->m_rough += rough_home;
+    ix->m_precise += c[2];
+    d.phase = 0;
+    // timings: every phase restarts the event chain with a marker, so gaps spent in the caller's collectives are not counted
+    for (size_t i = 1; i < ix->ev_used; i++) {
+        if (ix->ev_stage[i] < 0) continue;
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, ix->ev_pool[i - 1], ix->ev_pool[i]));
+        ix->ms[ix->ev_stage[i]] += t;
+    }
+    if (ix->ev_used >= 2) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, ix->ev_pool[0], ix->ev_pool[ix->ev_used - 1]));
+        ix->ms[ST_TOTAL] = t;
+    }
+    return RABITQ_OK;
+}
+
 }  // namespace
 
 // ===================================================================================================================
 extern "C" {
+
+int rabitq_dist_init(rabitq_index* idx, int rank, int world, size_t nq_local, size_t probe, size_t topk, size_t records_per_query,
+                     size_t* inbox_bytes) {
+    int rc = dist_init_impl(idx, rank, world, nq_local, probe, topk, records_per_query);
+    if (rc == 0 && inbox_bytes) *inbox_bytes = idx->dist.inbox_bytes;
+    return rc;
+}
+
+int rabitq_dist_ipc_handle(rabitq_index* idx, unsigned char out_handle[64]) {
+    if (!idx || !idx->dist.ready || !out_handle) return fail(RABITQ_EINVAL, "rabitq_dist_init first");
+    CU(cudaSetDevice(idx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, idx->dist.inbox));
+    std::memcpy(out_handle, &h, 64);
+    return RABITQ_OK;
+}
+
+int rabitq_dist_inbox_ptr(rabitq_index* idx, void** out) {
+    if (!idx || !idx->dist.ready || !out) return fail(RABITQ_EINVAL, "rabitq_dist_init first");
+    *out = idx->dist.inbox;
+    return RABITQ_OK;
+}
+
+int rabitq_dist_set_peer(rabitq_index* idx, int peer_rank, const unsigned char* ipc_handle, void* raw_ptr) {
+    return dist_set_peer_impl(idx, peer_rank, ipc_handle, raw_ptr);
+}
+
+size_t rabitq_dist_chunk_words(const rabitq_index* idx, size_t len) {
+    if (!idx || !idx->dist.ready) return 0;
+    return dist_chunk_words(idx, idx->dist.nq_l, len, idx->dist.P);
+}
+
+int rabitq_dist_front(rabitq_index* idx, const float* d_queries, size_t len, void* d_send) { return dist_front_impl(idx, d_queries, len, d_send); }
+int rabitq_dist_round1(rabitq_index* idx, const void* d_gathered, float* d_thr) { return dist_round1_impl(idx, d_gathered, d_thr); }
+int rabitq_dist_round2(rabitq_index* idx, uint32_t* d_status) { return dist_round2_impl(idx, d_status); }
+int rabitq_dist_finish(rabitq_index* idx, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count, uint32_t* d_status) {
+    return dist_finish_impl(idx, d_out_dist, d_out_ids, d_out_count, d_status);
+}
+
+int rabitq_min_f32_device(int device, float* d_dst, const float* d_src, size_t n, void* cuda_stream) {
+    if (!d_dst || !d_src) return fail(RABITQ_EINVAL, "null argument");
+    if (n == 0) return RABITQ_OK;
+    CU(cudaSetDevice(device));
+    rq::min_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_dst, d_src, n);
+    CU(cudaGetLastError());
+    return RABITQ_OK;
+}
 
 const char* rabitq_last_error(void) { return g_err.c_str(); }
 
@@ -966,15 +1353,15 @@ int rabitq_shard_range(const uint32_t* offsets, size_t k, int shard_rank, int sh
 }
 
 int rabitq_merge_topk_device(int device, const float* d_dist, const uint32_t* d_ids, int n_lists, size_t nq, size_t topk,
-                             float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count) {
+                             float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count, void* cuda_stream) {
     if (!d_dist || !d_ids || !d_out_dist || !d_out_ids || !d_out_count || n_lists < 1 || topk == 0)
         return fail(RABITQ_EINVAL, "bad argument");
     if (nq == 0) return RABITQ_OK;
     CU(cudaSetDevice(device));
-    rq::merge_topk_kernel<<<(unsigned)((nq + 3) / 4), 128>>>(d_dist, d_ids, n_lists, nq, (int)topk, d_out_dist, d_out_ids, d_out_count);
+    rq::merge_topk_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_dist, d_ids, n_lists, nq, (int)topk,
+                                                                                                       d_out_dist, d_out_ids, d_out_count);
     CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());
-    return RABITQ_OK;
+    return RABITQ_OK;  // stream-ordered: the caller synchronises (or keeps launching on the same stream)
 }
 
 void rabitq_metrics(const rabitq_index* idx, uint64_t out[4]) {

@@ -231,7 +231,8 @@ def test_sharded_union_equals_full(pair):
     oc = torch.empty((q.shape[0],), dtype=torch.int32, device="cuda")
     import ctypes as C
     rc = rb.lib().rabitq_merge_topk_device(0, C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()), S, q.shape[0], topk,
-                                           C.c_void_p(od.data_ptr()), C.c_void_p(oi.data_ptr()), C.c_void_p(oc.data_ptr()))
+                                           C.c_void_p(od.data_ptr()), C.c_void_p(oi.data_ptr()), C.c_void_p(oc.data_ptr()),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0
     md = od.cpu().numpy()
     # Shard-local thresholds are looser than the global one, so the merged list can only be equal or better.
