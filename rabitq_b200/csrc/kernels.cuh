@@ -915,11 +915,8 @@ struct RerankArgs {
     // distributed record sink (template SINK != 0): records go straight into the inbox of the
     // query's HOME rank -- peer memory over NVLink (one process per GPU) or plain device memory (ranks in one process)
     unsigned char* const* peers;  // inbox base of every rank
-    size_t off_r1cnt, off_r1rec, off_r2rec;  // byte offsets inside an inbox (same layout on every rank)
-    const uint32_t* r2_off;       // per query: first record inside this shard's region of the home inbox
-    const uint32_t* r2_cnt;       // per query: records this shard will write (0xffffffff = region overflow: skip)
+    size_t off_r1cnt, off_r1rec;  // byte offsets inside an inbox (same layout on every rank)
     int world, rank, nq_local, r1cap;
-    uint32_t cap2;                // records per (home, source) region
 };
 
 // One reranked candidate as shipped to the query's home rank: everything HeapReRanker::rank_batch (src/rerank.rs:83-101)
@@ -981,9 +978,7 @@ RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, fl
 // accepted candidate is a result candidate and get_result keeps the topk smallest, which is what the k-slot buffer holds.
 // SINK = 0: single-GPU replay.  SINK = 1 (distributed round 1, run by the shard that owns the query's nearest non-empty
 // cluster): the same sequential replay, and every candidate the reference computes an exact distance for is also written
-// to the home rank's inbox.  SINK = 2 (distributed round 2): the threshold is FROZEN at the value the reference holds at
-// the end of round 1 (an upper bound of every later threshold), every survivor gets its exact distance and is shipped;
-// no heap, no sequential dependency -- the home rank replays the union in visit order (home_replay_kernel).
+// to the home rank's inbox.  (The distributed round 2 has no sequential dependency and is a flat kernel: r2_exact_kernel.)
 template <bool HEUR, int SINK>
 __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int ch_lo, int p_hi, int ch_hi, int first, int finalize) {
     extern __shared__ __align__(16) unsigned char rr_smem_raw[];
@@ -1002,18 +997,12 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     uint32_t* qj = reinterpret_cast<uint32_t*>(qr + 64);    // [2][32]
     float2* sent = reinterpret_cast<float2*>(qj + 64);      // [4][32] staged survivors
     uint32_t* stot = reinterpret_cast<uint32_t*>(sent + 128);  // [4]
-    uint32_t* qp = stot + 4;                                   // [2][32] probe rank of queued candidates (SINK == 2)
-    uint32_t* swd = qp + 64;                                   // [4][32] word of staged survivors (SINK == 2)
     const uint32_t lt_mask = (1u << lane) - 1u;
-    if constexpr (SINK == 2) {
-        const uint32_t c2 = a.r2_cnt[q];
-        if (c2 == 0u || c2 == 0xffffffffu) return;  // nothing to ship / flagged overflow
-    }
 
     if (lane == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
     // prologue: every independent global load is issued before the first dependent use (the kernel is a chain of
     // memory latencies; the fewer links the better)
-    int cnt = (first || SINK == 2) ? 0 : (int)a.heap_cnt[q];
+    int cnt = first ? 0 : (int)a.heap_cnt[q];
     float thr = first ? 3.402823466e+38f : a.thr[q];   // the filter threshold of the reranker
     float hmax = 3.402823466e+38f;                      // largest distance among the k kept results (when cnt == k)
     float recent = first ? -3.402823466e+38f : a.h_recent[q];
@@ -1041,8 +1030,6 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     uint32_t nrec = 0;
     if constexpr (SINK == 1)
         rdst = reinterpret_cast<SurvRec*>(a.peers[home] + a.off_r1rec) + ((size_t)a.rank * a.nq_local + ql) * a.r1cap;
-    if constexpr (SINK == 2)
-        rdst = reinterpret_cast<SurvRec*>(a.peers[home] + a.off_r2rec) + (size_t)a.rank * a.cap2 + a.r2_off[q];
     int maxpos = 0;
     for (int s = lane; s < cnt; s += 32) {
         hd[s] = a.heap_dist[(size_t)q * k + s];
@@ -1065,7 +1052,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
         const bool mine = lane < n;
         const float rough = mine ? qr[w * 32 + lane] : 0.0f;
         const uint32_t j = mine ? qj[w * 32 + lane] : 0u;
-        const uint32_t act = __ballot_sync(FULL, mine && rough < thr);  // SINK == 2: thr is frozen, every queued lane passes
+        const uint32_t act = __ballot_sync(FULL, mine && rough < thr);
         computed += n;
         if (act) {
             const float* rw = rows + (size_t)w * R * pitch;
@@ -1099,17 +1086,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                 const float res0 = __shfl_sync(FULL, acc0, src), res1 = __shfl_sync(FULL, acc1, src);
                 if ((lane >> 3) == (g >> 3)) exact = ((lane >> 2) & 1) ? res1 : res0;
             }
-            if constexpr (SINK == 2) {  // ship (rough, exact, id, rank) of the whole wave, visit order kept
-                if (mine) {
-                    SurvRec rec;
-                    rec.rough = rough; rec.exact = exact; rec.id = a.map_ids[j]; rec.p = qp[w * 32 + lane];
-                    rdst[nrec + lane] = rec;
-                }
-                nrec += n;
-                precise += n;
-            }
             // in-order replay (rerank.rs:83-101)
-            uint32_t rem = SINK == 2 ? 0u : act;
+            uint32_t rem = act;
             while (rem) {
                 const int t = __ffs(rem) - 1;
                 rem &= rem - 1;
@@ -1158,7 +1136,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
 
     // queue candidates in visit order; the row gather of each is issued right here, so it is in flight while the
     // stream continues and while the previous wave is being replayed
-    auto enqueue = [&](uint32_t pm, float rough, uint32_t j, uint32_t widx) {
+    auto enqueue = [&](uint32_t pm, float rough, uint32_t j) {
         while (pm) {
             const int space = R - fill;
             const int rank = __popc(pm & lt_mask);
@@ -1167,16 +1145,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                 const int slot = fill + rank;
                 qr[f * 32 + slot] = rough;
                 qj[f * 32 + slot] = j;
-                if constexpr (SINK == 2) {  // probe rank of the slot that holds word `widx`: the last p with slot_local[p] <= widx - wb
-                    const uint32_t* sl = a.slot_local + (size_t)q * a.P;
-                    const uint32_t rel = widx - wb;
-                    int lo = 0, hi = a.P;
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (sl[mid] <= rel) lo = mid; else hi = mid;
-                    }
-                    qp[f * 32 + slot] = (uint32_t)lo;
-                }
+
                 mbar_expect_tx(&mbar[f], rowbytes);
                 tma_bulk_g2s(rows + ((size_t)f * R + slot) * pitch, a.base + (size_t)j * D, rowbytes, &mbar[f]);
             }
@@ -1229,7 +1198,6 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                 ent[u] = make_float2(3.402823466e+38f, 0.0f);
                 if ((uint32_t)lane < T) ent[u] = a.entries[(size_t)(w0 + u * 32 + pos) * 32 + (lane - src_excl)];
                 if (lane == 0) stot[u] = T;
-                if constexpr (SINK == 2) swd[u * 32 + lane] = w0 + u * 32 + pos;
             }
 #pragma unroll
             for (int u = 0; u < SB; u++) sent[u * 32 + lane] = ent[u];
@@ -1241,7 +1209,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
             {
                 const float2 en = sent[u * 32 + lane];
                 const uint32_t pm = __ballot_sync(FULL, (uint32_t)lane < T && en.x < thr);
-                if (pm) enqueue(pm, en.x, __float_as_uint(en.y), SINK == 2 ? swd[u * 32 + lane] : 0u);
+                if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
             }
             if (T > 32) {  // dense block (loose threshold, e.g. the first probed cluster): further chunks on demand
                 const uint32_t idx = w0 + u * 32 + lane;
@@ -1267,7 +1235,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                     float2 en = make_float2(3.402823466e+38f, 0.0f);
                     if (have) en = a.entries[(size_t)(w0 + u * 32 + pos) * 32 + (e - src_excl)];
                     const uint32_t pm = __ballot_sync(FULL, have && en.x < thr);
-                    if (pm) enqueue(pm, en.x, __float_as_uint(en.y), w0 + u * 32 + pos);
+                    if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
                 }
             }
         }
@@ -1276,10 +1244,6 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     if (pend_n) process(f ^ 1, pend_n);
     if (fill) process(f, fill);
 
-    if constexpr (SINK == 2) {
-        if (lane == 0) atomicAdd(&a.counters[1], (unsigned long long)computed);
-        return;
-    }
     if constexpr (SINK == 1) {  // only the owner of the window has words; it tells the home rank how many records to replay
         if (lane == 0 && wlo < whi)
             reinterpret_cast<uint32_t*>(a.peers[home] + a.off_r1cnt)[(size_t)a.rank * a.nq_local + ql] = min(nrec, (uint32_t)a.r1cap);
@@ -1439,8 +1403,10 @@ __global__ void r2_count_kernel(const uint32_t* __restrict__ bitmap, const uint3
 // with larger regions by the host, never silently truncated.
 __global__ void __launch_bounds__(1024) r2_offsets_kernel(uint32_t* __restrict__ r2_cnt, uint32_t* __restrict__ r2_off, int nq_l, uint32_t cap2,
                                                           unsigned char* const* __restrict__ peers, size_t off_r2tab, int rank,
-                                                          uint32_t* __restrict__ status) {
+                                                          uint32_t* __restrict__ status, uint32_t* __restrict__ home_tot) {
     __shared__ uint32_t wtot[33];
+    __shared__ uint32_t s_eff;
+    if (threadIdx.x == 0) s_eff = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int home = blockIdx.x;
     uint32_t* cnt = r2_cnt + (size_t)home * nq_l;
@@ -1469,19 +1435,128 @@ __global__ void __launch_bounds__(1024) r2_offsets_kernel(uint32_t* __restrict__
         if (lane == 31) wtot[32] = wi;
     }
     __syncthreads();
-    uint32_t run = wtot[warp] + inc - s;
+    uint32_t run = wtot[warp] + inc - s, eff = 0;
     for (int i = lo; i < hi; i++) {
         const uint32_t c = cnt[i];
         off[i] = run;
-        if ((unsigned long long)run + c > cap2) {
-            cnt[i] = 0xffffffffu;
+        if ((unsigned long long)run + c > cap2) {  // the running offset only grows: every later query with records is flagged too,
+            cnt[i] = 0xffffffffu;                  // so the records that ARE shipped stay contiguous from the region start
             tab[i] = make_uint2(run, 0xffffffffu);
             atomicOr(status, 1u);
         } else {
             tab[i] = make_uint2(run, c);
+            eff += c;
         }
         run += c;
     }
+    if (eff) atomicAdd(&s_eff, eff);
+    __syncthreads();
+    if (tid == 0) home_tot[home] = s_eff;  // records this shard ships to `home` = length of its run in the flat candidate list
+}
+
+// Flat candidate list of the frozen round: (rough, row, query, probe rank) of every survivor, home-major, then query-major,
+// then visit order -- the order the records will have in the home inboxes.  One warp per query streams its survivor words.
+struct __align__(16) Cand {
+    float rough;
+    uint32_t j, q, p;
+};
+
+__global__ void r2_compact_kernel(const uint32_t* __restrict__ bitmap, const float2* __restrict__ entries, const uint32_t* __restrict__ q_wbase,
+                                  const uint32_t* __restrict__ slot_local, const uint32_t* __restrict__ q_p0, const uint32_t* __restrict__ r2_cnt,
+                                  const uint32_t* __restrict__ r2_off, const uint32_t* __restrict__ home_tot, int nq, int nq_l, int P,
+                                  int p_lo, int ch_lo, Cand* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const uint32_t c2 = r2_cnt[q];
+    if (c2 == 0u || c2 == 0xffffffffu) return;  // nothing to ship / flagged overflow
+    const int home = q / nq_l;
+    uint32_t base = r2_off[q];
+    for (int h = 0; h < home; h++) base += home_tot[h];
+    const uint32_t wb = q_wbase[q], wend = q_wbase[q + 1];
+    const uint32_t* sl = slot_local + (size_t)q * P;
+    const int p = p_lo + (int)q_p0[q];
+    uint32_t wlo = wend;
+    if (p < P) {
+        const uint32_t s0 = wb + sl[p], s1 = (p + 1 < P) ? wb + sl[p + 1] : wend;
+        wlo = min(s0 + (uint32_t)ch_lo * (SCAN_THREADS / 32), s1);
+    }
+    uint32_t run = 0;
+    for (uint32_t w0 = wlo; w0 < wend; w0 += 32) {
+        const uint32_t m = (w0 + lane < wend) ? bitmap[w0 + lane] : 0u;
+        const uint32_t pc = __popc(m);
+        uint32_t incl = pc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t T = __shfl_sync(FULL, incl, 31);
+        for (uint32_t e0 = 0; e0 < T; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            int pos = 0;  // first word whose inclusive prefix exceeds e
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const uint32_t pv = __shfl_sync(FULL, incl, pos + s - 1);
+                if (pv <= e) pos += s;
+            }
+            pos = min(pos, 31);
+            const uint32_t src_excl = __shfl_sync(FULL, incl - pc, pos);
+            if (e < T) {
+                const float2 en = entries[(size_t)(w0 + pos) * 32 + (e - src_excl)];
+                const uint32_t rel = w0 + pos - wb;  // probe rank of the slot holding this word: the last p with slot_local[p] <= rel
+                int lo = 0, hi = P;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sl[mid] <= rel) lo = mid; else hi = mid;
+                }
+                Cand c;
+                c.rough = en.x; c.j = __float_as_uint(en.y); c.q = (uint32_t)q; c.p = (uint32_t)lo;
+                out[(size_t)base + run + e] = c;
+            }
+        }
+        run += T;
+    }
+}
+
+// Exact squared L2 of every candidate of the flat list against its (unrotated, padded) query, in the order of
+// simd::l2_squared_distance (src/simd.rs:14-73): 8 lanes = the 8 AVX lanes, lane v walks elements v, v+8, ... with one
+// fused multiply-add each, then reduce_f32_256.  Load-balanced over candidates, not queries (survivor counts are skewed).
+// The result is stored straight into the inbox of the query's home rank: peer memory over NVLink when that is another GPU.
+__global__ void __launch_bounds__(256) r2_exact_kernel(const Cand* __restrict__ cand, const uint32_t* __restrict__ home_tot, int world,
+                                                       const float* __restrict__ qpad, const float* __restrict__ base,
+                                                       const uint32_t* __restrict__ map_ids, int D, int nq_l, int rank, uint32_t cap2,
+                                                       unsigned char* const* __restrict__ peers, size_t off_r2rec,
+                                                       unsigned long long* __restrict__ counters) {
+    uint32_t total = 0;
+    for (int h = 0; h < world; h++) total += home_tot[h];
+    const int v = threadIdx.x & 7, sub = (threadIdx.x & 31) >> 3;
+    const uint32_t groups = (gridDim.x * blockDim.x) >> 3;
+    for (uint32_t gb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2; gb < total; gb += groups) {  // warp-uniform trip count
+        const uint32_t g = gb + sub;
+        const bool act = g < total;
+        const Cand c = cand[act ? g : total - 1];
+        const float* row = base + (size_t)c.j * D;
+        const float* qr = qpad + (size_t)c.q * D;
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int d = v; d < D; d += 8) {
+            const float f = __fsub_rn(__ldg(&row[d]), __ldg(&qr[d]));
+            acc = fmaf(f, f, acc);
+        }
+        acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
+        acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
+        acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
+        if (v == 0 && act) {
+            const int home = (int)(c.q / (uint32_t)nq_l);
+            uint32_t hb = 0;
+            for (int h = 0; h < home; h++) hb += home_tot[h];
+            SurvRec rec;
+            rec.rough = c.rough; rec.exact = acc; rec.id = map_ids[c.j]; rec.p = c.p;
+            reinterpret_cast<SurvRec*>(peers[home] + off_r2rec)[(size_t)rank * cap2 + (g - hb)] = rec;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[1], (unsigned long long)total);
 }
 
 // Final replay on the HOME rank: HeapReRanker::rank_batch (src/rerank.rs:81-106) over the union of the records every shard
@@ -1521,7 +1596,11 @@ __global__ void __launch_bounds__(128) home_replay_kernel(HomeArgs a) {
     uint32_t precise = 0;
 
     auto replay = [&](const SurvRec& rec, int n) {  // lanes 0..n-1 hold consecutive records
-        for (int t = 0; t < n; t++) {
+        // the threshold only decreases: a record that fails `rough < thr` now fails it later too, so only these are visited
+        uint32_t rem = __ballot_sync(FULL, lane < n && rec.rough < thr);
+        while (rem) {
+            const int t = __ffs(rem) - 1;
+            rem &= rem - 1;
             const float r = __shfl_sync(FULL, rec.rough, t), ex = __shfl_sync(FULL, rec.exact, t);
             const uint32_t id = __shfl_sync(FULL, rec.id, t);
             if (r < thr) {            // rerank.rs:84

@@ -135,7 +135,7 @@ struct rabitq_index {
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, cl_count,
         cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
-        entries, counters, out_dist, out_ids, out_count, r2_cnt, r2_off;
+        entries, counters, out_dist, out_ids, out_count, r2_cnt, r2_off, home_tot, cand;
     DistState dist;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
     // metrics (src/metrics.rs)
@@ -160,7 +160,7 @@ struct rabitq_index {
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &qrec, &cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count,
-                          &r2_cnt, &r2_off})
+                          &r2_cnt, &r2_off, &home_tot, &cand})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         for (auto e : ev_pool) cudaEventDestroy(e);
@@ -229,7 +229,6 @@ int finish_index(rabitq_index* ix) {
     CU(cudaFuncSetAttribute(rerank_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(rerank_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(rerank_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(rerank_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     return 0;
 }
@@ -779,7 +778,7 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     // issued at enqueue time, so a wave's rows are usually resident before it is replayed.  When the batch is small enough
     // the wave is shrunk further until every query-warp is co-resident (one wave of CTAs instead of two).
     auto rr_smem = [&](int R) {
-        return (int)((16 + (size_t)D * 4 + (size_t)2 * R * (D + 8) * 4 + 2 * topk * 4 + 2 * 64 * 4 + 128 * 8 + 16 + 64 * 4 + 128 * 4 + 15) / 16 * 16);
+        return (int)((16 + (size_t)D * 4 + (size_t)2 * R * (D + 8) * 4 + 2 * topk * 4 + 2 * 64 * 4 + 128 * 8 + 16 + 15) / 16 * 16);
     };
     auto rr_warps_per_block = [&](int smem) { return smem > 12 * 1024 ? 1 : 4; };
     auto rr_resident = [&](int R) {
@@ -799,7 +798,7 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     return 0;
 }
 
-enum RoundKind { ROUND_REPLAY, ROUND_DENSE, ROUND_SINK1, ROUND_SINK2 };
+enum RoundKind { ROUND_REPLAY, ROUND_SINK1 };
 
 // inverted probe lists + work list + scan of one window [lo, hi) of visit positions
 int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos hi, bool dense) {
@@ -841,7 +840,6 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
     const size_t rsmem = (size_t)rr_wpb * ra.smem_per_warp;
     const int f = is_first ? 1 : 0, l = is_last ? 1 : 0;
     if (kind == ROUND_SINK1) rerank_kernel<false, 1><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
-    else if (kind == ROUND_SINK2) rerank_kernel<false, 2><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
     else if (heuristic) rerank_kernel<true, 0><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
     else rerank_kernel<false, 0><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
     CU(cudaGetLastError()); ix->counts[5]++;
@@ -1092,6 +1090,8 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered, float* d_thr) {
     CU(ix->q_pbase.ensure((nq + 1) * 8));
     CU(ix->r2_cnt.ensure(nq * 4));
     CU(ix->r2_off.ensure(nq * 4));
+    CU(ix->home_tot.ensure(32 * 4));
+    CU(ix->cand.ensure((size_t)d.world * d.cap2 * sizeof(Cand)));
     if (tick(ix, -1)) return RABITQ_ECUDA;  // the all-gather sits between the phases: not ours to time
     dist_unpack_kernel<<<ix->sm_count * 8, 256, 0, st>>>(static_cast<const uint32_t*>(d_gathered), d.world, (int)d.nq_l, (int)d.len, (int)D, P,
                                                           ix->qpad.as<float>(), ix->y.as<float>(), ix->probe_ids.as<uint32_t>(),
@@ -1117,10 +1117,8 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered, float* d_thr) {
     d.sa.thr = d_thr;
     d.ra.thr = d_thr;
     d.ra.peers = d.peers_d;
-    d.ra.off_r1cnt = d.off_r1cnt; d.ra.off_r1rec = d.off_r1rec; d.ra.off_r2rec = d.off_r2rec;
-    d.ra.r2_off = ix->r2_off.as<uint32_t>();
-    d.ra.r2_cnt = ix->r2_cnt.as<uint32_t>();
-    d.ra.world = d.world; d.ra.rank = d.rank; d.ra.nq_local = (int)d.nq_l; d.ra.r1cap = (int)d.r1cap; d.ra.cap2 = d.cap2;
+    d.ra.off_r1cnt = d.off_r1cnt; d.ra.off_r1rec = d.off_r1rec;
+    d.ra.world = d.world; d.ra.rank = d.rank; d.ra.nq_local = (int)d.nq_l; d.ra.r1cap = (int)d.r1cap;
     const int fc = (int)(d.r1cap / SCAN_THREADS);
     if ((rc = run_round_scan(ix, nq, P, d.sa, Pos{0, 0}, Pos{0, fc}, false))) return rc;
     if ((rc = run_round_rerank(ix, nq, d.ra, Pos{0, 0}, Pos{0, fc}, true, false, false, ROUND_SINK1))) return rc;
@@ -1147,10 +1145,19 @@ int dist_round2_impl(rabitq_index* ix, uint32_t* d_status) {
                                                               ix->q_p0.as<uint32_t>(), (int)nq, P, 0, fc, ix->r2_cnt.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
     r2_offsets_kernel<<<d.world, 1024, 0, st>>>(ix->r2_cnt.as<uint32_t>(), ix->r2_off.as<uint32_t>(), (int)d.nq_l, d.cap2, d.peers_d, d.off_r2tab,
-                                                 d.rank, d_status);
+                                                 d.rank, d_status, ix->home_tot.as<uint32_t>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    r2_compact_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(ix->bitmap.as<uint32_t>(), ix->entries.as<float2>(), ix->q_wbase.as<uint32_t>(),
+                                                                ix->slot_local.as<uint32_t>(), ix->q_p0.as<uint32_t>(), ix->r2_cnt.as<uint32_t>(),
+                                                                ix->r2_off.as<uint32_t>(), ix->home_tot.as<uint32_t>(), (int)nq, (int)d.nq_l, P, 0, fc,
+                                                                ix->cand.as<Cand>());
     CU(cudaGetLastError()); ix->counts[5]++;
     if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
-    if ((rc = run_round_rerank(ix, nq, d.ra, Pos{0, fc}, Pos{P, 0}, false, false, false, ROUND_SINK2))) return rc;
+    r2_exact_kernel<<<ix->sm_count * 8, 256, 0, st>>>(ix->cand.as<Cand>(), ix->home_tot.as<uint32_t>(), d.world, ix->qpad.as<float>(), ix->base,
+                                                      ix->map_ids, (int)ix->D, (int)d.nq_l, d.rank, d.cap2, d.peers_d, d.off_r2rec,
+                                                      ix->counters.as<unsigned long long>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
     d.phase = 3;
     return RABITQ_OK;
 }
@@ -1192,10 +1199,12 @@ int dist_finish_impl(rabitq_index* ix, float* d_out_dist, uint32_t* d_out_ids, u
     ix->m_precise += c[2];
     d.phase = 0;
     // timings: every phase restarts the event chain with a marker, so gaps spent in the caller's collectives are not counted
+    static const bool trace = std::getenv("RABITQ_TRACE") != nullptr;
     for (size_t i = 1; i < ix->ev_used; i++) {
-        if (ix->ev_stage[i] < 0) continue;
         float t = 0;
         CU(cudaEventElapsedTime(&t, ix->ev_pool[i - 1], ix->ev_pool[i]));
+        if (trace) std::fprintf(stderr, "[rabitq trace r%d] ev %2zu stage %2d  %.4f ms\n", d.rank, i, ix->ev_stage[i], t);
+        if (ix->ev_stage[i] < 0) continue;
         ix->ms[ix->ev_stage[i]] += t;
     }
     if (ix->ev_used >= 2) {
