@@ -162,7 +162,8 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
 
 /* Integer tuning knobs (results never depend on them; tests sweep them): "first_chunks" = 128-vector chunks of the nearest
  * cluster that form the first rerank round (default 1, 0 = whole cluster); "scan_mode" = carry-save depth of the scan's
- * popcount (0 plain, 1 = 3->2, 2 = 7->3 compressors, -1 = by dimension); "rerank_rows" = rows per rerank wave (0 = auto). */
+ * popcount (0 plain, 1 = 3->2, 2 = 7->3 compressors, -1 = by dimension); "rerank_rows" = rows per rerank wave (0 = auto); "scan_slices" = shared-memory record slices per scan
+ * work item (default 1; hot clusters are cut into several items). */
 int rabitq_set_option(rabitq_index* idx, const char* name, long value);
 
 /* Launch everything on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) so

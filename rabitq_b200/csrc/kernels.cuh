@@ -596,14 +596,19 @@ __global__ void bucket_count_kernel(const uint32_t* __restrict__ probe_ids, cons
     atomicAdd(&cl_count[probe_ids[q * P + p]], 1u);
 }
 
+// Work items of one cluster in one round: (chunks of VT vectors in the window) x (slices of at most MS of the m records
+// probing the cluster).  Slicing the records keeps the items of a hot cluster (many queries, e.g. on a shard that serves
+// the whole batch with few clusters) as small as everybody else's, so the persistent grid stays balanced.
 RQ_DEV uint32_t chunk_count(uint32_t m, uint32_t n_c, int VT, uint32_t ch_min, uint32_t ch_max) {
     if (!m) return 0;
     const uint32_t nch = min((n_c + VT - 1) / VT, ch_max);
     return nch > ch_min ? nch - ch_min : 0;
 }
+RQ_DEV uint32_t slice_count(uint32_t m, uint32_t MS) { return (m + MS - 1) / MS; }
+constexpr int WORK_SLICE_SHIFT = 20;  // work.y = chunk | slice << 20
 
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __restrict__ cl_count, const uint32_t* __restrict__ offsets,
-                                                           int K, int VT, uint32_t ch_min, uint32_t ch_max, uint32_t* __restrict__ cl_start,
+                                                           int K, int VT, uint32_t MS, uint32_t ch_min, uint32_t ch_max, uint32_t* __restrict__ cl_start,
                                                            uint32_t* __restrict__ item_start, uint32_t* __restrict__ cl_cursor,
                                                            uint32_t* __restrict__ work_ctl /* [0] counter, [1] n_work */) {
     __shared__ uint32_t wa[33], wb[33];
@@ -614,7 +619,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __res
     for (int c = lo; c < hi; c++) {
         uint32_t m = cl_count[c], n_c = offsets[c + 1] - offsets[c];
         sa += m;
-        sb += chunk_count(m, n_c, VT, ch_min, ch_max);
+        sb += chunk_count(m, n_c, VT, ch_min, ch_max) * slice_count(m, MS);
     }
     uint32_t ia = sa, ib = sb;
 #pragma unroll
@@ -642,7 +647,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __res
         item_start[c] = rb;
         cl_cursor[c] = 0;
         ra += m;
-        rb += chunk_count(m, n_c, VT, ch_min, ch_max);
+        rb += chunk_count(m, n_c, VT, ch_min, ch_max) * slice_count(m, MS);
     }
     if (tid == 0) {
         cl_start[K] = wa[32];
@@ -666,11 +671,17 @@ __global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, const
     cl_items[cl_start[c] + pos] = (uint32_t)(q * P + p);
 }
 
-__global__ void work_items_kernel(const uint32_t* __restrict__ item_start, int K, uint32_t ch_min, uint2* __restrict__ work) {
+__global__ void work_items_kernel(const uint32_t* __restrict__ item_start, const uint32_t* __restrict__ cl_count, int K, uint32_t MS,
+                                  uint32_t ch_min, uint2* __restrict__ work) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= K) return;
-    uint32_t s = item_start[c], e = item_start[c + 1];
-    for (uint32_t i = s; i < e; i++) work[i] = make_uint2((uint32_t)c, ch_min + i - s);
+    const uint32_t s = item_start[c], e = item_start[c + 1];
+    if (s == e) return;
+    const uint32_t nsl = slice_count(cl_count[c], MS);
+    for (uint32_t i = s; i < e; i++) {
+        const uint32_t local = i - s;
+        work[i] = make_uint2((uint32_t)c, (ch_min + local / nsl) | ((local % nsl) << WORK_SLICE_SHIFT));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -752,6 +763,7 @@ struct ScanArgs {
     unsigned long long* counters;  // [0] survivors
     int P;
     int QS;                     // records per shared-memory slice
+    uint32_t MS;                // records per work item (a multiple of QS)
     // this round = visit positions (probe rank, 128-vector chunk) in [lo, hi), lexicographic
     int p_lo, ch_lo, p_hi, ch_hi;
 };
@@ -779,10 +791,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
         const uint32_t item = s_item;
         if (item >= a.work_ctl[1]) break;
         const uint2 wk = a.work[item];
-        const uint32_t c = wk.x, chunk = wk.y;
+        const uint32_t c = wk.x, chunk = wk.y & ((1u << WORK_SLICE_SHIFT) - 1u), slice = wk.y >> WORK_SLICE_SHIFT;
         const uint32_t off = a.offsets[c], n_c = a.offsets[c + 1] - off;
         const uint32_t nwords = (n_c + 31u) >> 5;
-        const uint32_t it0 = a.cl_start[c], m = a.cl_start[c + 1] - it0;
+        const uint32_t it0 = a.cl_start[c], m_all = a.cl_start[c + 1] - it0;
+        const uint32_t m = min(m_all, (slice + 1u) * a.MS);  // this item's records: [slice * MS, m)
 
         uint32_t code[VPT][W32];
         float4 fac[VPT];
@@ -817,7 +830,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
             }
         }
 
-        for (uint32_t s0 = 0; s0 < m; s0 += a.QS) {
+        for (uint32_t s0 = slice * a.MS; s0 < m; s0 += a.QS) {
             const int ns = min((uint32_t)a.QS, m - s0);
             __syncthreads();
             for (int i = tid; i < ns * RS4; i += SCAN_THREADS) {
@@ -1009,6 +1022,12 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     uint32_t wcount = first ? 0u : a.h_wcount[q];
     const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
     const int p0 = (int)a.q_p0[q];
+    if constexpr (SINK == 0) {  // issued before the dependent window lookups below: one link less in the latency chain
+        const float4* src = reinterpret_cast<const float4*>(a.qpad + (size_t)q * D);
+        float4* dst = reinterpret_cast<float4*>(qv);
+#pragma unroll 8
+        for (int d = lane; d < D / 4; d += 32) dst[d] = __ldg(&src[d]);
+    }
     // word window of this round: from (p_lo, ch_lo) to (p_hi, ch_hi) in visit order; a chunk is 128 vectors = 4 words
     auto word_at = [&](int pe, int ch) -> uint32_t {  // pe = effective rank
         const int p = pe + p0;
@@ -1018,7 +1037,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
         return min(s0 + (uint32_t)ch * (SCAN_THREADS / 32), s1);
     };
     const uint32_t wlo = word_at(p_lo, ch_lo), whi = word_at(p_hi, ch_hi);
-    if (wlo < whi) {  // a query without candidates in this window (e.g. another shard owns them) skips the row-sized load
+    if (SINK != 0 && wlo < whi) {  // distributed: most queries have no candidates in this shard's round-1 window; skip the row-sized load
         const float4* src = reinterpret_cast<const float4*>(a.qpad + (size_t)q * D);
         float4* dst = reinterpret_cast<float4*>(qv);
 #pragma unroll 8
@@ -1097,8 +1116,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                 if (r < thr) {
                     precise++;
                     uint32_t mid = 0;
-                    if (lane == 0) mid = a.map_ids[ju];
                     if constexpr (SINK == 1) {
+                        if (lane == 0) mid = a.map_ids[ju];
                         if (lane == 0 && nrec < (uint32_t)a.r1cap) {
                             SurvRec rec;
                             rec.rough = r; rec.exact = ex; rec.id = mid; rec.p = (uint32_t)(p0 + p_lo);
@@ -1109,7 +1128,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                     if (ex < thr) {
                         if (!HEUR || cnt < k || ex < hmax) {
                             const int slot = cnt < k ? cnt : maxpos;
-                            if (lane == 0) { hd[slot] = ex; hid[slot] = mid; }
+                            if (lane == 0) { hd[slot] = ex; hid[slot] = SINK == 1 ? mid : a.map_ids[ju]; }
                             if (cnt < k) cnt++;
                             __syncwarp();
                             if (cnt == k) {
@@ -1324,28 +1343,52 @@ __global__ void merge_topk_kernel(const float* __restrict__ dist, const uint32_t
 // Distributed pipeline: the index is sharded by cluster range, every rank is the HOME of a
 // contiguous slice of the query batch (front end + final replay) and a SOURCE of survivor records for all queries.
 
-// After the all-gather of the per-rank front-end products.  `gathered` = world chunks, each
-//   [q: nq_l x len][y: nq_l x D][probe ids: nq_l x P][probe dist: nq_l x P][p0: nq_l]   (4-byte units)
-// -> flat per-query arrays over the whole batch (global query gq = rank * nq_l + i), queries zero-padded to D.
+// Layout of one rank's all-gather chunk (4-byte words, every section padded to 16 bytes):
+//   [q: nq_l x len][y: nq_l x D][probe ids: nq_l x P][probe dist: nq_l x P][p0: nq_l]
+struct DistChunk {
+    size_t o_q, o_y, o_ids, o_dist, o_p0, words;
+};
+__host__ __device__ inline DistChunk dist_chunk_layout(size_t nq_l, size_t len, size_t D, size_t P) {
+    auto up4 = [](size_t x) { return (x + 3) & ~(size_t)3; };
+    DistChunk c;
+    c.o_q = 0;
+    c.o_y = up4(c.o_q + nq_l * len);
+    c.o_ids = up4(c.o_y + nq_l * D);
+    c.o_dist = up4(c.o_ids + nq_l * P);
+    c.o_p0 = up4(c.o_dist + nq_l * P);
+    c.words = up4(c.o_p0 + nq_l);
+    return c;
+}
+
+// After the all-gather of the per-rank front-end products: `gathered` = world chunks -> flat per-query arrays over the
+// whole batch (global query gq = rank * nq_l + i), queries zero-padded to D.  One warp per query, 128-bit copies.
 __global__ void dist_unpack_kernel(const uint32_t* __restrict__ gathered, int world, int nq_l, int len, int D, int P,
                                    float* __restrict__ qpad, float* __restrict__ y, uint32_t* __restrict__ probe_ids,
                                    float* __restrict__ probe_dist, uint32_t* __restrict__ q_p0) {
-    const size_t per_q = (size_t)D + D + 2 * (size_t)P + 1;  // output words per query
-    const size_t chunk = (size_t)nq_l * ((size_t)len + D + 2 * (size_t)P + 1);
-    const size_t total = (size_t)world * nq_l * per_q;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t gq = i / per_q;
-        const int e = (int)(i % per_q);
-        const int r = (int)(gq / nq_l), ql = (int)(gq % nq_l);
-        const uint32_t* c = gathered + (size_t)r * chunk;
-        const uint32_t* sec_q = c, *sec_y = sec_q + (size_t)nq_l * len, *sec_i = sec_y + (size_t)nq_l * D;
-        const uint32_t* sec_d = sec_i + (size_t)nq_l * P, *sec_p0 = sec_d + (size_t)nq_l * P;
-        if (e < D) qpad[gq * D + e] = e < len ? __uint_as_float(sec_q[(size_t)ql * len + e]) : 0.0f;
-        else if (e < 2 * D) y[gq * D + (e - D)] = __uint_as_float(sec_y[(size_t)ql * D + (e - D)]);
-        else if (e < 2 * D + P) probe_ids[gq * P + (e - 2 * D)] = sec_i[(size_t)ql * P + (e - 2 * D)];
-        else if (e < 2 * D + 2 * P) probe_dist[gq * P + (e - 2 * D - P)] = __uint_as_float(sec_d[(size_t)ql * P + (e - 2 * D - P)]);
-        else q_p0[gq] = sec_p0[ql];
+    const int lane = threadIdx.x & 31;
+    const size_t gq = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gq >= (size_t)world * nq_l) return;
+    const DistChunk L = dist_chunk_layout(nq_l, len, D, P);
+    const int r = (int)(gq / nq_l), ql = (int)(gq % nq_l);
+    const uint32_t* c = gathered + (size_t)r * L.words;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(c + L.o_y + (size_t)ql * D);
+        uint4* dst = reinterpret_cast<uint4*>(y + gq * D);
+        for (int i = lane; i < D / 4; i += 32) dst[i] = src[i];
     }
+    if ((len & 3) == 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(c + L.o_q + (size_t)ql * len);
+        uint4* dst = reinterpret_cast<uint4*>(qpad + gq * D);
+        for (int i = lane; i < D / 4; i += 32) dst[i] = i < len / 4 ? src[i] : make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        const uint32_t* src = c + L.o_q + (size_t)ql * len;
+        for (int i = lane; i < D; i += 32) qpad[gq * D + i] = i < len ? __uint_as_float(src[i]) : 0.0f;
+    }
+    for (int i = lane; i < P; i += 32) {
+        probe_ids[gq * P + i] = c[L.o_ids + (size_t)ql * P + i];
+        probe_dist[gq * P + i] = __uint_as_float(c[L.o_dist + (size_t)ql * P + i]);
+    }
+    if (lane == 0) q_p0[gq] = c[L.o_p0 + ql];
 }
 
 // Survivor-slot layout of one shard for probe lists that were selected elsewhere: per (query, rank) the exclusive prefix

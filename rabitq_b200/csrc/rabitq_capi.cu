@@ -132,6 +132,7 @@ struct rabitq_index {
     std::vector<uint32_t> rounds{0};
     int rerank_rows = 0;   // rows per rerank wave; 0 = by dimension
     int first_chunks = 1;  // 128-vector chunks of the nearest cluster in the first round (0 = the whole cluster)
+    int scan_slices = 1;   // shared-memory record slices per scan work item (hot clusters are cut into several items)
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, cl_count,
         cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
@@ -223,6 +224,7 @@ int finish_index(rabitq_index* ix) {
     if (const char* e = std::getenv("RABITQ_SCAN_MODE")) ix->scan_mode = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_FIRST_CHUNKS")) ix->first_chunks = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("RABITQ_RR_ROWS")) ix->rerank_rows = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_SCAN_SLICES")) ix->scan_slices = std::max(1, std::atoi(e));
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     CU(cudaMallocHost((void**)&ix->h_pin, 256));
@@ -555,11 +557,16 @@ int dump_impl(rabitq_index* ix, const char* dir) {
 }
 
 // ---- scan launch ------------------------------------------------------------------------------------------------
+// records per shared-memory slice of the scan (24 KB of records, at most one per thread)
+int scan_qs(const rabitq_index* ix) {
+    const int W32 = (int)ix->D / 32, RS = 4 * ((W32 + 3) & ~3) + 8;
+    return std::max(8, std::min(24576 / (RS * 4), SCAN_THREADS));
+}
+
 template <int W32, bool DENSE, int MODE>
 int launch_scan_m(rabitq_index* ix, ScanArgs& a) {
     constexpr int RS = 4 * ((W32 + 3) & ~3) + 8;
-    int qs = 24576 / (RS * 4);
-    qs = std::max(8, std::min(qs, SCAN_THREADS));
+    const int qs = scan_qs(ix);
     a.QS = qs;
     size_t smem = (size_t)qs * (RS * 4 + 8);
     auto kern = scan_kernel<W32, 1, DENSE, MODE>;
@@ -714,7 +721,9 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     CU(ix->item_start.ensure((size_t)(K + 1) * 4));
     CU(ix->cl_cursor.ensure((size_t)K * 4));
     CU(ix->cl_items.ensure(nb * (size_t)P * 4));
-    const size_t max_items = ix->n / SCAN_THREADS + (size_t)K + 1;
+    // records per work item: `scan_slices` shared-memory slices, raised so that the slice index fits its 12 bits
+    const uint32_t MS = (uint32_t)std::max<size_t>((size_t)scan_qs(ix) * std::max(1, ix->scan_slices), (nb + 4094) / 4095);
+    const size_t max_items = ix->n / SCAN_THREADS + (size_t)K + 2 + ((size_t)bo->total_words / 4 + nb * (size_t)P) / MS;
     CU(ix->work.ensure(max_items * 8));
     CU(ix->work_ctl.ensure(16));
     CU(ix->thr.ensure(nb * 4));
@@ -748,6 +757,7 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     sa.counters = ix->counters.as<unsigned long long>();
     sa.P = P;
     sa.QS = 0;
+    sa.MS = MS;
 
     RerankArgs ra;
     std::memset(&ra, 0, sizeof(ra));
@@ -813,7 +823,7 @@ int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos
     bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
                                                                           ix->cl_count.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
-    bucket_scan_kernel<<<1, 1024, 0, st>>>(ix->cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, ch_min, ch_max,
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(ix->cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, sa.MS, ch_min, ch_max,
                                            ix->cl_start.as<uint32_t>(), ix->item_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
                                            ix->work_ctl.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
@@ -821,7 +831,8 @@ int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos
                                                                          ix->cl_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
                                                                          ix->cl_items.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
-    work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(ix->item_start.as<uint32_t>(), K, ch_min, ix->work.as<uint2>());
+    work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(ix->item_start.as<uint32_t>(), ix->cl_count.as<uint32_t>(), K, sa.MS, ch_min,
+                                                       ix->work.as<uint2>());
     CU(cudaGetLastError()); ix->counts[5]++;
     if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
     sa.p_lo = lo.p; sa.ch_lo = lo.ch; sa.p_hi = hi.p; sa.ch_hi = hi.ch;
@@ -963,7 +974,7 @@ int stage_prefix(rabitq_index* ix, const float* queries, size_t nq, size_t len, 
 
 
 // ---- distributed pipeline: phases between the caller's collectives ---------------------------------
-size_t dist_chunk_words(const rabitq_index* ix, size_t nq_l, size_t len, int P) { return nq_l * (len + ix->D + 2 * (size_t)P + 1); }
+size_t dist_chunk_words(const rabitq_index* ix, size_t nq_l, size_t len, int P) { return dist_chunk_layout(nq_l, len, ix->D, (size_t)P).words; }
 
 int dist_init_impl(rabitq_index* ix, int rank, int world, size_t nq_l, size_t probe, size_t topk, size_t records_per_query) {
     if (!ix) return fail(RABITQ_EINVAL, "null index");
@@ -1051,15 +1062,12 @@ int dist_front_impl(rabitq_index* ix, const float* d_queries, size_t len, void* 
     if (rc) return rc;
     CU(cudaMemcpyAsync(ix->h_pin + 4, ix->q_pbase.as<unsigned long long>() + nq_l, 8, cudaMemcpyDeviceToHost, st));  // `rough` of the home queries
     uint32_t* send = static_cast<uint32_t*>(d_send);
-    CU(cudaMemcpyAsync(send, ix->qraw.p, nq_l * len * 4, cudaMemcpyDeviceToDevice, st));
-    send += nq_l * len;
-    CU(cudaMemcpyAsync(send, ix->y.p, nq_l * D * 4, cudaMemcpyDeviceToDevice, st));
-    send += nq_l * D;
-    CU(cudaMemcpyAsync(send, ix->probe_ids.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
-    send += nq_l * (size_t)P;
-    CU(cudaMemcpyAsync(send, ix->probe_dist.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
-    send += nq_l * (size_t)P;
-    CU(cudaMemcpyAsync(send, ix->q_p0.p, nq_l * 4, cudaMemcpyDeviceToDevice, st));
+    const DistChunk L = dist_chunk_layout(nq_l, len, D, (size_t)P);
+    CU(cudaMemcpyAsync(send + L.o_q, ix->qraw.p, nq_l * len * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(send + L.o_y, ix->y.p, nq_l * D * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(send + L.o_ids, ix->probe_ids.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(send + L.o_dist, ix->probe_dist.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(send + L.o_p0, ix->q_p0.p, nq_l * 4, cudaMemcpyDeviceToDevice, st));
     if (tick(ix, ST_SELECT)) return RABITQ_ECUDA;
     d.phase = 1;
     return RABITQ_OK;
@@ -1093,7 +1101,7 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered, float* d_thr) {
     CU(ix->home_tot.ensure(32 * 4));
     CU(ix->cand.ensure((size_t)d.world * d.cap2 * sizeof(Cand)));
     if (tick(ix, -1)) return RABITQ_ECUDA;  // the all-gather sits between the phases: not ours to time
-    dist_unpack_kernel<<<ix->sm_count * 8, 256, 0, st>>>(static_cast<const uint32_t*>(d_gathered), d.world, (int)d.nq_l, (int)d.len, (int)D, P,
+    dist_unpack_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(static_cast<const uint32_t*>(d_gathered), d.world, (int)d.nq_l, (int)d.len, (int)D, P,
                                                           ix->qpad.as<float>(), ix->y.as<float>(), ix->probe_ids.as<uint32_t>(),
                                                           ix->probe_dist.as<float>(), ix->q_p0.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
@@ -1400,6 +1408,7 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     if (n == "first_chunks") idx->first_chunks = (int)std::max(0L, value);
     else if (n == "scan_mode") idx->scan_mode = (int)value;
     else if (n == "rerank_rows") idx->rerank_rows = (int)value;
+    else if (n == "scan_slices") idx->scan_slices = (int)std::max(1L, value);
     else return fail(RABITQ_EINVAL, "unknown option: " + n);
     return RABITQ_OK;
 }

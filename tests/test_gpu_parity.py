@@ -149,11 +149,11 @@ def test_rounds_do_not_change_results(pair, rounds):
 
 
 @pytest.mark.parametrize("opt,val", [("first_chunks", 0), ("first_chunks", 3), ("scan_mode", 0), ("scan_mode", 1), ("scan_mode", 2),
-                                     ("rerank_rows", 1), ("rerank_rows", 3), ("rerank_rows", 32)])
+                                     ("rerank_rows", 1), ("rerank_rows", 3), ("rerank_rows", 32), ("scan_slices", 2), ("scan_slices", 7)])
 def test_tuning_knobs_do_not_change_results(pair, opt, val):
     q = pair["queries"]
     g = pair["gpu"]
-    default = {"first_chunks": 1, "scan_mode": -1, "rerank_rows": 0}[opt]
+    default = {"first_chunks": 1, "scan_mode": -1, "rerank_rows": 0, "scan_slices": 1}[opt]
     g.set_option(opt, val)
     try:
         g.metrics_reset()
