@@ -166,6 +166,13 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
  * work item (default 1; hot clusters are cut into several items). */
 int rabitq_set_option(rabitq_index* idx, const char* name, long value);
 
+/* The reference's OTHER query quantiser.  On a host without AVX2, `scalar_quantize` falls back to
+ * `scalar_quantize_raw` (src/utils.rs:194-209): q = ((r - lo) * (1/delta) + rand_bias[i]) as u8 -- truncation plus a random
+ * bias drawn at load time (src/rabitq.rs:119, never persisted), instead of the AVX2 path's round-half-even without bias.
+ * `bias` = dim floats (host pointer) switches K3 to that formula with the caller's bias, so both sides can be given the same
+ * noise; NULL restores the AVX2 semantics (the default and the parity target). */
+int rabitq_set_quantize_bias(rabitq_index* idx, const float* bias);
+
 /* Launch everything on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) so
  * the caller can bracket calls with its own CUDA events; NULL restores the handle's private stream. */
 int rabitq_set_stream(rabitq_index* idx, void* cuda_stream);

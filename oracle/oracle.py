@@ -49,6 +49,8 @@ def lib():
     L.orc_from_arrays.restype = C.c_void_p
     L.orc_from_arrays.argtypes = [C.c_uint32, C.c_size_t, C.c_size_t, c_f32p, c_f32p, c_f32p, c_u32p, c_u32p, c_u64p, c_f32p]
     L.orc_free.argtypes = [C.c_void_p]
+    L.orc_set_raw_bias.argtypes = [C.c_void_p, c_f32p]
+    L.orc_set_raw_bias.restype = None
     L.orc_dim.restype = C.c_uint32
     L.orc_dim.argtypes = [C.c_void_p]
     for name in ("orc_n", "orc_k"):
@@ -136,6 +138,15 @@ class OracleIndex:
         return cls(lib().orc_from_arrays(dim, base.shape[0], centroids.shape[0], _p(base, c_f32p), _p(orthogonal, c_f32p),
                                          _p(centroids, c_f32p), _p(offsets, c_u32p), _p(map_ids, c_u32p),
                                          _p(codes, c_u64p), _p(factors, c_f32p)))
+
+    def set_raw_bias(self, bias) -> None:
+        """bias (dim floats): quantise queries with scalar_quantize_raw (src/utils.rs:194-209); None: the AVX2 branch."""
+        if bias is None:
+            lib().orc_set_raw_bias(self._h, None)
+        else:
+            b = _f32(bias).reshape(-1)
+            assert b.shape[0] == self.dim
+            lib().orc_set_raw_bias(self._h, _p(b, c_f32p))
 
     def dump_to_dir(self, path: str) -> None:
         os.makedirs(path, exist_ok=True)

@@ -325,6 +325,7 @@ struct Index {
     std::vector<float> orth_rows;   // D x D as stored on disk:        orth_rows[r*D + i] = P[r][i]
     std::vector<float> centroids;   // k x D, rotated, centroid c contiguous (faer D x K col-major)
     std::vector<float> rand_bias;   // D, only used by the non-AVX2 twin (rabitq.rs:119)
+    bool use_raw_quantize = false;  // true: scalar_quantize takes its non-AVX2 branch (utils.rs:222-228) with rand_bias
     std::vector<uint32_t> offsets;  // k+1
     std::vector<uint32_t> map_ids;  // n
     std::vector<uint64_t> x_binary_vec;  // n * D/64
@@ -736,7 +737,9 @@ size_t query_impl(const Index& ix, const float* query, size_t len, size_t probe,
         simd_min_max_residual(residual.data(), y.data(), &ix.centroids[i * D], D, &lower_bound, &upper_bound);
         float delta = (upper_bound - lower_bound) * SCALAR;     // rabitq.rs:307
         float one_over_delta = 1.0f / delta;                    // :308 recip()
-        uint32_t scalar_sum = simd_scalar_quantize(quantized.data(), residual.data(), D, lower_bound, one_over_delta);
+        uint32_t scalar_sum = ix.use_raw_quantize   // utils.rs:213-232: AVX2 host -> simd, otherwise the raw twin with the bias
+                                  ? raw_scalar_quantize(quantized.data(), residual.data(), ix.rand_bias.data(), D, lower_bound, one_over_delta)
+                                  : simd_scalar_quantize(quantized.data(), residual.data(), D, lower_bound, one_over_delta);
         std::fill(binary_vec.begin(), binary_vec.end(), 0);
         simd_vector_binarize_query(quantized.data(), D, binary_vec.data());
         if (tr) {
@@ -818,6 +821,13 @@ void* orc_from_arrays(uint32_t dim, size_t n, size_t k, const float* base, const
     return idx;
 }
 void orc_free(void* idx) { delete static_cast<Index*>(idx); }
+// bias != NULL: query() quantises like the reference on a host WITHOUT AVX2 (scalar_quantize_raw with this rand_bias);
+// NULL: back to the AVX2 branch.
+void orc_set_raw_bias(void* idx, const float* bias) {
+    Index* ix = static_cast<Index*>(idx);
+    ix->use_raw_quantize = bias != nullptr;
+    if (bias) ix->rand_bias.assign(bias, bias + ix->dim);
+}
 
 uint32_t orc_dim(const void* idx) { return static_cast<const Index*>(idx)->dim; }
 size_t orc_n(const void* idx) { return static_cast<const Index*>(idx)->n; }

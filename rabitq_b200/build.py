@@ -1,4 +1,4 @@
-"""In-tree nvcc build of librabitq_b200.so (sm_100a only) and of the C++ CLI twin.
+"""In-tree nvcc build of librabitq_b200.so (sm_100a only) and of the C++ CLI and HTTP-service twins.
 
 The shared library travels to the GPU box with the repo snapshot; nothing is JIT-compiled at run time.
 """
@@ -13,6 +13,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librabitq_b200.so")
 CLI = os.path.join(HERE, "rabitq_cli")
+SERVICE = os.path.join(HERE, "rabitq_service")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -52,6 +53,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if os.path.exists(cli_src) and (force or _stale(CLI, srcs + [LIB])):
         gxx = shutil.which("g++") or "g++"
         subprocess.check_call([gxx, "-O2", "-std=c++17", "-o", CLI, cli_src, "-I", os.path.join(ROOT, "include"),
+                               "-L", HERE, "-lrabitq_b200", "-Wl,-rpath,$ORIGIN"], cwd=ROOT)
+    svc_src = os.path.join(CSRC, "service.cpp")
+    if os.path.exists(svc_src) and (force or _stale(SERVICE, srcs + [LIB])):
+        gxx = shutil.which("g++") or "g++"
+        subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-o", SERVICE, svc_src, "-I", os.path.join(ROOT, "include"),
                                "-L", HERE, "-lrabitq_b200", "-Wl,-rpath,$ORIGIN"], cwd=ROOT)
     return LIB
 

@@ -511,7 +511,7 @@ template <int W32T>  // W32T > 0: D = 32*W32T held in registers (one pass over m
 __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__ y, const float* __restrict__ cent,
                                                        const uint32_t* __restrict__ probe_ids, const float* __restrict__ probe_dist,
                                                        const uint32_t* __restrict__ slot_local, const uint32_t* __restrict__ q_wbase,
-                                                       const uint32_t* __restrict__ offsets,
+                                                       const uint32_t* __restrict__ offsets, const float* __restrict__ bias,
                                                        uint32_t* __restrict__ qrec, int nq, int P, int D) {
     const int lane = threadIdx.x & 31;
     const size_t gw = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -546,7 +546,13 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
     const float inv = __fdiv_rn(1.0f, delta);                       // :308 recip()
     int sum = 0;
     auto emit = [&](int g, float r) {
-        int qi = cvtps_epi32(__fmul_rn(__fsub_rn(r, mn), inv));
+        int qi;
+        if (bias) {  // scalar_quantize_raw (src/utils.rs:194-209): `((v - lo) * mul + bias[i]) as u8` = truncate, saturate, NaN -> 0
+            const float f = __fadd_rn(__fmul_rn(__fsub_rn(r, mn), inv), __ldg(&bias[g * 32 + lane]));
+            qi = (f != f) ? 0 : (f <= 0.0f ? 0 : (f >= 255.0f ? 255 : (int)f));
+        } else {
+            qi = cvtps_epi32(__fmul_rn(__fsub_rn(r, mn), inv));
+        }
         sum += qi;  // i32 lanes wrap like _mm256_add_epi32
         uint32_t b0 = __ballot_sync(FULL, qi & 1), b1 = __ballot_sync(FULL, qi & 2);
         uint32_t b2 = __ballot_sync(FULL, qi & 4), b3 = __ballot_sync(FULL, qi & 8);

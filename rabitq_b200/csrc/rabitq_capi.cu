@@ -121,6 +121,7 @@ struct rabitq_index {
     float* P = nullptr;           // D x D rows
     float* cent = nullptr;        // K x D
     uint32_t* offsets = nullptr;  // K+1, local rows
+    float* quant_bias = nullptr;  // D: non-NULL switches K3 to the reference's non-AVX2 quantiser (rabitq_set_quantize_bias)
     uint32_t* goffsets = nullptr; // K+1, rows of the WHOLE index (equal to offsets on an unsharded handle)
     uint32_t* row_bounds = nullptr;  // shard_count+1, global rows where the shards begin
     uint32_t* map_ids = nullptr;  // n
@@ -153,7 +154,7 @@ struct rabitq_index {
     ~rabitq_index() {
         cudaSetDevice(device);
         for (void* p : {(void*)base, (void*)P, (void*)cent, (void*)offsets, (void*)goffsets, (void*)row_bounds, (void*)map_ids, (void*)codes,
-                        (void*)factors, (void*)dist.peers_d})
+                        (void*)factors, (void*)dist.peers_d, (void*)quant_bias})
             if (p) cudaFree(p);
         for (size_t r = 0; r < dist.peers_h.size(); r++)
             if (dist.opened[r] && dist.peers_h[r]) cudaIpcCloseMemHandle(dist.peers_h[r]);
@@ -694,7 +695,7 @@ int run_quantize(rabitq_index* ix, size_t nb, int P) {
     const unsigned qgrid = (unsigned)((warps + 3) / 4);
     const uint32_t* skip = ix->shard_count > 1 ? ix->offsets : nullptr;
 #define QUANT_ARGS ix->y.as<float>(), ix->cent, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), \
-                   ix->q_wbase.as<uint32_t>(), skip, ix->qrec.as<uint32_t>(), (int)nb, P, D
+                   ix->q_wbase.as<uint32_t>(), skip, ix->quant_bias, ix->qrec.as<uint32_t>(), (int)nb, P, D
     switch (W32) {
         case 2: quantize_kernel<2><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
         case 4: quantize_kernel<4><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
@@ -1410,6 +1411,21 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     else if (n == "rerank_rows") idx->rerank_rows = (int)value;
     else if (n == "scan_slices") idx->scan_slices = (int)std::max(1L, value);
     else return fail(RABITQ_EINVAL, "unknown option: " + n);
+    return RABITQ_OK;
+}
+
+int rabitq_set_quantize_bias(rabitq_index* idx, const float* bias) {
+    if (!idx) return fail(RABITQ_EINVAL, "null index");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CU(cudaSetDevice(idx->device));
+    CU(cudaStreamSynchronize(idx->stream));
+    if (!bias) {
+        if (idx->quant_bias) cudaFree(idx->quant_bias);
+        idx->quant_bias = nullptr;
+        return RABITQ_OK;
+    }
+    if (!idx->quant_bias) CU(cudaMalloc((void**)&idx->quant_bias, (size_t)idx->D * 4));
+    CU(cudaMemcpy(idx->quant_bias, bias, (size_t)idx->D * 4, cudaMemcpyHostToDevice));
     return RABITQ_OK;
 }
 

@@ -62,3 +62,17 @@ def test_no_gpu_means_loud_failure(rb, case_d128):
         rb.RaBitQ.from_arrays(a["dim"], a["base"], a["orthogonal"], a["centroids"], a["offsets"], a["map_ids"], a["codes"], a["factors"])
     assert e.value.code == 3  # RABITQ_ECUDA
     assert "no CPU fallback" in str(e.value)
+
+
+def test_service_and_cli_twins_fail_loudly_without_an_index():
+    """The host-side twins are built in-tree; without a loadable index (and, here, without a device) they exit non-zero
+    with the reference's panic text instead of serving anything."""
+    import subprocess
+
+    from rabitq_b200 import build as bld
+
+    bld.build()
+    r = subprocess.run([bld.SERVICE, "-d", "/nonexistent/dir", "-p", "0"], capture_output=True, text=True, timeout=30)
+    assert r.returncode != 0 and "orthogonal.fvecs" in r.stderr
+    r = subprocess.run([bld.SERVICE], capture_output=True, text=True, timeout=30)
+    assert r.returncode == 2 and "--dir is required" in r.stderr

@@ -366,3 +366,36 @@ def test_cli_twin_trains_saves_loads(case_d128, tmp_path):
     assert "loading from" in out2.stderr
     rec = float(out2.stderr.split("recall: ")[1].split()[0])
     assert rec >= 0.9
+
+
+def test_raw_quantiser_with_explicit_bias(pair):
+    """the reference's non-AVX2 quantiser (`scalar_quantize_raw`, src/utils.rs:194-209: truncate + rand_bias)
+    with the bias handed to both sides: planes, sums, rough distances and final results equal the oracle's raw branch."""
+    q = pair["queries"]
+    g, o = pair["gpu"], pair["oracle"]
+    rng = np.random.default_rng(123)
+    bias = rng.random(g.dim, dtype=np.float32)  # Uniform[0, 1), gen_random_bias (src/utils.rs:36-40)
+    probe = 12
+    avx_planes = g.stage_quantize(q, probe)[3]
+    g.set_quantize_bias(bias)
+    o.set_raw_bias(bias)
+    try:
+        lo, delta, s, planes = g.stage_quantize(q, probe)
+        assert not np.array_equal(planes, avx_planes)  # it really is a different rounding
+        for i in range(q.shape[0]):
+            tr = o.trace(q[i], probe, 10)
+            assert np.array_equal(s[i], tr["sum"])
+            assert np.array_equal(planes[i], tr["planes"])
+            assert np.array_equal(lo[i].view(np.uint32), tr["lo"].view(np.uint32))
+        g.metrics_reset()
+        gd, gi, gc = g.query_batch(q, 24, 10)
+        r = o.query_batch(q, 24, 10)
+        for i in range(q.shape[0]):
+            c = int(gc[i])
+            assert _same_up_to_ties(pair, i, gd[i, :c], gi[i, :c], r["dist"][i, :c], r["ids"][i, :c]), f"query {i}"
+        assert g.metrics()["precise"] == r["precise"]
+    finally:
+        g.set_quantize_bias(None)
+        o.set_raw_bias(None)
+    # back on the AVX2 semantics
+    assert np.array_equal(g.stage_quantize(q, probe)[3], avx_planes)

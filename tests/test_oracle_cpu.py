@@ -259,3 +259,28 @@ def test_heuristic_reranker_runs(case_d128):
     q = case_d128["queries"][:8]
     r = case_d128["oracle"].query_batch(q, 16, 10, heuristic_rank=True)
     assert np.all(r["count"] == 10)
+
+
+def test_raw_bias_switch_changes_only_the_quantiser(oracle_lib):
+    """orc_set_raw_bias: the query path takes scalar_quantize's non-AVX2 branch (src/utils.rs:194-209); with bias = 0.5 the
+    truncation rounds half UP, so it differs from the AVX2 branch exactly where (r - lo) / delta sits on a .5 tie or where
+    round-half-even and truncate(+0.5) disagree -- and nowhere else."""
+    from tools import synth
+
+    base, queries, cent = synth.make_numpy(3000, 64, 8, 12, "sift", 77)
+    ix = oracle_lib.OracleIndex.from_arrays(base, cent, seed=3, nthreads=2)
+    a = ix.trace(queries[0], 4, 5)
+    ix.set_raw_bias(np.full(ix.dim, 0.5, np.float32))
+    b = ix.trace(queries[0], 4, 5)
+    ix.set_raw_bias(None)
+    c = ix.trace(queries[0], 4, 5)
+    assert np.array_equal(a["planes"], c["planes"]) and np.array_equal(a["sum"], c["sum"])
+    assert np.array_equal(a["lo"], b["lo"]) and np.array_equal(a["delta"], b["delta"])
+    qa, qb = a["quantized"].astype(np.int32), b["quantized"].astype(np.int32)
+    assert np.all(np.abs(qa - qb) <= 1)   # half-even vs half-up: at most one step apart, and only on ties
+    # the raw twin itself, element by element
+    v = np.array([0.0, 0.49, 0.5, 1.5, 2.5, 14.99, 15.0, 300.0, -3.0, np.nan], np.float32)
+    out = np.zeros(len(v), np.uint8)
+    s = oracle_lib.lib().orc_scalar_quantize_raw(out.ctypes.data_as(oracle_lib.c_u8p), v.ctypes.data_as(oracle_lib.c_f32p),
+                                                 np.full(len(v), 0.5, np.float32).ctypes.data_as(oracle_lib.c_f32p), len(v), 0.0, 1.0)
+    assert out.tolist() == [0, 0, 1, 2, 3, 15, 15, 255, 0, 0] and s == sum(out.tolist())
