@@ -307,8 +307,13 @@ def run_ours(args):
                          dtype=torch.float64, device=device)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         pairs_all = float(c[0])
+        per_rank = torch.zeros((world, 3), dtype=torch.float64, device=device)
+        mine = torch.tensor([counts["pairs"] / args.steps, stage_ms["scan"] / args.steps, stage_ms["total"] / args.steps], dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(per_rank.view(-1), mine)
+        per_rank = per_rank.cpu().tolist()
     else:
         pairs_all = float(counts["pairs"])
+        per_rank = None
 
     if rank == 0:
         bytes_per_pair = D // 8 + 16  # packed code + Factor
@@ -347,6 +352,9 @@ def run_ours(args):
                                   "exact_computed": counts["exact_computed"] // args.steps, "precise": counts["precise"] // args.steps},
             "clocks": clocks,
         }
+        if per_rank:
+            out["per_rank"] = {"pairs": [int(r[0]) for r in per_rank], "scan_ms": [round(r[1], 4) for r in per_rank],
+                               "busy_ms": [round(r[2], 4) for r in per_rank]}
         if not args.no_cpu and world >= 1:
             out["cpu_baseline"] = cpu_baseline(wl, probe, threads=1, budget_s=args.cpu_seconds)
         emit_json(out)

@@ -163,7 +163,10 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
 /* Integer tuning knobs (results never depend on them; tests sweep them): "first_chunks" = 128-vector chunks of the nearest
  * cluster that form the first rerank round (default 1, 0 = whole cluster); "scan_mode" = carry-save depth of the scan's
  * popcount (0 plain, 1 = 3->2, 2 = 7->3 compressors, -1 = by dimension); "rerank_rows" = rows per rerank wave (0 = auto); "scan_slices" = shared-memory record slices per scan
- * work item (default 1; hot clusters are cut into several items). */
+ * work item (default 1; hot clusters are cut into several items); "prefilter" = 1 (default) lets the centroid scan run as a
+ * TF32 tensor-core prefilter + exact recheck of the candidates when k >= 512 and probe <= k/8 (probe lists stay bit-identical),
+ * 0 = always all k exact distances; "prefilter_cap" = candidates per query the prefilter may certify (<= 1024; a query
+ * above it sends its batch to the exact path on the device). */
 int rabitq_set_option(rabitq_index* idx, const char* name, long value);
 
 /* The reference's OTHER query quantiser.  On a host without AVX2, `scalar_quantize` falls back to

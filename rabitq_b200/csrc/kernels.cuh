@@ -146,8 +146,12 @@ constexpr int CD_THREADS = CD_TC * CD_QG;
 constexpr int CD_DCH = 64;
 constexpr int CD_PITCH = CD_DCH + 4;
 
+// `run_if`: NULL = always; otherwise the kernel runs only when *run_if != 0 (the device-side fallback of the tensor-core
+// prefilter, prefilter.cuh: no host round trip decides whether the classic path is needed).
 __global__ void __launch_bounds__(CD_THREADS, 2) centroid_dist_kernel(const float* __restrict__ cent, const float* __restrict__ y,
-                                                                      float* __restrict__ out, int nq, int K, int D) {
+                                                                      float* __restrict__ out, int nq, int K, int D,
+                                                                      const uint32_t* __restrict__ run_if) {
+    if (run_if && *run_if == 0u) return;
     __shared__ __align__(16) float sc[CD_TC][CD_PITCH];
     __shared__ float4 sy[CD_QG * CD_TQ][CD_DCH / 4];
     const int tid = threadIdx.x;
@@ -251,7 +255,9 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
                                                                    const uint32_t* __restrict__ offsets_g,
                                                                    uint32_t* __restrict__ probe_ids, float* __restrict__ probe_dist,
                                                                    uint32_t* __restrict__ slot_local, uint32_t* __restrict__ q_words,
-                                                                   uint32_t* __restrict__ q_pairs, uint32_t* __restrict__ q_p0) {
+                                                                   uint32_t* __restrict__ q_pairs, uint32_t* __restrict__ q_p0,
+                                                                   const uint32_t* __restrict__ run_if) {
+    if (run_if && *run_if == 0u) return;
     extern __shared__ unsigned long long sel_buf[];  // Ppow2 (key,index) pairs, then (optionally) the K keys of this query
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_bucket, s_need, s_nout, s_p0;

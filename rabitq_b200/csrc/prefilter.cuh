@@ -1,0 +1,359 @@
+// prefilter.cuh -- tensor-core prefilter for the centroid scan + probe selection (src/rabitq.rs:283-297).
+//
+// The reference computes all K exact fp32 distances ||c - y||^2 per query (simd::l2_squared_distance, src/simd.rs:14-73)
+// and keeps the `probe` nearest.  The probe LIST must be exactly the reference's (the quantised query planes depend on it),
+// but that only needs exact distances for the centroids that can be among the `probe` nearest.  So:
+//   1. approximate keys  A[q][c] = ||c'||^2 - 2 <y', c'>  with y' = y - mu, c' = c - mu (mu = mean centroid: distances are
+//      translation invariant and centring shrinks the norms the error bound scales with), the inner products on the tensor
+//      cores in TF32 (operands rounded to TF32 once, fp32 accumulation);
+//   2. a RIGOROUS bound  |A[q][c] + ||y'||^2 - e[q][c]| <= m[q][c] = 2^-8 ||y'|| ||c'|| + 2^-14 (||y'|| + ||c'||)^2  on the
+//      difference to the reference's fp32 value e (TF32 operand rounding 2 * 2^-11, tensor-core accumulation <= D 2^-23,
+//      fp32 evaluation of the reference formula <= (D/8 + 4) 2^-24, each with >= 1.6x slack; D <= 2048);
+//   3. per query: a threshold tau with #{c : A_c <= tau} >= probe (256-bin histogram of the keys, verified by an exact
+//      count), candidates = {c : A_c - m_c <= tau + max_c m_c} -- a superset of the reference's probe set, ties included --
+//      EXACT distances for the candidates only, in the reference's AVX order, then the `probe` smallest by (distance, id).
+// The output is bit-identical to centroid_dist_kernel + select_probe_kernel; a query whose candidate set overflows raises a
+// flag and the batch is redone on that classic path.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace rq {
+
+RQ_DEV float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ---- index side: mu, c' = tf32(c - mu), ||c'||, ||c'||^2 ------------------------------------------------------------------
+__global__ void centroid_mean_kernel(const float* __restrict__ cent, int K, int D, float* __restrict__ mu) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    double s = 0.0;
+    for (int c = 0; c < K; c++) s += (double)cent[(size_t)c * D + d];
+    mu[d] = (float)(s / (double)K);
+}
+
+__global__ void centroid_center_kernel(const float* __restrict__ cent, const float* __restrict__ mu, int K, int D, float* __restrict__ chat,
+                                       float* __restrict__ cnorm, float* __restrict__ cnorm2, float* __restrict__ cnorm_max) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= K) return;
+    double s = 0.0;
+    for (int d = lane; d < D; d += 32) {
+        const float v = __fsub_rn(cent[(size_t)c * D + d], mu[d]);
+        chat[(size_t)c * D + d] = to_tf32(v);
+        s += (double)v * (double)v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) {
+        const float n2 = (float)s, n = (float)sqrt(s) * 1.0000005f;  // norm rounded UP: it only ever enters upper bounds
+        cnorm2[c] = n2;
+        cnorm[c] = n;
+        atomicMax(reinterpret_cast<int*>(cnorm_max), __float_as_int(n));  // non-negative floats order like ints
+    }
+}
+
+// ---- query side: y^ = tf32(y - mu), ||y - mu|| -----------------------------------------------------------------------------
+__global__ void query_center_kernel(const float* __restrict__ y, const float* __restrict__ mu, int nq, int D, float* __restrict__ yhat,
+                                    float* __restrict__ ynorm) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    float s = 0.0f;
+    for (int d = lane; d < D; d += 32) {
+        const float v = __fsub_rn(y[(size_t)q * D + d], mu[d]);
+        yhat[(size_t)q * D + d] = to_tf32(v);
+        s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) ynorm[q] = __fsqrt_ru(s) * 1.00001f;  // rounded up (32-term fp32 sum: relative error << 1e-5)
+}
+
+// ---- A[q][c] = ||c'||^2 - 2 <y^, c^> on the tensor cores (mma.sync m16n8k8 TF32, fp32 accumulate) ----------------------------
+// CTA tile BM queries x BN centroids, K-chunks of 32 staged in shared memory with cp.async (2 stages); every warp owns a
+// (BM/WM) x (BN/WN) sub-tile.  Both operands are d-contiguous ("K-major"); rows are padded to 36 floats so that the 8 x 4
+// lanes of a fragment load hit 32 different banks.
+constexpr int PF_BK = 32;
+constexpr int PF_PITCH = PF_BK + 4;
+
+RQ_DEV void cp_async16(void* smem, const void* gmem, bool pred) {
+    const uint32_t s = smem_u32(smem);
+    const int bytes = pred ? 16 : 0;  // src-size 0: zero-fill (rows past the end)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+
+template <int BM, int BN, int WM, int WN>
+__global__ void __launch_bounds__(WM * WN * 32) approx_gemm_tf32_kernel(const float* __restrict__ yhat, const float* __restrict__ chat,
+                                                                        const float* __restrict__ cnorm2, int nq, int K, int D,
+                                                                        float* __restrict__ A) {
+    constexpr int THREADS = WM * WN * 32;
+    constexpr int TM = BM / WM / 16, TN = BN / WN / 8;  // mma tiles per warp
+    extern __shared__ __align__(16) float pf_smem[];
+    float* sA = pf_smem;                              // [2][BM][PITCH]
+    float* sB = pf_smem + 2 * BM * PF_PITCH;          // [2][BN][PITCH]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WN, wn = warp % WN;
+    const int g = lane >> 2, t = lane & 3;
+    const int q0 = blockIdx.y * BM, c0 = blockIdx.x * BN;
+    float acc[TM][TN][4];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[i][j][e] = 0.0f;
+
+    auto load_stage = [&](int stage, int d0) {
+        float* a = sA + stage * BM * PF_PITCH;
+        float* b = sB + stage * BN * PF_PITCH;
+        for (int i = tid; i < BM * (PF_BK / 4); i += THREADS) {
+            const int row = i / (PF_BK / 4), c4 = i % (PF_BK / 4);
+            const bool ok = q0 + row < nq;
+            cp_async16(a + row * PF_PITCH + c4 * 4, yhat + (size_t)(ok ? q0 + row : 0) * D + d0 + c4 * 4, ok);
+        }
+        for (int i = tid; i < BN * (PF_BK / 4); i += THREADS) {
+            const int row = i / (PF_BK / 4), c4 = i % (PF_BK / 4);
+            const bool ok = c0 + row < K;
+            cp_async16(b + row * PF_PITCH + c4 * 4, chat + (size_t)(ok ? c0 + row : 0) * D + d0 + c4 * 4, ok);
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+
+    const int nk = D / PF_BK;
+    load_stage(0, 0);
+    for (int kb = 0; kb < nk; kb++) {
+        if (kb + 1 < nk) {
+            load_stage((kb + 1) & 1, (kb + 1) * PF_BK);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncthreads();
+        const float* a = sA + (kb & 1) * BM * PF_PITCH + (wm * TM * 16) * PF_PITCH;
+        const float* b = sB + (kb & 1) * BN * PF_PITCH + (wn * TN * 8) * PF_PITCH;
+#pragma unroll
+        for (int k8 = 0; k8 < PF_BK; k8 += 8) {
+            uint32_t af[TM][4], bf[TN][2];
+#pragma unroll
+            for (int i = 0; i < TM; i++) {
+                const float* p = a + (i * 16 + g) * PF_PITCH + k8 + t;
+                af[i][0] = __float_as_uint(p[0]);
+                af[i][1] = __float_as_uint(p[8 * PF_PITCH]);
+                af[i][2] = __float_as_uint(p[4]);
+                af[i][3] = __float_as_uint(p[8 * PF_PITCH + 4]);
+            }
+#pragma unroll
+            for (int j = 0; j < TN; j++) {
+                const float* p = b + (j * 8 + g) * PF_PITCH + k8 + t;
+                bf[j][0] = __float_as_uint(p[0]);
+                bf[j][1] = __float_as_uint(p[4]);
+            }
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++)
+                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(acc[i][j][0]), "+f"(acc[i][j][1]), "+f"(acc[i][j][2]), "+f"(acc[i][j][3])
+                                 : "r"(af[i][0]), "r"(af[i][1]), "r"(af[i][2]), "r"(af[i][3]), "r"(bf[j][0]), "r"(bf[j][1]));
+        }
+        __syncthreads();
+    }
+    // epilogue: A = ||c'||^2 - 2 S   (c fragment: rows g / g+8, columns 2t / 2t+1)
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+            const int c = c0 + wn * TN * 8 + j * 8 + 2 * t;
+            const int qa = q0 + wm * TM * 16 + i * 16 + g, qb = qa + 8;
+            const float n0 = c < K ? __ldg(&cnorm2[c]) : 0.0f, n1 = c + 1 < K ? __ldg(&cnorm2[c + 1]) : 0.0f;
+            if (c + 1 < K && (K & 1) == 0) {
+                if (qa < nq) *reinterpret_cast<float2*>(A + (size_t)qa * K + c) = make_float2(n0 - 2.0f * acc[i][j][0], n1 - 2.0f * acc[i][j][1]);
+                if (qb < nq) *reinterpret_cast<float2*>(A + (size_t)qb * K + c) = make_float2(n0 - 2.0f * acc[i][j][2], n1 - 2.0f * acc[i][j][3]);
+            } else {
+                if (c < K) {
+                    if (qa < nq) A[(size_t)qa * K + c] = n0 - 2.0f * acc[i][j][0];
+                    if (qb < nq) A[(size_t)qb * K + c] = n0 - 2.0f * acc[i][j][2];
+                }
+                if (c + 1 < K) {
+                    if (qa < nq) A[(size_t)qa * K + c + 1] = n1 - 2.0f * acc[i][j][1];
+                    if (qb < nq) A[(size_t)qb * K + c + 1] = n1 - 2.0f * acc[i][j][3];
+                }
+            }
+        }
+}
+
+// ---- per query: threshold, candidates, exact distances of the candidates, the P nearest by (distance, id) --------------------
+constexpr int PS_THREADS = 256;
+constexpr int PS_CAP = 1024;  // candidate capacity
+
+RQ_DEV float margin(float yn, float cn) {
+    const float s = __fadd_ru(yn, cn);
+    return __fadd_ru(__fmul_ru(__fmul_ru(yn, cn), 0.00390625f), __fmul_ru(__fmul_ru(s, s), 6.103515625e-05f));  // 2^-8, 2^-14
+}
+
+__global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
+    const float* __restrict__ A, const float* __restrict__ ynorm, const float* __restrict__ cnorm, const float* __restrict__ cnorm_max,
+    const float* __restrict__ y, const float* __restrict__ cent, int K, int P, int D, const uint32_t* __restrict__ offsets,
+    const uint32_t* __restrict__ offsets_g, uint32_t* __restrict__ probe_ids, float* __restrict__ probe_dist,
+    uint32_t* __restrict__ slot_local, uint32_t* __restrict__ q_words, uint32_t* __restrict__ q_pairs, uint32_t* __restrict__ q_p0,
+    uint32_t* __restrict__ fallback_flag, int cap /* <= PS_CAP; tests lower it to exercise the fallback */) {
+    extern __shared__ __align__(16) unsigned char ps_smem_raw[];
+    float* sy = reinterpret_cast<float*>(ps_smem_raw);                            // D
+    uint32_t* cid = reinterpret_cast<uint32_t*>(sy + D);                          // PS_CAP candidate ids
+    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(cid + PS_CAP);  // PS_CAP (okey(exact) << 32 | id)
+    uint32_t* words = reinterpret_cast<uint32_t*>(ckey + PS_CAP);                 // P
+    __shared__ uint32_t hist[256];
+    __shared__ float s_red[2 * (PS_THREADS / 32)];
+    __shared__ uint32_t s_ncand, s_nle, s_p0, s_pairs;
+    __shared__ uint32_t warp_tot[PS_THREADS / 32 + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t q = blockIdx.x;
+    const float* row = A + q * (size_t)K;
+    const float yn = ynorm[q], mmax = margin(yn, cnorm_max[0]);
+
+    for (int d = tid; d < D; d += PS_THREADS) sy[d] = y[q * (size_t)D + d];
+    // pass 1: range of the keys
+    float kmin = 3.402823466e+38f, kmax = -3.402823466e+38f;
+    for (int i = tid; i < K; i += PS_THREADS) {
+        const float v = __ldg(&row[i]);
+        kmin = fminf(kmin, v);
+        kmax = fmaxf(kmax, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = fminf(kmin, __shfl_xor_sync(FULL, kmin, o));
+        kmax = fmaxf(kmax, __shfl_xor_sync(FULL, kmax, o));
+    }
+    if (lane == 0) { s_red[warp] = kmin; s_red[PS_THREADS / 32 + warp] = kmax; }
+    hist[tid] = 0;
+    if (tid == 0) { s_p0 = 0xffffffffu; s_pairs = 0; }
+    __syncthreads();
+    kmin = s_red[0]; kmax = s_red[PS_THREADS / 32];
+#pragma unroll
+    for (int w = 1; w < PS_THREADS / 32; w++) { kmin = fminf(kmin, s_red[w]); kmax = fmaxf(kmax, s_red[PS_THREADS / 32 + w]); }
+    // pass 2: 256-bin histogram over [kmin, kmax]; only bins that can hold the P-th key matter, so the resolution is spent on
+    // the low quarter of the range (keys above it all land in the last bin)
+    const float range = fmaxf(kmax - kmin, 1e-30f);
+    const float hi = kmin + 0.25f * range;
+    const float scale = 255.0f / (0.25f * range);
+    for (int i = tid; i < K; i += PS_THREADS) {
+        const float v = __ldg(&row[i]);
+        const int b = v >= hi ? 255 : max(0, min(254, (int)((v - kmin) * scale)));
+        atomicAdd(&hist[b], 1u);
+    }
+    __syncthreads();
+    // first bin whose cumulative count reaches P (warp 0), as a float threshold tau; the exact count below validates it
+    __shared__ float s_tau;
+    if (warp == 0) {
+        uint32_t c[8], s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { c[j] = hist[lane * 8 + j]; s += c[j]; }
+        uint32_t inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += v;
+        }
+        uint32_t run = inc - s;
+        int found = -1;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            run += c[j];
+            if (found < 0 && run >= (uint32_t)P) found = lane * 8 + j;
+        }
+        const uint32_t has = __ballot_sync(FULL, found >= 0);
+        const int b = __shfl_sync(FULL, found, __ffs(has) - 1);
+        if (lane == 0) s_tau = b >= 254 ? kmax : kmin + (float)(b + 1) / scale * 1.0001f;
+    }
+    if (tid == 0) { s_ncand = 0; s_nle = 0; }
+    __syncthreads();
+    float tau = s_tau;
+    // pass 3: candidates {A_c - m_c <= tau + m_max}, and the exact count of {A_c <= tau} that makes tau a valid threshold
+    for (int attempt = 0; attempt < 3; attempt++) {
+        const float U = __fadd_ru(tau, mmax);
+        uint32_t nle = 0;
+        for (int i0 = 0; i0 < K; i0 += PS_THREADS) {
+            const int i = i0 + tid;
+            bool take = false;
+            if (i < K) {
+                const float v = __ldg(&row[i]);
+                nle += v <= tau;
+                take = __fsub_rd(v, margin(yn, __ldg(&cnorm[i]))) <= U;
+            }
+            const uint32_t m = __ballot_sync(FULL, take);
+            if (m) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_ncand, (uint32_t)__popc(m));
+                base = __shfl_sync(FULL, base, 0);
+                const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                if (take && pos < (uint32_t)PS_CAP) cid[pos] = (uint32_t)i;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nle += __shfl_xor_sync(FULL, nle, o);
+        if (lane == 0 && nle) atomicAdd(&s_nle, nle);
+        __syncthreads();
+        const uint32_t got = s_nle;
+        if (got >= (uint32_t)P) break;
+        // histogram rounding put the bin edge a hair too low: widen and repeat (rare)
+        __syncthreads();
+        if (tid == 0) { s_ncand = 0; s_nle = 0; }
+        tau = attempt == 0 ? kmin + (tau - kmin) * 1.5f + 1e-30f : kmax;
+        __syncthreads();
+    }
+    const uint32_t nc = s_ncand;
+    if (nc > (uint32_t)cap || s_nle < (uint32_t)P) {  // cannot certify this query here: the batch is redone on the classic path
+        if (tid == 0) atomicOr(fallback_flag, 1u);
+        return;
+    }
+    // exact distances of the candidates, order of simd::l2_squared_distance: 8 lanes per candidate = the 8 AVX lanes
+    {
+        const int v = lane & 7, sub = tid >> 3;  // PS_THREADS / 8 = 32 candidates per sweep
+        for (uint32_t c0 = 0; c0 < nc; c0 += PS_THREADS / 8) {
+            const uint32_t ci = c0 + sub;
+            const bool act = ci < nc;
+            const uint32_t id = cid[act ? ci : 0];
+            const float* cr = cent + (size_t)id * D;
+            float acc = 0.0f;
+#pragma unroll 4
+            for (int d = v; d < D; d += 8) {
+                const float f = __fsub_rn(__ldg(&cr[d]), sy[d]);  // diff = c - y (src/simd.rs:34-37)
+                acc = fmaf(f, f, acc);
+            }
+            acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
+            acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
+            acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
+            if (act && v == 0) ckey[ci] = ((unsigned long long)okey(acc) << 32) | id;
+        }
+    }
+    __syncthreads();
+    // the P smallest (key, id): rank by counting (candidates are few)
+    for (uint32_t ci = tid; ci < nc; ci += PS_THREADS) {
+        const unsigned long long me = ckey[ci];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < nc; j++) rank += ckey[j] < me;
+        if (rank < (uint32_t)P) {
+            const uint32_t id = (uint32_t)(me & 0xffffffffu);
+            probe_ids[q * P + rank] = id;
+            probe_dist[q * P + rank] = okey_to_float((uint32_t)(me >> 32));
+            const uint32_t n_c = offsets[id + 1] - offsets[id];
+            words[rank] = (n_c + 31u) >> 5;
+            const uint32_t n_g = offsets_g ? offsets_g[id + 1] - offsets_g[id] : n_c;
+            if (n_g) { atomicAdd(&s_pairs, n_g); atomicMin(&s_p0, rank); }
+        }
+    }
+    __syncthreads();
+    const uint32_t total_words = block_exclusive_scan<PS_THREADS>(words, P, warp_tot);
+    for (int p = tid; p < P; p += PS_THREADS) slot_local[q * P + p] = words[p];
+    if (tid == 0) {
+        q_pairs[q] = s_pairs;
+        q_words[q] = total_words;
+        q_p0[q] = s_p0 == 0xffffffffu ? 0u : s_p0;
+    }
+}
+
+}  // namespace rq

@@ -15,6 +15,7 @@
 
 #include "kernels.cuh"
 #include "build_index.cuh"
+#include "prefilter.cuh"
 #include <sys/stat.h>
 
 namespace {
@@ -121,6 +122,10 @@ struct rabitq_index {
     float* P = nullptr;           // D x D rows
     float* cent = nullptr;        // K x D
     uint32_t* offsets = nullptr;  // K+1, local rows
+    // tensor-core prefilter of the centroid scan (prefilter.cuh): mean centroid, centred TF32 centroids, their norms
+    float *pf_mu = nullptr, *pf_chat = nullptr, *pf_cnorm = nullptr, *pf_cnorm2 = nullptr, *pf_cnorm_max = nullptr;
+    int prefilter = 1;            // 0 = always the classic exact scan + select
+    int prefilter_cap = 1024;     // candidates per query the prefilter may certify (tests lower it to force the fallback)
     float* quant_bias = nullptr;  // D: non-NULL switches K3 to the reference's non-AVX2 quantiser (rabitq_set_quantize_bias)
     uint32_t* goffsets = nullptr; // K+1, rows of the WHOLE index (equal to offsets on an unsharded handle)
     uint32_t* row_bounds = nullptr;  // shard_count+1, global rows where the shards begin
@@ -137,7 +142,7 @@ struct rabitq_index {
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, cl_count,
         cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
-        entries, counters, out_dist, out_ids, out_count, r2_cnt, r2_off, home_tot, cand;
+        entries, counters, out_dist, out_ids, out_count, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_ynorm, pf_flag;
     DistState dist;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
     // metrics (src/metrics.rs)
@@ -154,7 +159,8 @@ struct rabitq_index {
     ~rabitq_index() {
         cudaSetDevice(device);
         for (void* p : {(void*)base, (void*)P, (void*)cent, (void*)offsets, (void*)goffsets, (void*)row_bounds, (void*)map_ids, (void*)codes,
-                        (void*)factors, (void*)dist.peers_d, (void*)quant_bias})
+                        (void*)factors, (void*)dist.peers_d, (void*)quant_bias, (void*)pf_mu, (void*)pf_chat, (void*)pf_cnorm, (void*)pf_cnorm2,
+                        (void*)pf_cnorm_max})
             if (p) cudaFree(p);
         for (size_t r = 0; r < dist.peers_h.size(); r++)
             if (dist.opened[r] && dist.peers_h[r]) cudaIpcCloseMemHandle(dist.peers_h[r]);
@@ -162,7 +168,7 @@ struct rabitq_index {
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &qrec, &cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count,
-                          &r2_cnt, &r2_off, &home_tot, &cand})
+                          &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_ynorm, &pf_flag})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         for (auto e : ev_pool) cudaEventDestroy(e);
@@ -233,8 +239,27 @@ int finish_index(rabitq_index* ix) {
     CU(cudaFuncSetAttribute(rerank_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(rerank_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(approx_gemm_tf32_kernel<128, 128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * PF_PITCH * 4));
+    if (const char* e = std::getenv("RABITQ_PREFILTER")) ix->prefilter = std::atoi(e);
+    {   // prefilter operands: mu, c^ = tf32(c - mu), ||c - mu||, ||c - mu||^2, max norm
+        const size_t K = ix->K, D = ix->D;
+        CU(cudaMalloc((void**)&ix->pf_mu, D * 4));
+        CU(cudaMalloc((void**)&ix->pf_chat, K * D * 4));
+        CU(cudaMalloc((void**)&ix->pf_cnorm, K * 4));
+        CU(cudaMalloc((void**)&ix->pf_cnorm2, K * 4));
+        CU(cudaMalloc((void**)&ix->pf_cnorm_max, 4));
+        CU(cudaMemset(ix->pf_cnorm_max, 0, 4));
+        centroid_mean_kernel<<<(unsigned)((D + 127) / 128), 128>>>(ix->cent, (int)K, (int)D, ix->pf_mu);
+        centroid_center_kernel<<<(unsigned)((K + 3) / 4), 128>>>(ix->cent, ix->pf_mu, (int)K, (int)D, ix->pf_chat, ix->pf_cnorm, ix->pf_cnorm2,
+                                                                  ix->pf_cnorm_max);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+    }
     return 0;
 }
+
+// Is the tensor-core prefilter worth it (and within its candidate capacity) for this (K, P)?
+bool use_prefilter(const rabitq_index* ix, int P) { return ix->prefilter && ix->K >= 512 && (size_t)P * 8 <= ix->K && P <= 384; }
 
 // Build a handle from host or device arrays (full index); keeps only this shard's rows.
 int make_index(uint32_t dim, size_t n_total, size_t K, const float* base, const float* orth, const float* cent,
@@ -445,7 +470,7 @@ int build_impl(const float* base, size_t n, size_t len, const float* centroids, 
             dim3 g1((unsigned)(D / ROT_TC), (unsigned)((rows + ROT_QG * ROT_TQ - 1) / (ROT_QG * ROT_TQ)));
             rotate_kernel<<<g1, ROT_THREADS>>>(xpad, ix->P, xp, (int)rows, (int)D);  // rabitq.rs:188
             dim3 g2((unsigned)((K + CD_TC - 1) / CD_TC), (unsigned)((rows + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ)));
-            centroid_dist_kernel<<<g2, CD_THREADS>>>(ix->cent, xp, dist, (int)rows, (int)K, (int)D);
+            centroid_dist_kernel<<<g2, CD_THREADS>>>(ix->cent, xp, dist, (int)rows, (int)K, (int)D, nullptr);
             argmin_rows_kernel<<<(unsigned)((rows + 3) / 4), 128>>>(dist, rows, (int)K, label + s0, min_dist + s0);
             encode_kernel<<<(unsigned)((rows + 3) / 4), 128>>>(xp, ix->cent, label + s0, min_dist + s0, rows, (int)D, codes_u + s0 * W32,
                                                                fac_u + s0, key_in + s0);
@@ -642,12 +667,50 @@ int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_ro
     if (stop_after_rotate) return 0;
 
     CU(ix->cdist.ensure(nb * (size_t)K * 4));
+    CU(ix->probe_ids.ensure(nb * P * 4));
+    CU(ix->probe_dist.ensure(nb * P * 4));
+    CU(ix->slot_local.ensure(nb * P * 4));
+    CU(ix->q_words.ensure(nb * 4));
+    CU(ix->q_pairs.ensure(nb * 4));
+    CU(ix->q_p0.ensure(nb * 4));
+    const bool pf = use_prefilter(ix, P);
+    const uint32_t* run_if = nullptr;
+    if (pf) {
+        // tensor-core prefilter (prefilter.cuh): approximate keys for all K, exact distances for the few candidates
+        CU(ix->pf_yhat.ensure(nb * (size_t)D * 4));
+        CU(ix->pf_ynorm.ensure(nb * 4));
+        CU(ix->pf_flag.ensure(4));
+        CU(cudaMemsetAsync(ix->pf_flag.p, 0, 4, st));
+        query_center_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, st>>>(ix->y.as<float>(), ix->pf_mu, (int)nb, D, ix->pf_yhat.as<float>(),
+                                                                      ix->pf_ynorm.as<float>());
+        CU(cudaGetLastError()); ix->counts[5]++;
+        const size_t tiles128 = ((nb + 127) / 128) * (size_t)((K + 127) / 128);
+        if (tiles128 >= (size_t)ix->sm_count) {
+            dim3 grid((K + 127) / 128, (unsigned)((nb + 127) / 128));
+            approx_gemm_tf32_kernel<128, 128, 2, 4><<<grid, 256, 2 * 256 * PF_PITCH * 4, st>>>(ix->pf_yhat.as<float>(), ix->pf_chat, ix->pf_cnorm2,
+                                                                                                (int)nb, K, D, ix->cdist.as<float>());
+        } else {
+            dim3 grid((K + 63) / 64, (unsigned)((nb + 63) / 64));
+            approx_gemm_tf32_kernel<64, 64, 2, 2><<<grid, 128, 2 * 128 * PF_PITCH * 4, st>>>(ix->pf_yhat.as<float>(), ix->pf_chat, ix->pf_cnorm2,
+                                                                                              (int)nb, K, D, ix->cdist.as<float>());
+        }
+        CU(cudaGetLastError()); ix->counts[5]++;
+        if (tick(ix, ST_CDIST)) return RABITQ_ECUDA;
+        const size_t ps_smem = (size_t)D * 4 + PS_CAP * 12 + (size_t)P * 4;
+        prefilter_select_kernel<<<(unsigned)nb, PS_THREADS, ps_smem, st>>>(
+            ix->cdist.as<float>(), ix->pf_ynorm.as<float>(), ix->pf_cnorm, ix->pf_cnorm_max, ix->y.as<float>(), ix->cent, K, P, D, ix->offsets,
+            global_view ? ix->goffsets : nullptr, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(),
+            ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), ix->q_p0.as<uint32_t>(), ix->pf_flag.as<uint32_t>(),
+            std::max(1, std::min(ix->prefilter_cap, PS_CAP)));
+        CU(cudaGetLastError()); ix->counts[5]++;
+        run_if = ix->pf_flag.as<uint32_t>();  // the classic kernels below run only if some query could not be certified
+    }
     {
         dim3 grid((K + CD_TC - 1) / CD_TC, (unsigned)((nb + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ)));
-        centroid_dist_kernel<<<grid, CD_THREADS, 0, st>>>(ix->cent, ix->y.as<float>(), ix->cdist.as<float>(), (int)nb, K, D);
+        centroid_dist_kernel<<<grid, CD_THREADS, 0, st>>>(ix->cent, ix->y.as<float>(), ix->cdist.as<float>(), (int)nb, K, D, run_if);
         CU(cudaGetLastError()); ix->counts[5]++;
     }
-    if (tick(ix, ST_CDIST)) return RABITQ_ECUDA;
+    if (!pf && tick(ix, ST_CDIST)) return RABITQ_ECUDA;
     CU(ix->probe_ids.ensure(nb * P * 4));
     CU(ix->probe_dist.ensure(nb * P * 4));
     CU(ix->slot_local.ensure(nb * P * 4));
@@ -665,7 +728,7 @@ int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_ro
         select_probe_kernel<<<(unsigned)nb, SEL_THREADS, sel_smem, st>>>(
             ix->cdist.as<float>(), K, P, Ppow2, cache_keys, ix->offsets, global_view ? ix->goffsets : nullptr, ix->probe_ids.as<uint32_t>(),
             ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(),
-            ix->q_p0.as<uint32_t>());
+            ix->q_p0.as<uint32_t>(), run_if);
         CU(cudaGetLastError()); ix->counts[5]++;
         query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nb,
                                                    ix->q_wbase.as<uint32_t>(), ix->q_pbase.as<unsigned long long>());
@@ -1410,6 +1473,8 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     else if (n == "scan_mode") idx->scan_mode = (int)value;
     else if (n == "rerank_rows") idx->rerank_rows = (int)value;
     else if (n == "scan_slices") idx->scan_slices = (int)std::max(1L, value);
+    else if (n == "prefilter") idx->prefilter = (int)value;
+    else if (n == "prefilter_cap") idx->prefilter_cap = (int)value;
     else return fail(RABITQ_EINVAL, "unknown option: " + n);
     return RABITQ_OK;
 }
@@ -1459,7 +1524,10 @@ int rabitq_stage_probe(rabitq_index* idx, const float* queries, size_t nq, size_
     if (!idx) return fail(RABITQ_EINVAL, "null index");
     std::lock_guard<std::mutex> lk(idx->mu);
     BatchOut bo;
+    const int pf_saved = idx->prefilter;
+    if (out_centroid_dist) idx->prefilter = 0;  // the full exact distance matrix only exists on the classic path
     int rc = stage_prefix(idx, queries, nq, len, probe, STOP_PROBE, &bo);
+    idx->prefilter = pf_saved;
     if (rc) return rc;
     if (out_centroid_dist) CU(cudaMemcpy(out_centroid_dist, idx->cdist.p, nq * idx->K * 4, cudaMemcpyDeviceToHost));
     if (out_probe_ids) CU(cudaMemcpy(out_probe_ids, idx->probe_ids.p, nq * bo.P * 4, cudaMemcpyDeviceToHost));

@@ -253,7 +253,9 @@ def test_probe_select_pivot_path_and_ties(oracle_lib):
     a = ix.arrays()
     g = rb.RaBitQ.from_arrays(a["dim"], a["base"], a["orthogonal"], a["centroids"], a["offsets"], a["map_ids"], a["codes"], a["factors"], device=0)
     for probe in (1, 7, 64, 144):  # 144 * 16 = 2304 -> still the pivot path; 145+ would fall back to radix
-        cd, pid, pd = g.stage_probe(queries, probe)
+        cd, pid, pd = g.stage_probe(queries, probe)              # classic path (the exact matrix is requested)
+        _, pid2, pd2 = g.stage_probe(queries, probe, want_all=False)  # tensor-core prefilter: duplicates = tied keys
+        assert np.array_equal(pid, pid2) and np.array_equal(pd.view(np.uint32), pd2.view(np.uint32))
         for i in range(queries.shape[0]):
             tr = ix.trace(queries[i], probe, 5)
             assert np.array_equal(pid[i], tr["probe_ids"]), (probe, i)
@@ -399,3 +401,55 @@ def test_raw_quantiser_with_explicit_bias(pair):
         o.set_raw_bias(None)
     # back on the AVX2 semantics
     assert np.array_equal(g.stage_quantize(q, probe)[3], avx_planes)
+
+
+# ---- tensor-core prefilter of the centroid scan (prefilter.cuh): probe lists must stay bit-identical ------------------------
+_PF_CASES = {}
+
+
+def _pf_case(name):
+    from tests.conftest import make_case
+
+    if name not in _PF_CASES:
+        spec = {"k1024_d128": (20000, 128, 32, 1024, "sift", 21), "k600_d96": (9000, 96, 24, 600, "deep", 22),
+                "k512_d960": (5000, 960, 16, 512, "gist", 23)}[name]
+        _PF_CASES[name] = make_case(name, *spec)
+    return _PF_CASES[name]
+
+
+@pytest.mark.parametrize("name", ["k1024_d128", "k600_d96", "k512_d960"])
+def test_prefilter_probe_lists_bit_exact(oracle_lib, name):
+    """K >= 512 and probe <= K/8: approximate TF32 keys on the tensor cores, exact recheck of the candidates.  The probe
+    ids and distances must equal the oracle's (and the classic path's), the fallback path as well."""
+    case = _pf_case(name)
+    if "gpu" not in case:
+        case["gpu"] = _gpu_index(case)
+    g, q = case["gpu"], case["queries"]
+    K = g.num_clusters
+    for probe in (1, 7, 32, K // 8):
+        tr = [case["oracle"].trace(q[i], probe, 5) for i in range(q.shape[0])]
+        for opt, val in (("prefilter", 1), ("prefilter_cap", 1), ("prefilter", 0)):
+            g.set_option(opt, val)
+            try:
+                _, pid, pd = g.stage_probe(q, probe, want_all=False)
+            finally:
+                g.set_option("prefilter", 1)
+                g.set_option("prefilter_cap", 1024)
+            for i in range(q.shape[0]):
+                assert np.array_equal(pid[i], tr[i]["probe_ids"]), (name, probe, opt, val, i)
+                assert np.array_equal(pd[i].view(np.uint32), tr[i]["probe_dist"].view(np.uint32)), (name, probe, opt, val, i)
+
+
+def test_prefilter_end_to_end_and_counters(oracle_lib):
+    case = _pf_case("k1024_d128")
+    if "gpu" not in case:
+        case["gpu"] = _gpu_index(case)
+    g, q = case["gpu"], case["queries"]
+    g.metrics_reset()
+    gd, gi, gc = g.query_batch(q, 64, 10)
+    o = case["oracle"].query_batch(q, 64, 10)
+    for i in range(q.shape[0]):
+        c = int(gc[i])
+        assert _same_up_to_ties(case, i, gd[i, :c], gi[i, :c], o["dist"][i, :c], o["ids"][i, :c]), f"query {i}"
+    m = g.metrics()
+    assert m["rough"] == o["rough"] and m["precise"] == o["precise"]
