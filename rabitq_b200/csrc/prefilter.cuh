@@ -216,65 +216,62 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
     const float yn = ynorm[q], mmax = margin(yn, cnorm_max[0]);
 
     for (int d = tid; d < D; d += PS_THREADS) sy[d] = y[q * (size_t)D + d];
-    // pass 1: range of the keys
-    float kmin = 3.402823466e+38f, kmax = -3.402823466e+38f;
-    for (int i = tid; i < K; i += PS_THREADS) {
-        const float v = __ldg(&row[i]);
-        kmin = fminf(kmin, v);
-        kmax = fmaxf(kmax, v);
-    }
+    // sample: 256 strided keys.  base = their minimum; hi = the largest of the minima of groups of G samples, i.e. roughly
+    // the (ln(256/G) + 0.6) / G quantile of the keys -- a little above the P/K quantile the threshold has to reach, so that
+    // only a small fraction of the keys enters the histogram (no hot bins) and the 255 bins below `hi` are narrow.
+    int G = 32;
+    while (G > 2 && (size_t)G * 4 * P > (size_t)K) G >>= 1;  // G ~ K / (4 P), a power of two in [2, 32]
+    float sv = __ldg(&row[(size_t)tid * K / PS_THREADS]);
+    float gmin = sv;
+    for (int o = 1; o < G; o <<= 1) gmin = fminf(gmin, __shfl_xor_sync(FULL, gmin, o));
+    float wmin = gmin, wmaxmin = gmin;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        kmin = fminf(kmin, __shfl_xor_sync(FULL, kmin, o));
-        kmax = fmaxf(kmax, __shfl_xor_sync(FULL, kmax, o));
+        wmin = fminf(wmin, __shfl_xor_sync(FULL, wmin, o));
+        wmaxmin = fmaxf(wmaxmin, __shfl_xor_sync(FULL, wmaxmin, o));
     }
-    if (lane == 0) { s_red[warp] = kmin; s_red[PS_THREADS / 32 + warp] = kmax; }
+    if (lane == 0) { s_red[warp] = wmin; s_red[PS_THREADS / 32 + warp] = wmaxmin; }
     hist[tid] = 0;
-    if (tid == 0) { s_p0 = 0xffffffffu; s_pairs = 0; }
+    if (tid == 0) { s_p0 = 0xffffffffu; s_pairs = 0; s_ncand = 0; s_nle = 0; }
     __syncthreads();
-    kmin = s_red[0]; kmax = s_red[PS_THREADS / 32];
+    float base = s_red[0], hi = s_red[PS_THREADS / 32];
 #pragma unroll
-    for (int w = 1; w < PS_THREADS / 32; w++) { kmin = fminf(kmin, s_red[w]); kmax = fmaxf(kmax, s_red[PS_THREADS / 32 + w]); }
-    // pass 2: 256-bin histogram over [kmin, kmax]; only bins that can hold the P-th key matter, so the resolution is spent on
-    // the low quarter of the range (keys above it all land in the last bin)
-    const float range = fmaxf(kmax - kmin, 1e-30f);
-    const float hi = kmin + 0.25f * range;
-    const float scale = 255.0f / (0.25f * range);
-    for (int i = tid; i < K; i += PS_THREADS) {
-        const float v = __ldg(&row[i]);
-        const int b = v >= hi ? 255 : max(0, min(254, (int)((v - kmin) * scale)));
-        atomicAdd(&hist[b], 1u);
-    }
-    __syncthreads();
-    // first bin whose cumulative count reaches P (warp 0), as a float threshold tau; the exact count below validates it
+    for (int w = 1; w < PS_THREADS / 32; w++) { base = fminf(base, s_red[w]); hi = fmaxf(hi, s_red[PS_THREADS / 32 + w]); }
     __shared__ float s_tau;
-    if (warp == 0) {
-        uint32_t c[8], s = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) { c[j] = hist[lane * 8 + j]; s += c[j]; }
-        uint32_t inc = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += v;
-        }
-        uint32_t run = inc - s;
-        int found = -1;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            run += c[j];
-            if (found < 0 && run >= (uint32_t)P) found = lane * 8 + j;
-        }
-        const uint32_t has = __ballot_sync(FULL, found >= 0);
-        const int b = __shfl_sync(FULL, found, __ffs(has) - 1);
-        if (lane == 0) s_tau = b >= 254 ? kmax : kmin + (float)(b + 1) / scale * 1.0001f;
-    }
-    if (tid == 0) { s_ncand = 0; s_nle = 0; }
-    __syncthreads();
-    float tau = s_tau;
-    // pass 3: candidates {A_c - m_c <= tau + m_max}, and the exact count of {A_c <= tau} that makes tau a valid threshold
+    float tau = 0.0f;
     for (int attempt = 0; attempt < 3; attempt++) {
-        const float U = __fadd_ru(tau, mmax);
+        // pass A: 255-bin histogram of the keys below hi (keys below `base` fall into bin 0)
+        const float scale = 255.0f / fmaxf(hi - base, 1e-30f);
+        for (int i = tid; i < K; i += PS_THREADS) {
+            const float v = __ldg(&row[i]);
+            if (v < hi) atomicAdd(&hist[max(0, min(254, (int)((v - base) * scale)))], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {  // first bin whose cumulative count reaches P -> tau = its upper edge (hi itself if none does)
+            uint32_t c[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { c[j] = hist[lane * 8 + j]; s += c[j]; }
+            uint32_t inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += v;
+            }
+            uint32_t run = inc - s;
+            int found = -1;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                run += c[j];
+                if (found < 0 && run >= (uint32_t)P) found = lane * 8 + j;
+            }
+            const uint32_t has = __ballot_sync(FULL, found >= 0);
+            const int bsel = has ? __shfl_sync(FULL, found, __ffs(has) - 1) : 255;
+            if (lane == 0) s_tau = bsel >= 254 ? hi : fminf(hi, base + (float)(bsel + 1) / scale * 1.0001f);
+        }
+        __syncthreads();
+        tau = s_tau;
+        // pass B: candidates {A_c - m_c <= tau + m_max}, and the exact count of {A_c <= tau} that certifies tau
+        const float U = __fadd_ru(tau, mmax), Uq = __fadd_ru(U, mmax);
         uint32_t nle = 0;
         for (int i0 = 0; i0 < K; i0 += PS_THREADS) {
             const int i = i0 + tid;
@@ -282,14 +279,14 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
             if (i < K) {
                 const float v = __ldg(&row[i]);
                 nle += v <= tau;
-                take = __fsub_rd(v, margin(yn, __ldg(&cnorm[i]))) <= U;
+                if (v <= Uq) take = __fsub_rd(v, margin(yn, __ldg(&cnorm[i]))) <= U;  // (quick reject first: m_c <= m_max)
             }
             const uint32_t m = __ballot_sync(FULL, take);
             if (m) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&s_ncand, (uint32_t)__popc(m));
-                base = __shfl_sync(FULL, base, 0);
-                const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                uint32_t pos0 = 0;
+                if (lane == 0) pos0 = atomicAdd(&s_ncand, (uint32_t)__popc(m));
+                pos0 = __shfl_sync(FULL, pos0, 0);
+                const uint32_t pos = pos0 + __popc(m & ((1u << lane) - 1u));
                 if (take && pos < (uint32_t)PS_CAP) cid[pos] = (uint32_t)i;
             }
         }
@@ -297,12 +294,12 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
         for (int o = 16; o > 0; o >>= 1) nle += __shfl_xor_sync(FULL, nle, o);
         if (lane == 0 && nle) atomicAdd(&s_nle, nle);
         __syncthreads();
-        const uint32_t got = s_nle;
-        if (got >= (uint32_t)P) break;
-        // histogram rounding put the bin edge a hair too low: widen and repeat (rare)
+        if (s_nle >= (uint32_t)P) break;
+        // fewer than P keys below hi (the sample was unlucky) or a bin edge a hair too low: widen and repeat (rare)
         __syncthreads();
+        hist[tid] = 0;
         if (tid == 0) { s_ncand = 0; s_nle = 0; }
-        tau = attempt == 0 ? kmin + (tau - kmin) * 1.5f + 1e-30f : kmax;
+        hi = attempt == 0 ? base + (hi - base) * 4.0f + 1e-30f : 3.402823466e+38f;
         __syncthreads();
     }
     const uint32_t nc = s_ncand;
