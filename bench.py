@@ -124,6 +124,8 @@ def build_workload(args, device, rank, world):
     else:
         shape, seed, name = synth.SHAPES[args.workload], synth.SEEDS[args.workload], args.workload
     n, dim, nq, k, flavour = shape
+    if args.nq:
+        nq = args.nq
     t0 = time.time()
     mix = synth.Mixture(dim, k, flavour, seed + 2, device)
     base = mix.draw(n, seed)
@@ -131,30 +133,43 @@ def build_workload(args, device, rank, world):
     cent = mix.centroids()
     torch.cuda.synchronize()
     t1 = time.time()
+    import rabitq_b200 as rb
+
     if getattr(args, "builder", "native") == "torch":
         ix = bi.build_index(base, cent, seed=seed + 3)
+        g0 = rb.RaBitQ.from_arrays(ix["dim"], ix["base"], ix["orthogonal"], ix["centroids"], ix["offsets"], ix["map_ids"], ix["codes"],
+                                   ix["factors"], device=device.index)
+        del ix
     else:  # index training by the library itself (rabitq_build = RaBitQ::from_path on the device)
-        import rabitq_b200 as rb
-
         g0 = rb.RaBitQ.build(base.contiguous(), cent.contiguous(), seed=seed + 3, device=device.index)
-        ix = g0.export_arrays(device_tensors=True)
-        g0.close()
     torch.cuda.synchronize()
     t2 = time.time()
-    truth = synth.brute_force_topk_torch(base, queries, TOPK)
+    # ground truth (exact fp32 brute force) for the queries recall is measured on: all of them, or the first `truth_queries` of
+    # every rank's slice when the batch is large
+    tq = min(nq, args.truth_queries) if args.truth_queries else nq
+    sel = torch.cat([torch.arange(r * nq, r * nq + tq, device=device) for r in range(world)])
+    truth = torch.zeros((nq * world, TOPK), dtype=torch.int32, device=device)
+    truth[sel] = synth.brute_force_topk_torch(base, queries[sel], TOPK)
     torch.cuda.synchronize()
     if rank == 0:
         log(f"[bench] {name}: n={n} dim={dim} nq={nq * world} k={k} ({flavour}); gen {t1 - t0:.1f}s build {t2 - t1:.1f}s truth {time.time() - t2:.1f}s")
     del base
-    return dict(name=name, n=n, dim=dim, nq=nq * world, k=k, flavour=flavour, queries=queries.contiguous(), truth=truth, index=ix)
+    torch.cuda.empty_cache()
+    if world > 1:  # every rank trained the whole index (same seeds, same result) and keeps its cluster range
+        g = g0.reshard(rank, world)
+        g0.close()
+    else:
+        g = g0
+    return dict(name=name, n=n, dim=dim, nq=nq * world, nq_rank=nq, truth_queries=tq, k=k, flavour=flavour, queries=queries.contiguous(),
+                truth=truth, handle=g, D=g.dim)
 
 
-def oracle_from_index(ix):
+def oracle_from_index(g):
+    """The CPU oracle over the arrays of an (unsharded) device handle."""
     from oracle import oracle as orc
-    from tools import build_index_torch as bi
 
     orc.build()
-    a = bi.to_numpy(ix)
+    a = g.export_arrays()
     return orc.OracleIndex.from_built(a["dim"], a["base"], a["orthogonal"], a["centroids"], a["offsets"], a["map_ids"], a["codes"], a["factors"])
 
 
@@ -177,10 +192,8 @@ def run_ours(args):
     rb.lib()  # fail loudly if the CUDA library is missing
 
     wl = build_workload(args, device, rank, world)
-    ix, queries, truth = wl["index"], wl["queries"], wl["truth"]
-    nq, D = wl["nq"], ix["dim"]
-    g = rb.RaBitQ.from_arrays(ix["dim"], ix["base"], ix["orthogonal"], ix["centroids"], ix["offsets"], ix["map_ids"], ix["codes"],
-                              ix["factors"], device=local, shard_rank=rank, shard_count=world)
+    queries, truth, g = wl["queries"], wl["truth"], wl["handle"]
+    nq, D = wl["nq"], wl["D"]
     stream = torch.cuda.Stream(device)  # a non-default stream shared by torch (events, NCCL) and the library's kernels
     torch.cuda.synchronize(device)
     torch.cuda.set_stream(stream)
@@ -208,8 +221,10 @@ def run_ours(args):
         d, i, c = dg.query_batch(q_local, probe, TOPK)
         return d, i
 
+    tq = wl["truth_queries"]  # recall is measured on the first tq queries of every rank's slice
+
     def global_recall(ids):
-        r = recall_at_k(ids, truth_local, TOPK)
+        r = recall_at_k(ids[:tq], truth_local[:tq], TOPK)
         if world > 1:
             t = torch.tensor([r], dtype=torch.float64, device=device)
             dist.all_reduce(t)
@@ -329,6 +344,7 @@ def run_ours(args):
             "config": {"workload": f"{wl['name']}: {wl['n']}x{wl['dim']} base ({wl['flavour']}-shaped mixture), {nq} queries/step, "
                                    f"{wl['k']} IVF centroids, nprobe={probe}, top-{TOPK}",
                        "nprobe": probe, "topk": TOPK, "recall_at_10": round(recall, 4), "recall_by_nprobe": sweep_log,
+                       "recall_measured_on": f"first {tq} queries of every rank's slice",
                        "timing": "CUDA events on the launch stream, L2 flushed (256 MB write) between timed steps",
                        "parallelism": "single GPU" if world == 1 else f"index sharded by cluster range over {world} GPUs, "
                                       f"every rank home of {nq // world} of the {nq} queries; NCCL all-gather of front-end products + "
@@ -367,7 +383,7 @@ def cpu_baseline(wl, probe, threads, budget_s, fixed_sample=None):
     """Time the oracle (port of the reference's AVX2 path) on a bounded sample of the same workload."""
     import numpy as np
 
-    o = oracle_from_index(wl["index"])
+    o = oracle_from_index(wl["handle"])
     q = wl["queries"].cpu().numpy()
     # calibrate on a few queries, then size the sample for ~budget_s of CPU work
     n0 = min(8 * threads, q.shape[0])
@@ -399,7 +415,8 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     import numpy as np
 
-    o = oracle_from_index(wl["index"])
+    o = oracle_from_index(wl["handle"])
+    wl["handle"].close()
     q = wl["queries"].cpu().numpy()
     # same rule as our arm: the smallest nprobe of the sweep whose recall@10 reaches the target (measured with this arm)
     probe, sweep_log = args.probe, {}
@@ -450,6 +467,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--shape", default=None, help="custom n,dim,nq,k[,flavour] (debug)")
     ap.add_argument("--probe", type=int, default=0, help="fix nprobe instead of sweeping to the target recall")
+    ap.add_argument("--nq", type=int, default=0, help="queries per step and GPU (default: the workload's)")
+    ap.add_argument("--truth-queries", type=int, default=0, help="measure recall on the first N queries only (large batches)")
     ap.add_argument("--rounds", default=None, help="rerank round boundaries, e.g. 0,1,8")
     ap.add_argument("--builder", default="native", choices=["native", "torch"], help="index training: rabitq_build (CUDA) or the torch harness")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

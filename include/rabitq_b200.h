@@ -76,6 +76,10 @@ int rabitq_dump_to_dir(rabitq_index* idx, const char* dir);
 int rabitq_export_arrays(rabitq_index* idx, float* base, float* orthogonal, float* centroids, uint32_t* offsets,
                          uint32_t* map_ids, uint64_t* codes, float* factors, int ptr_on_device);
 
+/* A new handle on the same device holding shard `shard_rank` of `shard_count` of an unsharded handle (device-to-device
+ * copies; the source handle stays valid and is usually freed afterwards).  Lets every rank train once and keep its part. */
+int rabitq_reshard(rabitq_index* idx, int shard_rank, int shard_count, rabitq_index** out);
+
 void rabitq_free(rabitq_index* idx);
 
 uint32_t rabitq_dim(const rabitq_index* idx);     /* padded D (multiple of 64)        */
@@ -166,7 +170,8 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
  * work item (default 1; hot clusters are cut into several items); "prefilter" = 1 (default) lets the centroid scan run as a
  * TF32 tensor-core prefilter + exact recheck of the candidates when k >= 512 and probe <= k/8 (probe lists stay bit-identical),
  * 0 = always all k exact distances; "prefilter_cap" = candidates per query the prefilter may certify (<= 1024; a query
- * above it sends its batch to the exact path on the device). */
+ * above it sends its batch to the exact path on the device); "prefilter_mode" = 1 plain TF32 keys, 3 = 3xTF32 split, 0 = off
+ * (the handle moves 1 -> 3 -> 0 by itself when batches cannot be certified). */
 int rabitq_set_option(rabitq_index* idx, const char* name, long value);
 
 /* The reference's OTHER query quantiser.  On a host without AVX2, `scalar_quantize` falls back to

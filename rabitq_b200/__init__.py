@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "rabitq_shard_range", "rabitq_merge_topk_device", "rabitq_metrics", "rabitq_metrics_reset", "rabitq_last_error", "rabitq_set_rounds",
     "rabitq_set_option", "rabitq_set_stream", "rabitq_last_timings", "rabitq_stage_rotate", "rabitq_stage_probe", "rabitq_stage_quantize", "rabitq_stage_scan",
     "rabitq_dist_init", "rabitq_dist_ipc_handle", "rabitq_dist_inbox_ptr", "rabitq_dist_set_peer", "rabitq_dist_chunk_words", "rabitq_dist_front",
-    "rabitq_dist_round1", "rabitq_dist_round2", "rabitq_dist_finish", "rabitq_min_f32_device", "rabitq_set_quantize_bias",
+    "rabitq_dist_round1", "rabitq_dist_round2", "rabitq_dist_finish", "rabitq_min_f32_device", "rabitq_set_quantize_bias", "rabitq_reshard",
 ]
 
 TIMING_STAGES = ["h2d_pad", "rotate", "centroid_dist", "select", "quantize", "bucket", "scan", "rerank", "d2h", "total"]
@@ -61,6 +61,7 @@ def lib():
     L.rabitq_from_path.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(vp)]
     L.rabitq_build.argtypes = [vp, C.c_size_t, C.c_size_t, vp, C.c_size_t, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]
     L.rabitq_dump_to_dir.argtypes = [vp, C.c_char_p]
+    L.rabitq_reshard.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
     L.rabitq_export_arrays.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
     L.rabitq_free.argtypes = [vp]
     L.rabitq_free.restype = None
@@ -193,6 +194,12 @@ class RaBitQ:
     def dump_to_dir(self, path) -> None:
         """`RaBitQ::dump_to_dir(path)` (src/rabitq.rs:128-156)."""
         _check(lib().rabitq_dump_to_dir(self._h, os.fsencode(str(path))))
+
+    def reshard(self, shard_rank: int, shard_count: int) -> "RaBitQ":
+        """Shard `shard_rank` of `shard_count` of this (unsharded) index as a new handle on the same device."""
+        h = C.c_void_p()
+        _check(lib().rabitq_reshard(self._h, shard_rank, shard_count, C.byref(h)))
+        return RaBitQ(h, self.device)
 
     def export_arrays(self, device_tensors: bool = False) -> dict:
         """The arrays of `struct RaBitQ` as numpy arrays (or torch CUDA tensors on this handle's device)."""

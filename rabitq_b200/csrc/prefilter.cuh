@@ -6,9 +6,12 @@
 //   1. approximate keys  A[q][c] = ||c'||^2 - 2 <y', c'>  with y' = y - mu, c' = c - mu (mu = mean centroid: distances are
 //      translation invariant and centring shrinks the norms the error bound scales with), the inner products on the tensor
 //      cores in TF32 (operands rounded to TF32 once, fp32 accumulation);
-//   2. a RIGOROUS bound  |A[q][c] + ||y'||^2 - e[q][c]| <= m[q][c] = 2^-8 ||y'|| ||c'|| + 2^-14 (||y'|| + ||c'||)^2  on the
-//      difference to the reference's fp32 value e (TF32 operand rounding 2 * 2^-11, tensor-core accumulation <= D 2^-23,
-//      fp32 evaluation of the reference formula <= (D/8 + 4) 2^-24, each with >= 1.6x slack; D <= 2048);
+//   2. a RIGOROUS bound  |A[q][c] + ||y'||^2 - e[q][c]| <= m[q][c] = alpha ||y'|| ||c'|| + 2^-21 (||y'|| + ||c'||)^2
+//      + gamma (A[q][c] + ||y'||^2)  on the difference to the reference's fp32 value e:  alpha = 2^-8 for plain TF32 operands
+//      (operand rounding 2 * 2^-11 and tensor-core accumulation <= D 2^-23 on each of the two sides, 1.6x slack) or
+//      (D + 64) 2^-21 for the 3xTF32 split (hi*hi + hi*lo + lo*hi: only the accumulation term is left, 4x slack); the second
+//      term covers the fp32 assembly of A; gamma = (D/8 + 8) 2^-23 the fp32 evaluation of the reference's own formula.  The
+//      handle starts with plain TF32 and moves to 3xTF32 (then to the exact path) when a batch cannot be certified;
 //   3. per query: a threshold tau with #{c : A_c <= tau} >= probe (256-bin histogram of the keys, verified by an exact
 //      count), candidates = {c : A_c - m_c <= tau + max_c m_c} -- a superset of the reference's probe set, ties included --
 //      EXACT distances for the candidates only, in the reference's AVX order, then the `probe` smallest by (distance, id).
@@ -36,14 +39,17 @@ __global__ void centroid_mean_kernel(const float* __restrict__ cent, int K, int 
 }
 
 __global__ void centroid_center_kernel(const float* __restrict__ cent, const float* __restrict__ mu, int K, int D, float* __restrict__ chat,
-                                       float* __restrict__ cnorm, float* __restrict__ cnorm2, float* __restrict__ cnorm_max) {
+                                       float* __restrict__ chat_lo, float* __restrict__ cnorm, float* __restrict__ cnorm2,
+                                       float* __restrict__ cnorm_max) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= K) return;
     double s = 0.0;
     for (int d = lane; d < D; d += 32) {
         const float v = __fsub_rn(cent[(size_t)c * D + d], mu[d]);
-        chat[(size_t)c * D + d] = to_tf32(v);
+        const float h = to_tf32(v);
+        chat[(size_t)c * D + d] = h;
+        chat_lo[(size_t)c * D + d] = to_tf32(__fsub_rn(v, h));  // 3xTF32 split: v = hi + lo up to 2^-22 |v|
         s += (double)v * (double)v;
     }
 #pragma unroll
@@ -58,14 +64,16 @@ __global__ void centroid_center_kernel(const float* __restrict__ cent, const flo
 
 // ---- query side: y^ = tf32(y - mu), ||y - mu|| -----------------------------------------------------------------------------
 __global__ void query_center_kernel(const float* __restrict__ y, const float* __restrict__ mu, int nq, int D, float* __restrict__ yhat,
-                                    float* __restrict__ ynorm) {
+                                    float* __restrict__ yhat_lo, float* __restrict__ ynorm) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
     float s = 0.0f;
     for (int d = lane; d < D; d += 32) {
         const float v = __fsub_rn(y[(size_t)q * D + d], mu[d]);
-        yhat[(size_t)q * D + d] = to_tf32(v);
+        const float h = to_tf32(v);
+        yhat[(size_t)q * D + d] = h;
+        if (yhat_lo) yhat_lo[(size_t)q * D + d] = to_tf32(__fsub_rn(v, h));
         s = fmaf(v, v, s);
     }
 #pragma unroll
@@ -89,7 +97,7 @@ RQ_DEV void cp_async16(void* smem, const void* gmem, bool pred) {
 template <int BM, int BN, int WM, int WN>
 __global__ void __launch_bounds__(WM * WN * 32) approx_gemm_tf32_kernel(const float* __restrict__ yhat, const float* __restrict__ chat,
                                                                         const float* __restrict__ cnorm2, int nq, int K, int D,
-                                                                        float* __restrict__ A) {
+                                                                        float* __restrict__ A, int accumulate) {
     constexpr int THREADS = WM * WN * 32;
     constexpr int TM = BM / WM / 16, TN = BN / WN / 8;  // mma tiles per warp
     extern __shared__ __align__(16) float pf_smem[];
@@ -162,25 +170,20 @@ __global__ void __launch_bounds__(WM * WN * 32) approx_gemm_tf32_kernel(const fl
         }
         __syncthreads();
     }
-    // epilogue: A = ||c'||^2 - 2 S   (c fragment: rows g / g+8, columns 2t / 2t+1)
+    // epilogue: A = ||c'||^2 - 2 S, or A -= 2 S for the cross terms of the 3xTF32 split   (c fragment: rows g / g+8, columns 2t / 2t+1)
 #pragma unroll
     for (int i = 0; i < TM; i++)
 #pragma unroll
         for (int j = 0; j < TN; j++) {
             const int c = c0 + wn * TN * 8 + j * 8 + 2 * t;
             const int qa = q0 + wm * TM * 16 + i * 16 + g, qb = qa + 8;
-            const float n0 = c < K ? __ldg(&cnorm2[c]) : 0.0f, n1 = c + 1 < K ? __ldg(&cnorm2[c + 1]) : 0.0f;
-            if (c + 1 < K && (K & 1) == 0) {
-                if (qa < nq) *reinterpret_cast<float2*>(A + (size_t)qa * K + c) = make_float2(n0 - 2.0f * acc[i][j][0], n1 - 2.0f * acc[i][j][1]);
-                if (qb < nq) *reinterpret_cast<float2*>(A + (size_t)qb * K + c) = make_float2(n0 - 2.0f * acc[i][j][2], n1 - 2.0f * acc[i][j][3]);
-            } else {
-                if (c < K) {
-                    if (qa < nq) A[(size_t)qa * K + c] = n0 - 2.0f * acc[i][j][0];
-                    if (qb < nq) A[(size_t)qb * K + c] = n0 - 2.0f * acc[i][j][2];
-                }
-                if (c + 1 < K) {
-                    if (qa < nq) A[(size_t)qa * K + c + 1] = n1 - 2.0f * acc[i][j][1];
-                    if (qb < nq) A[(size_t)qb * K + c + 1] = n1 - 2.0f * acc[i][j][3];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int cc = c + (e & 1), qq = (e & 2) ? qb : qa;
+                if (cc < K && qq < nq) {
+                    float* dst = A + (size_t)qq * K + cc;
+                    const float prev = accumulate ? *dst : __ldg(&cnorm2[cc]);
+                    *dst = prev - 2.0f * acc[i][j][e];
                 }
             }
         }
@@ -190,9 +193,11 @@ __global__ void __launch_bounds__(WM * WN * 32) approx_gemm_tf32_kernel(const fl
 constexpr int PS_THREADS = 256;
 constexpr int PS_CAP = 1024;  // candidate capacity
 
-RQ_DEV float margin(float yn, float cn) {
+// m = alpha yn cn + 2^-21 (yn + cn)^2 + gamma max(a + yn^2, 0), every operation rounded up (a = the approximate key)
+RQ_DEV float margin(float yn, float cn, float a, float alpha, float gamma) {
     const float s = __fadd_ru(yn, cn);
-    return __fadd_ru(__fmul_ru(__fmul_ru(yn, cn), 0.00390625f), __fmul_ru(__fmul_ru(s, s), 6.103515625e-05f));  // 2^-8, 2^-14
+    const float e = fmaxf(__fadd_ru(a, __fmul_ru(yn, yn)), 0.0f);
+    return __fadd_ru(__fadd_ru(__fmul_ru(__fmul_ru(yn, cn), alpha), __fmul_ru(__fmul_ru(s, s), 4.76837158203125e-07f)), __fmul_ru(e, gamma));
 }
 
 __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
     const float* __restrict__ y, const float* __restrict__ cent, int K, int P, int D, const uint32_t* __restrict__ offsets,
     const uint32_t* __restrict__ offsets_g, uint32_t* __restrict__ probe_ids, float* __restrict__ probe_dist,
     uint32_t* __restrict__ slot_local, uint32_t* __restrict__ q_words, uint32_t* __restrict__ q_pairs, uint32_t* __restrict__ q_p0,
-    uint32_t* __restrict__ fallback_flag, int cap /* <= PS_CAP; tests lower it to exercise the fallback */) {
+    uint32_t* __restrict__ fallback_flag, int cap /* <= PS_CAP; tests lower it to exercise the fallback */, float alpha, float gamma) {
     extern __shared__ __align__(16) unsigned char ps_smem_raw[];
     float* sy = reinterpret_cast<float*>(ps_smem_raw);                            // D
     uint32_t* cid = reinterpret_cast<uint32_t*>(sy + D);                          // PS_CAP candidate ids
@@ -213,17 +218,16 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t q = blockIdx.x;
     const float* row = A + q * (size_t)K;
-    const float yn = ynorm[q], mmax = margin(yn, cnorm_max[0]);
+    const float yn = ynorm[q], cn_max = cnorm_max[0];
 
     for (int d = tid; d < D; d += PS_THREADS) sy[d] = y[q * (size_t)D + d];
     // sample: 256 strided keys.  base = their minimum; hi = the largest of the minima of groups of G samples, i.e. roughly
     // the (ln(256/G) + 0.6) / G quantile of the keys -- a little above the P/K quantile the threshold has to reach, so that
     // only a small fraction of the keys enters the histogram (no hot bins) and the 255 bins below `hi` are narrow.
-    int G = 32;
-    while (G > 2 && (size_t)G * 4 * P > (size_t)K) G >>= 1;  // G ~ K / (4 P), a power of two in [2, 32]
-    float sv = __ldg(&row[(size_t)tid * K / PS_THREADS]);
-    float gmin = sv;
-    for (int o = 1; o < G; o <<= 1) gmin = fminf(gmin, __shfl_xor_sync(FULL, gmin, o));
+    int G = 64;
+    while (G > 2 && (size_t)G * 4 * P > (size_t)K) G >>= 1;  // G ~ K / (4 P), a power of two in [2, 64]
+    float gmin = __ldg(&row[(size_t)tid * K / PS_THREADS]);
+    for (int o = 1; o < min(G, 32); o <<= 1) gmin = fminf(gmin, __shfl_xor_sync(FULL, gmin, o));
     float wmin = gmin, wmaxmin = gmin;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -234,19 +238,46 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
     hist[tid] = 0;
     if (tid == 0) { s_p0 = 0xffffffffu; s_pairs = 0; s_ncand = 0; s_nle = 0; }
     __syncthreads();
-    float base = s_red[0], hi = s_red[PS_THREADS / 32];
+    float base = s_red[0], hi = -3.402823466e+38f;
 #pragma unroll
-    for (int w = 1; w < PS_THREADS / 32; w++) { base = fminf(base, s_red[w]); hi = fmaxf(hi, s_red[PS_THREADS / 32 + w]); }
+    for (int w = 1; w < PS_THREADS / 32; w++) base = fminf(base, s_red[w]);
+    if (G == 64) {  // groups of two warps
+#pragma unroll
+        for (int w = 0; w < PS_THREADS / 32; w += 2) hi = fmaxf(hi, fminf(s_red[w], s_red[w + 1]));
+    } else {
+#pragma unroll
+        for (int w = 0; w < PS_THREADS / 32; w++) hi = fmaxf(hi, s_red[PS_THREADS / 32 + w]);
+    }
+    const bool vec4 = (K & 3) == 0;
     __shared__ float s_tau;
-    float tau = 0.0f;
-    for (int attempt = 0; attempt < 3; attempt++) {
-        // pass A: 255-bin histogram of the keys below hi (keys below `base` fall into bin 0)
+    __shared__ uint32_t s_bin0;
+    float tau = 0.0f, kmin_true = 3.402823466e+38f;
+    int refines = 0;
+    for (int attempt = 0; attempt < 3;) {
+        // pass A: 255-bin histogram of the keys below hi (keys below `base` fall into bin 0); the true minimum rides along
         const float scale = 255.0f / fmaxf(hi - base, 1e-30f);
-        for (int i = tid; i < K; i += PS_THREADS) {
-            const float v = __ldg(&row[i]);
+        float vmin = 3.402823466e+38f;
+        auto hadd = [&](float v) {
+            vmin = fminf(vmin, v);
             if (v < hi) atomicAdd(&hist[max(0, min(254, (int)((v - base) * scale)))], 1u);
+        };
+        if (vec4) {  // 128-bit loads, several in flight per thread: the pass is a stream over K keys
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+#pragma unroll 4
+            for (int i4 = tid; i4 < K / 4; i4 += PS_THREADS) {
+                const float4 v = __ldg(&row4[i4]);
+                hadd(v.x); hadd(v.y); hadd(v.z); hadd(v.w);
+            }
+        } else {
+            for (int i = tid; i < K; i += PS_THREADS) hadd(__ldg(&row[i]));
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(FULL, vmin, o));
+        if (lane == 0) s_red[warp] = vmin;
         __syncthreads();
+        kmin_true = s_red[0];
+#pragma unroll
+        for (int w = 1; w < PS_THREADS / 32; w++) kmin_true = fminf(kmin_true, s_red[w]);
         if (warp == 0) {  // first bin whose cumulative count reaches P -> tau = its upper edge (hi itself if none does)
             uint32_t c[8], s = 0;
 #pragma unroll
@@ -266,29 +297,47 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
             }
             const uint32_t has = __ballot_sync(FULL, found >= 0);
             const int bsel = has ? __shfl_sync(FULL, found, __ffs(has) - 1) : 255;
-            if (lane == 0) s_tau = bsel >= 254 ? hi : fminf(hi, base + (float)(bsel + 1) / scale * 1.0001f);
+            if (lane == 0) {
+                s_tau = bsel >= 254 ? hi : fminf(hi, base + (float)(bsel + 1) / scale * 1.0001f);
+                s_bin0 = bsel == 0 ? hist[0] : 0u;
+            }
         }
         __syncthreads();
         tau = s_tau;
-        // pass B: candidates {A_c - m_c <= tau + m_max}, and the exact count of {A_c <= tau} that certifies tau
-        const float U = __fadd_ru(tau, mmax), Uq = __fadd_ru(U, mmax);
+        if (s_bin0 > 2u * (uint32_t)P + 32u && refines < 2 && kmin_true < tau) {
+            // the P-th key lies below the sampled range (P/K is smaller than the sample's resolution): the first bin holds far more
+            // than P keys.  Zoom in: histogram [true minimum, upper edge of that bin] instead.
+            refines++;
+            hi = tau;
+            base = kmin_true;
+            __syncthreads();
+            hist[tid] = 0;
+            __syncthreads();
+            continue;
+        }
+        // pass B: candidates {A_c - m_c <= tau + m_max}, and the exact count of {A_c <= tau} that certifies tau.
+        // The P keys <= tau have m_c <= mmax(tau); U bounds the reference's P-th distance (minus ||y'||^2); a candidate's own margin
+        // is taken at its own key (the gamma term grows with the key), bounded by 1.5 mmax(U) for the quick reject.
+        const float mmax = margin(yn, cn_max, tau, alpha, gamma);
+        const float U = __fadd_ru(tau, mmax);
+        const float Uq = __fadd_ru(U, __fmul_ru(margin(yn, cn_max, U, alpha, gamma), 1.5f));
         uint32_t nle = 0;
-        for (int i0 = 0; i0 < K; i0 += PS_THREADS) {
-            const int i = i0 + tid;
-            bool take = false;
-            if (i < K) {
-                const float v = __ldg(&row[i]);
-                nle += v <= tau;
-                if (v <= Uq) take = __fsub_rd(v, margin(yn, __ldg(&cnorm[i]))) <= U;  // (quick reject first: m_c <= m_max)
+        auto consider = [&](float v, int i) {  // candidates are rare: a plain shared-memory append is cheap enough
+            nle += v <= tau;
+            if (v <= Uq && __fsub_rd(v, margin(yn, __ldg(&cnorm[i]), v, alpha, gamma)) <= U) {  // (quick reject first)
+                const uint32_t pos = atomicAdd(&s_ncand, 1u);
+                if (pos < (uint32_t)PS_CAP) cid[pos] = (uint32_t)i;
             }
-            const uint32_t m = __ballot_sync(FULL, take);
-            if (m) {
-                uint32_t pos0 = 0;
-                if (lane == 0) pos0 = atomicAdd(&s_ncand, (uint32_t)__popc(m));
-                pos0 = __shfl_sync(FULL, pos0, 0);
-                const uint32_t pos = pos0 + __popc(m & ((1u << lane) - 1u));
-                if (take && pos < (uint32_t)PS_CAP) cid[pos] = (uint32_t)i;
+        };
+        if (vec4) {
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+#pragma unroll 4
+            for (int i4 = tid; i4 < K / 4; i4 += PS_THREADS) {
+                const float4 v = __ldg(&row4[i4]);
+                consider(v.x, 4 * i4); consider(v.y, 4 * i4 + 1); consider(v.z, 4 * i4 + 2); consider(v.w, 4 * i4 + 3);
             }
+        } else {
+            for (int i = tid; i < K; i += PS_THREADS) consider(__ldg(&row[i]), i);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nle += __shfl_xor_sync(FULL, nle, o);
@@ -300,11 +349,12 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
         hist[tid] = 0;
         if (tid == 0) { s_ncand = 0; s_nle = 0; }
         hi = attempt == 0 ? base + (hi - base) * 4.0f + 1e-30f : 3.402823466e+38f;
+        attempt++;
         __syncthreads();
     }
     const uint32_t nc = s_ncand;
     if (nc > (uint32_t)cap || s_nle < (uint32_t)P) {  // cannot certify this query here: the batch is redone on the classic path
-        if (tid == 0) atomicOr(fallback_flag, 1u);
+        if (tid == 0) atomicOr(fallback_flag, nc > (uint32_t)cap ? 1u : 2u);  // bit 0: too many candidates, bit 1: no valid threshold
         return;
     }
     // exact distances of the candidates, order of simd::l2_squared_distance: 8 lanes per candidate = the 8 AVX lanes

@@ -123,8 +123,11 @@ struct rabitq_index {
     float* cent = nullptr;        // K x D
     uint32_t* offsets = nullptr;  // K+1, local rows
     // tensor-core prefilter of the centroid scan (prefilter.cuh): mean centroid, centred TF32 centroids, their norms
-    float *pf_mu = nullptr, *pf_chat = nullptr, *pf_cnorm = nullptr, *pf_cnorm2 = nullptr, *pf_cnorm_max = nullptr;
+    float *pf_mu = nullptr, *pf_chat = nullptr, *pf_chat_lo = nullptr, *pf_cnorm = nullptr, *pf_cnorm2 = nullptr, *pf_cnorm_max = nullptr;
     int prefilter = 1;            // 0 = always the classic exact scan + select
+    int pf_mode = 1;              // 1 = plain TF32 keys, 3 = 3xTF32 split (tighter bound), 0 = gave up (exact path); adapts to the data
+    int pf_strikes = 0;           // batches the current mode could not certify
+    bool pf_pending = false;      // a fallback flag is on its way to h_pin[6]
     int prefilter_cap = 1024;     // candidates per query the prefilter may certify (tests lower it to force the fallback)
     float* quant_bias = nullptr;  // D: non-NULL switches K3 to the reference's non-AVX2 quantiser (rabitq_set_quantize_bias)
     uint32_t* goffsets = nullptr; // K+1, rows of the WHOLE index (equal to offsets on an unsharded handle)
@@ -142,7 +145,7 @@ struct rabitq_index {
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, cl_count,
         cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
-        entries, counters, out_dist, out_ids, out_count, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_ynorm, pf_flag;
+        entries, counters, out_dist, out_ids, out_count, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag;
     DistState dist;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
     // metrics (src/metrics.rs)
@@ -159,7 +162,7 @@ struct rabitq_index {
     ~rabitq_index() {
         cudaSetDevice(device);
         for (void* p : {(void*)base, (void*)P, (void*)cent, (void*)offsets, (void*)goffsets, (void*)row_bounds, (void*)map_ids, (void*)codes,
-                        (void*)factors, (void*)dist.peers_d, (void*)quant_bias, (void*)pf_mu, (void*)pf_chat, (void*)pf_cnorm, (void*)pf_cnorm2,
+                        (void*)factors, (void*)dist.peers_d, (void*)quant_bias, (void*)pf_mu, (void*)pf_chat, (void*)pf_chat_lo, (void*)pf_cnorm, (void*)pf_cnorm2,
                         (void*)pf_cnorm_max})
             if (p) cudaFree(p);
         for (size_t r = 0; r < dist.peers_h.size(); r++)
@@ -168,7 +171,7 @@ struct rabitq_index {
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &qrec, &cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count,
-                          &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_ynorm, &pf_flag})
+                          &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         for (auto e : ev_pool) cudaEventDestroy(e);
@@ -235,22 +238,25 @@ int finish_index(rabitq_index* ix) {
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     CU(cudaMallocHost((void**)&ix->h_pin, 256));
+    std::memset(ix->h_pin, 0, 256);
     CU(cudaFuncSetAttribute(rerank_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(rerank_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(rerank_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(approx_gemm_tf32_kernel<128, 128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * PF_PITCH * 4));
     if (const char* e = std::getenv("RABITQ_PREFILTER")) ix->prefilter = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_PREFILTER_MODE")) ix->pf_mode = std::atoi(e);
     {   // prefilter operands: mu, c^ = tf32(c - mu), ||c - mu||, ||c - mu||^2, max norm
         const size_t K = ix->K, D = ix->D;
         CU(cudaMalloc((void**)&ix->pf_mu, D * 4));
         CU(cudaMalloc((void**)&ix->pf_chat, K * D * 4));
+        CU(cudaMalloc((void**)&ix->pf_chat_lo, K * D * 4));
         CU(cudaMalloc((void**)&ix->pf_cnorm, K * 4));
         CU(cudaMalloc((void**)&ix->pf_cnorm2, K * 4));
         CU(cudaMalloc((void**)&ix->pf_cnorm_max, 4));
         CU(cudaMemset(ix->pf_cnorm_max, 0, 4));
         centroid_mean_kernel<<<(unsigned)((D + 127) / 128), 128>>>(ix->cent, (int)K, (int)D, ix->pf_mu);
-        centroid_center_kernel<<<(unsigned)((K + 3) / 4), 128>>>(ix->cent, ix->pf_mu, (int)K, (int)D, ix->pf_chat, ix->pf_cnorm, ix->pf_cnorm2,
+        centroid_center_kernel<<<(unsigned)((K + 3) / 4), 128>>>(ix->cent, ix->pf_mu, (int)K, (int)D, ix->pf_chat, ix->pf_chat_lo, ix->pf_cnorm, ix->pf_cnorm2,
                                                                   ix->pf_cnorm_max);
         CU(cudaGetLastError());
         CU(cudaDeviceSynchronize());
@@ -259,7 +265,25 @@ int finish_index(rabitq_index* ix) {
 }
 
 // Is the tensor-core prefilter worth it (and within its candidate capacity) for this (K, P)?
-bool use_prefilter(const rabitq_index* ix, int P) { return ix->prefilter && ix->K >= 512 && (size_t)P * 8 <= ix->K && P <= 384; }
+bool use_prefilter(const rabitq_index* ix, int P) {
+    return ix->prefilter && ix->pf_mode != 0 && ix->K >= 512 && (size_t)P * 8 <= ix->K && P <= 384;
+}
+
+// Host-side adaptation, called wherever the stream has just been synchronised: a batch the prefilter could not certify (it was
+// then answered by the exact kernels on the device) moves the handle to the tighter 3xTF32 keys, and a second one to the
+// exact path for good.  Results never depend on the mode.
+void prefilter_adapt(rabitq_index* ix) {
+    if (!ix->pf_pending) return;
+    ix->pf_pending = false;
+    if (ix->h_pin[6] == 0u) return;
+    if (std::getenv("RABITQ_TRACE")) std::fprintf(stderr, "[rabitq trace] prefilter mode %d could not certify a batch (reason bits %u)\n", ix->pf_mode, ix->h_pin[6]);
+    ix->h_pin[6] = 0u;
+    if (ix->prefilter_cap < PS_CAP) return;  // a test lowered the capacity to force the fallback: not the data's fault
+    if (++ix->pf_strikes >= 2) {
+        ix->pf_mode = ix->pf_mode == 1 ? 3 : 0;
+        ix->pf_strikes = 0;
+    }
+}
 
 // Build a handle from host or device arrays (full index); keeps only this shard's rows.
 int make_index(uint32_t dim, size_t n_total, size_t K, const float* base, const float* orth, const float* cent,
@@ -681,27 +705,40 @@ int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_ro
         CU(ix->pf_ynorm.ensure(nb * 4));
         CU(ix->pf_flag.ensure(4));
         CU(cudaMemsetAsync(ix->pf_flag.p, 0, 4, st));
+        const bool split = ix->pf_mode == 3;
+        if (split) CU(ix->pf_yhat_lo.ensure(nb * (size_t)D * 4));
         query_center_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, st>>>(ix->y.as<float>(), ix->pf_mu, (int)nb, D, ix->pf_yhat.as<float>(),
-                                                                      ix->pf_ynorm.as<float>());
+                                                                      split ? ix->pf_yhat_lo.as<float>() : nullptr, ix->pf_ynorm.as<float>());
         CU(cudaGetLastError()); ix->counts[5]++;
         const size_t tiles128 = ((nb + 127) / 128) * (size_t)((K + 127) / 128);
-        if (tiles128 >= (size_t)ix->sm_count) {
-            dim3 grid((K + 127) / 128, (unsigned)((nb + 127) / 128));
-            approx_gemm_tf32_kernel<128, 128, 2, 4><<<grid, 256, 2 * 256 * PF_PITCH * 4, st>>>(ix->pf_yhat.as<float>(), ix->pf_chat, ix->pf_cnorm2,
-                                                                                                (int)nb, K, D, ix->cdist.as<float>());
-        } else {
-            dim3 grid((K + 63) / 64, (unsigned)((nb + 63) / 64));
-            approx_gemm_tf32_kernel<64, 64, 2, 2><<<grid, 128, 2 * 128 * PF_PITCH * 4, st>>>(ix->pf_yhat.as<float>(), ix->pf_chat, ix->pf_cnorm2,
-                                                                                              (int)nb, K, D, ix->cdist.as<float>());
+        auto gemm = [&](const float* ya, const float* cb, int accumulate) {
+            if (tiles128 >= (size_t)ix->sm_count) {
+                dim3 grid((K + 127) / 128, (unsigned)((nb + 127) / 128));
+                approx_gemm_tf32_kernel<128, 128, 2, 4><<<grid, 256, 2 * 256 * PF_PITCH * 4, st>>>(ya, cb, ix->pf_cnorm2, (int)nb, K, D,
+                                                                                                    ix->cdist.as<float>(), accumulate);
+            } else {
+                dim3 grid((K + 63) / 64, (unsigned)((nb + 63) / 64));
+                approx_gemm_tf32_kernel<64, 64, 2, 2><<<grid, 128, 2 * 128 * PF_PITCH * 4, st>>>(ya, cb, ix->pf_cnorm2, (int)nb, K, D,
+                                                                                                  ix->cdist.as<float>(), accumulate);
+            }
+            ix->counts[5]++;
+        };
+        gemm(ix->pf_yhat.as<float>(), ix->pf_chat, 0);
+        if (split) {  // 3xTF32: hi*hi + hi*lo + lo*hi
+            gemm(ix->pf_yhat.as<float>(), ix->pf_chat_lo, 1);
+            gemm(ix->pf_yhat_lo.as<float>(), ix->pf_chat, 1);
         }
-        CU(cudaGetLastError()); ix->counts[5]++;
+        CU(cudaGetLastError());
         if (tick(ix, ST_CDIST)) return RABITQ_ECUDA;
         const size_t ps_smem = (size_t)D * 4 + PS_CAP * 12 + (size_t)P * 4;
         prefilter_select_kernel<<<(unsigned)nb, PS_THREADS, ps_smem, st>>>(
             ix->cdist.as<float>(), ix->pf_ynorm.as<float>(), ix->pf_cnorm, ix->pf_cnorm_max, ix->y.as<float>(), ix->cent, K, P, D, ix->offsets,
             global_view ? ix->goffsets : nullptr, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(),
             ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), ix->q_p0.as<uint32_t>(), ix->pf_flag.as<uint32_t>(),
-            std::max(1, std::min(ix->prefilter_cap, PS_CAP)));
+            std::max(1, std::min(ix->prefilter_cap, PS_CAP)), split ? (float)(2 * D + 64) * 4.76837158203125e-07f : 0.00390625f,
+            (float)(D / 8 + 8) * 1.1920928955078125e-07f);
+        CU(cudaMemcpyAsync(ix->h_pin + 6, ix->pf_flag.p, 4, cudaMemcpyDeviceToHost, st));
+        ix->pf_pending = true;
         CU(cudaGetLastError()); ix->counts[5]++;
         run_if = ix->pf_flag.as<uint32_t>();  // the classic kernels below run only if some query could not be certified
     }
@@ -744,6 +781,7 @@ int fetch_totals(rabitq_index* ix, size_t nb, BatchOut* bo) {
     CU(cudaMemcpyAsync(ix->h_pin + 2, ix->q_pbase.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
     if (tick(ix, ST_SELECT)) return RABITQ_ECUDA;
     CU(cudaStreamSynchronize(st));
+    prefilter_adapt(ix);
     bo->total_words = ix->h_pin[0];
     std::memcpy(&bo->total_pairs, ix->h_pin + 2, 8);
     return 0;
@@ -987,7 +1025,8 @@ int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, siz
     std::memset(ix->ms, 0, sizeof(ix->ms));
     std::memset(ix->counts, 0, sizeof(ix->counts));
     ix->ev_used = 0;
-    const size_t nbmax = pick_sub_batch(ix, nq, probe);
+    size_t nbmax = pick_sub_batch(ix, nq, probe);
+    nbmax = (nq + (nq + nbmax - 1) / nbmax - 1) / ((nq + nbmax - 1) / nbmax);  // equal sub-batches, not one full and one tiny
     cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     cudaMemcpyKind kout = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (tick(ix, -1)) return RABITQ_ECUDA;
@@ -1260,6 +1299,7 @@ int dist_finish_impl(rabitq_index* ix, float* d_out_dist, uint32_t* d_out_ids, u
     if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
     CU(cudaMemcpyAsync(ix->h_pin + 8, ix->counters.p, 32, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    prefilter_adapt(ix);
     unsigned long long c[4], rough_home;
     std::memcpy(c, ix->h_pin + 8, 32);
     std::memcpy(&rough_home, ix->h_pin + 4, 8);
@@ -1387,6 +1427,19 @@ int rabitq_from_path(const char* base_path, const char* centroid_path, uint64_t 
 
 int rabitq_dump_to_dir(rabitq_index* idx, const char* dir) { return dump_impl(idx, dir); }
 
+int rabitq_reshard(rabitq_index* idx, int shard_rank, int shard_count, rabitq_index** out) {
+    if (!idx || !out) return fail(RABITQ_EINVAL, "null argument");
+    if (idx->shard_count != 1) return fail(RABITQ_EUNSUPPORTED, "reshard needs an unsharded handle");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CU(cudaSetDevice(idx->device));
+    CU(cudaStreamSynchronize(idx->stream));
+    std::vector<uint32_t> off_h(idx->K + 1);
+    CU(cudaMemcpy(off_h.data(), idx->offsets, (idx->K + 1) * 4, cudaMemcpyDeviceToHost));
+    return make_index(idx->D, idx->n, idx->K, idx->base, idx->P, idx->cent, off_h.data(), idx->map_ids,
+                      reinterpret_cast<const uint64_t*>(idx->codes), reinterpret_cast<const float*>(idx->factors), true, idx->device, shard_rank,
+                      shard_count, out);
+}
+
 int rabitq_export_arrays(rabitq_index* idx, float* base, float* orthogonal, float* centroids, uint32_t* offsets, uint32_t* map_ids,
                          uint64_t* codes, float* factors, int ptr_on_device) {
     if (!idx) return fail(RABITQ_EINVAL, "null index");
@@ -1474,6 +1527,7 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     else if (n == "rerank_rows") idx->rerank_rows = (int)value;
     else if (n == "scan_slices") idx->scan_slices = (int)std::max(1L, value);
     else if (n == "prefilter") idx->prefilter = (int)value;
+    else if (n == "prefilter_mode") { idx->pf_mode = (int)value; idx->pf_strikes = 0; }
     else if (n == "prefilter_cap") idx->prefilter_cap = (int)value;
     else return fail(RABITQ_EINVAL, "unknown option: " + n);
     return RABITQ_OK;

@@ -428,13 +428,14 @@ def test_prefilter_probe_lists_bit_exact(oracle_lib, name):
     K = g.num_clusters
     for probe in (1, 7, 32, K // 8):
         tr = [case["oracle"].trace(q[i], probe, 5) for i in range(q.shape[0])]
-        for opt, val in (("prefilter", 1), ("prefilter_cap", 1), ("prefilter", 0)):
-            g.set_option(opt, val)
+        for opt, val in (("prefilter", 1), ("prefilter_mode", 3), ("prefilter_cap", 1), ("prefilter", 0)):
+            g.set_option(opt, val)   # plain TF32 keys, the 3xTF32 split, the device-side fallback, the classic path
             try:
                 _, pid, pd = g.stage_probe(q, probe, want_all=False)
             finally:
                 g.set_option("prefilter", 1)
                 g.set_option("prefilter_cap", 1024)
+                g.set_option("prefilter_mode", 1)
             for i in range(q.shape[0]):
                 assert np.array_equal(pid[i], tr[i]["probe_ids"]), (name, probe, opt, val, i)
                 assert np.array_equal(pd[i].view(np.uint32), tr[i]["probe_dist"].view(np.uint32)), (name, probe, opt, val, i)
