@@ -177,13 +177,26 @@ __global__ void __launch_bounds__(WM * WN * 32) approx_gemm_tf32_kernel(const fl
         for (int j = 0; j < TN; j++) {
             const int c = c0 + wn * TN * 8 + j * 8 + 2 * t;
             const int qa = q0 + wm * TM * 16 + i * 16 + g, qb = qa + 8;
+            if (c + 1 < K && (K & 1) == 0) {  // two adjacent columns per lane: 64-bit accesses
+                const float2 n01 = accumulate ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(cnorm2 + c));
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int cc = c + (e & 1), qq = (e & 2) ? qb : qa;
-                if (cc < K && qq < nq) {
-                    float* dst = A + (size_t)qq * K + cc;
-                    const float prev = accumulate ? *dst : __ldg(&cnorm2[cc]);
-                    *dst = prev - 2.0f * acc[i][j][e];
+                for (int h = 0; h < 2; h++) {
+                    const int qq = h ? qb : qa;
+                    if (qq < nq) {
+                        float2* dst = reinterpret_cast<float2*>(A + (size_t)qq * K + c);
+                        const float2 prev = accumulate ? *dst : n01;
+                        *dst = make_float2(prev.x - 2.0f * acc[i][j][2 * h], prev.y - 2.0f * acc[i][j][2 * h + 1]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int cc = c + (e & 1), qq = (e & 2) ? qb : qa;
+                    if (cc < K && qq < nq) {
+                        float* dst = A + (size_t)qq * K + cc;
+                        const float prev = accumulate ? *dst : __ldg(&cnorm2[cc]);
+                        *dst = prev - 2.0f * acc[i][j][e];
+                    }
                 }
             }
         }
