@@ -278,8 +278,10 @@ def run_ours(args):
         for k in rb.COUNT_NAMES:
             counts[k] += t[k]
 
+    torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off` sees exactly the timed steps (no data generation / index build)
     ms_dev = timed(step_dev, args.steps)
     torch.cuda.synchronize(device)
+    torch.cuda.cudart().cudaProfilerStop()
     if world > 1:
         dist.barrier()
 

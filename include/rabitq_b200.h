@@ -166,13 +166,19 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
 
 /* Integer tuning knobs (results never depend on them; tests sweep them): "first_chunks" = 128-vector chunks of the nearest
  * cluster that form the first rerank round (default 1, 0 = whole cluster); "scan_mode" = carry-save depth of the scan's
- * popcount (0 plain, 1 = 3->2, 2 = 7->3 compressors, -1 = by dimension); "rerank_rows" = rows per rerank wave (0 = auto); "scan_slices" = shared-memory record slices per scan
+ * popcount (0 plain, 1 = 3->2, 2 = 7->3 compressors, -1 = by dimension); "rerank_rows" = rows per rerank wave (0 = auto); "rerank_prefetch" = L2 prefetch of survivor rows ahead of the
+ * gather (default 0: measured slower on B200); "debug_rerank" = 1 keeps per-query rerank statistics for rabitq_debug_rerank_stats; "scan_slices" = shared-memory record slices per scan
  * work item (default 1; hot clusters are cut into several items); "prefilter" = 1 (default) lets the centroid scan run as a
  * TF32 tensor-core prefilter + exact recheck of the candidates when k >= 512 and probe <= k/8 (probe lists stay bit-identical),
  * 0 = always all k exact distances; "prefilter_cap" = candidates per query the prefilter may certify (<= 1024; a query
  * above it sends its batch to the exact path on the device); "prefilter_mode" = 1 plain TF32 keys, 3 = 3xTF32 split, 0 = off
  * (the handle moves 1 -> 3 -> 0 by itself when batches cannot be certified). */
 int rabitq_set_option(rabitq_index* idx, const char* name, long value);
+
+/* After a batch run with "debug_rerank" = 1: out[nq][2 rounds][8] = {SM cycles the query's warp spent in K5, waves, exact
+ * distances computed, survivor words streamed, cycles waiting for gathered rows, in the exact distances, in the replay, staging
+ * survivor words} of the last sub-batch.  Tuning aid; not part of the reference's surface. */
+int rabitq_debug_rerank_stats(rabitq_index* idx, uint32_t* out, size_t nq);
 
 /* The reference's OTHER query quantiser.  On a host without AVX2, `scalar_quantize` falls back to
  * `scalar_quantize_raw` (src/utils.rs:194-209): q = ((r - lo) * (1/delta) + rand_bias[i]) as u8 -- truncation plus a random

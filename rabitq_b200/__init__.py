@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "rabitq_shard_range", "rabitq_merge_topk_device", "rabitq_metrics", "rabitq_metrics_reset", "rabitq_last_error", "rabitq_set_rounds",
     "rabitq_set_option", "rabitq_set_stream", "rabitq_last_timings", "rabitq_stage_rotate", "rabitq_stage_probe", "rabitq_stage_quantize", "rabitq_stage_scan",
     "rabitq_dist_init", "rabitq_dist_ipc_handle", "rabitq_dist_inbox_ptr", "rabitq_dist_set_peer", "rabitq_dist_chunk_words", "rabitq_dist_front",
-    "rabitq_dist_round1", "rabitq_dist_round2", "rabitq_dist_finish", "rabitq_min_f32_device", "rabitq_set_quantize_bias", "rabitq_reshard",
+    "rabitq_dist_round1", "rabitq_dist_round2", "rabitq_dist_finish", "rabitq_min_f32_device", "rabitq_set_quantize_bias", "rabitq_reshard", "rabitq_debug_rerank_stats",
 ]
 
 TIMING_STAGES = ["h2d_pad", "rotate", "centroid_dist", "select", "quantize", "bucket", "scan", "rerank", "d2h", "total"]
@@ -96,6 +96,7 @@ def lib():
     L.rabitq_set_stream.argtypes = [vp, vp]
     L.rabitq_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.rabitq_set_quantize_bias.argtypes = [vp, vp]
+    L.rabitq_debug_rerank_stats.argtypes = [vp, vp, C.c_size_t]
     L.rabitq_stage_rotate.argtypes = [vp, vp, C.c_size_t, C.c_size_t, vp]
     L.rabitq_stage_probe.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp]
     L.rabitq_stage_quantize.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp, vp]
@@ -310,6 +311,12 @@ class RaBitQ:
 
     def set_option(self, name: str, value: int) -> None:
         _check(lib().rabitq_set_option(self._h, name.encode(), int(value)))
+
+    def debug_rerank_stats(self, nq: int) -> np.ndarray:
+        """[nq, 2 rounds, (cycles, waves, exact computed, words streamed, wait, l2, replay, stage cycles)] of the last batch (after set_option("debug_rerank", 1))."""
+        out = np.zeros((nq, 2, 8), np.uint32)
+        _check(lib().rabitq_debug_rerank_stats(self._h, C.c_void_p(out.ctypes.data), nq))
+        return out
 
     def set_quantize_bias(self, bias) -> None:
         """Switch the query quantiser to `scalar_quantize_raw` (src/utils.rs:194-209, the reference on a host without AVX2)

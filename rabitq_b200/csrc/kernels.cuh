@@ -74,63 +74,111 @@ __global__ void pad_queries_kernel(const float* __restrict__ q, float* __restric
 
 // ---------------------------------------------------------------------------------------------------------
 // K1: batched rotation y = q * P with the summation order of project -> simd::vector_dot_product
-// (src/utils.rs:237-258, src/simd.rs:257-314).  CTA tile = 64 output columns x 32 queries; the P tile (64 rows x
-// 64 columns, row r = P[r,:] as on disk) and the query tile are staged in shared memory with coalesced 128-bit
-// loads.  Thread = one column x 8 queries, 8 AVX-lane accumulators each.  CUDA cores by necessity: the quantised
-// codes downstream must be bit-exact, so y must be, so the 8-lane FMA association is reproduced (no 3xTF32).
-constexpr int ROT_TQ = 8;
-constexpr int ROT_QG = 4;
-constexpr int ROT_TC = 64;
-constexpr int ROT_THREADS = ROT_TC * ROT_QG;
-constexpr int ROT_RCH = 64;
+// (src/utils.rs:237-258, src/simd.rs:257-314): AVX lane l accumulates fma(q[r], P[r][c], acc_l) over r = l, l+8, ... in
+// ascending order and reduce_f32_256 adds the 8 lanes as ((0+4)+(1+5))+((2+6)+(3+7)).  CUDA cores by necessity: the
+// quantised codes downstream must be bit-exact, so y must be, so that association is reproduced (no 3xTF32).
+//
+// The kernel is bound by shared-memory operand bandwidth, so the register tile is made as large as the 8-lane structure
+// allows: a thread owns TWO of the eight AVX lanes (one packed fma.rn.f32x2 pair) of an 8-query x 8-column tile
+// (64 independent FFMA2 chains), four threads complete an output and combine their lane pairs with shuffles in the
+// reference's order at the end.  Per 8 rows a thread loads 8 + 8 64-bit operands for 64 FFMA2 (2 B per FFMA2; the
+// previous one-column-x-8-queries tile needed 9).  PT is P transposed (PT[c][r] = P[r][c], built once per index), so that a
+// thread's two rows of a column are adjacent; tiles are staged by a two-stage cp.async pipeline (the loads of rows
+// r0+64.. fly while rows r0.. are consumed); the 72-float pitch puts the 8 column groups of a warp on disjoint banks.
+constexpr int ROT_TC = 64;        // output columns per CTA
+constexpr int ROT_TQ = 32;        // queries per CTA (8 per warp)
+constexpr int ROT_THREADS = 128;
+constexpr int ROT_RCH = 64;       // rows of P per shared-memory stage
+constexpr int ROT_PITCH = ROT_RCH + 8;
 
-__global__ void __launch_bounds__(ROT_THREADS, 2) rotate_kernel(const float* __restrict__ qpad, const float* __restrict__ P,
+__global__ void transpose_square_kernel(const float* __restrict__ in, float* __restrict__ out, int D) {
+    __shared__ float t[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) t[i][threadIdx.x] = in[(size_t)(by + i) * D + bx + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) out[(size_t)(bx + i) * D + by + threadIdx.x] = t[threadIdx.x][i];
+}
+
+RQ_DEV void cp_async16(void* dst_smem, const void* src_gmem, bool valid) {  // 16 B global -> shared, zero-filled when !valid
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src_gmem), "r"(n) : "memory");
+}
+RQ_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+RQ_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int ROT_STAGE_FLOATS = (ROT_TC + ROT_TQ) * ROT_PITCH;
+constexpr int ROT_SMEM_BYTES = 2 * ROT_STAGE_FLOATS * 4;  // two stages (cp.async double buffer): 55 KB
+
+__global__ void __launch_bounds__(ROT_THREADS, 3) rotate_kernel(const float* __restrict__ qpad, const float* __restrict__ PT,
                                                                 float* __restrict__ y, int nq, int D) {
-    __shared__ __align__(16) float sP[ROT_RCH][ROT_TC];
-    __shared__ float4 sq[ROT_QG * ROT_TQ][ROT_RCH / 4];
-    const int tid = threadIdx.x;
-    const int cl = tid & (ROT_TC - 1), qg = tid / ROT_TC;
-    const int col0 = blockIdx.x * ROT_TC, col = col0 + cl;
-    const int qb = blockIdx.y * (ROT_QG * ROT_TQ), q0 = qb + qg * ROT_TQ;
-    f32x2 acc[ROT_TQ][4];
+    extern __shared__ __align__(16) float rot_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int v = lane & 3, g = lane >> 2;  // v: AVX lanes 2v, 2v+1;  g: columns g, g+8, ..., g+56 of the CTA tile
+    const int col0 = blockIdx.x * ROT_TC, qb = blockIdx.y * ROT_TQ;
+    auto load_stage = [&](int stage, int r0) {  // P tile (64 columns x 64 rows) and query tile (32 x 64) of rows [r0, r0 + 64)
+        float* sP = rot_smem + stage * ROT_STAGE_FLOATS;
+        float* sq = sP + ROT_TC * ROT_PITCH;
 #pragma unroll
-    for (int t = 0; t < ROT_TQ; t++)
-#pragma unroll
-        for (int v = 0; v < 4; v++) acc[t][v] = 0ull;
-    for (int r0 = 0; r0 < D; r0 += ROT_RCH) {
-#pragma unroll
-        for (int i = 0; i < (ROT_RCH * ROT_TC / 4) / ROT_THREADS; i++) {
-            const int idx = tid + i * ROT_THREADS, row = idx / (ROT_TC / 4), c4 = idx % (ROT_TC / 4);
-            *reinterpret_cast<float4*>(&sP[row][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(P + (size_t)(r0 + row) * D + col0) + c4);
+        for (int i = 0; i < (ROT_TC * ROT_RCH / 4) / ROT_THREADS; i++) {
+            const int idx = tid + i * ROT_THREADS, c = idx / (ROT_RCH / 4), r4 = idx % (ROT_RCH / 4);
+            cp_async16(sP + c * ROT_PITCH + r4 * 4, PT + (size_t)(col0 + c) * D + r0 + r4 * 4, true);
         }
 #pragma unroll
-        for (int i = 0; i < (ROT_QG * ROT_TQ * ROT_RCH / 4) / ROT_THREADS; i++) {
-            const int idx = tid + i * ROT_THREADS, row = idx / (ROT_RCH / 4), c4 = idx % (ROT_RCH / 4);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (qb + row < nq) v = __ldg(reinterpret_cast<const float4*>(qpad + (size_t)(qb + row) * D + r0) + c4);
-            sq[row][c4] = v;
+        for (int i = 0; i < (ROT_TQ * ROT_RCH / 4) / ROT_THREADS; i++) {
+            const int idx = tid + i * ROT_THREADS, row = idx / (ROT_RCH / 4), r4 = idx % (ROT_RCH / 4);
+            const bool ok = qb + row < nq;
+            cp_async16(sq + row * ROT_PITCH + r4 * 4, qpad + (size_t)(ok ? qb + row : 0) * D + r0 + r4 * 4, ok);
+        }
+        cp_async_commit();
+    };
+    f32x2 acc[8][8];
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[t][j] = 0ull;
+    const int nch = D / ROT_RCH;
+    load_stage(0, 0);
+    for (int it = 0; it < nch; it++) {
+        if (it + 1 < nch) {
+            load_stage((it + 1) & 1, (it + 1) * ROT_RCH);  // in flight while this stage is consumed
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        const float* sP = rot_smem + (it & 1) * ROT_STAGE_FLOATS + (size_t)g * ROT_PITCH + 2 * v;
+        const float* sq = rot_smem + (it & 1) * ROT_STAGE_FLOATS + ROT_TC * ROT_PITCH + (size_t)(warp * 8) * ROT_PITCH + 2 * v;
 #pragma unroll 2
         for (int r = 0; r < ROT_RCH; r += 8) {
-            f32x2 pv[4];
+            f32x2 pv[8], qv[8];
 #pragma unroll
-            for (int v = 0; v < 4; v++) pv[v] = pack2(sP[r + 2 * v][cl], sP[r + 2 * v + 1][cl]);
+            for (int j = 0; j < 8; j++) pv[j] = *reinterpret_cast<const f32x2*>(sP + 8 * j * ROT_PITCH + r);
 #pragma unroll
-            for (int t = 0; t < ROT_TQ; t++) {
-                const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&sq[qg * ROT_TQ + t][r / 4]);
-                const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(&sq[qg * ROT_TQ + t][r / 4 + 1]);
-                acc[t][0] = fma2(a.x, pv[0], acc[t][0]);  // AVX lanes 0,1
-                acc[t][1] = fma2(a.y, pv[1], acc[t][1]);  // 2,3
-                acc[t][2] = fma2(b.x, pv[2], acc[t][2]);  // 4,5
-                acc[t][3] = fma2(b.y, pv[3], acc[t][3]);  // 6,7
-            }
+            for (int t = 0; t < 8; t++) qv[t] = *reinterpret_cast<const f32x2*>(sq + t * ROT_PITCH + r);
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[t][j] = fma2(qv[t], pv[j], acc[t][j]);
         }
-        __syncthreads();
+        __syncthreads();  // the stage is refilled by the next iteration's load
     }
+    // reduce_f32_256: c_i = s_i + s_{i+4}; (c0 + c1) + (c2 + c3).  Thread v holds s_{2v}, s_{2v+1}; all four threads of a
+    // group end up with the same bits (fp32 addition commutes), thread v stores columns j = 2v, 2v+1.
 #pragma unroll
-    for (int t = 0; t < ROT_TQ; t++)
-        if (q0 + t < nq) y[(size_t)(q0 + t) * D + col] = reduce8p(acc[t]);
+    for (int t = 0; t < 8; t++) {
+        const int q = qb + warp * 8 + t;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float lo, hi, olo, ohi;
+            unpack2(acc[t][j], lo, hi);
+            unpack2(__shfl_xor_sync(FULL, acc[t][j], 2), olo, ohi);
+            const float s = __fadd_rn(__fadd_rn(lo, olo), __fadd_rn(hi, ohi));  // v even: c0 + c1, v odd: c2 + c3
+            const float res = __fadd_rn(s, __shfl_xor_sync(FULL, s, 1));
+            if ((j >> 1) == v && q < nq) y[(size_t)q * D + col0 + g + 8 * j] = res;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -937,6 +985,8 @@ struct RerankArgs {
     int nq, P, D, topk;
     int R;                        // rows per wave (<= 32)
     int smem_per_warp;            // bytes
+    int prefetch;                 // L2 prefetch of the survivors' base rows at discovery time (0 = off)
+    uint32_t* dbg;                // NULL, or nq x 2 rounds x {cycles, waves, computed, words, wait, l2, replay, stage} (rabitq_debug_rerank_stats)
     // distributed record sink (template SINK != 0): records go straight into the inbox of the
     // query's HOME rank -- peer memory over NVLink (one process per GPU) or plain device memory (ranks in one process)
     unsigned char* const* peers;  // inbox base of every rank
@@ -970,6 +1020,9 @@ RQ_DEV void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+RQ_DEV void prefetch_l2_bulk(const void* src_gmem, uint32_t bytes) {  // no destination: warms L2 ahead of the TMA row gather
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 RQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
     for (uint32_t spin = 0; !ok; spin++) {
@@ -982,6 +1035,13 @@ RQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, float& thr) {
+    if (k <= 32) {  // one redux + one ballot: the largest key, lowest slot among equals (what a sequential scan finds first)
+        const uint32_t key = lane < k ? okey(hd[lane]) : 0u;
+        const uint32_t bk = __reduce_max_sync(FULL, key);
+        maxpos = __ffs(__ballot_sync(FULL, lane < k && key == bk)) - 1;
+        thr = okey_to_float(bk);
+        return;
+    }
     uint32_t bk = 0;
     int bp = 0x7fffffff;
     for (int s = lane; s < k; s += 32) {
@@ -998,6 +1058,39 @@ RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, fl
     thr = okey_to_float(bk);
 }
 
+// Exact squared L2 of one staged row against the query in the order of simd::l2_squared_distance (src/simd.rs:14-73): AVX lane l
+// runs over elements l, l+8, ... ascending with diff = row - q rounded, then fma(diff, diff, acc); reduce_f32_256 adds the lanes
+// as ((0+4)+(1+5))+((2+6)+(3+7)).  FOUR threads per candidate, thread v4 owns AVX lanes 2*v4 and 2*v4+1 as one packed f32x2
+// (64-bit shared-memory loads, sub.rn.f32x2 + fma.rn.f32x2: half the instructions of a lane-per-thread loop).  The chain of D/8
+// dependent FMAs is the critical path of a wave, so the operands of the next 4 steps are loaded while the current 4 are
+// consumed (D is a multiple of 64).  All four threads return the same bits.
+RQ_DEV float l2_quad(const float* __restrict__ row, const float* __restrict__ qv, int D, int v4) {
+    const f32x2* rp = reinterpret_cast<const f32x2*>(row) + v4;  // pair (2 v4, 2 v4 + 1) of 8-element step i at rp[4 i]
+    const f32x2* qp = reinterpret_cast<const f32x2*>(qv) + v4;
+    f32x2 x[4], q[4], acc = 0ull;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { x[i] = rp[4 * i]; q[i] = qp[4 * i]; }
+    const int nblk = D / 32;
+    for (int b = 0; b < nblk; b++) {
+        const int o = 16 * min(b + 1, nblk - 1);  // the last block re-reads itself (unused)
+        f32x2 nx[4], nq[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { nx[i] = rp[o + 4 * i]; nq[i] = qp[o + 4 * i]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const f32x2 f = sub2(x[i], q[i]);
+            acc = fma2(f, f, acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) { x[i] = nx[i]; q[i] = nq[i]; }
+    }
+    float lo, hi, olo, ohi;
+    unpack2(acc, lo, hi);
+    unpack2(__shfl_xor_sync(FULL, acc, 2), olo, ohi);
+    const float s = __fadd_rn(__fadd_rn(lo, olo), __fadd_rn(hi, ohi));  // v4 even: c0 + c1, odd: c2 + c3
+    return __fadd_rn(s, __shfl_xor_sync(FULL, s, 1));
+}
+
 // HEUR = false: HeapReRanker (src/rerank.rs:61-114).  HEUR = true: HeuristicReRanker (src/rerank.rs:117-176): the filter
 // threshold is the largest accepted distance of the last WINDOW_SIZE = 12 accepted candidates (src/consts.rs:12); every
 // accepted candidate is a result candidate and get_result keeps the topk smallest, which is what the k-slot buffer holds.
@@ -1005,7 +1098,7 @@ RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, fl
 // cluster): the same sequential replay, and every candidate the reference computes an exact distance for is also written
 // to the home rank's inbox.  (The distributed round 2 has no sequential dependency and is a flat kernel: r2_exact_kernel.)
 template <bool HEUR, int SINK>
-__global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int ch_lo, int p_hi, int ch_hi, int first, int finalize) {
+__global__ void __launch_bounds__(128, 5) rerank_kernel(RerankArgs a, int p_lo, int ch_lo, int p_hi, int ch_hi, int first, int finalize) {
     extern __shared__ __align__(16) unsigned char rr_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int q = blockIdx.x * wpb + warp;
@@ -1024,6 +1117,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     uint32_t* stot = reinterpret_cast<uint32_t*>(sent + 128);  // [4]
     const uint32_t lt_mask = (1u << lane) - 1u;
 
+    const long long dbg_t0 = a.dbg ? clock64() : 0ll;
+    uint32_t dbg_waves = 0, dbg_wait = 0, dbg_l2 = 0, dbg_replay = 0, dbg_stage = 0;
+    const bool dbg_on = a.dbg != nullptr;
     if (lane == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
     // prologue: every independent global load is issued before the first dependent use (the kernel is a chain of
     // memory latencies; the fewer links the better)
@@ -1073,94 +1169,77 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     }
     uint32_t precise = 0, computed = 0, par = 0;
     int fill = 0, f = 0, pend_n = 0;  // wave being filled, its fill level, size of the closed-but-unprocessed wave (buffer f^1)
-    const int sub = lane >> 3, v = lane & 7;
 
     // process one closed wave: wait for its rows, all exact distances in parallel, in-order replay
     auto process = [&](int w, int n) {
+        long long dt0 = dbg_on ? clock64() : 0ll;
         if (lane == 0) mbar_arrive(&mbar[w]);
         mbar_wait(&mbar[w], (par >> w) & 1u);
         par ^= 1u << w;
+        if (dbg_on) { const long long t = clock64(); dbg_wait += (uint32_t)(t - dt0); dt0 = t; }
         const bool mine = lane < n;
         const float rough = mine ? qr[w * 32 + lane] : 0.0f;
         const uint32_t j = mine ? qj[w * 32 + lane] : 0u;
         const uint32_t act = __ballot_sync(FULL, mine && rough < thr);
         computed += n;
+        dbg_waves++;
         if (act) {
             const float* rw = rows + (size_t)w * R * pitch;
             float exact = 0.0f;
-            for (int g = 0; g < n; g += 8) {
-                const float* r0 = rw + (size_t)min(g + sub, R - 1) * pitch;
-                const float* r1 = rw + (size_t)min(g + 4 + sub, R - 1) * pitch;
-                float acc0 = 0.0f, acc1 = 0.0f;
-                if (g + 4 < n) {
-#pragma unroll 4
-                    for (int d = v; d < D; d += 8) {
-                        const float qd = qv[d];
-                        const float f0 = __fsub_rn(r0[d], qd), f1 = __fsub_rn(r1[d], qd);
-                        acc0 = fmaf(f0, f0, acc0);
-                        acc1 = fmaf(f1, f1, acc1);
+            for (int g = 0; g < n; g += 8) {  // 8 candidates per pass: lanes 4c .. 4c+3 compute candidate g + c
+                const float d2 = l2_quad(rw + (size_t)min(g + (lane >> 2), R - 1) * pitch, qv, D, lane & 3);
+                const float res = __shfl_sync(FULL, d2, 4 * ((lane - g) & 7));
+                if (lane >= g && lane < g + 8) exact = res;
+            }
+            if (dbg_on) { const long long t = clock64(); dbg_l2 += (uint32_t)(t - dt0); dt0 = t; }
+            // in-order replay (rerank.rs:83-101).  The threshold only moves when a candidate is ACCEPTED (rough < thr and
+            // exact < thr), so the stretch up to the next accepted candidate is evaluated in one step: every lane of the
+            // stretch with rough < thr is a candidate the reference computes an exact distance for.
+            uint32_t rem = act;
+            uint32_t mid = 0;
+            if constexpr (SINK == 1) mid = ((act >> lane) & 1u) ? a.map_ids[j] : 0u;
+            while (rem) {
+                const bool pass = ((rem >> lane) & 1u) && rough < thr;
+                const uint32_t pm = __ballot_sync(FULL, pass);
+                const uint32_t am = __ballot_sync(FULL, pass && exact < thr);
+                const int t = __ffs(am) - 1;                                    // the next accepted candidate (-1: none)
+                const uint32_t upto = am ? ((2u << t) - 1u) : FULL;             // lanes 0..t
+                const uint32_t cm = pm & upto;
+                precise += __popc(cm);
+                if constexpr (SINK == 1) {
+                    const uint32_t pos = nrec + __popc(cm & lt_mask);
+                    if (((cm >> lane) & 1u) && pos < (uint32_t)a.r1cap) {
+                        SurvRec rec;
+                        rec.rough = rough; rec.exact = exact; rec.id = mid; rec.p = (uint32_t)(p0 + p_lo);
+                        rdst[pos] = rec;
                     }
-                } else {
-#pragma unroll 4
-                    for (int d = v; d < D; d += 8) {
-                        const float f0 = __fsub_rn(r0[d], qv[d]);
-                        acc0 = fmaf(f0, f0, acc0);
+                    nrec += __popc(cm);
+                }
+                if (!am) break;
+                rem &= ~upto;
+                const float ex = __shfl_sync(FULL, exact, t);
+                if (!HEUR || cnt < k || ex < hmax) {
+                    const int slot = cnt < k ? cnt : maxpos;
+                    if (lane == t) { hd[slot] = ex; hid[slot] = SINK == 1 ? mid : j; }  // SINK == 0: the POSITION; map_ids at finalize
+                    if (cnt < k) cnt++;
+                    __syncwarp();
+                    if (cnt == k) {
+                        heap_recompute_max(hd, k, lane, maxpos, hmax);
+                        if constexpr (!HEUR) thr = hmax;  // rerank.rs:98-100
                     }
                 }
-                acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 4));
-                acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 4));
-                acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 1));
-                acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 1));
-                acc0 = __fadd_rn(acc0, __shfl_xor_sync(FULL, acc0, 2));
-                acc1 = __fadd_rn(acc1, __shfl_xor_sync(FULL, acc1, 2));
-                const int src = (lane & 3) * 8;
-                const float res0 = __shfl_sync(FULL, acc0, src), res1 = __shfl_sync(FULL, acc1, src);
-                if ((lane >> 3) == (g >> 3)) exact = ((lane >> 2) & 1) ? res1 : res0;
-            }
-            // in-order replay (rerank.rs:83-101)
-            uint32_t rem = act;
-            while (rem) {
-                const int t = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const float r = __shfl_sync(FULL, rough, t);
-                const float ex = __shfl_sync(FULL, exact, t);
-                const uint32_t ju = __shfl_sync(FULL, j, t);
-                if (r < thr) {
-                    precise++;
-                    uint32_t mid = 0;
-                    if constexpr (SINK == 1) {
-                        if (lane == 0) mid = a.map_ids[ju];
-                        if (lane == 0 && nrec < (uint32_t)a.r1cap) {
-                            SurvRec rec;
-                            rec.rough = r; rec.exact = ex; rec.id = mid; rec.p = (uint32_t)(p0 + p_lo);
-                            rdst[nrec] = rec;
-                        }
-                        nrec++;
-                    }
-                    if (ex < thr) {
-                        if (!HEUR || cnt < k || ex < hmax) {
-                            const int slot = cnt < k ? cnt : maxpos;
-                            if (lane == 0) { hd[slot] = ex; hid[slot] = SINK == 1 ? mid : a.map_ids[ju]; }
-                            if (cnt < k) cnt++;
-                            __syncwarp();
-                            if (cnt == k) {
-                                heap_recompute_max(hd, k, lane, maxpos, hmax);
-                                if constexpr (!HEUR) thr = hmax;  // rerank.rs:98-100
-                            }
-                        }
-                        if constexpr (HEUR) {  // rerank.rs:155-162
-                            wcount++;
-                            recent = fmaxf(recent, ex);
-                            if (wcount >= 12u) {
-                                thr = recent;
-                                wcount = 0;
-                                recent = -3.402823466e+38f;
-                            }
-                        }
+                if constexpr (HEUR) {  // rerank.rs:155-162
+                    wcount++;
+                    recent = fmaxf(recent, ex);
+                    if (wcount >= 12u) {
+                        thr = recent;
+                        wcount = 0;
+                        recent = -3.402823466e+38f;
                     }
                 }
             }
         }
+        if (dbg_on) dbg_replay += (uint32_t)(clock64() - dt0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // rows of this buffer are rewritten by later bulk copies
         __syncwarp();
     };
@@ -1196,13 +1275,21 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     // Super-block of SB x 32 words: SB independent bitmap loads per lane, then the first 32 survivors of every block
     // loaded back to back and staged in shared memory; the (rolled, single-instance) processing loop follows.
     constexpr int SB = 4;
+    uint32_t mnext[SB];  // bitmap words of the NEXT super-block, loaded one super-block ahead (one DRAM round trip less per block)
+#pragma unroll
+    for (int u = 0; u < SB; u++) {
+        const uint32_t idx = wlo + u * 32 + lane;
+        mnext[u] = idx < whi ? a.bitmap[idx] : 0u;
+    }
     for (uint32_t w0 = wlo; w0 < whi; w0 += 32 * SB) {
+        const long long ds0 = dbg_on ? clock64() : 0ll;
         {
             uint32_t m[SB], incl[SB];
 #pragma unroll
             for (int u = 0; u < SB; u++) {
-                const uint32_t idx = w0 + u * 32 + lane;
-                m[u] = idx < whi ? a.bitmap[idx] : 0u;
+                m[u] = mnext[u];
+                const uint32_t idx = w0 + 32 * SB + u * 32 + lane;
+                mnext[u] = idx < whi ? a.bitmap[idx] : 0u;
             }
 #pragma unroll
             for (int u = 0; u < SB; u++) {
@@ -1230,10 +1317,20 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                 if ((uint32_t)lane < T) ent[u] = a.entries[(size_t)(w0 + u * 32 + pos) * 32 + (lane - src_excl)];
                 if (lane == 0) stot[u] = T;
             }
+            // The gather of a row is a DRAM round trip in front of every wave; the survivors of the whole super-block are
+            // known here, long before their wave is filled, so their rows are pulled into L2 now (while the threshold is
+            // still +inf only as many as two waves hold).
+            if (a.prefetch) {
+#pragma unroll
+                for (int u = 0; u < SB; u++)
+                    if (ent[u].x < thr && (thr < 3.402823466e+38f || lane < 2 * R))
+                        prefetch_l2_bulk(a.base + (size_t)__float_as_uint(ent[u].y) * D, rowbytes);
+            }
 #pragma unroll
             for (int u = 0; u < SB; u++) sent[u * 32 + lane] = ent[u];
             __syncwarp();
         }
+        if (dbg_on) dbg_stage += (uint32_t)(clock64() - ds0);
         for (int u = 0; u < SB; u++) {
             const uint32_t T = stot[u];
             if (T == 0) continue;  // uniform
@@ -1252,9 +1349,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                     if (lane >= o) inc += t;
                 }
                 const uint32_t exc = inc - __popc(mm);
-                for (uint32_t e0 = 32; e0 < T; e0 += 32) {
+                auto load_chunk = [&](uint32_t e0) -> float2 {  // survivors e0 .. e0+31 of the block, one per lane
                     const uint32_t e = e0 + lane;
-                    const bool have = e < T;
                     int pos = 0;
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) {
@@ -1264,9 +1360,16 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
                     pos = min(pos, 31);
                     const uint32_t src_excl = __shfl_sync(FULL, exc, pos);
                     float2 en = make_float2(3.402823466e+38f, 0.0f);
-                    if (have) en = a.entries[(size_t)(w0 + u * 32 + pos) * 32 + (e - src_excl)];
-                    const uint32_t pm = __ballot_sync(FULL, have && en.x < thr);
+                    if (e < T) en = a.entries[(size_t)(w0 + u * 32 + pos) * 32 + (e - src_excl)];
+                    return en;
+                };
+                float2 en = load_chunk(32);
+                for (uint32_t e0 = 32; e0 < T; e0 += 32) {  // the next chunk's entries fly while this chunk's waves are replayed
+                    float2 nxt = make_float2(3.402823466e+38f, 0.0f);
+                    if (e0 + 32 < T) nxt = load_chunk(e0 + 32);
+                    const uint32_t pm = __ballot_sync(FULL, e0 + lane < T && en.x < thr);
                     if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
+                    en = nxt;
                 }
             }
         }
@@ -1278,6 +1381,11 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
     if constexpr (SINK == 1) {  // only the owner of the window has words; it tells the home rank how many records to replay
         if (lane == 0 && wlo < whi)
             reinterpret_cast<uint32_t*>(a.peers[home] + a.off_r1cnt)[(size_t)a.rank * a.nq_local + ql] = min(nrec, (uint32_t)a.r1cap);
+    }
+    if (a.dbg && lane == 0) {
+        uint32_t* o = a.dbg + ((size_t)q * 2 + (first ? 0 : 1)) * 8;
+        o[0] = (uint32_t)(clock64() - dbg_t0); o[1] = dbg_waves; o[2] = computed; o[3] = whi - wlo;
+        o[4] = dbg_wait; o[5] = dbg_l2; o[6] = dbg_replay; o[7] = dbg_stage;
     }
     if (lane == 0) {
         a.q_precise[q] = (first ? 0u : a.q_precise[q]) + precise;
@@ -1291,8 +1399,13 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankArgs a, int p_lo, int
         }
         if (lane == 0) { a.heap_cnt[q] = (uint32_t)cnt; a.thr[q] = thr; a.h_recent[q] = recent; a.h_wcount[q] = wcount; }
     } else {
-        // ascending by (distance, id): rank by counting
+        // ascending by (distance, id): rank by counting.  The heap holds positions (no map_ids load inside the sequential replay);
+        // the original ids (rerank.rs:94) are looked up here, k independent loads.
         __syncwarp();
+        if constexpr (SINK == 0) {
+            for (int s = lane; s < cnt; s += 32) hid[s] = a.map_ids[hid[s]];
+            __syncwarp();
+        }
         for (int s = lane; s < k; s += 32) {
             if (s < cnt) {
                 const uint32_t ks = okey(hd[s]), is = hid[s];

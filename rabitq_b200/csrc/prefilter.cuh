@@ -88,11 +88,7 @@ __global__ void query_center_kernel(const float* __restrict__ y, const float* __
 constexpr int PF_BK = 32;
 constexpr int PF_PITCH = PF_BK + 4;
 
-RQ_DEV void cp_async16(void* smem, const void* gmem, bool pred) {
-    const uint32_t s = smem_u32(smem);
-    const int bytes = pred ? 16 : 0;  // src-size 0: zero-fill (rows past the end)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes));
-}
+// (cp_async16 / cp_async_commit / cp_async_wait: kernels.cuh)
 
 template <int BM, int BN, int WM, int WN>
 __global__ void __launch_bounds__(WM * WN * 32) approx_gemm_tf32_kernel(const float* __restrict__ yhat, const float* __restrict__ chat,

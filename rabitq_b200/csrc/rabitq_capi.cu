@@ -120,6 +120,7 @@ struct rabitq_index {
     // resident index (HBM)
     float* base = nullptr;        // n x D
     float* P = nullptr;           // D x D rows
+    float* PT = nullptr;          // P transposed (PT[c][r] = P[r][c]): the operand layout of K1
     float* cent = nullptr;        // K x D
     uint32_t* offsets = nullptr;  // K+1, local rows
     // tensor-core prefilter of the centroid scan (prefilter.cuh): mean centroid, centred TF32 centroids, their norms
@@ -137,15 +138,18 @@ struct rabitq_index {
     float4* factors = nullptr;    // n
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev_totals = nullptr;  // marks the arrival of the slot totals in h_pin
     std::mutex mu;
     std::vector<uint32_t> rounds{0};
     int rerank_rows = 0;   // rows per rerank wave; 0 = by dimension
+    int debug_rerank = 0;     // per-query rerank statistics (rabitq_debug_rerank_stats)
+    int rerank_prefetch = 0;  // L2 prefetch of survivor rows in the rerank stream (rabitq_set_option("rerank_prefetch"))
     int first_chunks = 1;  // 128-vector chunks of the nearest cluster in the first round (0 = the whole cluster)
     int scan_slices = 1;   // shared-memory record slices per scan work item (hot clusters are cut into several items)
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, cl_count,
         cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
-        entries, counters, out_dist, out_ids, out_count, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag;
+        entries, counters, out_dist, out_ids, out_count, rr_dbg, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag;
     DistState dist;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
     // metrics (src/metrics.rs)
@@ -162,7 +166,7 @@ struct rabitq_index {
     ~rabitq_index() {
         cudaSetDevice(device);
         for (void* p : {(void*)base, (void*)P, (void*)cent, (void*)offsets, (void*)goffsets, (void*)row_bounds, (void*)map_ids, (void*)codes,
-                        (void*)factors, (void*)dist.peers_d, (void*)quant_bias, (void*)pf_mu, (void*)pf_chat, (void*)pf_chat_lo, (void*)pf_cnorm, (void*)pf_cnorm2,
+                        (void*)factors, (void*)PT, (void*)dist.peers_d, (void*)quant_bias, (void*)pf_mu, (void*)pf_chat, (void*)pf_chat_lo, (void*)pf_cnorm, (void*)pf_cnorm2,
                         (void*)pf_cnorm_max})
             if (p) cudaFree(p);
         for (size_t r = 0; r < dist.peers_h.size(); r++)
@@ -170,11 +174,12 @@ struct rabitq_index {
         if (dist.inbox) cudaFree(dist.inbox);
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &qrec, &cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &thr, &heap_dist,
-                          &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count,
+                          &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count, &rr_dbg,
                           &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         for (auto e : ev_pool) cudaEventDestroy(e);
+        if (ev_totals) cudaEventDestroy(ev_totals);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 };
@@ -193,6 +198,26 @@ int tick(rabitq_index* ix, int stage) {
     ix->ev_stage[ix->ev_used] = stage;
     CU(cudaEventRecord(ix->ev_pool[ix->ev_used], ix->stream));
     ix->ev_used++;
+    return 0;
+}
+
+// PT = P^T, once per index (K1 reads a column's rows contiguously)
+int make_pt(rabitq_index* ix) {
+    const int D = (int)ix->D;
+    if (!ix->PT) {
+        CU(cudaMalloc((void**)&ix->PT, (size_t)D * D * 4));
+        CU(cudaFuncSetAttribute(rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROT_SMEM_BYTES));
+    }
+    transpose_square_kernel<<<dim3(D / 32, D / 32), dim3(32, 8)>>>(ix->P, ix->PT, D);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// K1 for `rows` padded vectors (queries, centroids or base rows at build time)
+int launch_rotate(rabitq_index* ix, const float* in, float* out, size_t rows, cudaStream_t st) {
+    dim3 grid((unsigned)(ix->D / ROT_TC), (unsigned)((rows + ROT_TQ - 1) / ROT_TQ));
+    rotate_kernel<<<grid, ROT_THREADS, ROT_SMEM_BYTES, st>>>(in, ix->PT, out, (int)rows, (int)ix->D);
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -231,9 +256,11 @@ int finish_index(rabitq_index* ix) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ix->device));
     ix->sm_count = prop.multiProcessorCount;
+    if (make_pt(ix)) return RABITQ_ECUDA;
     if (const char* e = std::getenv("RABITQ_SCAN_MODE")) ix->scan_mode = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_FIRST_CHUNKS")) ix->first_chunks = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("RABITQ_RR_ROWS")) ix->rerank_rows = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_RR_PREFETCH")) ix->rerank_prefetch = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_SCAN_SLICES")) ix->scan_slices = std::max(1, std::atoi(e));
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
@@ -464,9 +491,7 @@ int build_impl(const float* base, size_t n, size_t len, const float* centroids, 
         float* cpad = nullptr;
         CU(tmp.alloc((void**)&cpad, K * D * 4));
         pad_queries_kernel<<<(unsigned)((K * D + 255) / 256), 256>>>(d_cent_in, cpad, K, (int)len, (int)D);
-        dim3 grid((unsigned)(D / ROT_TC), (unsigned)((K + ROT_QG * ROT_TQ - 1) / (ROT_QG * ROT_TQ)));
-        rotate_kernel<<<grid, ROT_THREADS>>>(cpad, ix->P, ix->cent, (int)K, (int)D);
-        CU(cudaGetLastError());
+        if (make_pt(ix) || launch_rotate(ix, cpad, ix->cent, K, 0)) return RABITQ_ECUDA;
     }
     // --- per-vector label, code, Factor; chunks keep the distance tile around 1 GiB ---
     uint32_t *label = nullptr, *codes_u = nullptr, *vals_in = nullptr, *vals_out = nullptr, *counts = nullptr;
@@ -491,8 +516,7 @@ int build_impl(const float* base, size_t n, size_t len, const float* centroids, 
         for (size_t s0 = 0; s0 < n; s0 += CH) {
             const size_t rows = std::min(CH, n - s0);
             pad_queries_kernel<<<(unsigned)((rows * D + 255) / 256), 256>>>(d_base_in + s0 * len, xpad, rows, (int)len, (int)D);
-            dim3 g1((unsigned)(D / ROT_TC), (unsigned)((rows + ROT_QG * ROT_TQ - 1) / (ROT_QG * ROT_TQ)));
-            rotate_kernel<<<g1, ROT_THREADS>>>(xpad, ix->P, xp, (int)rows, (int)D);  // rabitq.rs:188
+            if (launch_rotate(ix, xpad, xp, rows, 0)) return RABITQ_ECUDA;  // rabitq.rs:188
             dim3 g2((unsigned)((K + CD_TC - 1) / CD_TC), (unsigned)((rows + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ)));
             centroid_dist_kernel<<<g2, CD_THREADS>>>(ix->cent, xp, dist, (int)rows, (int)K, (int)D, nullptr);
             argmin_rows_kernel<<<(unsigned)((rows + 3) / 4), 128>>>(dist, rows, (int)K, label + s0, min_dist + s0);
@@ -682,11 +706,8 @@ int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_ro
         CU(cudaGetLastError()); ix->counts[5]++;
     }
     if (tick(ix, ST_H2D)) return RABITQ_ECUDA;
-    {
-        dim3 grid(D / ROT_TC, (unsigned)((nb + ROT_QG * ROT_TQ - 1) / (ROT_QG * ROT_TQ)));
-        rotate_kernel<<<grid, ROT_THREADS, 0, st>>>(ix->qpad.as<float>(), ix->P, ix->y.as<float>(), (int)nb, D);
-        CU(cudaGetLastError()); ix->counts[5]++;
-    }
+    if (launch_rotate(ix, ix->qpad.as<float>(), ix->y.as<float>(), nb, st)) return RABITQ_ECUDA;
+    ix->counts[5]++;
     if (tick(ix, ST_ROTATE)) return RABITQ_ECUDA;
     if (stop_after_rotate) return 0;
 
@@ -774,13 +795,20 @@ int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_ro
     return 0;
 }
 
-// totals of the slot layout to the host (sizes the survivor slots); synchronises the stream
-int fetch_totals(rabitq_index* ix, size_t nb, BatchOut* bo) {
+// totals of the slot layout to the host (they size the survivor slots).  post_totals enqueues the copy, wait_totals blocks
+// the host until it has landed: the caller launches K3 in between, so the GPU is never idle while the host sleeps.
+int post_totals(rabitq_index* ix, size_t nb) {
     cudaStream_t st = ix->stream;
     CU(cudaMemcpyAsync(ix->h_pin, ix->q_wbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ix->h_pin + 2, ix->q_pbase.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
+    if (!ix->ev_totals) CU(cudaEventCreateWithFlags(&ix->ev_totals, cudaEventDisableTiming));
+    CU(cudaEventRecord(ix->ev_totals, st));
     if (tick(ix, ST_SELECT)) return RABITQ_ECUDA;
-    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int wait_totals(rabitq_index* ix, BatchOut* bo) {
+    CU(cudaEventSynchronize(ix->ev_totals));
     prefilter_adapt(ix);
     bo->total_words = ix->h_pin[0];
     std::memcpy(&bo->total_pairs, ix->h_pin + 2, 8);
@@ -905,6 +933,12 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
             if (rr_resident(R) >= nb) { ra.R = R; break; }
     ra.R = (int)std::max<size_t>(1, std::min<size_t>(ra.R, (80 * 1024) / (2 * (size_t)(D + 8) * 4)));  // <= 80 KB of row buffers per warp
     ra.smem_per_warp = rr_smem(ra.R);
+    ra.prefetch = ix->rerank_prefetch;
+    if (ix->debug_rerank) {
+        CU(ix->rr_dbg.ensure(nb * 16 * 4));
+        CU(cudaMemsetAsync(ix->rr_dbg.p, 0, nb * 16 * 4, st));
+        ra.dbg = ix->rr_dbg.as<uint32_t>();
+    }
     *sa_out = sa;
     *ra_out = ra;
     return 0;
@@ -966,9 +1000,10 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     bo->P = P;
     int rc = run_front(ix, nb, len, P, stop == STOP_ROTATE, false);
     if (rc || stop == STOP_ROTATE) return rc;
-    if ((rc = fetch_totals(ix, nb, bo))) return rc;
-    if (stop == STOP_PROBE) return 0;
-    if ((rc = run_quantize(ix, nb, P)) || stop == STOP_QUANT) return rc;
+    if ((rc = post_totals(ix, nb))) return rc;
+    if (stop == STOP_PROBE) return wait_totals(ix, bo);
+    if ((rc = run_quantize(ix, nb, P))) return rc;
+    if ((rc = wait_totals(ix, bo)) || stop == STOP_QUANT) return rc;
     ScanArgs sa;
     RerankArgs ra;
     if ((rc = setup_rounds(ix, nb, P, topk, bo, &sa, &ra))) return rc;
@@ -1217,10 +1252,11 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered, float* d_thr) {
     CU(cudaGetLastError()); ix->counts[5]++;
     BatchOut bo;
     bo.P = P;
-    int rc = fetch_totals(ix, nq, &bo);
+    int rc = post_totals(ix, nq);
     if (rc) return rc;
-    ix->counts[0] += bo.total_pairs;
     if ((rc = run_quantize(ix, nq, P))) return rc;
+    if ((rc = wait_totals(ix, &bo))) return rc;
+    ix->counts[0] += bo.total_pairs;
     if ((rc = setup_rounds(ix, nq, P, d.topk, &bo, &d.sa, &d.ra))) return rc;
     fill_f32_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(d_thr, nq, 3.402823466e+38f);
     CU(cudaGetLastError()); ix->counts[5]++;
@@ -1525,11 +1561,23 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     if (n == "first_chunks") idx->first_chunks = (int)std::max(0L, value);
     else if (n == "scan_mode") idx->scan_mode = (int)value;
     else if (n == "rerank_rows") idx->rerank_rows = (int)value;
+    else if (n == "rerank_prefetch") idx->rerank_prefetch = (int)value;
+    else if (n == "debug_rerank") idx->debug_rerank = (int)value;
     else if (n == "scan_slices") idx->scan_slices = (int)std::max(1L, value);
     else if (n == "prefilter") idx->prefilter = (int)value;
     else if (n == "prefilter_mode") { idx->pf_mode = (int)value; idx->pf_strikes = 0; }
     else if (n == "prefilter_cap") idx->prefilter_cap = (int)value;
     else return fail(RABITQ_EINVAL, "unknown option: " + n);
+    return RABITQ_OK;
+}
+
+int rabitq_debug_rerank_stats(rabitq_index* idx, uint32_t* out, size_t nq) {
+    if (!idx || !out) return fail(RABITQ_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CU(cudaSetDevice(idx->device));
+    if (!idx->rr_dbg.p || idx->rr_dbg.cap < nq * 16 * 4) return fail(RABITQ_EINVAL, "set_option(\"debug_rerank\", 1) and run a batch of at least nq queries first");
+    CU(cudaStreamSynchronize(idx->stream));
+    CU(cudaMemcpy(out, idx->rr_dbg.p, nq * 16 * 4, cudaMemcpyDeviceToHost));
     return RABITQ_OK;
 }
 
