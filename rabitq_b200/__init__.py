@@ -284,6 +284,13 @@ class RaBitQ:
         _check(lib().rabitq_query_batch(self._h, _ptr(q), nq, ln, probe, topk, int(heuristic_rank), _ptr(d), _ptr(ids), _ptr(cnt)))
         return d, ids, cnt
 
+    def query_batch_device_into(self, queries, probe: int, topk: int, d, ids, cnt, heuristic_rank: bool = False):
+        """Device-resident call with caller-owned CUDA output tensors: nothing is allocated and no device-wide synchronisation is
+        issued here, so the caller's stream (see `set_stream`) orders the inputs.  The serving loop / bench.py's device leg."""
+        nq, ln = queries.shape
+        _check(lib().rabitq_query_batch_device(self._h, C.c_void_p(queries.data_ptr()), nq, ln, probe, topk, int(heuristic_rank),
+                                               C.c_void_p(d.data_ptr()), C.c_void_p(ids.data_ptr()), C.c_void_p(cnt.data_ptr())))
+
     def query_batch_into(self, q_host: np.ndarray, probe: int, topk: int, d: np.ndarray, ids: np.ndarray, cnt: np.ndarray):
         """Host-buffer call with caller-owned outputs (used by bench.py's end-to-end leg with pinned memory)."""
         nq, ln = q_host.shape

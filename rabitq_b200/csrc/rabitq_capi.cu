@@ -110,6 +110,18 @@ struct DistState {
     float* d_thr = nullptr;
 };
 
+// Inverted probe lists + scan work list of ONE rerank round (K4's input).  One set per round: the sets of all rounds are built
+// on a side stream while K3 runs, so no round waits for its lists.
+struct ListSet {
+    DevBuf cl_count, cl_start, item_start, cl_cursor, cl_items, work, work_ctl;
+    cudaEvent_t ready = nullptr;
+    void release() {
+        for (DevBuf* b : {&cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl}) b->release();
+        if (ready) cudaEventDestroy(ready);
+        ready = nullptr;
+    }
+};
+
 struct rabitq_index {
     int device = 0;
     uint32_t D = 0;
@@ -139,6 +151,9 @@ struct rabitq_index {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_totals = nullptr;  // marks the arrival of the slot totals in h_pin
+    cudaStream_t aux_stream = nullptr;  // side stream: the rounds' inverted lists are built here, concurrently with K3
+    cudaEvent_t ev_fork = nullptr;      // recorded on `stream` after K2b: everything the lists depend on is done
+    std::vector<ListSet> lists;
     std::mutex mu;
     std::vector<uint32_t> rounds{0};
     int rerank_rows = 0;   // rows per rerank wave; 0 = by dimension
@@ -147,8 +162,7 @@ struct rabitq_index {
     int first_chunks = 1;  // 128-vector chunks of the nearest cluster in the first round (0 = the whole cluster)
     int scan_slices = 1;   // shared-memory record slices per scan work item (hot clusters are cut into several items)
     // work buffers
-    DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, cl_count,
-        cl_start, item_start, cl_cursor, cl_items, work, work_ctl, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
+    DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
         entries, counters, out_dist, out_ids, out_count, rr_dbg, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag;
     DistState dist;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
@@ -161,6 +175,7 @@ struct rabitq_index {
     std::vector<int> ev_stage;
     size_t ev_used = 0;
     int scan_blocks_per_sm = 0;
+    size_t max_items = 0;  // capacity of a round's scan work list for the current sub-batch (setup_rounds)
     int scan_mode = -1;  // -1 = default; RABITQ_SCAN_MODE overrides (tuning)
 
     ~rabitq_index() {
@@ -173,13 +188,16 @@ struct rabitq_index {
             if (dist.opened[r] && dist.peers_h[r]) cudaIpcCloseMemHandle(dist.peers_h[r]);
         if (dist.inbox) cudaFree(dist.inbox);
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
-                          &qrec, &cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &thr, &heap_dist,
+                          &qrec, &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count, &rr_dbg,
                           &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         for (auto e : ev_pool) cudaEventDestroy(e);
         if (ev_totals) cudaEventDestroy(ev_totals);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto& l : lists) l.release();
+        if (aux_stream) cudaStreamDestroy(aux_stream);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 };
@@ -264,6 +282,8 @@ int finish_index(rabitq_index* ix) {
     if (const char* e = std::getenv("RABITQ_SCAN_SLICES")) ix->scan_slices = std::max(1, std::atoi(e));
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
+    CU(cudaStreamCreateWithFlags(&ix->aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&ix->h_pin, 256));
     std::memset(ix->h_pin, 0, 256);
     CU(cudaFuncSetAttribute(rerank_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -803,6 +823,7 @@ int post_totals(rabitq_index* ix, size_t nb) {
     CU(cudaMemcpyAsync(ix->h_pin + 2, ix->q_pbase.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
     if (!ix->ev_totals) CU(cudaEventCreateWithFlags(&ix->ev_totals, cudaEventDisableTiming));
     CU(cudaEventRecord(ix->ev_totals, st));
+    CU(cudaEventRecord(ix->ev_fork, st));
     if (tick(ix, ST_SELECT)) return RABITQ_ECUDA;
     return 0;
 }
@@ -846,16 +867,9 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     const size_t words = std::max<uint32_t>(bo->total_words, 1);
     CU(ix->bitmap.ensure(words * 4));
     CU(ix->entries.ensure(words * 32 * 8));
-    CU(ix->cl_count.ensure((size_t)K * 4));
-    CU(ix->cl_start.ensure((size_t)(K + 1) * 4));
-    CU(ix->item_start.ensure((size_t)(K + 1) * 4));
-    CU(ix->cl_cursor.ensure((size_t)K * 4));
-    CU(ix->cl_items.ensure(nb * (size_t)P * 4));
     // records per work item: `scan_slices` shared-memory slices, raised so that the slice index fits its 12 bits
     const uint32_t MS = (uint32_t)std::max<size_t>((size_t)scan_qs(ix) * std::max(1, ix->scan_slices), (nb + 4094) / 4095);
-    const size_t max_items = ix->n / SCAN_THREADS + (size_t)K + 2 + ((size_t)bo->total_words / 4 + nb * (size_t)P) / MS;
-    CU(ix->work.ensure(max_items * 8));
-    CU(ix->work_ctl.ensure(16));
+    ix->max_items = ix->n / SCAN_THREADS + (size_t)K + 2 + ((size_t)bo->total_words / 4 + nb * (size_t)P) / MS;
     CU(ix->thr.ensure(nb * 4));
     CU(ix->heap_dist.ensure(nb * topk * 4));
     CU(ix->heap_ids.ensure(nb * topk * 4));
@@ -875,10 +889,6 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     sa.codes = ix->codes;
     sa.factors = ix->factors;
     sa.offsets = ix->offsets;
-    sa.cl_start = ix->cl_start.as<uint32_t>();
-    sa.cl_items = ix->cl_items.as<uint32_t>();
-    sa.work = ix->work.as<uint2>();
-    sa.work_ctl = ix->work_ctl.as<uint32_t>();
     sa.qrec = ix->qrec.as<uint32_t>();
     sa.thr = ix->thr.as<float>();
     sa.q_p0 = ix->q_p0.as<uint32_t>();
@@ -946,30 +956,57 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
 
 enum RoundKind { ROUND_REPLAY, ROUND_SINK1 };
 
-// inverted probe lists + work list + scan of one window [lo, hi) of visit positions
-int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos hi, bool dense) {
+// inverted probe lists + scan work list of one window [lo, hi) of visit positions into list set `set`, on stream `st`
+int build_lists(rabitq_index* ix, size_t nb, int P, uint32_t MS, Pos lo, Pos hi, size_t set, cudaStream_t st) {
     const int K = (int)ix->K;
-    cudaStream_t st = ix->stream;
+    if (ix->lists.size() <= set) ix->lists.resize(set + 1);
+    ListSet& L = ix->lists[set];
+    CU(L.cl_count.ensure((size_t)K * 4));
+    CU(L.cl_start.ensure((size_t)(K + 1) * 4));
+    CU(L.item_start.ensure((size_t)(K + 1) * 4));
+    CU(L.cl_cursor.ensure((size_t)K * 4));
+    CU(L.cl_items.ensure(nb * (size_t)P * 4));
+    CU(L.work.ensure(ix->max_items * 8));
+    CU(L.work_ctl.ensure(16));
+    if (!L.ready) CU(cudaEventCreateWithFlags(&L.ready, cudaEventDisableTiming));
     const int p_lo = lo.p, p_hi_incl = std::min(P, hi.p + (hi.ch > 0 ? 1 : 0));  // ranks that have items in this round
     const bool single_rank = p_hi_incl == p_lo + 1;
     const uint32_t ch_min = single_rank ? (uint32_t)lo.ch : 0u;
     const uint32_t ch_max = (single_rank && hi.ch > 0) ? (uint32_t)hi.ch : 0xffffffffu;
     const size_t items = nb * (size_t)(p_hi_incl - p_lo);
-    CU(cudaMemsetAsync(ix->cl_count.p, 0, (size_t)K * 4, st));
+    CU(cudaMemsetAsync(L.cl_count.p, 0, (size_t)K * 4, st));
     bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
-                                                                          ix->cl_count.as<uint32_t>());
+                                                                          L.cl_count.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
-    bucket_scan_kernel<<<1, 1024, 0, st>>>(ix->cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, sa.MS, ch_min, ch_max,
-                                           ix->cl_start.as<uint32_t>(), ix->item_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
-                                           ix->work_ctl.as<uint32_t>());
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(L.cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, MS, ch_min, ch_max,
+                                           L.cl_start.as<uint32_t>(), L.item_start.as<uint32_t>(), L.cl_cursor.as<uint32_t>(),
+                                           L.work_ctl.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
     bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
-                                                                         ix->cl_start.as<uint32_t>(), ix->cl_cursor.as<uint32_t>(),
-                                                                         ix->cl_items.as<uint32_t>());
+                                                                         L.cl_start.as<uint32_t>(), L.cl_cursor.as<uint32_t>(),
+                                                                         L.cl_items.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
-    work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(ix->item_start.as<uint32_t>(), ix->cl_count.as<uint32_t>(), K, sa.MS, ch_min,
-                                                       ix->work.as<uint2>());
+    work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(), K, MS, ch_min, L.work.as<uint2>());
     CU(cudaGetLastError()); ix->counts[5]++;
+    CU(cudaEventRecord(L.ready, st));
+    return 0;
+}
+
+// scan of one window [lo, hi) of visit positions over list set `set`; `lists_built` = the set was built ahead on the side stream
+// (the main stream only waits for it), otherwise it is built here, in line
+int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos hi, bool dense, size_t set = 0, bool lists_built = false) {
+    cudaStream_t st = ix->stream;
+    if (!lists_built) {
+        int rc = build_lists(ix, nb, P, sa.MS, lo, hi, set, st);
+        if (rc) return rc;
+    } else {
+        CU(cudaStreamWaitEvent(st, ix->lists[set].ready, 0));
+    }
+    ListSet& L = ix->lists[set];
+    sa.cl_start = L.cl_start.as<uint32_t>();
+    sa.cl_items = L.cl_items.as<uint32_t>();
+    sa.work = L.work.as<uint2>();
+    sa.work_ctl = L.work_ctl.as<uint32_t>();
     if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
     sa.p_lo = lo.p; sa.ch_lo = lo.ch; sa.p_hi = hi.p; sa.ch_hi = hi.ch;
     int rc = dense ? launch_scan<true>(ix, sa) : launch_scan<false>(ix, sa);
@@ -1018,8 +1055,12 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
             if ((int)r > 0 && (int)r < P && (int)r > bounds.back().p) bounds.push_back({(int)r, 0});
         bounds.push_back({P, 0});
     }
+    // the lists of every round depend on K2b only: built on the side stream (forked after K2b) while K3 runs on the main one
+    CU(cudaStreamWaitEvent(ix->aux_stream, ix->ev_fork, 0));
+    for (size_t r = 0; r + 1 < bounds.size(); r++)
+        if ((rc = build_lists(ix, nb, P, sa.MS, bounds[r], bounds[r + 1], r, ix->aux_stream))) return rc;
     for (size_t r = 0; r + 1 < bounds.size(); r++) {
-        if ((rc = run_round_scan(ix, nb, P, sa, bounds[r], bounds[r + 1], stop == STOP_SCAN_DENSE))) return rc;
+        if ((rc = run_round_scan(ix, nb, P, sa, bounds[r], bounds[r + 1], stop == STOP_SCAN_DENSE, r, true))) return rc;
         if (stop == STOP_SCAN_DENSE) return 0;
         if ((rc = run_round_rerank(ix, nb, ra, bounds[r], bounds[r + 1], r == 0, r + 2 == bounds.size(), heuristic, ROUND_REPLAY))) return rc;
     }
