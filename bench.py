@@ -101,8 +101,9 @@ def measured_peak_hbm():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the main scan launch, from the committed `ncu --set full` captures
-# (profiles/scan_kernel_full_r01b.txt); a static per-launch figure, not re-measured by this run.
-SCAN_DRAM_TRAFFIC = {"c2": 152.3e6, "c1": 249.9e6}
+# (profiles/scan_kernel_full_r01k.txt); a static per-launch figure, not re-measured by this run.
+SCAN_DRAM_TRAFFIC = {"c2": 150.1e6, "c1": 246.3e6}
+SCAN_DRAM_TRAFFIC_SOURCE = "ncu --set full, profiles/scan_kernel_full_r01k.txt (bytes per main scan launch)"
 
 
 def recall_at_k(ids, truth, k):
@@ -371,7 +372,7 @@ def run_ours(args):
             "gpu_launches": int(counts["kernel_launches"]),
             "roofline": {"bound": "hbm", "kernel": "rq::scan_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": SCAN_DRAM_TRAFFIC.get(args.workload) if not args.shape else None,
-                         "traffic_source": "ncu --set full, profiles/scan_kernel_full_r01b.txt (bytes per main scan launch)", "peak_source": peak_src,
+                         "traffic_source": SCAN_DRAM_TRAFFIC_SOURCE, "peak_source": peak_src,
                          "algorithmic_bytes_per_pair": bytes_per_pair, "pairs_per_step": counts["pairs"] // args.steps,
                          "scan_ms_per_step": round(scan_ms / args.steps, 4), "scan_launches_per_step": counts["scan_launches"] // args.steps,
                          "gpairs_per_s": round(counts["pairs"] / (scan_ms * 1e-3) / 1e9, 2) if scan_ms > 0 else 0.0,

@@ -176,7 +176,7 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
 int rabitq_set_option(rabitq_index* idx, const char* name, long value);
 
 /* After a batch run with "debug_rerank" = 1: out[nq][2 rounds][8] = {SM cycles the query's warp spent in K5, waves, exact
- * distances computed, survivor words streamed, cycles waiting for gathered rows, in the exact distances, in the replay, staging
+ * distances computed, cycles inside enqueue (including the waves processed there), cycles waiting for gathered rows, in the exact distances, in the replay, staging
  * survivor words} of the last sub-batch.  Tuning aid; not part of the reference's surface. */
 int rabitq_debug_rerank_stats(rabitq_index* idx, uint32_t* out, size_t nq);
 

@@ -320,7 +320,7 @@ class RaBitQ:
         _check(lib().rabitq_set_option(self._h, name.encode(), int(value)))
 
     def debug_rerank_stats(self, nq: int) -> np.ndarray:
-        """[nq, 2 rounds, (cycles, waves, exact computed, words streamed, wait, l2, replay, stage cycles)] of the last batch (after set_option("debug_rerank", 1))."""
+        """[nq, 2 rounds, (cycles, waves, exact computed, enqueue, wait, l2, replay, stage cycles)] of the last batch (after set_option("debug_rerank", 1))."""
         out = np.zeros((nq, 2, 8), np.uint32)
         _check(lib().rabitq_debug_rerank_stats(self._h, C.c_void_p(out.ctypes.data), nq))
         return out

@@ -204,8 +204,12 @@ __global__ void __launch_bounds__(CD_THREADS, 2) centroid_dist_kernel(const floa
     __shared__ float4 sy[CD_QG * CD_TQ][CD_DCH / 4];
     const int tid = threadIdx.x;
     const int cl = tid & (CD_TC - 1), qg = tid / CD_TC;
-    const int c0 = blockIdx.x * CD_TC, c = c0 + cl;
-    const int qb = blockIdx.y * (CD_QG * CD_TQ), q0 = qb + qg * CD_TQ;
+    // tiles (64 centroids x 32 queries) are walked with a grid-stride loop: as the prefilter's fallback the kernel is launched
+    // with a small grid, so the usual case (flag clear) costs a few hundred exiting CTAs instead of one per tile
+    const int tiles_c = (K + CD_TC - 1) / CD_TC, tiles_q = (nq + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ);
+    for (long long tile = blockIdx.x; tile < (long long)tiles_c * tiles_q; tile += gridDim.x) {
+    const int c0 = (int)(tile % tiles_c) * CD_TC, c = c0 + cl;
+    const int qb = (int)(tile / tiles_c) * (CD_QG * CD_TQ), q0 = qb + qg * CD_TQ;
     f32x2 acc[CD_TQ][4];
 #pragma unroll
     for (int t = 0; t < CD_TQ; t++)
@@ -247,6 +251,7 @@ __global__ void __launch_bounds__(CD_THREADS, 2) centroid_dist_kernel(const floa
 #pragma unroll
         for (int t = 0; t < CD_TQ; t++)
             if (q0 + t < nq) out[(size_t)(q0 + t) * K + c] = reduce8p(acc[t]);
+    }
     }
 }
 
@@ -566,22 +571,37 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
                                                        const uint32_t* __restrict__ probe_ids, const float* __restrict__ probe_dist,
                                                        const uint32_t* __restrict__ slot_local, const uint32_t* __restrict__ q_wbase,
                                                        const uint32_t* __restrict__ offsets, const float* __restrict__ bias,
-                                                       uint32_t* __restrict__ qrec, int nq, int P, int D) {
+                                                       uint32_t* __restrict__ qrec, int nq, int P, int D, int pch) {
     const int lane = threadIdx.x & 31;
-    const size_t gw = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (gw >= (size_t)nq * P) return;
-    const size_t q = gw / P;
-    const uint32_t c = probe_ids[gw];
-    if (offsets && offsets[c + 1] == offsets[c]) return;  // cluster held by another shard: its record is never read
+    // a warp takes `pch` consecutive probe ranks of ONE query (pch > 1 only when the query fits in registers, W32T > 0): the
+    // rotated query is loaded once per warp instead of once per record
+    const size_t wid = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const size_t chunks = ((size_t)P + pch - 1) / pch;
+    if (wid >= (size_t)nq * chunks) return;
+    const size_t q = wid / chunks;
+    const int p_begin = (int)(wid % chunks) * pch, p_end = min(P, p_begin + pch);
     const float* yr = y + q * (size_t)D;
-    const float* cr = cent + (size_t)c * D;
     const int W32 = W32T > 0 ? W32T : D / 32, WP = (W32 + 3) & ~3, RS = 4 * WP + 8;  // plane stride padded to 128 bits
+    // the record is assembled in shared memory (lane 0 holds every ballot word) and leaves with coalesced 128-bit stores: lane 0
+    // writing it word by word to global memory cost 24 (D=128) .. 128 (D=960) scattered 4-byte stores per record
+    extern __shared__ __align__(16) uint32_t qz_smem[];
+    uint32_t* sr = qz_smem + (size_t)(threadIdx.x >> 5) * RS;
+    float yv[W32T > 0 ? W32T : 1];
+    if constexpr (W32T > 0) {
+#pragma unroll
+        for (int g = 0; g < W32T; g++) yv[g] = __ldg(&yr[g * 32 + lane]);
+    }
+    for (int p = p_begin; p < p_end; p++) {
+    const size_t gw = q * (size_t)P + p;
+    const uint32_t c = probe_ids[gw];
+    if (offsets && offsets[c + 1] == offsets[c]) continue;  // cluster held by another shard: its record is never read
+    const float* cr = cent + (size_t)c * D;
     uint32_t* rec = qrec + gw * (size_t)RS;
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
     float rr[W32T > 0 ? W32T : 1];
     if constexpr (W32T > 0) {
 #pragma unroll
-        for (int g = 0; g < W32T; g++) rr[g] = __fsub_rn(__ldg(&yr[g * 32 + lane]), __ldg(&cr[g * 32 + lane]));
+        for (int g = 0; g < W32T; g++) rr[g] = __fsub_rn(yv[g], __ldg(&cr[g * 32 + lane]));
 #pragma unroll
         for (int g = 0; g < W32T; g++) { mn = fminf(mn, rr[g]); mx = fmaxf(mx, rr[g]); }
     } else {
@@ -611,12 +631,14 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
         uint32_t b0 = __ballot_sync(FULL, qi & 1), b1 = __ballot_sync(FULL, qi & 2);
         uint32_t b2 = __ballot_sync(FULL, qi & 4), b3 = __ballot_sync(FULL, qi & 8);
         if (lane == 0) {
-            rec[0 * WP + g] = b0;
-            rec[1 * WP + g] = b1;
-            rec[2 * WP + g] = b2;
-            rec[3 * WP + g] = b3;
+            sr[0 * WP + g] = b0;
+            sr[1 * WP + g] = b1;
+            sr[2 * WP + g] = b2;
+            sr[3 * WP + g] = b3;
         }
     };
+    if (lane < 4)
+        for (int w = W32; w < WP; w++) sr[lane * WP + w] = 0u;  // plane padding (never ANDed by K4)
     if constexpr (W32T > 0) {
 #pragma unroll
         for (int g = 0; g < W32T; g++) emit(g, rr[g]);
@@ -627,15 +649,19 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
     if (lane == 0) {
         const float ycd = probe_dist[gw];
-        float* rf = reinterpret_cast<float*>(rec + 4 * WP);
+        float* rf = reinterpret_cast<float*>(sr + 4 * WP);
         rf[0] = mn;
         rf[1] = delta;
         rf[2] = __uint2float_rn((uint32_t)sum);  // `scalar_sum as f32`, rabitq.rs:322
         rf[3] = ycd;
         rf[4] = __fsqrt_rn(ycd);                 // rabitq.rs:346
-        rec[4 * WP + 5] = (uint32_t)sum;
-        rec[4 * WP + 6] = q_wbase[q] + slot_local[gw];
-        rec[4 * WP + 7] = c;
+        sr[4 * WP + 5] = (uint32_t)sum;
+        sr[4 * WP + 6] = q_wbase[q] + slot_local[gw];
+        sr[4 * WP + 7] = c;
+    }
+    __syncwarp();
+    for (int i = lane; i < RS / 4; i += 32) reinterpret_cast<uint4*>(rec)[i] = reinterpret_cast<const uint4*>(sr)[i];
+    __syncwarp();  // the staging area is rewritten by the next record
     }
 }
 
@@ -986,7 +1012,7 @@ struct RerankArgs {
     int R;                        // rows per wave (<= 32)
     int smem_per_warp;            // bytes
     int prefetch;                 // L2 prefetch of the survivors' base rows at discovery time (0 = off)
-    uint32_t* dbg;                // NULL, or nq x 2 rounds x {cycles, waves, computed, words, wait, l2, replay, stage} (rabitq_debug_rerank_stats)
+    uint32_t* dbg;                // NULL, or nq x 2 rounds x {cycles, waves, computed, enqueue (incl. the waves processed inside), wait, l2, replay, stage} (rabitq_debug_rerank_stats)
     // distributed record sink (template SINK != 0): records go straight into the inbox of the
     // query's HOME rank -- peer memory over NVLink (one process per GPU) or plain device memory (ranks in one process)
     unsigned char* const* peers;  // inbox base of every rank
@@ -1118,7 +1144,7 @@ __global__ void __launch_bounds__(128, 5) rerank_kernel(RerankArgs a, int p_lo, 
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     const long long dbg_t0 = a.dbg ? clock64() : 0ll;
-    uint32_t dbg_waves = 0, dbg_wait = 0, dbg_l2 = 0, dbg_replay = 0, dbg_stage = 0;
+    uint32_t dbg_waves = 0, dbg_wait = 0, dbg_l2 = 0, dbg_replay = 0, dbg_stage = 0, dbg_enq = 0;
     const bool dbg_on = a.dbg != nullptr;
     if (lane == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
     // prologue: every independent global load is issued before the first dependent use (the kernel is a chain of
@@ -1247,19 +1273,20 @@ __global__ void __launch_bounds__(128, 5) rerank_kernel(RerankArgs a, int p_lo, 
     // queue candidates in visit order; the row gather of each is issued right here, so it is in flight while the
     // stream continues and while the previous wave is being replayed
     auto enqueue = [&](uint32_t pm, float rough, uint32_t j) {
+        const long long de0 = dbg_on ? clock64() : 0ll;
         while (pm) {
             const int space = R - fill;
             const int rank = __popc(pm & lt_mask);
             const bool take = ((pm >> lane) & 1u) && rank < space;
+            const uint32_t took = __ballot_sync(FULL, take);
+            if (lane == __ffs(took) - 1) mbar_expect_tx(&mbar[f], rowbytes * (uint32_t)__popc(took));  // one update for the whole batch of rows
+            __syncwarp();
             if (take) {
                 const int slot = fill + rank;
                 qr[f * 32 + slot] = rough;
                 qj[f * 32 + slot] = j;
-
-                mbar_expect_tx(&mbar[f], rowbytes);
                 tma_bulk_g2s(rows + ((size_t)f * R + slot) * pitch, a.base + (size_t)j * D, rowbytes, &mbar[f]);
             }
-            const uint32_t took = __ballot_sync(FULL, take);
             pm &= ~took;
             fill += __popc(took);
             __syncwarp();
@@ -1270,6 +1297,7 @@ __global__ void __launch_bounds__(128, 5) rerank_kernel(RerankArgs a, int p_lo, 
                 fill = 0;
             }
         }
+        if (dbg_on) dbg_enq += (uint32_t)(clock64() - de0);
     };
 
     // Super-block of SB x 32 words: SB independent bitmap loads per lane, then the first 32 survivors of every block
@@ -1384,7 +1412,7 @@ __global__ void __launch_bounds__(128, 5) rerank_kernel(RerankArgs a, int p_lo, 
     }
     if (a.dbg && lane == 0) {
         uint32_t* o = a.dbg + ((size_t)q * 2 + (first ? 0 : 1)) * 8;
-        o[0] = (uint32_t)(clock64() - dbg_t0); o[1] = dbg_waves; o[2] = computed; o[3] = whi - wlo;
+        o[0] = (uint32_t)(clock64() - dbg_t0); o[1] = dbg_waves; o[2] = computed; o[3] = dbg_enq;
         o[4] = dbg_wait; o[5] = dbg_l2; o[6] = dbg_replay; o[7] = dbg_stage;
     }
     if (lane == 0) {
@@ -1698,27 +1726,32 @@ __global__ void __launch_bounds__(256) r2_exact_kernel(const Cand* __restrict__ 
                                                        unsigned long long* __restrict__ counters) {
     uint32_t total = 0;
     for (int h = 0; h < world; h++) total += home_tot[h];
-    const int v = threadIdx.x & 7, sub = (threadIdx.x & 31) >> 3;
-    const uint32_t groups = (gridDim.x * blockDim.x) >> 3;
-    for (uint32_t gb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2; gb < total; gb += groups) {  // warp-uniform trip count
+    // TWO threads per candidate: thread h owns AVX lanes 4h..4h+3 of simd::l2_squared_distance as two packed f32x2 chains and reads
+    // its half of every 8-element step with one 128-bit load (row and query), so a warp keeps 16 rows streaming.
+    const int h = threadIdx.x & 1, sub = (threadIdx.x & 31) >> 1;
+    const uint32_t groups = (gridDim.x * blockDim.x) >> 1;
+    for (uint32_t gb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 4; gb < total; gb += groups) {  // warp-uniform trip count
         const uint32_t g = gb + sub;
         const bool act = g < total;
         const Cand c = cand[act ? g : total - 1];
-        const float* row = base + (size_t)c.j * D;
-        const float* qr = qpad + (size_t)c.q * D;
-        float acc = 0.0f;
-#pragma unroll 8
-        for (int d = v; d < D; d += 8) {
-            const float f = __fsub_rn(__ldg(&row[d]), __ldg(&qr[d]));
-            acc = fmaf(f, f, acc);
+        const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(base + (size_t)c.j * D) + h;
+        const ulonglong2* qp = reinterpret_cast<const ulonglong2*>(qpad + (size_t)c.q * D) + h;
+        f32x2 a0 = 0ull, a1 = 0ull;
+#pragma unroll 8  // 16 independent 128-bit loads in flight per thread: the chain is a sequence of DRAM round trips otherwise
+        for (int i = 0; i < D / 8; i++) {
+            const ulonglong2 x = __ldg(&rp[2 * i]), y = __ldg(&qp[2 * i]);
+            const f32x2 f0 = sub2(x.x, y.x), f1 = sub2(x.y, y.y);  // diff = row - q (src/simd.rs:34-37)
+            a0 = fma2(f0, f0, a0);
+            a1 = fma2(f1, f1, a1);
         }
-        acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
-        acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
-        acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
-        if (v == 0 && act) {
+        float p0, p1, p2, p3, o0, o1, o2, o3;  // reduce_f32_256: (s0+s4 + s1+s5) + (s2+s6 + s3+s7); both threads get the same bits
+        unpack2(a0, p0, p1); unpack2(a1, p2, p3);
+        unpack2(__shfl_xor_sync(FULL, a0, 1), o0, o1); unpack2(__shfl_xor_sync(FULL, a1, 1), o2, o3);
+        const float acc = __fadd_rn(__fadd_rn(__fadd_rn(p0, o0), __fadd_rn(p1, o1)), __fadd_rn(__fadd_rn(p2, o2), __fadd_rn(p3, o3)));
+        if (h == 0 && act) {
             const int home = (int)(c.q / (uint32_t)nq_l);
             uint32_t hb = 0;
-            for (int h = 0; h < home; h++) hb += home_tot[h];
+            for (int hh = 0; hh < home; hh++) hb += home_tot[hh];
             SurvRec rec;
             rec.rough = c.rough; rec.exact = acc; rec.id = map_ids[c.j]; rec.p = c.p;
             reinterpret_cast<SurvRec*>(peers[home] + off_r2rec)[(size_t)rank * cap2 + (g - hb)] = rec;

@@ -163,9 +163,13 @@ struct rabitq_index {
     int scan_slices = 1;   // shared-memory record slices per scan work item (hot clusters are cut into several items)
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
-        entries, counters, out_dist, out_ids, out_count, rr_dbg, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag;
+        entries, counters, out_all, rr_dbg, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag;
     DistState dist;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
+    float* ovr_dist = nullptr;  // device-pointer call answered in one sub-batch: K5 writes straight into the caller's tensors
+    uint32_t *ovr_ids = nullptr, *ovr_count = nullptr;
+    uint32_t* h_out = nullptr;  // pinned staging of a sub-batch's results (host-pointer calls)
+    size_t h_out_cap = 0;
     // metrics (src/metrics.rs)
     uint64_t m_query = 0, m_rough = 0, m_precise = 0;
     // last-call measurements
@@ -189,10 +193,11 @@ struct rabitq_index {
         if (dist.inbox) cudaFree(dist.inbox);
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &qrec, &thr, &heap_dist,
-                          &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_dist, &out_ids, &out_count, &rr_dbg,
+                          &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_all, &rr_dbg,
                           &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
+        if (h_out) cudaFreeHost(h_out);
         for (auto e : ev_pool) cudaEventDestroy(e);
         if (ev_totals) cudaEventDestroy(ev_totals);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -537,7 +542,7 @@ int build_impl(const float* base, size_t n, size_t len, const float* centroids, 
             const size_t rows = std::min(CH, n - s0);
             pad_queries_kernel<<<(unsigned)((rows * D + 255) / 256), 256>>>(d_base_in + s0 * len, xpad, rows, (int)len, (int)D);
             if (launch_rotate(ix, xpad, xp, rows, 0)) return RABITQ_ECUDA;  // rabitq.rs:188
-            dim3 g2((unsigned)((K + CD_TC - 1) / CD_TC), (unsigned)((rows + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ)));
+            const unsigned g2 = (unsigned)(((K + CD_TC - 1) / CD_TC) * ((rows + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ)));
             centroid_dist_kernel<<<g2, CD_THREADS>>>(ix->cent, xp, dist, (int)rows, (int)K, (int)D, nullptr);
             argmin_rows_kernel<<<(unsigned)((rows + 3) / 4), 128>>>(dist, rows, (int)K, label + s0, min_dist + s0);
             encode_kernel<<<(unsigned)((rows + 3) / 4), 128>>>(xp, ix->cent, label + s0, min_dist + s0, rows, (int)D, codes_u + s0 * W32,
@@ -784,7 +789,8 @@ int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_ro
         run_if = ix->pf_flag.as<uint32_t>();  // the classic kernels below run only if some query could not be certified
     }
     {
-        dim3 grid((K + CD_TC - 1) / CD_TC, (unsigned)((nb + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ)));
+        const size_t tiles = (size_t)((K + CD_TC - 1) / CD_TC) * ((nb + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ));
+        const unsigned grid = (unsigned)std::min<size_t>(tiles, run_if ? (size_t)ix->sm_count * 2 : ((size_t)1 << 30));
         centroid_dist_kernel<<<grid, CD_THREADS, 0, st>>>(ix->cent, ix->y.as<float>(), ix->cdist.as<float>(), (int)nb, K, D, run_if);
         CU(cudaGetLastError()); ix->counts[5]++;
     }
@@ -841,17 +847,22 @@ int run_quantize(rabitq_index* ix, size_t nb, int P) {
     const int D = (int)ix->D, W32 = D / 32, WP = (W32 + 3) & ~3, RS = 4 * WP + 8;
     cudaStream_t st = ix->stream;
     CU(ix->qrec.ensure(nb * (size_t)P * RS * 4));
-    size_t warps = nb * (size_t)P;
+    // probe ranks per warp: 1 for the generic kernel; for D <= 256 (query in registers) as many as keep >= ~64 warps per SM in the grid
+    int pch = 1;
+    if (W32 == 2 || W32 == 4 || W32 == 6 || W32 == 8)
+        while (pch < 8 && pch * 2 <= P && nb * (size_t)((P + 2 * pch - 1) / (2 * pch)) >= (size_t)ix->sm_count * 64) pch *= 2;
+    size_t warps = nb * (size_t)((P + pch - 1) / pch);
     const unsigned qgrid = (unsigned)((warps + 3) / 4);
+    const size_t qsmem = (size_t)4 * RS * 4;  // one record per warp, staged for the coalesced store
     const uint32_t* skip = ix->shard_count > 1 ? ix->offsets : nullptr;
 #define QUANT_ARGS ix->y.as<float>(), ix->cent, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), \
-                   ix->q_wbase.as<uint32_t>(), skip, ix->quant_bias, ix->qrec.as<uint32_t>(), (int)nb, P, D
+                   ix->q_wbase.as<uint32_t>(), skip, ix->quant_bias, ix->qrec.as<uint32_t>(), (int)nb, P, D, pch
     switch (W32) {
-        case 2: quantize_kernel<2><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
-        case 4: quantize_kernel<4><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
-        case 6: quantize_kernel<6><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
-        case 8: quantize_kernel<8><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
-        default: quantize_kernel<0><<<qgrid, 128, 0, st>>>(QUANT_ARGS); break;
+        case 2: quantize_kernel<2><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
+        case 4: quantize_kernel<4><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
+        case 6: quantize_kernel<6><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
+        case 8: quantize_kernel<8><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
+        default: quantize_kernel<0><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
     }
 #undef QUANT_ARGS
     CU(cudaGetLastError()); ix->counts[5]++;
@@ -878,9 +889,7 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     CU(ix->h_recent.ensure(nb * 4));
     CU(ix->h_wcount.ensure(nb * 4));
     CU(ix->counters.ensure(64));
-    CU(ix->out_dist.ensure(nb * topk * 4));
-    CU(ix->out_ids.ensure(nb * topk * 4));
-    CU(ix->out_count.ensure(nb * 4));
+    CU(ix->out_all.ensure(nb * topk * 8 + nb * 4));  // [dist nb x topk | ids nb x topk | count nb]: one D2H for the three results
     CU(cudaMemsetAsync(ix->counters.p, 0, 64, st));
     fill_f32_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(ix->thr.as<float>(), nb, 3.402823466e+38f);
     CU(cudaGetLastError()); ix->counts[5]++;
@@ -917,9 +926,10 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     ra.h_recent = ix->h_recent.as<float>();
     ra.h_wcount = ix->h_wcount.as<uint32_t>();
     ra.counters = ix->counters.as<unsigned long long>();
-    ra.out_dist = ix->out_dist.as<float>();
-    ra.out_ids = ix->out_ids.as<uint32_t>();
-    ra.out_count = ix->out_count.as<uint32_t>();
+    ra.out_dist = ix->out_all.as<float>();
+    ra.out_ids = ix->out_all.as<uint32_t>() + nb * topk;
+    ra.out_count = ix->out_all.as<uint32_t>() + 2 * nb * topk;
+    if (ix->ovr_dist) { ra.out_dist = ix->ovr_dist; ra.out_ids = ix->ovr_ids; if (ix->ovr_count) ra.out_count = ix->ovr_count; }
     ra.nq = (int)nb;
     ra.P = P;
     ra.D = D;
@@ -1111,14 +1121,36 @@ int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, siz
         CU(ix->qraw.ensure(nb * len * 4));
         CU(cudaMemcpyAsync(ix->qraw.p, queries + q0 * len, nb * len * 4, kin, ix->stream));
         BatchOut bo;
+        const bool direct = on_device && nb == nq;
+        if (direct) { ix->ovr_dist = out_dist; ix->ovr_ids = out_ids; ix->ovr_count = out_count; }
         rc = run_sub_batch(ix, nb, len, probe, topk, heuristic != 0, STOP_NONE, &bo);
+        ix->ovr_dist = nullptr; ix->ovr_ids = nullptr; ix->ovr_count = nullptr;
         if (rc) return rc;
-        CU(cudaMemcpyAsync(out_dist + q0 * topk, ix->out_dist.p, nb * topk * 4, kout, ix->stream));
-        CU(cudaMemcpyAsync(out_ids + q0 * topk, ix->out_ids.p, nb * topk * 4, kout, ix->stream));
-        if (out_count) CU(cudaMemcpyAsync(out_count + q0, ix->out_count.p, nb * 4, kout, ix->stream));
+        const uint32_t* oa = ix->out_all.as<uint32_t>();
+        const size_t out_words = nb * topk * 2 + nb;
+        if (direct) {
+        } else if (on_device) {
+            CU(cudaMemcpyAsync(out_dist + q0 * topk, oa, nb * topk * 4, kout, ix->stream));
+            CU(cudaMemcpyAsync(out_ids + q0 * topk, oa + nb * topk, nb * topk * 4, kout, ix->stream));
+            if (out_count) CU(cudaMemcpyAsync(out_count + q0, oa + 2 * nb * topk, nb * 4, kout, ix->stream));
+        } else {  // ONE copy into pinned staging (the caller's buffers may be pageable); scattered to them after the sync below
+            if (ix->h_out_cap < out_words * 4) {
+                if (ix->h_out) cudaFreeHost(ix->h_out);
+                ix->h_out = nullptr;
+                ix->h_out_cap = 0;
+                CU(cudaMallocHost((void**)&ix->h_out, out_words * 4 + out_words / 2));
+                ix->h_out_cap = out_words * 4 + out_words / 2;
+            }
+            CU(cudaMemcpyAsync(ix->h_out, oa, out_words * 4, cudaMemcpyDeviceToHost, ix->stream));
+        }
         CU(cudaMemcpyAsync(ix->h_pin + 8, ix->counters.p, 32, cudaMemcpyDeviceToHost, ix->stream));
         if (tick(ix, ST_D2H)) return RABITQ_ECUDA;
         CU(cudaStreamSynchronize(ix->stream));
+        if (!on_device) {
+            std::memcpy(out_dist + q0 * topk, ix->h_out, nb * topk * 4);
+            std::memcpy(out_ids + q0 * topk, ix->h_out + nb * topk, nb * topk * 4);
+            if (out_count) std::memcpy(out_count + q0, ix->h_out + 2 * nb * topk, nb * 4);
+        }
         unsigned long long c[4];
         std::memcpy(c, ix->h_pin + 8, 32);
         ix->counts[0] += bo.total_pairs;
@@ -1308,7 +1340,11 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered, float* d_thr) {
     d.ra.off_r1cnt = d.off_r1cnt; d.ra.off_r1rec = d.off_r1rec;
     d.ra.world = d.world; d.ra.rank = d.rank; d.ra.nq_local = (int)d.nq_l; d.ra.r1cap = (int)d.r1cap;
     const int fc = (int)(d.r1cap / SCAN_THREADS);
-    if ((rc = run_round_scan(ix, nq, P, d.sa, Pos{0, 0}, Pos{0, fc}, false))) return rc;
+    // both rounds' inverted lists on the side stream (they depend on the unpacked probe lists only), concurrently with K3
+    CU(cudaStreamWaitEvent(ix->aux_stream, ix->ev_fork, 0));
+    if ((rc = build_lists(ix, nq, P, d.sa.MS, Pos{0, 0}, Pos{0, fc}, 0, ix->aux_stream))) return rc;
+    if ((rc = build_lists(ix, nq, P, d.sa.MS, Pos{0, fc}, Pos{P, 0}, 1, ix->aux_stream))) return rc;
+    if ((rc = run_round_scan(ix, nq, P, d.sa, Pos{0, 0}, Pos{0, fc}, false, 0, true))) return rc;
     if ((rc = run_round_rerank(ix, nq, d.ra, Pos{0, 0}, Pos{0, fc}, true, false, false, ROUND_SINK1))) return rc;
     d.phase = 2;
     return RABITQ_OK;
@@ -1327,7 +1363,7 @@ int dist_round2_impl(rabitq_index* ix, uint32_t* d_status) {
     const int P = d.P, fc = (int)(d.r1cap / SCAN_THREADS);
     if (tick(ix, -1)) return RABITQ_ECUDA;
     CU(cudaMemsetAsync(d_status, 0, 4, st));
-    int rc = run_round_scan(ix, nq, P, d.sa, Pos{0, fc}, Pos{P, 0}, false);
+    int rc = run_round_scan(ix, nq, P, d.sa, Pos{0, fc}, Pos{P, 0}, false, 1, true);
     if (rc) return rc;
     r2_count_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(ix->bitmap.as<uint32_t>(), ix->q_wbase.as<uint32_t>(), ix->slot_local.as<uint32_t>(),
                                                               ix->q_p0.as<uint32_t>(), (int)nq, P, 0, fc, ix->r2_cnt.as<uint32_t>());
