@@ -149,6 +149,9 @@ int rabitq_dist_round2(rabitq_index* idx, uint32_t* d_status /* 1 word */);
 /* d_status bits after the step: 1 = a (home, source) record region overflowed, 2 = this home saw an overflowed segment;
  * non-zero on any rank => repeat the step after rabitq_dist_init with a larger records_per_query. */
 int rabitq_dist_finish(rabitq_index* idx, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count, uint32_t* d_status);
+/* The status word as rabitq_dist_finish left it (it is copied to the host by that call's own synchronisation), so the caller
+ * need not read `d_status` back itself.  0 = results valid; non-zero = an inbox region overflowed somewhere: grow and repeat. */
+int rabitq_dist_last_status(const rabitq_index* idx, uint32_t* out_status);
 /* dst[i] = min(dst[i], src[i]) on the device: the all-reduce(min) when all ranks live in one process. */
 int rabitq_min_f32_device(int device, float* d_dst, const float* d_src, size_t n, void* cuda_stream);
 

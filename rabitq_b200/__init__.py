@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "rabitq_shard_range", "rabitq_merge_topk_device", "rabitq_metrics", "rabitq_metrics_reset", "rabitq_last_error", "rabitq_set_rounds",
     "rabitq_set_option", "rabitq_set_stream", "rabitq_last_timings", "rabitq_stage_rotate", "rabitq_stage_probe", "rabitq_stage_quantize", "rabitq_stage_scan",
     "rabitq_dist_init", "rabitq_dist_ipc_handle", "rabitq_dist_inbox_ptr", "rabitq_dist_set_peer", "rabitq_dist_chunk_words", "rabitq_dist_front",
-    "rabitq_dist_round1", "rabitq_dist_round2", "rabitq_dist_finish", "rabitq_min_f32_device", "rabitq_set_quantize_bias", "rabitq_reshard", "rabitq_debug_rerank_stats",
+    "rabitq_dist_round1", "rabitq_dist_round2", "rabitq_dist_finish", "rabitq_min_f32_device", "rabitq_set_quantize_bias", "rabitq_reshard", "rabitq_debug_rerank_stats", "rabitq_dist_last_status",
 ]
 
 TIMING_STAGES = ["h2d_pad", "rotate", "centroid_dist", "select", "quantize", "bucket", "scan", "rerank", "d2h", "total"]

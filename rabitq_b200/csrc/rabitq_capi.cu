@@ -178,6 +178,7 @@ struct rabitq_index {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_stage;
     size_t ev_used = 0;
+    bool timings_pending = false;  // the last call's event chain has not been turned into ms[] yet
     int scan_blocks_per_sm = 0;
     size_t max_items = 0;  // capacity of a round's scan work list for the current sub-batch (setup_rounds)
     int scan_mode = -1;  // -1 = default; RABITQ_SCAN_MODE overrides (tuning)
@@ -244,12 +245,23 @@ int launch_rotate(rabitq_index* ix, const float* in, float* out, size_t rows, cu
     return 0;
 }
 
+// Stage timings are read from the event chain LAZILY (rabitq_last_timings): ~20 cudaEventElapsedTime calls cost tens of
+// microseconds of host time, which a serving loop that never asks for them should not pay between batches.
 int collect_timings(rabitq_index* ix) {
     CU(cudaStreamSynchronize(ix->stream));
+    ix->timings_pending = true;
+    return 0;
+}
+
+int resolve_timings(rabitq_index* ix) {
+    if (!ix->timings_pending) return 0;
+    ix->timings_pending = false;
+    static const bool trace = std::getenv("RABITQ_TRACE") != nullptr;
     for (size_t i = 1; i < ix->ev_used; i++) {
-        if (ix->ev_stage[i] < 0) continue;  // a restart marker
         float t = 0;
-        CU(cudaEventElapsedTime(&t, ix->ev_pool[i - 1], ix->ev_pool[i]));
+        if (trace || ix->ev_stage[i] >= 0) CU(cudaEventElapsedTime(&t, ix->ev_pool[i - 1], ix->ev_pool[i]));
+        if (trace) std::fprintf(stderr, "[rabitq trace r%d] ev %2zu stage %2d  %.4f ms\n", ix->shard_rank, i, ix->ev_stage[i], t);
+        if (ix->ev_stage[i] < 0) continue;  // a restart marker: gaps spent in the caller's collectives are not counted
         ix->ms[ix->ev_stage[i]] += t;
     }
     if (ix->ev_used >= 2) {
@@ -1109,6 +1121,7 @@ int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, siz
     std::lock_guard<std::mutex> lk(ix->mu);
     CU(cudaSetDevice(ix->device));
     std::memset(ix->ms, 0, sizeof(ix->ms));
+    ix->timings_pending = false;
     std::memset(ix->counts, 0, sizeof(ix->counts));
     ix->ev_used = 0;
     size_t nbmax = pick_sub_batch(ix, nq, probe);
@@ -1173,6 +1186,7 @@ int stage_prefix(rabitq_index* ix, const float* queries, size_t nq, size_t len, 
     CU(cudaSetDevice(ix->device));
     ix->ev_used = 0;
     std::memset(ix->ms, 0, sizeof(ix->ms));
+    ix->timings_pending = false;
     std::memset(ix->counts, 0, sizeof(ix->counts));
     CU(ix->qraw.ensure(nq * len * 4));
     CU(cudaMemcpyAsync(ix->qraw.p, queries, nq * len * 4, cudaMemcpyHostToDevice, ix->stream));
@@ -1259,6 +1273,7 @@ int dist_front_impl(rabitq_index* ix, const float* d_queries, size_t len, void* 
     std::lock_guard<std::mutex> lk(ix->mu);
     CU(cudaSetDevice(ix->device));
     std::memset(ix->ms, 0, sizeof(ix->ms));
+    ix->timings_pending = false;
     std::memset(ix->counts, 0, sizeof(ix->counts));
     ix->ev_used = 0;
     d.len = len;
@@ -1411,6 +1426,7 @@ int dist_finish_impl(rabitq_index* ix, float* d_out_dist, uint32_t* d_out_ids, u
     CU(cudaGetLastError()); ix->counts[5]++;
     if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
     CU(cudaMemcpyAsync(ix->h_pin + 8, ix->counters.p, 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ix->h_pin + 16, d_status, 4, cudaMemcpyDeviceToHost, st));  // rabitq_dist_last_status: no second sync for the caller
     CU(cudaStreamSynchronize(st));
     prefilter_adapt(ix);
     unsigned long long c[4], rough_home;
@@ -1423,20 +1439,7 @@ int dist_finish_impl(rabitq_index* ix, float* d_out_dist, uint32_t* d_out_ids, u
     ix->m_rough += rough_home;
     ix->m_precise += c[2];
     d.phase = 0;
-    // timings: every phase restarts the event chain with a marker, so gaps spent in the caller's collectives are not counted
-    static const bool trace = std::getenv("RABITQ_TRACE") != nullptr;
-    for (size_t i = 1; i < ix->ev_used; i++) {
-        float t = 0;
-        CU(cudaEventElapsedTime(&t, ix->ev_pool[i - 1], ix->ev_pool[i]));
-        if (trace) std::fprintf(stderr, "[rabitq trace r%d] ev %2zu stage %2d  %.4f ms\n", d.rank, i, ix->ev_stage[i], t);
-        if (ix->ev_stage[i] < 0) continue;
-        ix->ms[ix->ev_stage[i]] += t;
-    }
-    if (ix->ev_used >= 2) {
-        float t = 0;
-        CU(cudaEventElapsedTime(&t, ix->ev_pool[0], ix->ev_pool[ix->ev_used - 1]));
-        ix->ms[ST_TOTAL] = t;
-    }
+    ix->timings_pending = true;  // every phase restarted the event chain with a marker; resolved on demand
     return RABITQ_OK;
 }
 
@@ -1481,6 +1484,12 @@ int rabitq_dist_round1(rabitq_index* idx, const void* d_gathered, float* d_thr) 
 int rabitq_dist_round2(rabitq_index* idx, uint32_t* d_status) { return dist_round2_impl(idx, d_status); }
 int rabitq_dist_finish(rabitq_index* idx, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count, uint32_t* d_status) {
     return dist_finish_impl(idx, d_out_dist, d_out_ids, d_out_count, d_status);
+}
+
+int rabitq_dist_last_status(const rabitq_index* idx, uint32_t* out_status) {
+    if (!idx || !out_status) return fail(RABITQ_EINVAL, "null argument");
+    *out_status = idx->h_pin[16];
+    return RABITQ_OK;
 }
 
 int rabitq_min_f32_device(int device, float* d_dst, const float* d_src, size_t n, void* cuda_stream) {
@@ -1682,6 +1691,12 @@ int rabitq_set_stream(rabitq_index* idx, void* cuda_stream) {
 
 int rabitq_last_timings(const rabitq_index* idx, float ms[10], uint64_t counts[6]) {
     if (!idx) return fail(RABITQ_EINVAL, "null index");
+    {
+        rabitq_index* ix = const_cast<rabitq_index*>(idx);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        CU(cudaSetDevice(ix->device));
+        if (resolve_timings(ix)) return RABITQ_ECUDA;
+    }
     if (ms) std::memcpy(ms, idx->ms, sizeof(float) * 10);
     if (counts) std::memcpy(counts, idx->counts, sizeof(uint64_t) * 6);
     return RABITQ_OK;

@@ -154,9 +154,13 @@ class _RankState:
     def round2(self):
         _check(lib().rabitq_dist_round2(self.shard._h, C.c_void_p(self.status.data_ptr())))
 
-    def finish(self):
+    def finish(self) -> int:
+        """Runs the home replay, synchronises the stream and returns the step's status word (0 = results valid)."""
         _check(lib().rabitq_dist_finish(self.shard._h, C.c_void_p(self.out_d.data_ptr()), C.c_void_p(self.out_i.data_ptr()),
                                         C.c_void_p(self.out_c.data_ptr()), C.c_void_p(self.status.data_ptr())))
+        st = C.c_uint32(0)
+        _check(lib().rabitq_dist_last_status(self.shard._h, C.byref(st)))
+        return int(st.value)
 
 
 class DistributedRaBitQ:
@@ -212,8 +216,8 @@ class DistributedRaBitQ:
             self.comm.all_reduce_min(st.thr)
             st.round2()
             self.comm.all_reduce_max(st.status)   # barrier: every shard's records are in the inboxes + global overflow verdict
-            st.finish()                           # (a home sets bit 2 only if some source set bit 1, which everybody already knows)
-            if int(st.status.item()) == 0:
+            status = st.finish()                  # (a home sets bit 2 only if some source set bit 1, which everybody already knows)
+            if status == 0:
                 return st.out_d, st.out_i, st.out_c
             self.rpq *= 4  # an inbox region overflowed somewhere: every rank grows and repeats the step
         raise RabitqError(5, "survivor-record regions still overflow after growing; raise records_per_query")
@@ -259,9 +263,7 @@ def run_virtual_ranks(shards: list[RaBitQ], queries, probe: int, topk: int, reco
         for st in states:
             st.thr.copy_(thr)
             st.round2()
-        for st in states:                                           # (stream order = the barrier)
-            st.finish()
-        status = max(int(st.status.item()) for st in states)
+        status = max(st.finish() for st in states)                  # (stream order = the barrier)
         if status == 0:
             return (torch.cat([st.out_d for st in states]), torch.cat([st.out_i for st in states]), torch.cat([st.out_c for st in states]), states)
         if not grow or records_per_query > (1 << 22):

@@ -1,4 +1,3 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --workload c1 --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_c1_r01m.json 2> gpurun_out/bench_c1_r01m.err
-python bench.py --workload c3 --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_c3_r01m.json 2> gpurun_out/bench_c3_r01m.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_c2_g8_r01n.json 2> gpurun_out/bench_c2_g8_r01n.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_c2_g4_r01n.json 2> gpurun_out/bench_c2_g4_r01n.err
