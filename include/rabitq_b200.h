@@ -145,6 +145,15 @@ int rabitq_dist_set_peer(rabitq_index* idx, int peer_rank, const unsigned char* 
 size_t rabitq_dist_chunk_words(const rabitq_index* idx, size_t len);
 int rabitq_dist_front(rabitq_index* idx, const float* d_queries, size_t len, void* d_send);
 int rabitq_dist_round1(rabitq_index* idx, const void* d_gathered, float* d_thr /* world*nq_local */);
+/* The same front end in two halves, so that the all-gather of the big part overlaps the centroid scan: `front_rotate` (pad, rotate)
+ * fills d_send_qy = [q | y] (rabitq_dist_chunk_words_qy words per rank), the caller starts its all-gather asynchronously,
+ * `front_select` (centroid distances, probe selection) fills d_send_meta = [probe ids | probe distances | first non-empty rank]
+ * (rabitq_dist_chunk_words_meta words), second all-gather, then `round1_split` takes the two gathered buffers. */
+size_t rabitq_dist_chunk_words_qy(const rabitq_index* idx, size_t len);
+size_t rabitq_dist_chunk_words_meta(const rabitq_index* idx, size_t len);
+int rabitq_dist_front_rotate(rabitq_index* idx, const float* d_queries, size_t len, void* d_send_qy);
+int rabitq_dist_front_select(rabitq_index* idx, void* d_send_meta);
+int rabitq_dist_round1_split(rabitq_index* idx, const void* d_gathered_qy, const void* d_gathered_meta, float* d_thr);
 int rabitq_dist_round2(rabitq_index* idx, uint32_t* d_status /* 1 word */);
 /* d_status bits after the step: 1 = a (home, source) record region overflowed, 2 = this home saw an overflowed segment;
  * non-zero on any rank => repeat the step after rabitq_dist_init with a larger records_per_query. */

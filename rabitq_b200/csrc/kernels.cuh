@@ -1500,6 +1500,9 @@ __global__ void merge_topk_kernel(const float* __restrict__ dist, const uint32_t
 //   [q: nq_l x len][y: nq_l x D][probe ids: nq_l x P][probe dist: nq_l x P][p0: nq_l]
 struct DistChunk {
     size_t o_q, o_y, o_ids, o_dist, o_p0, words;
+    // the same products as TWO chunks, so that the (big) q/y part can be all-gathered while the centroid scan still runs:
+    // part A = [q | y] (words_a), part B = [ids | dist | p0] (words_b); a_* / b_* are offsets inside the respective part
+    size_t a_q, a_y, words_a, b_ids, b_dist, b_p0, words_b;
 };
 __host__ __device__ inline DistChunk dist_chunk_layout(size_t nq_l, size_t len, size_t D, size_t P) {
     auto up4 = [](size_t x) { return (x + 3) & ~(size_t)3; };
@@ -1510,38 +1513,49 @@ __host__ __device__ inline DistChunk dist_chunk_layout(size_t nq_l, size_t len, 
     c.o_dist = up4(c.o_ids + nq_l * P);
     c.o_p0 = up4(c.o_dist + nq_l * P);
     c.words = up4(c.o_p0 + nq_l);
+    c.a_q = 0;
+    c.a_y = c.o_y;
+    c.words_a = c.o_ids;
+    c.b_ids = 0;
+    c.b_dist = c.o_dist - c.o_ids;
+    c.b_p0 = c.o_p0 - c.o_ids;
+    c.words_b = c.words - c.o_ids;
     return c;
 }
 
 // After the all-gather of the per-rank front-end products: `gathered` = world chunks -> flat per-query arrays over the
 // whole batch (global query gq = rank * nq_l + i), queries zero-padded to D.  One warp per query, 128-bit copies.
-__global__ void dist_unpack_kernel(const uint32_t* __restrict__ gathered, int world, int nq_l, int len, int D, int P,
-                                   float* __restrict__ qpad, float* __restrict__ y, uint32_t* __restrict__ probe_ids,
-                                   float* __restrict__ probe_dist, uint32_t* __restrict__ q_p0) {
+__global__ void dist_unpack_kernel(const uint32_t* __restrict__ gathered_a, size_t stride_a, const uint32_t* __restrict__ gathered_b,
+                                   size_t stride_b, int world, int nq_l, int len, int D, int P, float* __restrict__ qpad,
+                                   float* __restrict__ y, uint32_t* __restrict__ probe_ids, float* __restrict__ probe_dist,
+                                   uint32_t* __restrict__ q_p0) {
+    // gathered_a / stride_a: rank r's [q | y] part starts at gathered_a + r * stride_a; gathered_b likewise for [ids | dist | p0]
+    // (one buffer with the combined chunk layout, or the two buffers of the split all-gather)
     const int lane = threadIdx.x & 31;
     const size_t gq = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gq >= (size_t)world * nq_l) return;
     const DistChunk L = dist_chunk_layout(nq_l, len, D, P);
     const int r = (int)(gq / nq_l), ql = (int)(gq % nq_l);
-    const uint32_t* c = gathered + (size_t)r * L.words;
+    const uint32_t* ca = gathered_a + (size_t)r * stride_a;
+    const uint32_t* cb = gathered_b + (size_t)r * stride_b;
     {
-        const uint4* src = reinterpret_cast<const uint4*>(c + L.o_y + (size_t)ql * D);
+        const uint4* src = reinterpret_cast<const uint4*>(ca + L.a_y + (size_t)ql * D);
         uint4* dst = reinterpret_cast<uint4*>(y + gq * D);
         for (int i = lane; i < D / 4; i += 32) dst[i] = src[i];
     }
     if ((len & 3) == 0) {
-        const uint4* src = reinterpret_cast<const uint4*>(c + L.o_q + (size_t)ql * len);
+        const uint4* src = reinterpret_cast<const uint4*>(ca + L.a_q + (size_t)ql * len);
         uint4* dst = reinterpret_cast<uint4*>(qpad + gq * D);
         for (int i = lane; i < D / 4; i += 32) dst[i] = i < len / 4 ? src[i] : make_uint4(0u, 0u, 0u, 0u);
     } else {
-        const uint32_t* src = c + L.o_q + (size_t)ql * len;
+        const uint32_t* src = ca + L.a_q + (size_t)ql * len;
         for (int i = lane; i < D; i += 32) qpad[gq * D + i] = i < len ? __uint_as_float(src[i]) : 0.0f;
     }
     for (int i = lane; i < P; i += 32) {
-        probe_ids[gq * P + i] = c[L.o_ids + (size_t)ql * P + i];
-        probe_dist[gq * P + i] = __uint_as_float(c[L.o_dist + (size_t)ql * P + i]);
+        probe_ids[gq * P + i] = cb[L.b_ids + (size_t)ql * P + i];
+        probe_dist[gq * P + i] = __uint_as_float(cb[L.b_dist + (size_t)ql * P + i]);
     }
-    if (lane == 0) q_p0[gq] = c[L.o_p0 + ql];
+    if (lane == 0) q_p0[gq] = cb[L.b_p0 + ql];
 }
 
 // Survivor-slot layout of one shard for probe lists that were selected elsewhere: per (query, rank) the exclusive prefix

@@ -732,8 +732,10 @@ struct Pos { int p, ch; };  // a visit position: (effective probe rank, 128-vect
 
 // K0-K2b for nb queries already in ix->qraw (nb x len): pad, rotate, centroid distances, probe selection.  `global_view`:
 // pair counts and the first non-empty rank refer to the whole index (distributed front end) instead of this shard's rows.
+int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view);
+
 int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_rotate, bool global_view) {
-    const int D = (int)ix->D, K = (int)ix->K;
+    const int D = (int)ix->D;
     cudaStream_t st = ix->stream;
     CU(ix->qpad.ensure(nb * D * 4));
     CU(ix->y.ensure(nb * D * 4));
@@ -747,7 +749,13 @@ int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_ro
     ix->counts[5]++;
     if (tick(ix, ST_ROTATE)) return RABITQ_ECUDA;
     if (stop_after_rotate) return 0;
+    return run_front_select(ix, nb, P, global_view);
+}
 
+// K2p / K2 / K2b for nb rotated queries in ix->y (the second half of the front end)
+int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
+    const int D = (int)ix->D, K = (int)ix->K;
+    cudaStream_t st = ix->stream;
     CU(ix->cdist.ensure(nb * (size_t)K * 4));
     CU(ix->probe_ids.ensure(nb * P * 4));
     CU(ix->probe_dist.ensure(nb * P * 4));
@@ -1264,10 +1272,13 @@ int dist_set_peer_impl(rabitq_index* ix, int r, const unsigned char* ipc_handle,
     return RABITQ_OK;
 }
 
-// Phase 1 (home): front end of this rank's nq_l queries -> its chunk of the all-gather.
-int dist_front_impl(rabitq_index* ix, const float* d_queries, size_t len, void* d_send) {
+// Phase 1 (home): front end of this rank's nq_l queries -> its chunk(s) of the all-gather.  Two halves, so that the caller can
+// start the all-gather of the big [q | y] part while the centroid scan and the probe selection still run:
+//   1a  pad + rotate          -> d_send_qy   (words_a of dist_chunk_layout)
+//   1b  K2p / K2 / K2b        -> d_send_meta (words_b)
+int dist_front_rotate_impl(rabitq_index* ix, const float* d_queries, size_t len, void* d_send_qy) {
     if (!ix || !ix->dist.ready) return fail(RABITQ_EINVAL, "rabitq_dist_init first");
-    if (!d_queries || !d_send) return fail(RABITQ_EINVAL, "null argument");
+    if (!d_queries || !d_send_qy) return fail(RABITQ_EINVAL, "null argument");
     DistState& d = ix->dist;
     if ((len + 63) / 64 * 64 != ix->D) return fail(RABITQ_EINVAL, "assertion `left == right` failed: dim != query.len().div_ceil(64) * 64");
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -1278,32 +1289,57 @@ int dist_front_impl(rabitq_index* ix, const float* d_queries, size_t len, void* 
     ix->ev_used = 0;
     d.len = len;
     const size_t nq_l = d.nq_l, D = ix->D;
-    const int P = d.P;
     cudaStream_t st = ix->stream;
     if (tick(ix, -1)) return RABITQ_ECUDA;
     CU(cudaMemsetAsync(d.inbox + d.off_r1cnt, 0, (size_t)d.world * nq_l * 4, st));  // before the all-gather = before any owner writes
     CU(ix->qraw.ensure(nq_l * len * 4));
     CU(cudaMemcpyAsync(ix->qraw.p, d_queries, nq_l * len * 4, cudaMemcpyDeviceToDevice, st));
-    int rc = run_front(ix, nq_l, len, P, false, true);
+    int rc = run_front(ix, nq_l, len, d.P, true, true);
+    if (rc) return rc;
+    uint32_t* send = static_cast<uint32_t*>(d_send_qy);
+    const DistChunk L = dist_chunk_layout(nq_l, len, D, (size_t)d.P);
+    CU(cudaMemcpyAsync(send + L.a_q, ix->qraw.p, nq_l * len * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(send + L.a_y, ix->y.p, nq_l * D * 4, cudaMemcpyDeviceToDevice, st));
+    if (tick(ix, ST_ROTATE)) return RABITQ_ECUDA;
+    d.phase = 10;
+    return RABITQ_OK;
+}
+
+int dist_front_select_impl(rabitq_index* ix, void* d_send_meta) {
+    if (!ix || !ix->dist.ready || ix->dist.phase != 10) return fail(RABITQ_EINVAL, "rabitq_dist_front_rotate first");
+    if (!d_send_meta) return fail(RABITQ_EINVAL, "null argument");
+    DistState& d = ix->dist;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    const size_t nq_l = d.nq_l, D = ix->D;
+    const int P = d.P;
+    cudaStream_t st = ix->stream;
+    int rc = run_front_select(ix, nq_l, P, true);
     if (rc) return rc;
     CU(cudaMemcpyAsync(ix->h_pin + 4, ix->q_pbase.as<unsigned long long>() + nq_l, 8, cudaMemcpyDeviceToHost, st));  // `rough` of the home queries
-    uint32_t* send = static_cast<uint32_t*>(d_send);
-    const DistChunk L = dist_chunk_layout(nq_l, len, D, (size_t)P);
-    CU(cudaMemcpyAsync(send + L.o_q, ix->qraw.p, nq_l * len * 4, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(send + L.o_y, ix->y.p, nq_l * D * 4, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(send + L.o_ids, ix->probe_ids.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(send + L.o_dist, ix->probe_dist.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(send + L.o_p0, ix->q_p0.p, nq_l * 4, cudaMemcpyDeviceToDevice, st));
+    uint32_t* send = static_cast<uint32_t*>(d_send_meta);
+    const DistChunk L = dist_chunk_layout(nq_l, d.len, D, (size_t)P);
+    CU(cudaMemcpyAsync(send + L.b_ids, ix->probe_ids.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(send + L.b_dist, ix->probe_dist.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(send + L.b_p0, ix->q_p0.p, nq_l * 4, cudaMemcpyDeviceToDevice, st));
     if (tick(ix, ST_SELECT)) return RABITQ_ECUDA;
     d.phase = 1;
     return RABITQ_OK;
 }
 
+// the two halves into ONE chunk (combined layout: part B follows part A)
+int dist_front_impl(rabitq_index* ix, const float* d_queries, size_t len, void* d_send) {
+    int rc = dist_front_rotate_impl(ix, d_queries, len, d_send);
+    if (rc) return rc;
+    const DistChunk L = dist_chunk_layout(ix->dist.nq_l, len, ix->D, (size_t)ix->dist.P);
+    return dist_front_select_impl(ix, static_cast<uint32_t*>(d_send) + L.words_a);
+}
+
 // Phase 2 (source): the whole batch's products -> local slots, query records, round 1 (first chunk of the nearest non-empty
 // cluster) on the shard that owns it; the round-1 threshold of every owned query lands in d_thr (others keep +FLT_MAX).
-int dist_round1_impl(rabitq_index* ix, const void* d_gathered, float* d_thr) {
+int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a, const void* d_gathered_b, size_t stride_b, float* d_thr) {
     if (!ix || !ix->dist.ready || ix->dist.phase != 1) return fail(RABITQ_EINVAL, "rabitq_dist_front first");
-    if (!d_gathered || !d_thr) return fail(RABITQ_EINVAL, "null argument");
+    if (!d_gathered_a || !d_gathered_b || !d_thr) return fail(RABITQ_EINVAL, "null argument");
     DistState& d = ix->dist;
     for (int r = 0; r < d.world; r++)
         if (!d.peers_h[r]) return fail(RABITQ_EINVAL, "peer inbox of rank " + std::to_string(r) + " not set (rabitq_dist_set_peer)");
@@ -1327,7 +1363,8 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered, float* d_thr) {
     CU(ix->home_tot.ensure(32 * 4));
     CU(ix->cand.ensure((size_t)d.world * d.cap2 * sizeof(Cand)));
     if (tick(ix, -1)) return RABITQ_ECUDA;  // the all-gather sits between the phases: not ours to time
-    dist_unpack_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(static_cast<const uint32_t*>(d_gathered), d.world, (int)d.nq_l, (int)d.len, (int)D, P,
+    dist_unpack_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(static_cast<const uint32_t*>(d_gathered_a), stride_a,
+                                                          static_cast<const uint32_t*>(d_gathered_b), stride_b, d.world, (int)d.nq_l, (int)d.len, (int)D, P,
                                                           ix->qpad.as<float>(), ix->y.as<float>(), ix->probe_ids.as<uint32_t>(),
                                                           ix->probe_dist.as<float>(), ix->q_p0.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
@@ -1480,7 +1517,28 @@ size_t rabitq_dist_chunk_words(const rabitq_index* idx, size_t len) {
 }
 
 int rabitq_dist_front(rabitq_index* idx, const float* d_queries, size_t len, void* d_send) { return dist_front_impl(idx, d_queries, len, d_send); }
-int rabitq_dist_round1(rabitq_index* idx, const void* d_gathered, float* d_thr) { return dist_round1_impl(idx, d_gathered, d_thr); }
+int rabitq_dist_round1(rabitq_index* idx, const void* d_gathered, float* d_thr) {
+    if (!idx || !idx->dist.ready) return fail(RABITQ_EINVAL, "rabitq_dist_init first");
+    const DistChunk L = dist_chunk_layout(idx->dist.nq_l, idx->dist.len, idx->D, (size_t)idx->dist.P);
+    return dist_round1_impl(idx, d_gathered, L.words, d_gathered ? static_cast<const uint32_t*>(d_gathered) + L.words_a : nullptr, L.words, d_thr);
+}
+size_t rabitq_dist_chunk_words_qy(const rabitq_index* idx, size_t len) {
+    if (!idx || !idx->dist.ready) return 0;
+    return dist_chunk_layout(idx->dist.nq_l, len, idx->D, (size_t)idx->dist.P).words_a;
+}
+size_t rabitq_dist_chunk_words_meta(const rabitq_index* idx, size_t len) {
+    if (!idx || !idx->dist.ready) return 0;
+    return dist_chunk_layout(idx->dist.nq_l, len, idx->D, (size_t)idx->dist.P).words_b;
+}
+int rabitq_dist_front_rotate(rabitq_index* idx, const float* d_queries, size_t len, void* d_send_qy) {
+    return dist_front_rotate_impl(idx, d_queries, len, d_send_qy);
+}
+int rabitq_dist_front_select(rabitq_index* idx, void* d_send_meta) { return dist_front_select_impl(idx, d_send_meta); }
+int rabitq_dist_round1_split(rabitq_index* idx, const void* d_gathered_qy, const void* d_gathered_meta, float* d_thr) {
+    if (!idx || !idx->dist.ready) return fail(RABITQ_EINVAL, "rabitq_dist_init first");
+    const DistChunk L = dist_chunk_layout(idx->dist.nq_l, idx->dist.len, idx->D, (size_t)idx->dist.P);
+    return dist_round1_impl(idx, d_gathered_qy, L.words_a, d_gathered_meta, L.words_b, d_thr);
+}
 int rabitq_dist_round2(rabitq_index* idx, uint32_t* d_status) { return dist_round2_impl(idx, d_status); }
 int rabitq_dist_finish(rabitq_index* idx, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count, uint32_t* d_status) {
     return dist_finish_impl(idx, d_out_dist, d_out_ids, d_out_count, d_status);

@@ -3,8 +3,9 @@
 Two ways to answer a batch:
 
 * `DistributedRaBitQ` (the product path): every rank is the HOME of its own slice of the query batch.  The phases of the
-  C ABI (`rabitq_dist_front / round1 / round2 / finish`) run between three collectives on one CUDA stream -- an
-  all-gather of the front-end products, an all-reduce(min) of the round-1 thresholds, an all-reduce(max) of a status word
+  C ABI (`rabitq_dist_front_rotate / front_select / round1_split / round2 / finish`) run between the collectives on one CUDA
+  stream -- an all-gather of the rotated queries that is STARTED ASYNCHRONOUSLY and overlaps the centroid scan, a small
+  all-gather of the probe lists, an all-reduce(min) of the round-1 thresholds, an all-reduce(max) of a status word
   that doubles as the barrier -- while the survivor records themselves travel by peer stores from the kernel that computes
   the exact distances straight into the home rank's inbox (CUDA IPC memory over NVLink).  Results, distances and the
   `precise` counter are IDENTICAL to the single-process reference (src/rerank.rs:81-106 replayed on the union).
@@ -19,6 +20,7 @@ The reference is single-process; this module is the only 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -45,6 +47,11 @@ class TorchComm:
 
     def all_gather(self, out_t, in_t):
         self.dist.all_gather_into_tensor(out_t, in_t, group=self.group)
+
+    def all_gather_start(self, out_t, in_t):
+        """Asynchronous all-gather: enqueued behind the work already on the current stream, runs on the backend's own stream
+        while the caller keeps launching kernels; `.wait()` on the returned handle orders the current stream after it."""
+        return self.dist.all_gather_into_tensor(out_t, in_t, group=self.group, async_op=True)
 
     def all_reduce_min(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
@@ -124,9 +131,12 @@ class _RankState:
         _check(lib().rabitq_dist_init(shard._h, rank, world, nq_local, probe, topk, records_per_query, C.byref(nbytes)))
         self.inbox_bytes = int(nbytes.value)
         dev = torch.device("cuda", shard.device)
-        words = int(lib().rabitq_dist_chunk_words(shard._h, length))
-        self.send = torch.empty(words, dtype=torch.int32, device=dev)
-        self.gathered = torch.empty(words * world, dtype=torch.int32, device=dev)
+        wa = int(lib().rabitq_dist_chunk_words_qy(shard._h, length))     # [q | y]: the big part, gathered while K2 runs
+        wb = int(lib().rabitq_dist_chunk_words_meta(shard._h, length))   # [probe ids | probe distances | first non-empty rank]
+        self.send_qy = torch.empty(wa, dtype=torch.int32, device=dev)
+        self.send_meta = torch.empty(wb, dtype=torch.int32, device=dev)
+        self.gathered_qy = torch.empty(wa * world, dtype=torch.int32, device=dev)
+        self.gathered_meta = torch.empty(wb * world, dtype=torch.int32, device=dev)
         self.thr = torch.empty(nq_local * world, dtype=torch.float32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self.out_d = torch.empty((nq_local, topk), dtype=torch.float32, device=dev)
@@ -144,12 +154,16 @@ class _RankState:
         return int(p.value)
 
     # phases (everything asynchronous on the shard's stream, except the one host read that sizes the survivor slots)
-    def front(self, q_dev):
+    def front_rotate(self, q_dev):
         assert q_dev.is_cuda and q_dev.is_contiguous() and tuple(q_dev.shape) == (self.nq_local, self.len), tuple(q_dev.shape)
-        _check(lib().rabitq_dist_front(self.shard._h, C.c_void_p(q_dev.data_ptr()), self.len, C.c_void_p(self.send.data_ptr())))
+        _check(lib().rabitq_dist_front_rotate(self.shard._h, C.c_void_p(q_dev.data_ptr()), self.len, C.c_void_p(self.send_qy.data_ptr())))
+
+    def front_select(self):
+        _check(lib().rabitq_dist_front_select(self.shard._h, C.c_void_p(self.send_meta.data_ptr())))
 
     def round1(self):
-        _check(lib().rabitq_dist_round1(self.shard._h, C.c_void_p(self.gathered.data_ptr()), C.c_void_p(self.thr.data_ptr())))
+        _check(lib().rabitq_dist_round1_split(self.shard._h, C.c_void_p(self.gathered_qy.data_ptr()), C.c_void_p(self.gathered_meta.data_ptr()),
+                                              C.c_void_p(self.thr.data_ptr())))
 
     def round2(self):
         _check(lib().rabitq_dist_round2(self.shard._h, C.c_void_p(self.status.data_ptr())))
@@ -170,6 +184,7 @@ class DistributedRaBitQ:
     def __init__(self, shard: RaBitQ, comm: TorchComm | None = None, records_per_query: int = 256):
         self.shard, self.comm = shard, comm or TorchComm()
         self.rpq = records_per_query
+        self.overlap = os.environ.get("RABITQ_DIST_OVERLAP", "1") != "0"
         self._st: _RankState | None = None
 
     @classmethod
@@ -210,8 +225,16 @@ class DistributedRaBitQ:
         self.shard.set_stream(cur)
         for _ in range(max_retries + 1):
             st = self._state(nq_local, length, probe, topk)
-            st.front(queries_local)
-            self.comm.all_gather(st.gathered, st.send)
+            st.front_rotate(queries_local)
+            if self.overlap:
+                work = self.comm.all_gather_start(st.gathered_qy, st.send_qy)   # 7.7 KB per query: in flight during K2 / K2b
+                st.front_select()
+                self.comm.all_gather(st.gathered_meta, st.send_meta)
+                work.wait()
+            else:  # (A/B switch: RABITQ_DIST_OVERLAP=0)
+                self.comm.all_gather(st.gathered_qy, st.send_qy)
+                st.front_select()
+                self.comm.all_gather(st.gathered_meta, st.send_meta)
             st.round1()
             self.comm.all_reduce_min(st.thr)
             st.round2()
@@ -252,10 +275,13 @@ def run_virtual_ranks(shards: list[RaBitQ], queries, probe: int, topk: int, reco
                     if a is not b:
                         _check(lib().rabitq_dist_set_peer(a.shard._h, b.rank, None, C.c_void_p(b.inbox_ptr())))
         for r, st in enumerate(states):
-            st.front(queries[r * nq_l:(r + 1) * nq_l])
-        gathered = torch.cat([st.send for st in states])           # all-gather
+            st.front_rotate(queries[r * nq_l:(r + 1) * nq_l])
+            st.front_select()
+        gathered_qy = torch.cat([st.send_qy for st in states])     # the two all-gathers
+        gathered_meta = torch.cat([st.send_meta for st in states])
         for st in states:
-            st.gathered.copy_(gathered)
+            st.gathered_qy.copy_(gathered_qy)
+            st.gathered_meta.copy_(gathered_meta)
             st.round1()
         thr = states[0].thr.clone()                                 # all-reduce(min)
         for st in states[1:]:

@@ -68,6 +68,53 @@ def test_virtual_ranks_identical_to_unsharded_oracle(case, world, probe, topk):
             s.close()
 
 
+def test_combined_chunk_entries_equal_split_ones(case_d128):
+    """`rabitq_dist_front` + `rabitq_dist_round1` (ONE chunk per rank, one all-gather) give the same step as the split entries
+    (`front_rotate` / `front_select` / `round1_split`) that the product path overlaps with its all-gathers."""
+    import ctypes as C
+
+    import torch
+
+    from rabitq_b200 import distributed as rd
+    from rabitq_b200 import _check, lib
+
+    world, probe, topk = 2, 16, 10
+    q = np.ascontiguousarray(case_d128["queries"][: case_d128["queries"].shape[0] // world * world])
+    shards = _shards(case_d128, world)
+    try:
+        qd = torch.from_numpy(q).cuda()
+        d0, i0, c0, states = rd.run_virtual_ranks(shards, qd, probe, topk)
+        side = torch.cuda.Stream(qd.device)
+        with torch.cuda.stream(side):
+            for s in shards:
+                s.set_stream(side.cuda_stream)
+            nq_l, length = q.shape[0] // world, q.shape[1]
+            words = int(lib().rabitq_dist_chunk_words(shards[0]._h, length))
+            assert words == int(lib().rabitq_dist_chunk_words_qy(shards[0]._h, length)) + int(lib().rabitq_dist_chunk_words_meta(shards[0]._h, length))
+            sends = [torch.empty(words, dtype=torch.int32, device=qd.device) for _ in range(world)]
+            for r, st in enumerate(states):
+                _check(lib().rabitq_dist_front(st.shard._h, C.c_void_p(qd[r * nq_l:(r + 1) * nq_l].data_ptr()), length, C.c_void_p(sends[r].data_ptr())))
+            gathered = torch.cat(sends)
+            for st in states:
+                _check(lib().rabitq_dist_round1(st.shard._h, C.c_void_p(gathered.data_ptr()), C.c_void_p(st.thr.data_ptr())))
+            thr = states[0].thr.clone()
+            for st in states[1:]:
+                _check(lib().rabitq_min_f32_device(qd.device.index, C.c_void_p(thr.data_ptr()), C.c_void_p(st.thr.data_ptr()), thr.numel(),
+                                                   C.c_void_p(side.cuda_stream)))
+            for st in states:
+                st.thr.copy_(thr)
+                st.round2()
+            assert max(st.finish() for st in states) == 0
+            d1 = torch.cat([st.out_d for st in states])
+            i1 = torch.cat([st.out_i for st in states])
+            c1 = torch.cat([st.out_c for st in states])
+            side.synchronize()
+        assert torch.equal(d0, d1) and torch.equal(i0, i1) and torch.equal(c0, c1)
+    finally:
+        for s in shards:
+            s.close()
+
+
 def test_virtual_ranks_region_overflow_is_reported(case_d128):
     """A survivor-record region that is too small must raise, never truncate silently."""
     import torch
