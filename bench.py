@@ -101,9 +101,9 @@ def measured_peak_hbm():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the main scan launch, from the committed `ncu --set full` captures
-# (profiles/scan_kernel_full_r01k.txt); a static per-launch figure, not re-measured by this run.
-SCAN_DRAM_TRAFFIC = {"c2": 150.1e6, "c1": 246.3e6}
-SCAN_DRAM_TRAFFIC_SOURCE = "ncu --set full, profiles/scan_kernel_full_r01k.txt (bytes per main scan launch)"
+# (profiles/scan_kernel_full_r01p.txt); a static per-launch figure, not re-measured by this run.
+SCAN_DRAM_TRAFFIC = {"c2": 152.8e6, "c1": 248.0e6}
+SCAN_DRAM_TRAFFIC_SOURCE = "ncu --set full, profiles/scan_kernel_full_r01p.txt (bytes per main scan launch)"
 
 
 def recall_at_k(ids, truth, k):

@@ -1117,6 +1117,24 @@ RQ_DEV float l2_quad(const float* __restrict__ row, const float* __restrict__ qv
     return __fadd_rn(s, __shfl_xor_sync(FULL, s, 1));
 }
 
+// Same distance with the ROW IN GLOBAL MEMORY (a rotated centroid, L2-resident) and the query in shared memory: 64-bit read-only
+// loads, eight steps in flight.  Used by the prefilter's exact recheck (prefilter.cuh); diff = row - q as in the reference.
+RQ_DEV float l2_quad_global(const float* __restrict__ row, const float* __restrict__ qs, int D, int v4) {
+    const f32x2* rp = reinterpret_cast<const f32x2*>(row) + v4;
+    const f32x2* qp = reinterpret_cast<const f32x2*>(qs) + v4;
+    f32x2 acc = 0ull;
+#pragma unroll 8
+    for (int i = 0; i < D / 8; i++) {
+        const f32x2 f = sub2(__ldg(&rp[4 * i]), qp[4 * i]);
+        acc = fma2(f, f, acc);
+    }
+    float lo, hi, olo, ohi;
+    unpack2(acc, lo, hi);
+    unpack2(__shfl_xor_sync(FULL, acc, 2), olo, ohi);
+    const float s = __fadd_rn(__fadd_rn(lo, olo), __fadd_rn(hi, ohi));
+    return __fadd_rn(s, __shfl_xor_sync(FULL, s, 1));
+}
+
 // HEUR = false: HeapReRanker (src/rerank.rs:61-114).  HEUR = true: HeuristicReRanker (src/rerank.rs:117-176): the filter
 // threshold is the largest accepted distance of the last WINDOW_SIZE = 12 accepted candidates (src/consts.rs:12); every
 // accepted candidate is a result candidate and get_result keeps the topk smallest, which is what the k-slot buffer holds.

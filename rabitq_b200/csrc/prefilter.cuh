@@ -366,24 +366,16 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
         if (tid == 0) atomicOr(fallback_flag, nc > (uint32_t)cap ? 1u : 2u);  // bit 0: too many candidates, bit 1: no valid threshold
         return;
     }
-    // exact distances of the candidates, order of simd::l2_squared_distance: 8 lanes per candidate = the 8 AVX lanes
+    // exact distances of the candidates, order of simd::l2_squared_distance: four threads per candidate, two AVX lanes each
+    // (packed f32x2, 64-bit loads of the centroid row; kernels.cuh l2_quad_global)
     {
-        const int v = lane & 7, sub = tid >> 3;  // PS_THREADS / 8 = 32 candidates per sweep
-        for (uint32_t c0 = 0; c0 < nc; c0 += PS_THREADS / 8) {
+        const int v4 = lane & 3, sub = tid >> 2;  // PS_THREADS / 4 = 64 candidates per sweep
+        for (uint32_t c0 = 0; c0 < nc; c0 += PS_THREADS / 4) {
             const uint32_t ci = c0 + sub;
             const bool act = ci < nc;
             const uint32_t id = cid[act ? ci : 0];
-            const float* cr = cent + (size_t)id * D;
-            float acc = 0.0f;
-#pragma unroll 4
-            for (int d = v; d < D; d += 8) {
-                const float f = __fsub_rn(__ldg(&cr[d]), sy[d]);  // diff = c - y (src/simd.rs:34-37)
-                acc = fmaf(f, f, acc);
-            }
-            acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
-            acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
-            acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
-            if (act && v == 0) ckey[ci] = ((unsigned long long)okey(acc) << 32) | id;
+            const float acc = l2_quad_global(cent + (size_t)id * D, sy, D, v4);  // diff = c - y (src/simd.rs:34-37)
+            if (act && v4 == 0) ckey[ci] = ((unsigned long long)okey(acc) << 32) | id;
         }
     }
     __syncthreads();
