@@ -178,7 +178,7 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
 
 /* Integer tuning knobs (results never depend on them; tests sweep them): "first_chunks" = 128-vector chunks of the nearest
  * cluster that form the first rerank round (default 1, 0 = whole cluster); "scan_mode" = carry-save depth of the scan's
- * popcount (0 plain, 1 = 3->2, 2 = 7->3 compressors, -1 = by dimension); "rerank_rows" = rows per rerank wave (0 = auto); "rerank_prefetch" = L2 prefetch of survivor rows ahead of the
+ * popcount (0 plain, 1 = 3->2, 2 = 7->3 compressors, 3 = half the words by 7->3 and the rest by 3->2, -1 = by dimension); "rerank_rows" = rows per rerank wave (0 = auto); "rerank_prefetch" = L2 prefetch of survivor rows ahead of the
  * gather (default 0: measured slower on B200); "debug_rerank" = 1 keeps per-query rerank statistics for rabitq_debug_rerank_stats; "scan_slices" = shared-memory record slices per scan
  * work item (default 1; hot clusters are cut into several items); "prefilter" = 1 (default) lets the centroid scan run as a
  * TF32 tensor-core prefilter + exact recheck of the candidates when k >= 512 and probe <= k/8 (probe lists stay bit-identical),

@@ -808,7 +808,7 @@ RQ_DEV uint32_t plane_sum(const uint32_t (&x)[W32], const uint32_t* pl) {
         if (w + 3 < W32) a[w + 3] = x[w + 3] & p.w;
     }
     uint32_t ones = 0, twos = 0, fours = 0;
-    constexpr int G7 = (MODE == 2) ? W32 / 7 : 0;
+    constexpr int G7 = (MODE == 2) ? W32 / 7 : (MODE == 3) ? W32 / 14 : 0;  // MODE 3: half the words by 7->3, the rest by 3->2 (ALU/XU balance)
     constexpr int R7 = W32 - 7 * G7;
     constexpr int G3 = (MODE >= 1) ? R7 / 3 : 0;
     constexpr int R3 = R7 - 3 * G3;

@@ -690,7 +690,7 @@ int launch_scan_m(rabitq_index* ix, ScanArgs& a) {
     return 0;
 }
 
-// carry-save depth of the popcount (kernels.cuh plane_sum): 0 plain, 1 = 3->2 compressors, 2 = 7->3 compressors
+// carry-save depth of the popcount (kernels.cuh plane_sum): 0 plain, 1 = 3->2 compressors, 2 = 7->3 compressors, 3 = half / half
 int scan_mode(const rabitq_index* ix) {
     if (ix->scan_mode >= 0) return ix->scan_mode;
     return ix->D / 32 >= 14 ? 2 : 1;  // measured on B200: 7->3 compressors win at D=960, 3->2 at D=128 (profiles/)
@@ -703,6 +703,9 @@ int launch_scan_t(rabitq_index* ix, ScanArgs& a) {
         switch (scan_mode(ix)) {
             case 0: return launch_scan_m<W32, false, 0>(ix, a);
             case 2: return launch_scan_m<W32, false, 2>(ix, a);
+            case 3:
+                if constexpr (W32 >= 14) return launch_scan_m<W32, false, 3>(ix, a);
+                else return launch_scan_m<W32, false, 2>(ix, a);
             default: return launch_scan_m<W32, false, 1>(ix, a);
         }
     }

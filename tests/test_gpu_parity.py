@@ -148,7 +148,7 @@ def test_rounds_do_not_change_results(pair, rounds):
         g.set_rounds([0])
 
 
-@pytest.mark.parametrize("opt,val", [("first_chunks", 0), ("first_chunks", 3), ("scan_mode", 0), ("scan_mode", 1), ("scan_mode", 2),
+@pytest.mark.parametrize("opt,val", [("first_chunks", 0), ("first_chunks", 3), ("scan_mode", 0), ("scan_mode", 1), ("scan_mode", 2), ("scan_mode", 3),
                                      ("rerank_rows", 1), ("rerank_rows", 3), ("rerank_rows", 32), ("scan_slices", 2), ("scan_slices", 7)])
 def test_tuning_knobs_do_not_change_results(pair, opt, val):
     q = pair["queries"]
