@@ -284,3 +284,64 @@ def test_raw_bias_switch_changes_only_the_quantiser(oracle_lib):
     s = oracle_lib.lib().orc_scalar_quantize_raw(out.ctypes.data_as(oracle_lib.c_u8p), v.ctypes.data_as(oracle_lib.c_f32p),
                                                  np.full(len(v), 0.5, np.float32).ctypes.data_as(oracle_lib.c_f32p), len(v), 0.0, 1.0)
     assert out.tolist() == [0, 0, 1, 2, 3, 15, 15, 255, 0, 0] and s == sum(out.tolist())
+
+
+# ---- the sequential rerankers, restated a second time in plain Python ---------------------------------------------------------
+def _py_rerank(rough, pos, exact_of, map_ids, topk, heuristic):
+    """src/rerank.rs:81-113 (HeapReRanker) and :142-176 (HeuristicReRanker), statement by statement, on Python floats holding
+    fp32 values.  Independent of the oracle's C++ heap / window code: only the visit order and the exact distances are shared."""
+    import heapq
+
+    FLT_MAX, FLT_MIN = float(np.finfo(np.float32).max), float(np.finfo(np.float32).min)
+    thr, precise = FLT_MAX, 0
+    if not heuristic:
+        heap = []  # BinaryHeap<(Ord32, AlwaysEqual<u32>)> = max-heap on the distance: heapq on the negated key
+        for r, u in zip(rough, pos):
+            if r < thr:                                     # :84
+                acc = exact_of(u)
+                precise += 1
+                if acc < thr:                               # :92
+                    heapq.heappush(heap, (-acc, int(map_ids[u])))
+                    if len(heap) > topk:                    # :95
+                        heapq.heappop(heap)
+                    if len(heap) == topk:                   # :98
+                        thr = -heap[0][0]
+        return sorted(-d for d, _ in heap), precise
+    arr, count, recent = [], 0, FLT_MIN
+    for r, u in zip(rough, pos):
+        if r < thr:                                         # :145
+            acc = exact_of(u)
+            precise += 1
+            if acc < thr:                                   # :153
+                arr.append((acc, int(map_ids[u])))
+                count += 1
+                recent = max(recent, acc)
+                if count >= 12:                             # WINDOW_SIZE, src/consts.rs:12
+                    thr, count, recent = recent, 0, FLT_MIN
+    return sorted(d for d, _ in arr)[: min(topk, len(arr))], precise       # get_result: the topk smallest
+
+
+@pytest.mark.parametrize("case_name", ["case_d128", "case_d96", "case_d960"])
+@pytest.mark.parametrize("heuristic", [False, True])
+def test_rerankers_against_python_restatement(request, case_name, heuristic):
+    from oracle import oracle as orc
+
+    case = request.getfixturevalue(case_name)
+    a, o = case["arrays"], case["oracle"]
+    D = a["dim"]
+    L = orc.lib()
+    for probe, topk in [(4, 10), (24, 10), (12, 1), (16, 40)]:
+        for qi in range(0, case["queries"].shape[0], 5):
+            q = case["queries"][qi]
+            tr = o.trace(q, probe, topk, heuristic_rank=heuristic)
+            qpad = np.zeros(D, np.float32)
+            qpad[: q.shape[0]] = q
+
+            def exact_of(u):
+                row = np.ascontiguousarray(a["base"][u], dtype=np.float32)
+                return float(np.float32(L.orc_l2_squared_distance(_p(row, f32p), _p(qpad, f32p), D)))
+
+            dists, precise = _py_rerank([float(x) for x in tr["rough"]], [int(x) for x in tr["pair_pos"]], exact_of, a["map_ids"], topk, heuristic)
+            assert precise == tr["precise"], (case_name, probe, topk, qi)
+            got = sorted(d for d, _ in tr["result"])
+            assert np.array_equal(np.array(dists, np.float32).view(np.uint32), np.array(got, np.float32).view(np.uint32)), (case_name, probe, topk, qi)
