@@ -345,3 +345,58 @@ def test_rerankers_against_python_restatement(request, case_name, heuristic):
             assert precise == tr["precise"], (case_name, probe, topk, qi)
             got = sorted(d for d, _ in tr["result"])
             assert np.array_equal(np.array(dists, np.float32).view(np.uint32), np.array(got, np.float32).view(np.uint32)), (case_name, probe, topk, qi)
+
+
+# ---- bit-exact numpy emulations of the fp32 evaluation ORDER (not just the value) ---------------------------------------------
+def _fma32(a, b, c):
+    """fp32 fused multiply-add: the product of two fp32 values is exact in fp64 (24 + 24 bits), one rounding of the sum."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def _reduce8(acc):
+    """reduce_f32_256 (src/simd.rs:292-303): ((s0+s4)+(s1+s5)) + ((s2+s6)+(s3+s7)), every sum rounded to fp32; acc: [8, ...]."""
+    c = (acc[:4] + acc[4:]).astype(np.float32)
+    return ((c[0] + c[1]).astype(np.float32) + (c[2] + c[3]).astype(np.float32)).astype(np.float32)
+
+
+@pytest.mark.parametrize("case_name", ["case_d128", "case_d96"])
+def test_rotation_and_estimator_order_bit_exact(request, case_name):
+    """`project` = `vector_dot_product(vec, P.col(i))` (src/utils.rs:237-258, src/simd.rs:257-314): lane l accumulates
+    fma(q[r], P[r, i], acc_l) over r = l, l+8, ... ascending, then reduce_f32_256; and `calculate_rough_distance`
+    (src/rabitq.rs:352-363) left to right in fp32.  Emulated in numpy with explicit roundings; must equal the oracle's bits."""
+    case = request.getfixturevalue(case_name)
+    a, o = case["arrays"], case["oracle"]
+    D = a["dim"]
+    P = a["orthogonal"]
+    for qi in (0, 3):
+        q = case["queries"][qi]
+        tr = o.trace(q, 5, 10)
+        qp = np.zeros(D, np.float32)
+        qp[: len(q)] = q
+        acc = np.zeros((8, D), np.float32)
+        for r in range(D):  # sequential over rows, vectorised over the D output columns
+            acc[r % 8] = _fma32(np.full(D, qp[r], np.float32), P[r, :], acc[r % 8])
+        y = _reduce8(acc)
+        assert np.array_equal(y.view(np.uint32), tr["y"].view(np.uint32))
+        # centroid distances: l2_squared_distance(centroid, y) (src/rabitq.rs:283-293, src/simd.rs:14-73): diff = c - y, fma(diff, diff, acc)
+        cent = a["centroids"]
+        acc = np.zeros((8, cent.shape[0]), np.float32)
+        for d in range(D):
+            diff = (cent[:, d] - y[d]).astype(np.float32)
+            acc[d % 8] = _fma32(diff, diff, acc[d % 8])
+        cd = _reduce8(acc)
+        assert np.array_equal(cd.view(np.uint32), tr["centroid_dist"].view(np.uint32))
+        # the estimator, term by term in fp32
+        t = 0
+        f32 = np.float32
+        for p, c in enumerate(tr["probe_ids"]):
+            ycd, lo, delta, ssum = f32(tr["probe_dist"][p]), f32(tr["lo"][p]), f32(tr["delta"][p]), f32(tr["sum"][p])
+            sq = np.sqrt(ycd, dtype=np.float32)
+            for j in range(a["offsets"][c], a["offsets"][c + 1]):
+                ip, ppc, err, cds = (f32(x) for x in a["factors"][j])
+                ab = f32(tr["abdp"][t])
+                e = f32(f32(cds + ycd) + f32(lo * ppc))
+                e = f32(e + f32(f32(f32(f32(f32(2.0) * ab) - ssum) * ip) * delta))
+                e = f32(e - f32(err * sq))
+                assert e.view(np.uint32) == f32(tr["rough"][t]).view(np.uint32), (qi, p, j)
+                t += 1
