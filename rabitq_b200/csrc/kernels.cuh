@@ -984,8 +984,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
 // the cluster ascending) and queues the candidates whose estimate is still below the current threshold.  A full
 // queue is a WAVE: the raw base rows of the wave are gathered into shared memory with one TMA bulk copy per row
 // (cp.async.bulk, completion on an mbarrier), every exact squared L2 of the wave is computed in parallel --
-// 8 lanes per candidate = the 8 AVX lanes of simd::l2_squared_distance (src/simd.rs:14-73), same per-lane
-// order, same final reduction -- and the wave is then replayed in order with the reference's two strict tests.
+// four threads per candidate, each owning two of the 8 AVX lanes of simd::l2_squared_distance (src/simd.rs:14-73) as one
+// packed f32x2 chain, same per-lane order, same final reduction (l2_quad) -- and the wave is then replayed in order with the
+// reference's two strict tests, one stretch (up to the next accepted candidate) per step.
 // Heap contents, the threshold trajectory and the `precise` counter are exactly those of the sequential loop;
 // speculation only costs extra gathers.
 struct RerankArgs {
