@@ -61,6 +61,28 @@ def _worker(rank, world, port, ret):
     if rank == 0:
         ret["same"] = same
         ret["rough_total"] = 0
+    # the collectives of the distributed step as DistributedRaBitQ issues them: the asynchronous all-gather of the big part
+    # overlapping "work", a second synchronous one behind it, min / max all-reduces
+    comm = rd.TorchComm()
+    assert (comm.rank, comm.world) == (rank, world)
+    big_in = torch.full((1024,), float(rank), dtype=torch.float32)
+    big_out = torch.empty(1024 * world, dtype=torch.float32)
+    small_in = torch.full((8,), float(10 + rank), dtype=torch.float32)
+    small_out = torch.empty(8 * world, dtype=torch.float32)
+    work = comm.all_gather_start(big_out, big_in)
+    small_in += 0  # (the caller keeps computing here)
+    comm.all_gather(small_out, small_in)
+    work.wait()
+    for rr in range(world):
+        assert torch.all(big_out[rr * 1024:(rr + 1) * 1024] == float(rr)) and torch.all(small_out[rr * 8:(rr + 1) * 8] == float(10 + rr))
+    thr = torch.tensor([3.0 + rank, 7.0 - rank], dtype=torch.float32)
+    comm.all_reduce_min(thr)
+    assert thr.tolist() == [3.0, 7.0 - (world - 1)]
+    status = torch.tensor([rank], dtype=torch.int32)
+    comm.all_reduce_max(status)
+    assert int(status[0]) == world - 1
+    handles = comm.exchange_bytes(bytes([rank]) * 64)
+    assert [h[0] for h in handles] == list(range(world))
     t = torch.tensor([r["rough"]], dtype=torch.int64)
     dist.all_reduce(t)
     if rank == 0:
