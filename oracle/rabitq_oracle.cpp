@@ -13,7 +13,10 @@
 // reference ships no tests, golden vectors or fixtures for this path.
 // The oracle is therefore pinned only by (i) the reference's own AVX2-vs-scalar twin
 // implementations restated below and cross-checked in tests/, (ii) an independent float64
-// numpy model of the estimator (tests/model_f64.py), (iii) recall against brute force.
+// numpy model of the estimator (tests/model_f64.py), (iii) recall against brute force, (iv) a second,
+// plain-Python restatement of both rerankers replayed over the visit-order trace, (v) numpy emulations of
+// the fp32 evaluation ORDER of project / the centroid distances / the estimator that must match bit for bit
+// (tests/test_oracle_cpu.py; DESIGN.md section 2 lists all seven pins).
 //
 // Build: see oracle/Makefile  (g++ -O2 -mavx2 -mfma -ffp-contract=off; never -ffast-math,
 // never -mpopcnt: the reference's scalar popcount path is compiled without the popcnt target
