@@ -557,14 +557,28 @@ __global__ void __launch_bounds__(1024) query_base_scan_kernel(const uint32_t* _
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K3: per (query, probed cluster): residual, min/max, 4-bit scalar quantisation, bit-planes
-// (src/rabitq.rs:305-317 -> src/simd.rs:117-173, 185-247, 83-107).  One warp per (q, p); the movemask of the
-// AVX2 code becomes __ballot_sync.  Output is one packed record per (q, p):
-//   u32[0 .. 4*WP)    planes, plane-major, plane stride WP = W32 rounded up to 4: plane b word w = bit b of q_u[32w .. 32w+31]
-//   f32[4*WP + 0..3]  lower_bound, delta, (f32) sum q_u, y_c_distance_square
-//   f32[4*WP + 4]     sqrt(y_c_distance_square)
-//   u32[4*WP + 5]     sum q_u (raw u32)     u32[+6] first 32-vector word of this slot     u32[+7] cluster id
+// K3: per (query, probed cluster): residual, min/max, 4-bit scalar quantisation
+// (src/rabitq.rs:305-317 -> src/simd.rs:117-173, 185-247).  One warp per (q, p).  The reference goes on to split the
+// 4-bit codes into bit-planes (vector_binarize_query, src/simd.rs:83-107) because its inner product is AND + popcount; here
+// the inner product  abdp = sum_d bit_d * (q_u[d] & 15)  (the same integer, src/utils.rs:113-135) runs on the tensor cores as a
+// u8 x u8 -> s32 contraction (K4), so the record keeps the codes as BYTES, already in the order and scale K4's B fragments want:
+//   u8[0 .. D)        byte rec_pos(d) = (q_u[d] & 15) << (3 - (d & 3))
+//   f32[D/4 + 0..3]   lower_bound, delta, (f32) sum q_u, y_c_distance_square
+//   f32[D/4 + 4]      sqrt(y_c_distance_square)
+//   u32[D/4 + 5]      sum q_u (raw u32)     u32[+6] first 32-vector word of this slot     u32[+7] cluster id
+// Why the scale: K4 expands a 32-bit code word w into the A fragment with ONE AND per register, a = w & (0x01010101 << t)
+// (t = lane & 3), so the byte of bit 8i+t holds 2^t instead of 1; the matching query byte carries 2^(3-t), every product is
+// 8 * bit * q and the accumulator is 8 * abdp, exactly (integers, |acc| <= 120 * D).
 constexpr float SCALAR_1_15 = 1.0f / 15.0f;  // src/consts.rs:10
+constexpr int REC_META_BYTES = 32;
+
+// byte position of dimension d inside a record: k-step j = d / 32 (one 32-bit code word = one m16n8k32 step), class t = d & 3
+// (the quad lane that owns the element), half h = (d >> 2) & 1 (fragment register b0 / b1), i = (d & 31) >> 3 (byte inside the
+// register).  Two k-steps are interleaved so that a lane's bytes of steps 2jj and 2jj+1 are one 128-bit load.
+__host__ __device__ __forceinline__ int rec_pos(int d) {
+    const int j = d >> 5, r = d & 31;
+    return 64 * (j >> 1) + 16 * (r & 3) + 8 * (j & 1) + 4 * ((r >> 2) & 1) + (r >> 3);
+}
 
 template <int W32T>  // W32T > 0: D = 32*W32T held in registers (one pass over memory); 0: any D, two passes
 __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__ y, const float* __restrict__ cent,
@@ -581,11 +595,14 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
     const size_t q = wid / chunks;
     const int p_begin = (int)(wid % chunks) * pch, p_end = min(P, p_begin + pch);
     const float* yr = y + q * (size_t)D;
-    const int W32 = W32T > 0 ? W32T : D / 32, WP = (W32 + 3) & ~3, RS = 4 * WP + 8;  // plane stride padded to 128 bits
-    // the record is assembled in shared memory (lane 0 holds every ballot word) and leaves with coalesced 128-bit stores: lane 0
-    // writing it word by word to global memory cost 24 (D=128) .. 128 (D=960) scattered 4-byte stores per record
+    const int W32 = W32T > 0 ? W32T : D / 32, RS = (D + REC_META_BYTES) / 4;  // record words
+    // the record is assembled in shared memory and leaves with coalesced 128-bit stores
     extern __shared__ __align__(16) uint32_t qz_smem[];
     uint32_t* sr = qz_smem + (size_t)(threadIdx.x >> 5) * RS;
+    unsigned char* sb = reinterpret_cast<unsigned char*>(sr);
+    // this lane's byte of k-step g sits at sb[lane_pos + 64 * (g >> 1) + 8 * (g & 1)]   (rec_pos with r = lane)
+    const int lane_pos = 16 * (lane & 3) + 4 * ((lane >> 2) & 1) + (lane >> 3);
+    const int lane_shift = 3 - (lane & 3);
     float yv[W32T > 0 ? W32T : 1];
     if constexpr (W32T > 0) {
 #pragma unroll
@@ -628,17 +645,9 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
             qi = cvtps_epi32(__fmul_rn(__fsub_rn(r, mn), inv));
         }
         sum += qi;  // i32 lanes wrap like _mm256_add_epi32
-        uint32_t b0 = __ballot_sync(FULL, qi & 1), b1 = __ballot_sync(FULL, qi & 2);
-        uint32_t b2 = __ballot_sync(FULL, qi & 4), b3 = __ballot_sync(FULL, qi & 8);
-        if (lane == 0) {
-            sr[0 * WP + g] = b0;
-            sr[1 * WP + g] = b1;
-            sr[2 * WP + g] = b2;
-            sr[3 * WP + g] = b3;
-        }
+        // only bits 0..3 of the stored byte reach the bit-planes of the reference (src/simd.rs:95-104)
+        sb[lane_pos + 64 * (g >> 1) + 8 * (g & 1)] = (unsigned char)((qi & 15) << lane_shift);
     };
-    if (lane < 4)
-        for (int w = W32; w < WP; w++) sr[lane * WP + w] = 0u;  // plane padding (never ANDed by K4)
     if constexpr (W32T > 0) {
 #pragma unroll
         for (int g = 0; g < W32T; g++) emit(g, rr[g]);
@@ -649,15 +658,15 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
     if (lane == 0) {
         const float ycd = probe_dist[gw];
-        float* rf = reinterpret_cast<float*>(sr + 4 * WP);
+        float* rf = reinterpret_cast<float*>(sr + D / 4);
         rf[0] = mn;
         rf[1] = delta;
         rf[2] = __uint2float_rn((uint32_t)sum);  // `scalar_sum as f32`, rabitq.rs:322
         rf[3] = ycd;
         rf[4] = __fsqrt_rn(ycd);                 // rabitq.rs:346
-        sr[4 * WP + 5] = (uint32_t)sum;
-        sr[4 * WP + 6] = q_wbase[q] + slot_local[gw];
-        sr[4 * WP + 7] = c;
+        sr[D / 4 + 5] = (uint32_t)sum;
+        sr[D / 4 + 6] = q_wbase[q] + slot_local[gw];
+        sr[D / 4 + 7] = c;
     }
     __syncwarp();
     for (int i = lane; i < RS / 4; i += 32) reinterpret_cast<uint4*>(rec)[i] = reinterpret_cast<const uint4*>(sr)[i];
@@ -691,7 +700,18 @@ RQ_DEV uint32_t chunk_count(uint32_t m, uint32_t n_c, int VT, uint32_t ch_min, u
     return nch > ch_min ? nch - ch_min : 0;
 }
 RQ_DEV uint32_t slice_count(uint32_t m, uint32_t MS) { return (m + MS - 1) / MS; }
-constexpr int WORK_SLICE_SHIFT = 20;  // work.y = chunk | slice << 20
+
+// One unit of scan work = (cluster, chunk of 128 vectors, slice of <= MS of the records probing the cluster), flattened so that
+// the scan's producer warp needs ONE load to know everything about it.
+struct __align__(16) ScanItem {
+    uint32_t rec_begin;  // first record: index into cl_items
+    uint32_t nr;         // records of this item
+    uint32_t chunk_g;    // chunk index in the scan-layout copy of the codes (scan_layout_kernel)
+    uint32_t chunk;      // chunk inside the cluster (visit position)
+    uint32_t jbase;      // sorted position of the chunk's first vector
+    uint32_t nv;         // vectors in the chunk (<= 128)
+    uint32_t pad0, pad1;
+};
 
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __restrict__ cl_count, const uint32_t* __restrict__ offsets,
                                                            int K, int VT, uint32_t MS, uint32_t ch_min, uint32_t ch_max, uint32_t* __restrict__ cl_start,
@@ -757,16 +777,25 @@ __global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, const
     cl_items[cl_start[c] + pos] = (uint32_t)(q * P + p);
 }
 
-__global__ void work_items_kernel(const uint32_t* __restrict__ item_start, const uint32_t* __restrict__ cl_count, int K, uint32_t MS,
-                                  uint32_t ch_min, uint2* __restrict__ work) {
+__global__ void work_items_kernel(const uint32_t* __restrict__ item_start, const uint32_t* __restrict__ cl_count,
+                                  const uint32_t* __restrict__ cl_start, const uint32_t* __restrict__ offsets,
+                                  const uint32_t* __restrict__ chunk_start, int K, uint32_t MS, uint32_t ch_min, ScanItem* __restrict__ work) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= K) return;
     const uint32_t s = item_start[c], e = item_start[c + 1];
     if (s == e) return;
-    const uint32_t nsl = slice_count(cl_count[c], MS);
+    const uint32_t m = cl_count[c], nsl = slice_count(m, MS), off = offsets[c], n_c = offsets[c + 1] - off;
     for (uint32_t i = s; i < e; i++) {
-        const uint32_t local = i - s;
-        work[i] = make_uint2((uint32_t)c, (ch_min + local / nsl) | ((local % nsl) << WORK_SLICE_SHIFT));
+        const uint32_t local = i - s, chunk = ch_min + local / nsl, slice = local % nsl;
+        ScanItem w;
+        w.rec_begin = cl_start[c] + slice * MS;
+        w.nr = min(MS, m - slice * MS);
+        w.chunk_g = chunk_start[c] + chunk;
+        w.chunk = chunk;
+        w.jbase = off + chunk * 128u;
+        w.nv = min(128u, n_c - chunk * 128u);
+        w.pad0 = w.pad1 = 0u;
+        work[i] = w;
     }
 }
 
@@ -775,204 +804,323 @@ __global__ void work_items_kernel(const uint32_t* __restrict__ item_start, const
 // (src/rabitq.rs:336-367, src/utils.rs:113-135, src/simd.rs:326-384) fused with the threshold filter of
 // HeapReRanker::rank_batch (src/rerank.rs:84) and an ORDER-PRESERVING compaction.
 //
-// Cluster-major: a CTA takes a work item (cluster, chunk of VT vectors), loads each vector's packed code
-// (128-bit coalesced loads) and Factor (one float4) into REGISTERS once, then streams the records of every
-// (query, probe) item that probes this cluster through shared memory; each thread does AND+__popc over the 4
-// bit-planes, evaluates the estimator in the reference's association without contraction and tests
-// `rough < thr[q]`.  Per warp and query: one ballot word -> bitmap[slot word], survivors' (rough, j) packed at
-// the start of the word's 32-entry block.  No atomics, deterministic layout, visit order preserved.
-// Carry-save popcount: POPC issues on the XU pipe (measured ~28 lane-ops/clk/SM on sm_100a, profiles/pipe_bench_r01.txt)
-// and saturates long before the ALU pipe, so words of equal weight are first compressed 3 -> 2 (or 7 -> 3) with
-// LOP3 full adders.  Integer-exact: popc(a)+popc(b)+popc(c) == popc(a^b^c) + 2*popc(maj(a,b,c)).
-RQ_DEV uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-}
-RQ_DEV uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
+// The reference evaluates  abdp = sum_p popc(x & plane_p) << p,  which is the integer  sum_d bit_d * (q_u[d] & 15):  a
+// (vectors x D) . (D x records) contraction of a 0/1 matrix with a 4-bit matrix.  Cluster-major, on the tensor cores, as a
+// warp-specialised persistent kernel:
+//   * the PRODUCER warp pulls work items (cluster, chunk of 128 vectors, <= 8*NT*sub records probing the cluster) off a global
+//     counter and fills a ring of shared-memory stages with TMA bulk copies (cp.async.bulk, completion on an mbarrier): the
+//     chunk's packed codes and Factors, kept in HBM in exactly the image the consumers read (scan_layout_kernel, built once per
+//     index), and one copy per record (K3 wrote them in fragment order); it also resolves each record's threshold and round
+//     window.  All global-memory latency -- work list, inverted list, records, codes -- lives in this warp, S-1 stages ahead;
+//   * four CONSUMER warps own 32 vectors each (two m16 tiles) x 8*NT records (NT n8 tiles) of s32 accumulators.  Per k-step
+//     (32 dimensions = one code word) a lane builds its A fragments from the packed word with one AND per register (+ one
+//     shift for the upper nibbles) -- the bits are never expanded in memory -- loads its B fragments (query code bytes) with
+//     one 128-bit shared-memory load per two k-steps and issues mma.sync.m16n8k32.s32.u8.u8.s32 (SASS IMMA.16832.U8.U8):
+//     integer, exact;
+//   * epilogue on the accumulator fragments: the estimator in the reference's association with IEEE roundings, the strict test
+//     `rough < thr[q]`, one ballot per fragment register; a record's 32-vector bitmap word is assembled from four ballots by
+//     rotate+mask, survivors' (rough, j) are packed at the start of the word's 32-entry block in vector order.  No atomics,
+//     deterministic layout, visit order preserved.
+// Row r of M-tile mt is vector 4*(r & 7) + 2*mt + (r >> 3) of the warp's 32: a lane's four accumulator rows are four
+// CONSECUTIVE vectors (one 64-bit load per vector and k-step pair), and ballot bit 4g+t of register-row s lands on bitmap
+// bit 4g+s by a rotation.
+RQ_DEV void mma_u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// sum_w popc(x[w] & pl[w]) over one bit-plane (pl in shared memory, 16-byte aligned, padded to 4 words)
-template <int W32, int MODE>
-RQ_DEV uint32_t plane_sum(const uint32_t (&x)[W32], const uint32_t* pl) {
-    uint32_t a[W32];
-#pragma unroll
-    for (int w = 0; w < W32; w += 4) {  // planes are padded to a multiple of 4 words: always 128-bit broadcast loads
-        const uint4 p = *reinterpret_cast<const uint4*>(pl + w);
-        a[w] = x[w] & p.x;
-        if (w + 1 < W32) a[w + 1] = x[w + 1] & p.y;
-        if (w + 2 < W32) a[w + 2] = x[w + 2] & p.z;
-        if (w + 3 < W32) a[w + 3] = x[w + 3] & p.w;
+RQ_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+RQ_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+RQ_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {  // no arrive: only raises the pending transaction count
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+RQ_DEV void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+RQ_DEV void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+RQ_DEV void prefetch_l2_bulk(const void* src_gmem, uint32_t bytes) {  // no destination: warms L2 ahead of the TMA row gather
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+RQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; spin++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (spin > (1u << 24)) __trap();  // a lost transaction must fail loudly, never hang the GPU
     }
-    uint32_t ones = 0, twos = 0, fours = 0;
-    constexpr int G7 = (MODE == 2) ? W32 / 7 : (MODE == 3) ? W32 / 14 : 0;  // MODE 3: half the words by 7->3, the rest by 3->2 (ALU/XU balance)
-    constexpr int R7 = W32 - 7 * G7;
-    constexpr int G3 = (MODE >= 1) ? R7 / 3 : 0;
-    constexpr int R3 = R7 - 3 * G3;
-#pragma unroll
-    for (int g = 0; g < G7; g++) {
-        const int w = 7 * g;
-        const uint32_t s1 = xor3(a[w], a[w + 1], a[w + 2]), c1 = maj3(a[w], a[w + 1], a[w + 2]);
-        const uint32_t s2 = xor3(a[w + 3], a[w + 4], a[w + 5]), c2 = maj3(a[w + 3], a[w + 4], a[w + 5]);
-        const uint32_t s3 = xor3(s1, s2, a[w + 6]), c3 = maj3(s1, s2, a[w + 6]);
-        ones += __popc(s3);
-        twos += __popc(xor3(c1, c2, c3));
-        fours += __popc(maj3(c1, c2, c3));
+}
+
+// Scan-layout copy of the codes and Factors, built once per index: for every cluster, chunks of 128 vectors (the last one
+// zero-padded); a chunk's image is [D/64][128] uint2 -- words (2jj, 2jj+1) of the vector in slot (v & ~31) | (v & 3) << 3 |
+// (v >> 2) & 7 -- followed, in a second array, by its 128 Factors in the same slot order.  One TMA bulk copy stages it.
+__global__ void __launch_bounds__(128) scan_layout_kernel(const uint32_t* __restrict__ codes, const float4* __restrict__ factors,
+                                                          const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ chunk_start,
+                                                          int K, int JJ, uint2* __restrict__ scan_codes, float4* __restrict__ scan_fac) {
+    const uint32_t b = blockIdx.x;
+    int lo = 0, hi = K;  // largest c with chunk_start[c] <= b  (clusters without vectors own no chunk)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_start[mid] <= b) lo = mid; else hi = mid;
     }
-#pragma unroll
-    for (int g = 0; g < G3; g++) {
-        const int w = 7 * G7 + 3 * g;
-        ones += __popc(xor3(a[w], a[w + 1], a[w + 2]));
-        twos += __popc(maj3(a[w], a[w + 1], a[w + 2]));
+    const uint32_t c = (uint32_t)lo, off = offsets[c], n_c = offsets[c + 1] - off;
+    const uint32_t v0 = (b - chunk_start[c]) * 128u, nv = min(128u, n_c - v0);
+    const uint2* src = reinterpret_cast<const uint2*>(codes + (size_t)(off + v0) * (2 * JJ));
+    uint2* dst = scan_codes + (size_t)b * JJ * 128;
+    const uint32_t tot = nv * (uint32_t)JJ;
+    for (uint32_t i = threadIdx.x; i < 128u * JJ; i += 128u) {
+        const uint32_t v = i / JJ, jj = i - v * JJ;
+        dst[jj * 128 + ((v & ~31u) | ((v & 3u) << 3) | ((v >> 2) & 7u))] = i < tot ? src[i] : make_uint2(0u, 0u);
     }
-#pragma unroll
-    for (int i = 0; i < R3; i++) ones += __popc(a[7 * G7 + 3 * G3 + i]);
-    return ones + (twos << 1) + (fours << 2);
+    const uint32_t t = threadIdx.x;
+    scan_fac[(size_t)b * 128 + ((t & ~31u) | ((t & 3u) << 3) | ((t >> 2) & 7u))] = t < nv ? factors[off + v0 + t] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 struct ScanArgs {
-    const uint32_t* codes;      // n x W32
-    const float4* factors;      // n
-    const uint32_t* offsets;    // K+1 (local to this shard)
-    const uint32_t* cl_start;   // K+1
+    const uint2* scan_codes;    // chunks x [D/64][128]
+    const float4* scan_fac;     // chunks x 128
     const uint32_t* cl_items;   // (q*P+p) per cluster
-    const uint2* work;          // (cluster, chunk)
+    const ScanItem* work;
     uint32_t* work_ctl;         // [0] counter [1] n_work
-    const uint32_t* qrec;       // records
+    const uint32_t* qrec;       // records (K3)
     const float* thr;           // per query
     const uint32_t* q_p0;       // per query: first probe rank with vectors on this shard
     uint32_t* bitmap;           // per slot word
     float2* entries;            // per slot word: 32 x (rough, j as bits)
     unsigned long long* counters;  // [0] survivors
     int P;
-    int QS;                     // records per shared-memory slice
-    uint32_t MS;                // records per work item (a multiple of QS)
+    int D;
+    int rec_pitch;              // bytes between records in shared memory (== 64 mod 128: conflict-free fragment loads)
+    int stages;                 // ring depth
+    int sub;                    // passes of 8*NT records per stage
+    uint32_t MS;                // records per work item (<= 8*NT*sub)
     // this round = visit positions (probe rank, 128-vector chunk) in [lo, hi), lexicographic
     int p_lo, ch_lo, p_hi, ch_hi;
 };
 
-constexpr int SCAN_THREADS = 128;
+constexpr int SCAN_CONSUMERS = 128;               // four consumer warps = 128 vectors per chunk
+constexpr int SCAN_THREADS = SCAN_CONSUMERS;      // (vectors per chunk; the work-list builders use this name)
+constexpr int SCAN_BLOCK = SCAN_CONSUMERS + 32;   // + the producer warp
 
-template <int W32, int VPT, bool DENSE, int MODE>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
-    constexpr int WP = (W32 + 3) & ~3;  // padded plane stride
-    constexpr int RS = 4 * WP + 8;    // record words
-    constexpr int RS4 = RS / 4;       // record uint4s
-    constexpr int VT = SCAN_THREADS * VPT;
-    extern __shared__ uint4 s_rec[];  // QS records, then QS thresholds
-    __shared__ uint32_t s_item;
-    float* s_thr = reinterpret_cast<float*>(s_rec + (size_t)a.QS * RS4);
-    int* s_rank = reinterpret_cast<int*>(s_thr + a.QS);
+__host__ __device__ __forceinline__ int scan_rec_pitch(int D) { return (D & 127) ? D + 128 : D + 64; }
+// one stage: codes | Factors | records | (thr, flag) per record | header
+__host__ __device__ __forceinline__ size_t scan_stage_bytes(int D, int nrs) {
+    return (((size_t)16 * D + 2048 + (size_t)nrs * scan_rec_pitch(D) + (size_t)nrs * 8 + 32) + 127) & ~(size_t)127;
+}
+__host__ __device__ __forceinline__ size_t scan_smem_bytes(int D, int nrs, int stages) { return 128 + (size_t)stages * scan_stage_bytes(D, nrs); }
+
+template <int NT, bool DENSE>
+__global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(ScanArgs a) {
+    constexpr int NR = 8 * NT;  // records per pass
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    const int D = a.D, JJ = D >> 6, pitch = a.rec_pitch, S = a.stages, NRS = NR * a.sub;
+    const size_t stage_bytes = scan_stage_bytes(D, NRS);
+    uint64_t* full = reinterpret_cast<uint64_t*>(scan_smem);  // [S] producer -> consumers (32 arrivals + bytes)
+    uint64_t* empty = full + 8;                               // [S] consumers -> producer (4 arrivals)
+    unsigned char* stage0 = scan_smem + 128;
+    const size_t o_fac = (size_t)16 * D, o_rec = o_fac + 2048, o_tf = o_rec + (size_t)NRS * pitch, o_hdr = o_tf + (size_t)NRS * 8;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    unsigned long long n_surv = 0;
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 32); mbar_init(&empty[s], SCAN_CONSUMERS / 32); }
+    }
+    __syncthreads();
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = atomicAdd(&a.work_ctl[0], 1u);
-        __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= a.work_ctl[1]) break;
-        const uint2 wk = a.work[item];
-        const uint32_t c = wk.x, chunk = wk.y & ((1u << WORK_SLICE_SHIFT) - 1u), slice = wk.y >> WORK_SLICE_SHIFT;
-        const uint32_t off = a.offsets[c], n_c = a.offsets[c + 1] - off;
-        const uint32_t nwords = (n_c + 31u) >> 5;
-        const uint32_t it0 = a.cl_start[c], m_all = a.cl_start[c + 1] - it0;
-        const uint32_t m = min(m_all, (slice + 1u) * a.MS);  // this item's records: [slice * MS, m)
-
-        uint32_t code[VPT][W32];
-        float4 fac[VPT];
-        uint32_t jpos[VPT], wloc[VPT];
-        bool valid[VPT];
-#pragma unroll
-        for (int i = 0; i < VPT; i++) {
-            wloc[i] = chunk * (VT / 32) + warp * VPT + i;
-            uint32_t vloc = wloc[i] * 32 + lane;
-            valid[i] = vloc < n_c;
-            jpos[i] = off + vloc;
-            if (valid[i]) {
-                const uint32_t* cp = a.codes + (size_t)jpos[i] * W32;
-                if constexpr (W32 % 4 == 0) {
-#pragma unroll
-                    for (int w = 0; w < W32; w += 4) {
-                        uint4 v = __ldg(reinterpret_cast<const uint4*>(cp + w));
-                        code[i][w] = v.x; code[i][w + 1] = v.y; code[i][w + 2] = v.z; code[i][w + 3] = v.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int w = 0; w < W32; w += 2) {
-                        uint2 v = __ldg(reinterpret_cast<const uint2*>(cp + w));
-                        code[i][w] = v.x; code[i][w + 1] = v.y;
-                    }
-                }
-                fac[i] = __ldg(&a.factors[jpos[i]]);
-            } else {
-#pragma unroll
-                for (int w = 0; w < W32; w++) code[i][w] = 0;
-                fac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == SCAN_CONSUMERS / 32) {
+        // ---------------- producer ----------------------------------------------------------------------------------------
+        const uint32_t n_work = a.work_ctl[1];
+        const uint32_t rec_bytes = (uint32_t)(D + REC_META_BYTES);
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&a.work_ctl[0], 1u);
+        item = __shfl_sync(FULL, item, 0);
+        for (uint32_t it = 0;; it++) {
+            const int st = (int)(it % (uint32_t)S);
+            const uint32_t ph = (it / (uint32_t)S) & 1u;
+            unsigned char* sp = stage0 + (size_t)st * stage_bytes;
+            int* hdr = reinterpret_cast<int*>(sp + o_hdr);
+            const bool done = item >= n_work;
+            ScanItem w;
+            uint32_t next = 0;
+            if (!done) {
+                const uint4* wp = reinterpret_cast<const uint4*>(a.work + item);
+                const uint4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+                w.rec_begin = w0.x; w.nr = w0.y; w.chunk_g = w0.z; w.chunk = w0.w; w.jbase = w1.x; w.nv = w1.y;
+                if (lane == 0) next = atomicAdd(&a.work_ctl[0], 1u);  // in flight while this item is staged
             }
-        }
-
-        for (uint32_t s0 = slice * a.MS; s0 < m; s0 += a.QS) {
-            const int ns = min((uint32_t)a.QS, m - s0);
-            __syncthreads();
-            for (int i = tid; i < ns * RS4; i += SCAN_THREADS) {
-                int r = i / RS4, w4 = i % RS4;
-                uint32_t it = a.cl_items[it0 + s0 + r];
-                s_rec[r * RS4 + w4] = __ldg(reinterpret_cast<const uint4*>(a.qrec + (size_t)it * RS) + w4);
+            mbar_wait(&empty[st], ph ^ 1u);  // the consumers released this stage (passes at once on its first use)
+            if (done) {
+                if (lane == 0) hdr[0] = -1;
+                mbar_arrive(&full[st]);
+                break;
             }
-            if (tid < ns) {
-                const uint32_t it = a.cl_items[it0 + s0 + tid];
-                s_thr[tid] = a.thr[it / a.P];
-                s_rank[tid] = (int)(it % a.P) - (int)a.q_p0[it / a.P];
+            if (lane == 0) {
+                mbar_expect_tx(&full[st], (uint32_t)(16 * D + 2048));
+                tma_bulk_g2s(sp, a.scan_codes + (size_t)w.chunk_g * JJ * 128, (uint32_t)(16 * D), &full[st]);
+                tma_bulk_g2s(sp + o_fac, a.scan_fac + (size_t)w.chunk_g * 128, 2048u, &full[st]);
+                hdr[0] = (int)w.nr; hdr[1] = (int)w.jbase; hdr[2] = (int)w.nv; hdr[3] = (int)w.chunk;
             }
-            __syncthreads();
-            for (int r = 0; r < ns; r++) {
-                const uint32_t* rec = reinterpret_cast<const uint32_t*>(s_rec + r * RS4);
-                const float4 sc = *reinterpret_cast<const float4*>(rec + 4 * WP);      // lo, delta, sum, ycd
-                const float sq = *reinterpret_cast<const float*>(rec + 4 * WP + 4);    // sqrt(ycd)
-                const uint32_t wbase = rec[4 * WP + 6];
-                const float thr = s_thr[r];
-                {   // is (rank, chunk) inside this round's window?  (uniform over the CTA)
-                    const int pr = s_rank[r], ch = (int)chunk;
+            float2* tf = reinterpret_cast<float2*>(sp + o_tf);
+            for (uint32_t r = lane; r < (uint32_t)NRS; r += 32) {
+                float th = 0.f;
+                uint32_t fl = 0u;
+                if (r < w.nr) {
+                    const uint32_t id = __ldg(&a.cl_items[w.rec_begin + r]), q = id / (uint32_t)a.P;
+                    mbar_expect_tx(&full[st], rec_bytes);
+                    tma_bulk_g2s(sp + o_rec + (size_t)r * pitch, reinterpret_cast<const unsigned char*>(a.qrec) + (size_t)id * rec_bytes, rec_bytes,
+                                 &full[st]);
+                    th = a.thr[q];
+                    // is (rank, chunk) inside this round's window?
+                    const int pr = (int)(id - q * (uint32_t)a.P) - (int)a.q_p0[q], ch = (int)w.chunk;
                     const bool ge_lo = pr > a.p_lo || (pr == a.p_lo && ch >= a.ch_lo);
                     const bool lt_hi = pr < a.p_hi || (pr == a.p_hi && ch < a.ch_hi);
-                    if (!(ge_lo && lt_hi)) continue;
+                    fl = (ge_lo && lt_hi) ? 1u : 0u;
+                }
+                tf[r] = make_float2(th, __uint_as_float(fl));
+            }
+            mbar_arrive(&full[st]);  // release: this lane's stores are visible to whoever observes the phase
+            item = __shfl_sync(FULL, next, 0);
+        }
+        return;
+    }
+
+    // ---------------- consumers -------------------------------------------------------------------------------------------
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t amask = 0x01010101u << t;
+    unsigned long long n_surv = 0;
+    for (uint32_t it = 0;; it++) {
+        const int st = (int)(it % (uint32_t)S);
+        const uint32_t ph = (it / (uint32_t)S) & 1u;
+        unsigned char* sp = stage0 + (size_t)st * stage_bytes;
+        mbar_wait(&full[st], ph);
+        const int4 hdr = *reinterpret_cast<const int4*>(sp + o_hdr);
+        if (hdr.x < 0) break;
+        const int nr_all = hdr.x;
+        const uint32_t nv = (uint32_t)hdr.z, wloc = (uint32_t)hdr.w * (SCAN_CONSUMERS / 32) + warp;  // this warp's 32-vector word inside the cluster
+        if ((uint32_t)(warp * 32) < nv) {
+            const uint2* cp = reinterpret_cast<const uint2*>(sp) + warp * 32 + g;
+            const float4* s_fac = reinterpret_cast<const float4*>(sp + o_fac);
+            const float2* s_tf = reinterpret_cast<const float2*>(sp + o_tf);
+            const uint32_t jbase = (uint32_t)hdr.y + warp * 32 + 4 * g;
+#pragma unroll 1
+            for (int r0 = 0; r0 < nr_all; r0 += NR) {
+                const int nr = min(NR, nr_all - r0), ntiles = (nr + 7) >> 3;
+                const unsigned char* s_rec = sp + o_rec + (size_t)r0 * pitch;
+                int acc[2][NT][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                        for (int r = 0; r < 4; r++) acc[mt][nt][r] = 0;
+                {
+                    const unsigned char* bp = s_rec + (size_t)g * pitch + 16 * t;
+#pragma unroll 1
+                    for (int jj = 0; jj < JJ; jj++) {
+                        uint32_t af[2][2][4];  // [k-step of the pair][M-tile][fragment register]
+#pragma unroll
+                        for (int s = 0; s < 4; s++) {  // vector 4g+s = M-tile s>>1, row g + 8*(s&1): registers (s&1) (k 0..15) and (s&1)+2 (k 16..31)
+                            const uint2 w = cp[jj * 128 + 8 * s];
+                            af[0][s >> 1][s & 1] = w.x & amask;
+                            af[0][s >> 1][(s & 1) + 2] = (w.x >> 4) & amask;
+                            af[1][s >> 1][s & 1] = w.y & amask;
+                            af[1][s >> 1][(s & 1) + 2] = (w.y >> 4) & amask;
+                        }
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) {
+                            if (nt < ntiles) {  // warp-uniform
+                                const uint4 b = *reinterpret_cast<const uint4*>(bp + (size_t)nt * 8 * pitch + 64 * jj);
+                                mma_u8(acc[0][nt], af[0][0], b.x, b.y);
+                                mma_u8(acc[1][nt], af[0][1], b.x, b.y);
+                                mma_u8(acc[0][nt], af[1][0], b.z, b.w);
+                                mma_u8(acc[1][nt], af[1][1], b.z, b.w);
+                            }
+                        }
+                    }
+                }
+
+                // ---- epilogue: estimator + filter + order-preserving compaction on the accumulator fragments ------------
+                float4 fac[4];
+                bool valid[4];
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    fac[s] = s_fac[warp * 32 + 8 * s + g];
+                    valid[s] = (uint32_t)(warp * 32 + 4 * g + s) < nv;
                 }
 #pragma unroll
-                for (int i = 0; i < VPT; i++) {
-                    const uint32_t a0 = plane_sum<W32, MODE>(code[i], rec + 0 * WP), a1 = plane_sum<W32, MODE>(code[i], rec + 1 * WP);
-                    const uint32_t a2 = plane_sum<W32, MODE>(code[i], rec + 2 * WP), a3 = plane_sum<W32, MODE>(code[i], rec + 3 * WP);
-                    const uint32_t abdp = a0 + (a1 << 1) + (a2 << 2) + (a3 << 3);  // utils.rs:113-135
-                    // rabitq.rs:352-363, left-to-right, no contraction:
-                    //   ((((cds + ycd) + lo*ppc) + ((2*abdp - sum) * ip) * delta) - err * sqrt(ycd))
-                    const float t1 = __fadd_rn(fac[i].w, sc.w);
-                    const float t3 = __fadd_rn(t1, __fmul_rn(sc.x, fac[i].y));
-                    const float t4 = __fsub_rn(__fmul_rn(2.0f, __uint2float_rn(abdp)), sc.z);
-                    const float t6 = __fmul_rn(__fmul_rn(t4, fac[i].x), sc.y);
-                    const float rough = __fsub_rn(__fadd_rn(t3, t6), __fmul_rn(fac[i].z, sq));
-                    if (wloc[i] < nwords) {  // warp-uniform
-                        const size_t word = (size_t)wbase + wloc[i];
-                        if constexpr (DENSE) {
-                            if (valid[i]) a.entries[word * 32 + lane] = make_float2(rough, __uint_as_float(abdp));
-                        } else {
-                            const bool pass = valid[i] && (rough < thr);  // rerank.rs:84
-                            const uint32_t mask = __ballot_sync(FULL, pass);
-                            if (lane == 0) a.bitmap[word] = mask;
-                            if (pass) a.entries[word * 32 + __popc(mask & lt_mask)] = make_float2(rough, __uint_as_float(jpos[i]));
-                            n_surv += pass;
+                for (int nt = 0; nt < NT; nt++) {
+                    if (nt >= ntiles) continue;  // warp-uniform
+                    uint32_t bal[2][4];
+                    float rough[2][4];
+                    size_t word[2];
+                    uint32_t fl[2];
+#pragma unroll
+                    for (int o = 0; o < 2; o++) {
+                        const int col = nt * 8 + 2 * t + o;
+                        const float4 m0 = *reinterpret_cast<const float4*>(s_rec + (size_t)col * pitch + D);       // lo, delta, sum, ycd
+                        const float4 m1 = *reinterpret_cast<const float4*>(s_rec + (size_t)col * pitch + D + 16);  // sqrt(ycd), -, wbase, -
+                        const float2 tf = s_tf[r0 + col];
+                        fl[o] = __float_as_uint(tf.y);
+                        word[o] = (size_t)__float_as_uint(m1.z) + wloc;
+#pragma unroll
+                        for (int s = 0; s < 4; s++) {
+                            const int iacc = acc[s >> 1][nt][(s & 1) * 2 + o];  // = 8 * abdp
+                            // rabitq.rs:352-363, left-to-right:  ((((cds + ycd) + lo*ppc) + ((2*abdp - sum) * ip) * delta) - err * sqrt(ycd))
+                            // 2*abdp is exact, so fma(0.25, 8*abdp, -sum) rounds once exactly like `2.0 * abdp as f32 - sum`
+                            const float t1 = __fadd_rn(fac[s].w, m0.w);
+                            const float t3 = __fadd_rn(t1, __fmul_rn(m0.x, fac[s].y));
+                            const float t4 = fmaf(0.25f, __int2float_rn(iacc), -m0.z);
+                            const float t6 = __fmul_rn(__fmul_rn(t4, fac[s].x), m0.y);
+                            rough[o][s] = __fsub_rn(__fadd_rn(t3, t6), __fmul_rn(fac[s].z, m1.x));
+                            if constexpr (DENSE) {
+                                if (valid[s] && fl[o]) a.entries[word[o] * 32 + 4 * g + s] = make_float2(rough[o][s], __uint_as_float((uint32_t)iacc >> 3));
+                            } else {
+                                bal[o][s] = __ballot_sync(FULL, valid[s] && fl[o] && (rough[o][s] < tf.x));  // rerank.rs:84
+                            }
+                        }
+                    }
+                    if constexpr (!DENSE) {
+                        const uint32_t any = bal[0][0] | bal[0][1] | bal[0][2] | bal[0][3] | bal[1][0] | bal[1][1] | bal[1][2] | bal[1][3];
+                        uint32_t bm[2] = {0u, 0u};
+                        if (any) {  // warp-uniform
+#pragma unroll
+                            for (int o = 0; o < 2; o++)
+#pragma unroll
+                                for (int s = 0; s < 4; s++)  // ballot bit 4g'+t of register-row s  ->  bitmap bit 4g'+s
+                                    bm[o] |= __funnelshift_r(bal[o][s], bal[o][s], (t - s) & 31) & (0x11111111u << s);
+#pragma unroll
+                            for (int o = 0; o < 2; o++)
+#pragma unroll
+                                for (int s = 0; s < 4; s++)
+                                    if ((bal[o][s] >> lane) & 1u)
+                                        a.entries[word[o] * 32 + __popc(bm[o] & ((1u << (4 * g + s)) - 1u))] =
+                                            make_float2(rough[o][s], __uint_as_float(jbase + s));
+                            if (lane == 0) {
+#pragma unroll
+                                for (int o = 0; o < 2; o++)
+#pragma unroll
+                                    for (int s = 0; s < 4; s++) n_surv += __popc(bal[o][s]);
+                            }
+                        }
+                        if (g == 0) {  // lanes 0..3 hold the flags / slot words of columns 2t, 2t+1
+                            if (fl[0]) a.bitmap[word[0]] = bm[0];
+                            if (fl[1]) a.bitmap[word[1]] = bm[1];
                         }
                     }
                 }
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
     }
     if constexpr (!DENSE) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n_surv += __shfl_xor_sync(FULL, n_surv, o);
         if (lane == 0 && n_surv) atomicAdd(&a.counters[0], n_surv);
     }
 }
@@ -1029,37 +1177,6 @@ struct __align__(16) SurvRec {
     uint32_t id;   // original id (map_ids applied, rerank.rs:94)
     uint32_t p;    // probe rank of the cluster the candidate lives in
 };
-
-RQ_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-RQ_DEV void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-RQ_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {  // no arrive: only raises the pending transaction count
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-RQ_DEV void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-RQ_DEV void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-RQ_DEV void prefetch_l2_bulk(const void* src_gmem, uint32_t bytes) {  // no destination: warms L2 ahead of the TMA row gather
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
-}
-RQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    for (uint32_t spin = 0; !ok; spin++) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok)
-                     : "r"(smem_u32(bar)), "r"(parity)
-                     : "memory");
-        if (spin > (1u << 24)) __trap();  // a lost transaction must fail loudly, never hang the GPU
-    }
-}
 
 RQ_DEV void heap_recompute_max(const float* hd, int k, int lane, int& maxpos, float& thr) {
     if (k <= 32) {  // one redux + one ballot: the largest key, lowest slot among equals (what a sequential scan finds first)

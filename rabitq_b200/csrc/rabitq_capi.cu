@@ -148,6 +148,11 @@ struct rabitq_index {
     uint32_t* map_ids = nullptr;  // n
     uint32_t* codes = nullptr;    // n x D/32
     float4* factors = nullptr;    // n
+    // scan-layout copy of codes + Factors (kernels.cuh scan_layout_kernel): per cluster, chunks of 128 vectors in the image K4 stages
+    uint2* scan_codes = nullptr;      // chunks x [D/64][128]
+    float4* scan_fac = nullptr;       // chunks x 128
+    uint32_t* chunk_start = nullptr;  // K+1: first chunk of every cluster
+    size_t n_chunks = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_totals = nullptr;  // marks the arrival of the slot totals in h_pin
@@ -180,13 +185,15 @@ struct rabitq_index {
     size_t ev_used = 0;
     bool timings_pending = false;  // the last call's event chain has not been turned into ms[] yet
     int scan_blocks_per_sm = 0;
+    bool scan_attr_done[2][4] = {{false, false, false, false}, {false, false, false, false}};
+    int scan_stages = 0;   // ring depth of the scan (0 = by dimension)
     size_t max_items = 0;  // capacity of a round's scan work list for the current sub-batch (setup_rounds)
     int scan_mode = -1;  // -1 = default; RABITQ_SCAN_MODE overrides (tuning)
 
     ~rabitq_index() {
         cudaSetDevice(device);
         for (void* p : {(void*)base, (void*)P, (void*)cent, (void*)offsets, (void*)goffsets, (void*)row_bounds, (void*)map_ids, (void*)codes,
-                        (void*)factors, (void*)PT, (void*)dist.peers_d, (void*)quant_bias, (void*)pf_mu, (void*)pf_chat, (void*)pf_chat_lo, (void*)pf_cnorm, (void*)pf_cnorm2,
+                        (void*)factors, (void*)scan_codes, (void*)scan_fac, (void*)chunk_start, (void*)PT, (void*)dist.peers_d, (void*)quant_bias, (void*)pf_mu, (void*)pf_chat, (void*)pf_chat_lo, (void*)pf_cnorm, (void*)pf_cnorm2,
                         (void*)pf_cnorm_max})
             if (p) cudaFree(p);
         for (size_t r = 0; r < dist.peers_h.size(); r++)
@@ -297,6 +304,7 @@ int finish_index(rabitq_index* ix) {
     if (const char* e = std::getenv("RABITQ_RR_ROWS")) ix->rerank_rows = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_RR_PREFETCH")) ix->rerank_prefetch = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_SCAN_SLICES")) ix->scan_slices = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RABITQ_SCAN_STAGES")) ix->scan_stages = std::max(0, std::atoi(e));
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     CU(cudaStreamCreateWithFlags(&ix->aux_stream, cudaStreamNonBlocking));
@@ -310,6 +318,27 @@ int finish_index(rabitq_index* ix) {
     CU(cudaFuncSetAttribute(approx_gemm_tf32_kernel<128, 128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * PF_PITCH * 4));
     if (const char* e = std::getenv("RABITQ_PREFILTER")) ix->prefilter = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_PREFILTER_MODE")) ix->pf_mode = std::atoi(e);
+    {   // scan-layout copy of the codes and Factors: what K4's producer warp stages with one TMA bulk copy per chunk
+        const size_t K = ix->K, JJ = ix->D / 64;
+        std::vector<uint32_t> off_h(K + 1), cs(K + 1);
+        CU(cudaMemcpy(off_h.data(), ix->offsets, (K + 1) * 4, cudaMemcpyDeviceToHost));
+        size_t tot = 0;
+        for (size_t c = 0; c < K; c++) {
+            cs[c] = (uint32_t)tot;
+            tot += ((size_t)(off_h[c + 1] - off_h[c]) + SCAN_THREADS - 1) / SCAN_THREADS;
+        }
+        cs[K] = (uint32_t)tot;
+        if (tot >= ((size_t)1 << 32)) return fail(RABITQ_EUNSUPPORTED, "too many scan chunks");
+        ix->n_chunks = tot;
+        CU(cudaMalloc((void**)&ix->chunk_start, (K + 1) * 4));
+        CU(cudaMemcpy(ix->chunk_start, cs.data(), (K + 1) * 4, cudaMemcpyHostToDevice));
+        CU(cudaMalloc((void**)&ix->scan_codes, std::max<size_t>(tot * JJ * 128 * 8, 16)));
+        CU(cudaMalloc((void**)&ix->scan_fac, std::max<size_t>(tot * 128 * 16, 16)));
+        if (tot) {
+            scan_layout_kernel<<<(unsigned)tot, 128>>>(ix->codes, ix->factors, ix->offsets, ix->chunk_start, (int)K, (int)JJ, ix->scan_codes, ix->scan_fac);
+            CU(cudaGetLastError());
+        }
+    }
     {   // prefilter operands: mu, c^ = tf32(c - mu), ||c - mu||, ||c - mu||^2, max norm
         const size_t K = ix->K, D = ix->D;
         CU(cudaMalloc((void**)&ix->pf_mu, D * 4));
@@ -668,57 +697,62 @@ int dump_impl(rabitq_index* ix, const char* dir) {
 }
 
 // ---- scan launch ------------------------------------------------------------------------------------------------
-// records per shared-memory slice of the scan (24 KB of records, at most one per thread)
-int scan_qs(const rabitq_index* ix) {
-    const int W32 = (int)ix->D / 32, RS = 4 * ((W32 + 3) & ~3) + 8;
-    return std::max(8, std::min(24576 / (RS * 4), SCAN_THREADS));
+// Geometry of the scan's shared-memory ring for this dimension: NT record tiles (of 8) per consumer pass, `sub` passes per
+// stage (records per stage = work-item size = 8 * NT * sub), `stages` ring slots.  Small dimensions take deep rings of big
+// stages (the epilogue dominates and every stage re-copies the chunk's codes); large ones shrink until one CTA fits.
+// "scan_mode" 0..2 forces NT = 1, 2, 4 (tests run every instantiation).
+struct ScanGeom { int nt, sub, stages; };
+ScanGeom scan_geom(const rabitq_index* ix) {
+    const int D = (int)ix->D;
+    const size_t cap = (size_t)227 * 1024, third = (size_t)74 * 1024, half = (size_t)112 * 1024;
+    ScanGeom g{4, 1, 2};
+    if (ix->scan_mode >= 0 && ix->scan_mode <= 2) g.nt = 1 << ix->scan_mode;
+    else if (scan_smem_bytes(D, 32, 2) > half) g.nt = scan_smem_bytes(D, 16, 2) <= cap ? 2 : 1;
+    const int nr = 8 * g.nt;
+    if (scan_smem_bytes(D, 2 * nr, 3) <= third) { g.sub = 2; g.stages = 3; }
+    else if (scan_smem_bytes(D, nr, 3) <= third) { g.sub = 1; g.stages = 3; }
+    else if (scan_smem_bytes(D, nr, 2) <= cap) { g.sub = 1; g.stages = 2; }
+    else { g.sub = 1; g.stages = 1; }
+    if (ix->scan_stages > 0) g.stages = std::min(8, ix->scan_stages);
+    while (g.stages > 1 && scan_smem_bytes(D, nr * g.sub, g.stages) > cap) g.stages--;
+    return g;
+}
+int scan_qs(const rabitq_index* ix) {  // records per stage
+    const ScanGeom g = scan_geom(ix);
+    return 8 * g.nt * g.sub;
 }
 
-template <int W32, bool DENSE, int MODE>
-int launch_scan_m(rabitq_index* ix, ScanArgs& a) {
-    constexpr int RS = 4 * ((W32 + 3) & ~3) + 8;
-    const int qs = scan_qs(ix);
-    a.QS = qs;
-    size_t smem = (size_t)qs * (RS * 4 + 8);
-    auto kern = scan_kernel<W32, 1, DENSE, MODE>;
+template <int NT, bool DENSE>
+int launch_scan_nt(rabitq_index* ix, ScanArgs& a, const ScanGeom& g) {
+    const size_t smem = scan_smem_bytes((int)ix->D, 8 * NT * g.sub, g.stages);
+    if (smem > (size_t)227 * 1024) return fail(RABITQ_EUNSUPPORTED, "dim too large for the code scan's shared-memory staging (dim <= 8192)");
+    auto kern = scan_mma_kernel<NT, DENSE>;
+    bool& attr_done = ix->scan_attr_done[DENSE ? 1 : 0][NT == 4 ? 2 : NT == 2 ? 1 : 0];
+    if (!attr_done) {  // once per handle (= per device) and instantiation; always the maximum, other handles share the function
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
     int bps = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SCAN_THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SCAN_BLOCK, smem));
     bps = std::max(1, bps);
     ix->scan_blocks_per_sm = bps;
-    kern<<<ix->sm_count * bps, SCAN_THREADS, smem, ix->stream>>>(a);
+    kern<<<ix->sm_count * bps, SCAN_BLOCK, smem, ix->stream>>>(a);
     CU(cudaGetLastError()); ix->counts[5]++;
     return 0;
 }
 
-// carry-save depth of the popcount (kernels.cuh plane_sum): 0 plain, 1 = 3->2 compressors, 2 = 7->3 compressors, 3 = half / half
-int scan_mode(const rabitq_index* ix) {
-    if (ix->scan_mode >= 0) return ix->scan_mode;
-    return ix->D / 32 >= 14 ? 2 : 1;  // measured on B200: 7->3 compressors win at D=960, 3->2 at D=128 (profiles/)
-}
-
-template <int W32, bool DENSE>
-int launch_scan_t(rabitq_index* ix, ScanArgs& a) {
-    if constexpr (DENSE) return launch_scan_m<W32, true, 0>(ix, a);
-    else {
-        switch (scan_mode(ix)) {
-            case 0: return launch_scan_m<W32, false, 0>(ix, a);
-            case 2: return launch_scan_m<W32, false, 2>(ix, a);
-            case 3:
-                if constexpr (W32 >= 14) return launch_scan_m<W32, false, 3>(ix, a);
-                else return launch_scan_m<W32, false, 2>(ix, a);
-            default: return launch_scan_m<W32, false, 1>(ix, a);
-        }
-    }
-}
-
 template <bool DENSE>
 int launch_scan(rabitq_index* ix, ScanArgs& a) {
-    switch (ix->D / 32) {
-#define C(w) case w: return launch_scan_t<w, DENSE>(ix, a);
-        C(2) C(4) C(6) C(8) C(10) C(12) C(14) C(16) C(18) C(20) C(24) C(28) C(30) C(32) C(40) C(48) C(64)
-#undef C
-        default:
-            return fail(RABITQ_EUNSUPPORTED, "code scan is instantiated for dim in {64..640 step 64, 768, 896, 960, 1024, 1280, 1536, 2048}");
+    const int D = (int)ix->D;
+    const ScanGeom g = scan_geom(ix);
+    a.D = D;
+    a.rec_pitch = scan_rec_pitch(D);
+    a.stages = g.stages;
+    a.sub = g.sub;
+    switch (g.nt) {
+        case 4: return launch_scan_nt<4, DENSE>(ix, a, g);
+        case 2: return launch_scan_nt<2, DENSE>(ix, a, g);
+        default: return launch_scan_nt<1, DENSE>(ix, a, g);
     }
 }
 
@@ -867,7 +901,7 @@ int wait_totals(rabitq_index* ix, BatchOut* bo) {
 
 // K3 for every (query, rank) of the batch; on a shard, pairs whose cluster lives elsewhere are skipped
 int run_quantize(rabitq_index* ix, size_t nb, int P) {
-    const int D = (int)ix->D, W32 = D / 32, WP = (W32 + 3) & ~3, RS = 4 * WP + 8;
+    const int D = (int)ix->D, W32 = D / 32, RS = (D + REC_META_BYTES) / 4;  // record words: D code bytes + scalars
     cudaStream_t st = ix->stream;
     CU(ix->qrec.ensure(nb * (size_t)P * RS * 4));
     // probe ranks per warp: 1 for the generic kernel; for D <= 256 (query in registers) as many as keep >= ~64 warps per SM in the grid
@@ -901,8 +935,8 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     const size_t words = std::max<uint32_t>(bo->total_words, 1);
     CU(ix->bitmap.ensure(words * 4));
     CU(ix->entries.ensure(words * 32 * 8));
-    // records per work item: `scan_slices` shared-memory slices, raised so that the slice index fits its 12 bits
-    const uint32_t MS = (uint32_t)std::max<size_t>((size_t)scan_qs(ix) * std::max(1, ix->scan_slices), (nb + 4094) / 4095);
+    // records per work item = per shared-memory stage of the scan; "scan_slices" > 1 cuts items smaller (partial stages: a test knob)
+    const uint32_t MS = (uint32_t)std::max(1, scan_qs(ix) / std::max(1, ix->scan_slices));
     ix->max_items = ix->n / SCAN_THREADS + (size_t)K + 2 + ((size_t)bo->total_words / 4 + nb * (size_t)P) / MS;
     CU(ix->thr.ensure(nb * 4));
     CU(ix->heap_dist.ensure(nb * topk * 4));
@@ -918,9 +952,8 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     CU(cudaGetLastError()); ix->counts[5]++;
 
     ScanArgs sa;
-    sa.codes = ix->codes;
-    sa.factors = ix->factors;
-    sa.offsets = ix->offsets;
+    sa.scan_codes = ix->scan_codes;
+    sa.scan_fac = ix->scan_fac;
     sa.qrec = ix->qrec.as<uint32_t>();
     sa.thr = ix->thr.as<float>();
     sa.q_p0 = ix->q_p0.as<uint32_t>();
@@ -928,7 +961,6 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     sa.entries = ix->entries.as<float2>();
     sa.counters = ix->counters.as<unsigned long long>();
     sa.P = P;
-    sa.QS = 0;
     sa.MS = MS;
 
     RerankArgs ra;
@@ -999,7 +1031,7 @@ int build_lists(rabitq_index* ix, size_t nb, int P, uint32_t MS, Pos lo, Pos hi,
     CU(L.item_start.ensure((size_t)(K + 1) * 4));
     CU(L.cl_cursor.ensure((size_t)K * 4));
     CU(L.cl_items.ensure(nb * (size_t)P * 4));
-    CU(L.work.ensure(ix->max_items * 8));
+    CU(L.work.ensure(ix->max_items * sizeof(ScanItem)));
     CU(L.work_ctl.ensure(16));
     if (!L.ready) CU(cudaEventCreateWithFlags(&L.ready, cudaEventDisableTiming));
     const int p_lo = lo.p, p_hi_incl = std::min(P, hi.p + (hi.ch > 0 ? 1 : 0));  // ranks that have items in this round
@@ -1019,7 +1051,8 @@ int build_lists(rabitq_index* ix, size_t nb, int P, uint32_t MS, Pos lo, Pos hi,
                                                                          L.cl_start.as<uint32_t>(), L.cl_cursor.as<uint32_t>(),
                                                                          L.cl_items.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
-    work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(), K, MS, ch_min, L.work.as<uint2>());
+    work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(), L.cl_start.as<uint32_t>(), ix->offsets,
+                                                       ix->chunk_start, K, MS, ch_min, L.work.as<ScanItem>());
     CU(cudaGetLastError()); ix->counts[5]++;
     CU(cudaEventRecord(L.ready, st));
     return 0;
@@ -1036,9 +1069,8 @@ int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos
         CU(cudaStreamWaitEvent(st, ix->lists[set].ready, 0));
     }
     ListSet& L = ix->lists[set];
-    sa.cl_start = L.cl_start.as<uint32_t>();
     sa.cl_items = L.cl_items.as<uint32_t>();
-    sa.work = L.work.as<uint2>();
+    sa.work = L.work.as<ScanItem>();
     sa.work_ctl = L.work_ctl.as<uint32_t>();
     if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
     sa.p_lo = lo.p; sa.ch_lo = lo.ch; sa.p_hi = hi.p; sa.ch_hi = hi.ch;
@@ -1711,6 +1743,7 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     else if (n == "rerank_prefetch") idx->rerank_prefetch = (int)value;
     else if (n == "debug_rerank") idx->debug_rerank = (int)value;
     else if (n == "scan_slices") idx->scan_slices = (int)std::max(1L, value);
+    else if (n == "scan_stages") idx->scan_stages = (int)std::max(0L, value);
     else if (n == "prefilter") idx->prefilter = (int)value;
     else if (n == "prefilter_mode") { idx->pf_mode = (int)value; idx->pf_strikes = 0; }
     else if (n == "prefilter_cap") idx->prefilter_cap = (int)value;
@@ -1797,16 +1830,24 @@ int rabitq_stage_quantize(rabitq_index* idx, const float* queries, size_t nq, si
     BatchOut bo;
     int rc = stage_prefix(idx, queries, nq, len, probe, STOP_QUANT, &bo);
     if (rc) return rc;
-    const size_t W32 = idx->D / 32, WP = (W32 + 3) & ~(size_t)3, RS = 4 * WP + 8, items = nq * bo.P;
+    const size_t D = idx->D, W32 = D / 32, RS = (D + REC_META_BYTES) / 4, items = nq * bo.P;
     std::vector<uint32_t> rec(items * RS);
     CU(cudaMemcpy(rec.data(), idx->qrec.p, items * RS * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> planes(4 * W32);
     for (size_t i = 0; i < items; i++) {
         const uint32_t* r = &rec[i * RS];
-        if (out_planes)  // [4][W64] u64 little-endian == [4][W32] u32
-            for (size_t b = 0; b < 4; b++) std::memcpy(out_planes + i * 2 * W32 + b * (W32 / 2), r + b * WP, W32 * 4);
-        if (out_lo) std::memcpy(&out_lo[i], r + 4 * WP + 0, 4);
-        if (out_delta) std::memcpy(&out_delta[i], r + 4 * WP + 1, 4);
-        if (out_sum) out_sum[i] = r[4 * WP + 5];
+        if (out_planes) {  // vector_binarize_query (src/simd.rs:83-107) of the record's 4-bit codes: [4][W64] u64 little-endian == [4][W32] u32
+            const unsigned char* cb = reinterpret_cast<const unsigned char*>(r);
+            std::fill(planes.begin(), planes.end(), 0u);
+            for (size_t d = 0; d < D; d++) {
+                const uint32_t q4 = (uint32_t)cb[rec_pos((int)d)] >> (3 - (d & 3));
+                for (size_t b = 0; b < 4; b++) planes[b * W32 + d / 32] |= ((q4 >> b) & 1u) << (d & 31);
+            }
+            std::memcpy(out_planes + i * 2 * W32, planes.data(), 4 * W32 * 4);
+        }
+        if (out_lo) std::memcpy(&out_lo[i], r + D / 4 + 0, 4);
+        if (out_delta) std::memcpy(&out_delta[i], r + D / 4 + 1, 4);
+        if (out_sum) out_sum[i] = r[D / 4 + 5];
     }
     return RABITQ_OK;
 }

@@ -15,6 +15,8 @@ DIM_CASES = {
     "d250": (4000, 250, 16, 24, "deep", 23),    # 250 -> padded to 256, W32 = 8
     "d448": (3000, 448, 16, 16, "gist", 24),    # generic quantiser, W32 = 14
     "d1536": (2500, 1536, 12, 16, "embed", 25),  # config 4's dimension
+    "d704": (2500, 704, 12, 16, "gist", 26),     # a dim % 64 == 0 no template ever named (W32 = 22: odd count of k-step quads)
+    "d3072": (1500, 3072, 8, 12, "embed", 27),   # text-embedding-3-large; 4 record tiles no longer fit next to the chunk's codes
 }
 
 
