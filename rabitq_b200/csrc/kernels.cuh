@@ -580,22 +580,24 @@ __host__ __device__ __forceinline__ int rec_pos(int d) {
     return 64 * (j >> 1) + 16 * (r & 3) + 8 * (j & 1) + 4 * ((r >> 2) & 1) + (r >> 3);
 }
 
-template <int W32T>  // W32T > 0: D = 32*W32T held in registers (one pass over memory); 0: any D, two passes
+// K3 walks ONE ROUND'S INVERTED LIST (cluster -> the (q, p) items probing it, bucket_fill_kernel) and writes the record of
+// list slot i to qrec + i * rec_stride: the records of a cluster are then contiguous in HBM, in the order K4 consumes them,
+// and K4's producer stages all the records of a work item with a single TMA bulk copy.  (A rank-0 record lives in both the
+// first-chunk round's list and the main round's list and is simply computed for each.)  rec_stride is K4's shared-memory
+// record pitch (scan_rec_pitch), so the HBM image is the shared-memory image.
+template <int W32T>  // W32T > 0: D = 32*W32T, the centroid is held in registers across consecutive slots of one cluster; 0: any D
 __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__ y, const float* __restrict__ cent,
-                                                       const uint32_t* __restrict__ probe_ids, const float* __restrict__ probe_dist,
+                                                       const uint2* __restrict__ cl_items, const uint32_t* __restrict__ n_items_ptr,
+                                                       const float* __restrict__ probe_dist,
                                                        const uint32_t* __restrict__ slot_local, const uint32_t* __restrict__ q_wbase,
                                                        const uint32_t* __restrict__ offsets, const float* __restrict__ bias,
-                                                       uint32_t* __restrict__ qrec, int nq, int P, int D, int pch) {
+                                                       unsigned char* __restrict__ qrec, int rec_stride, int P, int D, int pch) {
     const int lane = threadIdx.x & 31;
-    // a warp takes `pch` consecutive probe ranks of ONE query (pch > 1 only when the query fits in registers, W32T > 0): the
-    // rotated query is loaded once per warp instead of once per record
     const size_t wid = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    const size_t chunks = ((size_t)P + pch - 1) / pch;
-    if (wid >= (size_t)nq * chunks) return;
-    const size_t q = wid / chunks;
-    const int p_begin = (int)(wid % chunks) * pch, p_end = min(P, p_begin + pch);
-    const float* yr = y + q * (size_t)D;
-    const int W32 = W32T > 0 ? W32T : D / 32, RS = (D + REC_META_BYTES) / 4;  // record words
+    const size_t n_items = *n_items_ptr;
+    const size_t i_begin = wid * (size_t)pch, i_end = min(n_items, i_begin + (size_t)pch);
+    if (i_begin >= n_items) return;
+    const int W32 = W32T > 0 ? W32T : D / 32, RS = (D + REC_META_BYTES) / 4;  // record words (without the pitch padding)
     // the record is assembled in shared memory and leaves with coalesced 128-bit stores
     extern __shared__ __align__(16) uint32_t qz_smem[];
     uint32_t* sr = qz_smem + (size_t)(threadIdx.x >> 5) * RS;
@@ -603,22 +605,39 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
     // this lane's byte of k-step g sits at sb[lane_pos + 64 * (g >> 1) + 8 * (g & 1)]   (rec_pos with r = lane)
     const int lane_pos = 16 * (lane & 3) + 4 * ((lane >> 2) & 1) + (lane >> 3);
     const int lane_shift = 3 - (lane & 3);
-    float yv[W32T > 0 ? W32T : 1];
-    if constexpr (W32T > 0) {
-#pragma unroll
-        for (int g = 0; g < W32T; g++) yv[g] = __ldg(&yr[g * 32 + lane]);
+    float cv[W32T > 0 ? W32T : 1];
+    uint32_t c_held = 0xffffffffu;
+    // lane l fetches everything slot i_begin + l needs besides the two rows: one dependent chain for the warp's slots, not one per slot
+    uint2 my_item = make_uint2(0u, 0u);
+    float my_ycd = 0.f;
+    uint32_t my_wb = 0u, my_skip = 1u;
+    if (i_begin + lane < i_end) {
+        my_item = __ldg(&cl_items[i_begin + lane]);  // (q * P + p, cluster)
+        my_ycd = probe_dist[my_item.x];
+        my_wb = q_wbase[my_item.x / (uint32_t)P] + slot_local[my_item.x];
+        my_skip = (offsets && offsets[my_item.y + 1] == offsets[my_item.y]) ? 1u : 0u;  // cluster held by another shard: its record is never read
     }
-    for (int p = p_begin; p < p_end; p++) {
-    const size_t gw = q * (size_t)P + p;
-    const uint32_t c = probe_ids[gw];
-    if (offsets && offsets[c + 1] == offsets[c]) continue;  // cluster held by another shard: its record is never read
+    for (size_t slot = i_begin; slot < i_end; slot++) {
+    const int sl = (int)(slot - i_begin);
+    const size_t gw = __shfl_sync(FULL, my_item.x, sl);
+    const uint32_t c = __shfl_sync(FULL, my_item.y, sl);
+    const float ycd = __shfl_sync(FULL, my_ycd, sl);
+    const uint32_t wb = __shfl_sync(FULL, my_wb, sl);
+    if (__shfl_sync(FULL, my_skip, sl)) continue;
+    const size_t q = gw / (size_t)P;
+    const float* yr = y + q * (size_t)D;
     const float* cr = cent + (size_t)c * D;
-    uint32_t* rec = qrec + gw * (size_t)RS;
+    uint32_t* rec = reinterpret_cast<uint32_t*>(qrec + slot * (size_t)rec_stride);
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
     float rr[W32T > 0 ? W32T : 1];
     if constexpr (W32T > 0) {
+        if (c != c_held) {  // warp-uniform
 #pragma unroll
-        for (int g = 0; g < W32T; g++) rr[g] = __fsub_rn(yv[g], __ldg(&cr[g * 32 + lane]));
+            for (int g = 0; g < W32T; g++) cv[g] = __ldg(&cr[g * 32 + lane]);
+            c_held = c;
+        }
+#pragma unroll
+        for (int g = 0; g < W32T; g++) rr[g] = __fsub_rn(__ldg(&yr[g * 32 + lane]), cv[g]);
 #pragma unroll
         for (int g = 0; g < W32T; g++) { mn = fminf(mn, rr[g]); mx = fmaxf(mx, rr[g]); }
     } else {
@@ -657,7 +676,6 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
     if (lane == 0) {
-        const float ycd = probe_dist[gw];
         float* rf = reinterpret_cast<float*>(sr + D / 4);
         rf[0] = mn;
         rf[1] = delta;
@@ -665,7 +683,7 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
         rf[3] = ycd;
         rf[4] = __fsqrt_rn(ycd);                 // rabitq.rs:346
         sr[D / 4 + 5] = (uint32_t)sum;
-        sr[D / 4 + 6] = q_wbase[q] + slot_local[gw];
+        sr[D / 4 + 6] = wb;
         sr[D / 4 + 7] = c;
     }
     __syncwarp();
@@ -765,7 +783,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __res
 
 __global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, const uint32_t* __restrict__ q_p0, size_t nq, int P,
                                    int p_lo, int p_hi, const uint32_t* __restrict__ cl_start, uint32_t* __restrict__ cl_cursor,
-                                   uint32_t* __restrict__ cl_items) {
+                                   uint2* __restrict__ cl_items /* (q*P+p, cluster) */) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     int R = p_hi - p_lo;
     if (i >= nq * (size_t)R) return;
@@ -774,7 +792,7 @@ __global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, const
     if (p >= P) return;
     uint32_t c = probe_ids[q * P + p];
     uint32_t pos = atomicAdd(&cl_cursor[c], 1u);
-    cl_items[cl_start[c] + pos] = (uint32_t)(q * P + p);
+    cl_items[cl_start[c] + pos] = make_uint2((uint32_t)(q * P + p), c);
 }
 
 __global__ void work_items_kernel(const uint32_t* __restrict__ item_start, const uint32_t* __restrict__ cl_count,
@@ -825,7 +843,8 @@ __global__ void work_items_kernel(const uint32_t* __restrict__ item_start, const
 // CONSECUTIVE vectors (one 64-bit load per vector and k-step pair), and ballot bit 4g+t of register-row s lands on bitmap
 // bit 4g+s by a rotation.
 RQ_DEV void mma_u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    // volatile: a pure asm may be speculated out of the `nt < ntiles` guards (it was: every record tile was multiplied, used or not)
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -849,14 +868,27 @@ RQ_DEV void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, u
 RQ_DEV void prefetch_l2_bulk(const void* src_gmem, uint32_t bytes) {  // no destination: warms L2 ahead of the TMA row gather
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
+template <int SLEEP_NS = 0>
 RQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait suspends the warp in hardware only briefly; a waiter that expects to wait long (the scan's producer, which runs
+    // stages ahead) sleeps between attempts instead of burning issue slots.  A lost transaction must fail loudly, never hang
+    // the GPU: trap after ~4 s.
     uint32_t ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
     for (uint32_t spin = 0; !ok; spin++) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok)
-                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "r"(addr), "r"(parity)
                      : "memory");
-        if (spin > (1u << 24)) __trap();  // a lost transaction must fail loudly, never hang the GPU
+        if (!ok) {
+            if constexpr (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+            if ((spin & 63u) == 63u) {
+                const long long now = clock64();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 8000000000ll) __trap();
+            }
+        }
     }
 }
 
@@ -882,16 +914,18 @@ __global__ void __launch_bounds__(128) scan_layout_kernel(const uint32_t* __rest
         dst[jj * 128 + ((v & ~31u) | ((v & 3u) << 3) | ((v >> 2) & 7u))] = i < tot ? src[i] : make_uint2(0u, 0u);
     }
     const uint32_t t = threadIdx.x;
-    scan_fac[(size_t)b * 128 + ((t & ~31u) | ((t & 3u) << 3) | ((t >> 2) & 7u))] = t < nv ? factors[off + v0 + t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // padding slots of the last chunk: center_distance_square = +inf, so their estimate is +inf / NaN and `rough < thr` is false
+    scan_fac[(size_t)b * 128 + ((t & ~31u) | ((t & 3u) << 3) | ((t >> 2) & 7u))] =
+        t < nv ? factors[off + v0 + t] : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
 }
 
 struct ScanArgs {
     const uint2* scan_codes;    // chunks x [D/64][128]
     const float4* scan_fac;     // chunks x 128
-    const uint32_t* cl_items;   // (q*P+p) per cluster
+    const uint2* cl_items;      // (q*P+p, cluster) per cluster
     const ScanItem* work;
     uint32_t* work_ctl;         // [0] counter [1] n_work
-    const uint32_t* qrec;       // records (K3)
+    const unsigned char* qrec;  // this round's records (K3), list order, rec_pitch bytes apart
     const float* thr;           // per query
     const uint32_t* q_p0;       // per query: first probe rank with vectors on this shard
     uint32_t* bitmap;           // per slot word
@@ -918,8 +952,8 @@ __host__ __device__ __forceinline__ size_t scan_stage_bytes(int D, int nrs) {
 }
 __host__ __device__ __forceinline__ size_t scan_smem_bytes(int D, int nrs, int stages) { return 128 + (size_t)stages * scan_stage_bytes(D, nrs); }
 
-template <int NT, bool DENSE>
-__global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(ScanArgs a) {
+template <int NT, bool DENSE, int MINB>  // MINB: CTAs per SM the register allocation must allow (3 for small dims, 2 when shared memory allows no more anyway)
+__global__ void __launch_bounds__(SCAN_BLOCK, MINB) scan_mma_kernel(ScanArgs a) {
     constexpr int NR = 8 * NT;  // records per pass
     extern __shared__ __align__(128) unsigned char scan_smem[];
     const int D = a.D, JJ = D >> 6, pitch = a.rec_pitch, S = a.stages, NRS = NR * a.sub;
@@ -937,7 +971,6 @@ __global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(S
     if (warp == SCAN_CONSUMERS / 32) {
         // ---------------- producer ----------------------------------------------------------------------------------------
         const uint32_t n_work = a.work_ctl[1];
-        const uint32_t rec_bytes = (uint32_t)(D + REC_META_BYTES);
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(&a.work_ctl[0], 1u);
         item = __shfl_sync(FULL, item, 0);
@@ -955,7 +988,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(S
                 w.rec_begin = w0.x; w.nr = w0.y; w.chunk_g = w0.z; w.chunk = w0.w; w.jbase = w1.x; w.nv = w1.y;
                 if (lane == 0) next = atomicAdd(&a.work_ctl[0], 1u);  // in flight while this item is staged
             }
-            mbar_wait(&empty[st], ph ^ 1u);  // the consumers released this stage (passes at once on its first use)
+            mbar_wait<400>(&empty[st], ph ^ 1u);  // the consumers released this stage (passes at once on its first use)
             if (done) {
                 if (lane == 0) hdr[0] = -1;
                 mbar_arrive(&full[st]);
@@ -967,21 +1000,24 @@ __global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(S
                 tma_bulk_g2s(sp + o_fac, a.scan_fac + (size_t)w.chunk_g * 128, 2048u, &full[st]);
                 hdr[0] = (int)w.nr; hdr[1] = (int)w.jbase; hdr[2] = (int)w.nv; hdr[3] = (int)w.chunk;
             }
+            if (lane == 1) {  // the item's records are contiguous in HBM (K3 wrote them in list order, at the shared-memory pitch)
+                const uint32_t bytes = w.nr * (uint32_t)pitch;
+                mbar_expect_tx(&full[st], bytes);
+                tma_bulk_g2s(sp + o_rec, a.qrec + (size_t)w.rec_begin * pitch, bytes, &full[st]);
+            }
             float2* tf = reinterpret_cast<float2*>(sp + o_tf);
             for (uint32_t r = lane; r < (uint32_t)NRS; r += 32) {
-                float th = 0.f;
+                float th = __int_as_float(0xff800000);  // -inf: nothing passes (unused column, or a record outside this round's window)
                 uint32_t fl = 0u;
                 if (r < w.nr) {
-                    const uint32_t id = __ldg(&a.cl_items[w.rec_begin + r]), q = id / (uint32_t)a.P;
-                    mbar_expect_tx(&full[st], rec_bytes);
-                    tma_bulk_g2s(sp + o_rec + (size_t)r * pitch, reinterpret_cast<const unsigned char*>(a.qrec) + (size_t)id * rec_bytes, rec_bytes,
-                                 &full[st]);
-                    th = a.thr[q];
+                    const uint32_t id = __ldg(&a.cl_items[w.rec_begin + r]).x, q = id / (uint32_t)a.P;
+                    const float thq = a.thr[q];
                     // is (rank, chunk) inside this round's window?
                     const int pr = (int)(id - q * (uint32_t)a.P) - (int)a.q_p0[q], ch = (int)w.chunk;
                     const bool ge_lo = pr > a.p_lo || (pr == a.p_lo && ch >= a.ch_lo);
                     const bool lt_hi = pr < a.p_hi || (pr == a.p_hi && ch < a.ch_hi);
                     fl = (ge_lo && lt_hi) ? 1u : 0u;
+                    if (fl) th = thq;
                 }
                 tf[r] = make_float2(th, __uint_as_float(fl));
             }
@@ -994,12 +1030,18 @@ __global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(S
     // ---------------- consumers -------------------------------------------------------------------------------------------
     const int g = lane >> 2, t = lane & 3;
     const uint32_t amask = 0x01010101u << t;
-    unsigned long long n_surv = 0;
+    uint32_t n_mine = 0;  // survivors counted by this lane (bitmap words it wrote)
+    uint32_t lt[4], rot[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        lt[s] = (1u << (4 * g + s)) - 1u;  // vectors before 4g+s in the warp's 32
+        rot[s] = (uint32_t)(t - s) & 31u;
+    }
     for (uint32_t it = 0;; it++) {
         const int st = (int)(it % (uint32_t)S);
         const uint32_t ph = (it / (uint32_t)S) & 1u;
         unsigned char* sp = stage0 + (size_t)st * stage_bytes;
-        mbar_wait(&full[st], ph);
+        mbar_wait<100>(&full[st], ph);
         const int4 hdr = *reinterpret_cast<const int4*>(sp + o_hdr);
         if (hdr.x < 0) break;
         const int nr_all = hdr.x;
@@ -1033,14 +1075,22 @@ __global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(S
                             af[1][s >> 1][s & 1] = w.y & amask;
                             af[1][s >> 1][(s & 1) + 2] = (w.y >> 4) & amask;
                         }
+                        uint4 bf[NT];  // all B fragments first, then the MMAs k-step by k-step: 2*NT independent accumulators between dependent issues
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++)
+                            if (nt < ntiles) bf[nt] = *reinterpret_cast<const uint4*>(bp + (size_t)nt * 8 * pitch + 64 * jj);
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) {
                             if (nt < ntiles) {  // warp-uniform
-                                const uint4 b = *reinterpret_cast<const uint4*>(bp + (size_t)nt * 8 * pitch + 64 * jj);
-                                mma_u8(acc[0][nt], af[0][0], b.x, b.y);
-                                mma_u8(acc[1][nt], af[0][1], b.x, b.y);
-                                mma_u8(acc[0][nt], af[1][0], b.z, b.w);
-                                mma_u8(acc[1][nt], af[1][1], b.z, b.w);
+                                mma_u8(acc[0][nt], af[0][0], bf[nt].x, bf[nt].y);
+                                mma_u8(acc[1][nt], af[0][1], bf[nt].x, bf[nt].y);
+                            }
+                        }
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) {
+                            if (nt < ntiles) {
+                                mma_u8(acc[0][nt], af[1][0], bf[nt].z, bf[nt].w);
+                                mma_u8(acc[1][nt], af[1][1], bf[nt].z, bf[nt].w);
                             }
                         }
                     }
@@ -1048,27 +1098,27 @@ __global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(S
 
                 // ---- epilogue: estimator + filter + order-preserving compaction on the accumulator fragments ------------
                 float4 fac[4];
-                bool valid[4];
 #pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    fac[s] = s_fac[warp * 32 + 8 * s + g];
-                    valid[s] = (uint32_t)(warp * 32 + 4 * g + s) < nv;
-                }
+                for (int s = 0; s < 4; s++) fac[s] = s_fac[warp * 32 + 8 * s + g];
 #pragma unroll
                 for (int nt = 0; nt < NT; nt++) {
                     if (nt >= ntiles) continue;  // warp-uniform
                     uint32_t bal[2][4];
+                    bool pass[2][4];
                     float rough[2][4];
-                    size_t word[2];
+                    float2* ebase[2];
+                    uint32_t* bword[2];
                     uint32_t fl[2];
 #pragma unroll
                     for (int o = 0; o < 2; o++) {
                         const int col = nt * 8 + 2 * t + o;
                         const float4 m0 = *reinterpret_cast<const float4*>(s_rec + (size_t)col * pitch + D);       // lo, delta, sum, ycd
                         const float4 m1 = *reinterpret_cast<const float4*>(s_rec + (size_t)col * pitch + D + 16);  // sqrt(ycd), -, wbase, -
-                        const float2 tf = s_tf[r0 + col];
+                        const float2 tf = s_tf[r0 + col];  // threshold (-inf: column unused / outside the round's window), flag
                         fl[o] = __float_as_uint(tf.y);
-                        word[o] = (size_t)__float_as_uint(m1.z) + wloc;
+                        const size_t word = (size_t)__float_as_uint(m1.z) + wloc;
+                        ebase[o] = a.entries + word * 32;
+                        bword[o] = a.bitmap + word;
 #pragma unroll
                         for (int s = 0; s < 4; s++) {
                             const int iacc = acc[s >> 1][nt][(s & 1) * 2 + o];  // = 8 * abdp
@@ -1080,9 +1130,12 @@ __global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(S
                             const float t6 = __fmul_rn(__fmul_rn(t4, fac[s].x), m0.y);
                             rough[o][s] = __fsub_rn(__fadd_rn(t3, t6), __fmul_rn(fac[s].z, m1.x));
                             if constexpr (DENSE) {
-                                if (valid[s] && fl[o]) a.entries[word[o] * 32 + 4 * g + s] = make_float2(rough[o][s], __uint_as_float((uint32_t)iacc >> 3));
+                                if ((uint32_t)(warp * 32 + 4 * g + s) < nv && fl[o])
+                                    ebase[o][4 * g + s] = make_float2(rough[o][s], __uint_as_float((uint32_t)iacc >> 3));
                             } else {
-                                bal[o][s] = __ballot_sync(FULL, valid[s] && fl[o] && (rough[o][s] < tf.x));  // rerank.rs:84
+                                // rerank.rs:84 (strict).  Padding vectors carry cds = +inf and switched-off columns thr = -inf: both fail here
+                                pass[o][s] = rough[o][s] < tf.x;
+                                bal[o][s] = __ballot_sync(FULL, pass[o][s]);
                             }
                         }
                     }
@@ -1094,24 +1147,17 @@ __global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(S
                             for (int o = 0; o < 2; o++)
 #pragma unroll
                                 for (int s = 0; s < 4; s++)  // ballot bit 4g'+t of register-row s  ->  bitmap bit 4g'+s
-                                    bm[o] |= __funnelshift_r(bal[o][s], bal[o][s], (t - s) & 31) & (0x11111111u << s);
+                                    bm[o] |= __funnelshift_r(bal[o][s], bal[o][s], rot[s]) & (0x11111111u << s);
 #pragma unroll
                             for (int o = 0; o < 2; o++)
 #pragma unroll
                                 for (int s = 0; s < 4; s++)
-                                    if ((bal[o][s] >> lane) & 1u)
-                                        a.entries[word[o] * 32 + __popc(bm[o] & ((1u << (4 * g + s)) - 1u))] =
-                                            make_float2(rough[o][s], __uint_as_float(jbase + s));
-                            if (lane == 0) {
-#pragma unroll
-                                for (int o = 0; o < 2; o++)
-#pragma unroll
-                                    for (int s = 0; s < 4; s++) n_surv += __popc(bal[o][s]);
-                            }
+                                    if (pass[o][s]) ebase[o][__popc(bm[o] & lt[s])] = make_float2(rough[o][s], __uint_as_float(jbase + s));
                         }
                         if (g == 0) {  // lanes 0..3 hold the flags / slot words of columns 2t, 2t+1
-                            if (fl[0]) a.bitmap[word[0]] = bm[0];
-                            if (fl[1]) a.bitmap[word[1]] = bm[1];
+                            if (fl[0]) *bword[0] = bm[0];
+                            if (fl[1]) *bword[1] = bm[1];
+                            n_mine += __popc(bm[0]) + __popc(bm[1]);
                         }
                     }
                 }
@@ -1121,7 +1167,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK, NT >= 4 ? 3 : 4) scan_mma_kernel(S
         if (lane == 0) mbar_arrive(&empty[st]);
     }
     if constexpr (!DENSE) {
-        if (lane == 0 && n_surv) atomicAdd(&a.counters[0], n_surv);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_mine += __shfl_xor_sync(FULL, n_mine, o);
+        if (lane == 0 && n_mine) atomicAdd(&a.counters[0], (unsigned long long)n_mine);
     }
 }
 

@@ -114,9 +114,12 @@ struct DistState {
 // on a side stream while K3 runs, so no round waits for its lists.
 struct ListSet {
     DevBuf cl_count, cl_start, item_start, cl_cursor, cl_items, work, work_ctl;
-    cudaEvent_t ready = nullptr;
+    DevBuf qrec;            // this round's records (K3), in list order: a cluster's records are contiguous
+    size_t cap_items = 0;   // upper bound of the list's length (queries x ranks of the window)
+    uint32_t MS = 0, ch_min = 0;
+    cudaEvent_t ready = nullptr;  // inverted list built (K3 and the work-item pass wait for it)
     void release() {
-        for (DevBuf* b : {&cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl}) b->release();
+        for (DevBuf* b : {&cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &qrec}) b->release();
         if (ready) cudaEventDestroy(ready);
         ready = nullptr;
     }
@@ -167,7 +170,7 @@ struct rabitq_index {
     int first_chunks = 1;  // 128-vector chunks of the nearest cluster in the first round (0 = the whole cluster)
     int scan_slices = 1;   // shared-memory record slices per scan work item (hot clusters are cut into several items)
     // work buffers
-    DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, qrec, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
+    DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
         entries, counters, out_all, rr_dbg, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag;
     DistState dist;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
@@ -187,6 +190,7 @@ struct rabitq_index {
     int scan_blocks_per_sm = 0;
     bool scan_attr_done[2][4] = {{false, false, false, false}, {false, false, false, false}};
     int scan_stages = 0;   // ring depth of the scan (0 = by dimension)
+    int scan_sub = 0;      // consumer passes per stage (0 = by dimension)
     size_t max_items = 0;  // capacity of a round's scan work list for the current sub-batch (setup_rounds)
     int scan_mode = -1;  // -1 = default; RABITQ_SCAN_MODE overrides (tuning)
 
@@ -200,7 +204,7 @@ struct rabitq_index {
             if (dist.opened[r] && dist.peers_h[r]) cudaIpcCloseMemHandle(dist.peers_h[r]);
         if (dist.inbox) cudaFree(dist.inbox);
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
-                          &qrec, &thr, &heap_dist,
+                          &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_all, &rr_dbg,
                           &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag})
             b->release();
@@ -305,6 +309,7 @@ int finish_index(rabitq_index* ix) {
     if (const char* e = std::getenv("RABITQ_RR_PREFETCH")) ix->rerank_prefetch = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_SCAN_SLICES")) ix->scan_slices = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RABITQ_SCAN_STAGES")) ix->scan_stages = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("RABITQ_SCAN_SUB")) ix->scan_sub = std::max(0, std::atoi(e));
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     CU(cudaStreamCreateWithFlags(&ix->aux_stream, cudaStreamNonBlocking));
@@ -704,17 +709,28 @@ int dump_impl(rabitq_index* ix, const char* dir) {
 struct ScanGeom { int nt, sub, stages; };
 ScanGeom scan_geom(const rabitq_index* ix) {
     const int D = (int)ix->D;
-    const size_t cap = (size_t)227 * 1024, third = (size_t)74 * 1024, half = (size_t)112 * 1024;
-    ScanGeom g{4, 1, 2};
-    if (ix->scan_mode >= 0 && ix->scan_mode <= 2) g.nt = 1 << ix->scan_mode;
-    else if (scan_smem_bytes(D, 32, 2) > half) g.nt = scan_smem_bytes(D, 16, 2) <= cap ? 2 : 1;
-    const int nr = 8 * g.nt;
-    if (scan_smem_bytes(D, 2 * nr, 3) <= third) { g.sub = 2; g.stages = 3; }
-    else if (scan_smem_bytes(D, nr, 3) <= third) { g.sub = 1; g.stages = 3; }
-    else if (scan_smem_bytes(D, nr, 2) <= cap) { g.sub = 1; g.stages = 2; }
-    else { g.sub = 1; g.stages = 1; }
+    // shared memory per CTA that still lets 3 / 2 / 1 CTAs share an SM (227 KB usable, 1 KB reserved per CTA)
+    const size_t tiers[3] = {(size_t)74 * 1024, (size_t)112 * 1024, (size_t)227 * 1024};
+    // measured on B200 (C1: D=128, C2: D=960): residency beats tile size -- three CTAs of 16 records per stage outrun two of 32 --
+    // and a third ring slot only pays where stages are small
+    static const int shapes[3][2] = {{2, 3}, {1, 3}, {1, 2}};  // (sub, stages), in order of preference
+    ScanGeom g{1, 1, 1};
+    bool found = false;
+    const int forced_nt = (ix->scan_mode >= 0 && ix->scan_mode <= 2) ? (1 << ix->scan_mode) : 0;
+    for (int tier = 0; tier < 3 && !found; tier++)
+        for (int nt : {4, 2, 1}) {
+            if (forced_nt && nt != forced_nt) continue;
+            if (!forced_nt && tier == 0 && nt == 1) continue;  // 8 records per pass rebuild the A fragments too often: rather two CTAs
+            for (const auto& sh : shapes)
+                if (scan_smem_bytes(D, 8 * nt * sh[0], sh[1]) <= tiers[tier]) { g = ScanGeom{nt, sh[0], sh[1]}; found = true; break; }
+            if (found) break;
+        }
+    if (!found) g = ScanGeom{forced_nt ? forced_nt : 1, 1, 1};  // one stage, no overlap (dim > ~4600)
+    const size_t cap = tiers[2];
+    if (ix->scan_sub > 0) g.sub = std::min(8, ix->scan_sub);
     if (ix->scan_stages > 0) g.stages = std::min(8, ix->scan_stages);
-    while (g.stages > 1 && scan_smem_bytes(D, nr * g.sub, g.stages) > cap) g.stages--;
+    while (g.sub > 1 && scan_smem_bytes(D, 8 * g.nt * g.sub, 1) > cap) g.sub--;
+    while (g.stages > 1 && scan_smem_bytes(D, 8 * g.nt * g.sub, g.stages) > cap) g.stages--;
     return g;
 }
 int scan_qs(const rabitq_index* ix) {  // records per stage
@@ -722,12 +738,12 @@ int scan_qs(const rabitq_index* ix) {  // records per stage
     return 8 * g.nt * g.sub;
 }
 
-template <int NT, bool DENSE>
+template <int NT, bool DENSE, int MINB>
 int launch_scan_nt(rabitq_index* ix, ScanArgs& a, const ScanGeom& g) {
     const size_t smem = scan_smem_bytes((int)ix->D, 8 * NT * g.sub, g.stages);
     if (smem > (size_t)227 * 1024) return fail(RABITQ_EUNSUPPORTED, "dim too large for the code scan's shared-memory staging (dim <= 8192)");
-    auto kern = scan_mma_kernel<NT, DENSE>;
-    bool& attr_done = ix->scan_attr_done[DENSE ? 1 : 0][NT == 4 ? 2 : NT == 2 ? 1 : 0];
+    auto kern = scan_mma_kernel<NT, DENSE, MINB>;
+    bool& attr_done = ix->scan_attr_done[DENSE ? 1 : 0][MINB == 3 ? 3 : NT == 4 ? 2 : NT == 2 ? 1 : 0];
     if (!attr_done) {  // once per handle (= per device) and instantiation; always the maximum, other handles share the function
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
@@ -749,10 +765,13 @@ int launch_scan(rabitq_index* ix, ScanArgs& a) {
     a.rec_pitch = scan_rec_pitch(D);
     a.stages = g.stages;
     a.sub = g.sub;
+    if constexpr (!DENSE) {  // three CTAs per SM want <= 128 registers; where shared memory allows two anyway, the compiler gets 200
+        if (g.nt == 4 && scan_smem_bytes(D, 8 * g.nt * g.sub, g.stages) <= (size_t)74 * 1024) return launch_scan_nt<4, false, 3>(ix, a, g);
+    }
     switch (g.nt) {
-        case 4: return launch_scan_nt<4, DENSE>(ix, a, g);
-        case 2: return launch_scan_nt<2, DENSE>(ix, a, g);
-        default: return launch_scan_nt<1, DENSE>(ix, a, g);
+        case 4: return launch_scan_nt<4, DENSE, 2>(ix, a, g);
+        case 2: return launch_scan_nt<2, DENSE, 2>(ix, a, g);
+        default: return launch_scan_nt<1, DENSE, 2>(ix, a, g);
     }
 }
 
@@ -899,21 +918,31 @@ int wait_totals(rabitq_index* ix, BatchOut* bo) {
     return 0;
 }
 
-// K3 for every (query, rank) of the batch; on a shard, pairs whose cluster lives elsewhere are skipped
-int run_quantize(rabitq_index* ix, size_t nb, int P) {
+// records per work item of the scan = per shared-memory stage; "scan_slices" > 1 cuts items smaller (partial stages: a test knob)
+uint32_t scan_ms(const rabitq_index* ix) { return (uint32_t)std::max(1, scan_qs(ix) / std::max(1, ix->scan_slices)); }
+
+// K3 over the inverted list of round `set` (built on the side stream: the main stream waits for it here); on a shard, items
+// whose cluster lives elsewhere are skipped
+int run_quantize_list(rabitq_index* ix, int P, size_t set) {
     const int D = (int)ix->D, W32 = D / 32, RS = (D + REC_META_BYTES) / 4;  // record words: D code bytes + scalars
     cudaStream_t st = ix->stream;
-    CU(ix->qrec.ensure(nb * (size_t)P * RS * 4));
-    // probe ranks per warp: 1 for the generic kernel; for D <= 256 (query in registers) as many as keep >= ~64 warps per SM in the grid
+    ListSet& L = ix->lists[set];
+    const int pitch = scan_rec_pitch(D);
+    CU(L.qrec.ensure(std::max<size_t>(L.cap_items, 1) * (size_t)pitch));
+    CU(cudaStreamWaitEvent(st, L.ready, 0));
+    // consecutive list slots per warp: 1 for the generic kernel; for D <= 256 (centroid in registers across the slots of one
+    // cluster) as many as keep >= ~64 warps per SM in the grid
     int pch = 1;
     if (W32 == 2 || W32 == 4 || W32 == 6 || W32 == 8)
-        while (pch < 8 && pch * 2 <= P && nb * (size_t)((P + 2 * pch - 1) / (2 * pch)) >= (size_t)ix->sm_count * 64) pch *= 2;
-    size_t warps = nb * (size_t)((P + pch - 1) / pch);
+        while (pch < 8 && L.cap_items / (size_t)(2 * pch) >= (size_t)ix->sm_count * 64) pch *= 2;
+    const size_t warps = (L.cap_items + pch - 1) / pch;
+    if (warps == 0) return 0;
     const unsigned qgrid = (unsigned)((warps + 3) / 4);
     const size_t qsmem = (size_t)4 * RS * 4;  // one record per warp, staged for the coalesced store
     const uint32_t* skip = ix->shard_count > 1 ? ix->offsets : nullptr;
-#define QUANT_ARGS ix->y.as<float>(), ix->cent, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), \
-                   ix->q_wbase.as<uint32_t>(), skip, ix->quant_bias, ix->qrec.as<uint32_t>(), (int)nb, P, D, pch
+#define QUANT_ARGS ix->y.as<float>(), ix->cent, L.cl_items.as<uint2>(), L.cl_start.as<uint32_t>() + ix->K,                                \
+                   ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), ix->q_wbase.as<uint32_t>(), skip, ix->quant_bias,           \
+                   L.qrec.as<unsigned char>(), pitch, P, D, pch
     switch (W32) {
         case 2: quantize_kernel<2><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
         case 4: quantize_kernel<4><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
@@ -923,7 +952,6 @@ int run_quantize(rabitq_index* ix, size_t nb, int P) {
     }
 #undef QUANT_ARGS
     CU(cudaGetLastError()); ix->counts[5]++;
-    if (tick(ix, ST_QUANT)) return RABITQ_ECUDA;
     return 0;
 }
 
@@ -935,8 +963,7 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     const size_t words = std::max<uint32_t>(bo->total_words, 1);
     CU(ix->bitmap.ensure(words * 4));
     CU(ix->entries.ensure(words * 32 * 8));
-    // records per work item = per shared-memory stage of the scan; "scan_slices" > 1 cuts items smaller (partial stages: a test knob)
-    const uint32_t MS = (uint32_t)std::max(1, scan_qs(ix) / std::max(1, ix->scan_slices));
+    const uint32_t MS = scan_ms(ix);
     ix->max_items = ix->n / SCAN_THREADS + (size_t)K + 2 + ((size_t)bo->total_words / 4 + nb * (size_t)P) / MS;
     CU(ix->thr.ensure(nb * 4));
     CU(ix->heap_dist.ensure(nb * topk * 4));
@@ -954,7 +981,7 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     ScanArgs sa;
     sa.scan_codes = ix->scan_codes;
     sa.scan_fac = ix->scan_fac;
-    sa.qrec = ix->qrec.as<uint32_t>();
+    sa.qrec = nullptr;  // per round (run_round_scan)
     sa.thr = ix->thr.as<float>();
     sa.q_p0 = ix->q_p0.as<uint32_t>();
     sa.bitmap = ix->bitmap.as<uint32_t>();
@@ -1021,57 +1048,62 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
 
 enum RoundKind { ROUND_REPLAY, ROUND_SINK1 };
 
-// inverted probe lists + scan work list of one window [lo, hi) of visit positions into list set `set`, on stream `st`
+// inverted probe list (cluster -> records) of one window [lo, hi) of visit positions into list set `set`, on stream `st`;
+// also counts the window's scan work items.  Needs nothing but K2b's products: built for every round before K3.
 int build_lists(rabitq_index* ix, size_t nb, int P, uint32_t MS, Pos lo, Pos hi, size_t set, cudaStream_t st) {
     const int K = (int)ix->K;
     if (ix->lists.size() <= set) ix->lists.resize(set + 1);
     ListSet& L = ix->lists[set];
-    CU(L.cl_count.ensure((size_t)K * 4));
-    CU(L.cl_start.ensure((size_t)(K + 1) * 4));
-    CU(L.item_start.ensure((size_t)(K + 1) * 4));
-    CU(L.cl_cursor.ensure((size_t)K * 4));
-    CU(L.cl_items.ensure(nb * (size_t)P * 4));
-    CU(L.work.ensure(ix->max_items * sizeof(ScanItem)));
-    CU(L.work_ctl.ensure(16));
-    if (!L.ready) CU(cudaEventCreateWithFlags(&L.ready, cudaEventDisableTiming));
     const int p_lo = lo.p, p_hi_incl = std::min(P, hi.p + (hi.ch > 0 ? 1 : 0));  // ranks that have items in this round
     const bool single_rank = p_hi_incl == p_lo + 1;
     const uint32_t ch_min = single_rank ? (uint32_t)lo.ch : 0u;
     const uint32_t ch_max = (single_rank && hi.ch > 0) ? (uint32_t)hi.ch : 0xffffffffu;
     const size_t items = nb * (size_t)(p_hi_incl - p_lo);
+    L.cap_items = items;
+    L.MS = MS;
+    L.ch_min = ch_min;
+    CU(L.cl_count.ensure((size_t)K * 4));
+    CU(L.cl_start.ensure((size_t)(K + 1) * 4));
+    CU(L.item_start.ensure((size_t)(K + 1) * 4));
+    CU(L.cl_cursor.ensure((size_t)K * 4));
+    CU(L.cl_items.ensure(std::max<size_t>(items, 1) * 8));
+    CU(L.work_ctl.ensure(16));
+    if (!L.ready) CU(cudaEventCreateWithFlags(&L.ready, cudaEventDisableTiming));
     CU(cudaMemsetAsync(L.cl_count.p, 0, (size_t)K * 4, st));
-    bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
-                                                                          L.cl_count.as<uint32_t>());
-    CU(cudaGetLastError()); ix->counts[5]++;
+    if (items) {
+        bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
+                                                                              L.cl_count.as<uint32_t>());
+        CU(cudaGetLastError()); ix->counts[5]++;
+    }
     bucket_scan_kernel<<<1, 1024, 0, st>>>(L.cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, MS, ch_min, ch_max,
                                            L.cl_start.as<uint32_t>(), L.item_start.as<uint32_t>(), L.cl_cursor.as<uint32_t>(),
                                            L.work_ctl.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
-    bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
-                                                                         L.cl_start.as<uint32_t>(), L.cl_cursor.as<uint32_t>(),
-                                                                         L.cl_items.as<uint32_t>());
-    CU(cudaGetLastError()); ix->counts[5]++;
-    work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(), L.cl_start.as<uint32_t>(), ix->offsets,
-                                                       ix->chunk_start, K, MS, ch_min, L.work.as<ScanItem>());
-    CU(cudaGetLastError()); ix->counts[5]++;
+    if (items) {
+        bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
+                                                                             L.cl_start.as<uint32_t>(), L.cl_cursor.as<uint32_t>(),
+                                                                             L.cl_items.as<uint2>());
+        CU(cudaGetLastError()); ix->counts[5]++;
+    }
     CU(cudaEventRecord(L.ready, st));
     return 0;
 }
 
-// scan of one window [lo, hi) of visit positions over list set `set`; `lists_built` = the set was built ahead on the side stream
-// (the main stream only waits for it), otherwise it is built here, in line
-int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos hi, bool dense, size_t set = 0, bool lists_built = false) {
+// scan of one window [lo, hi) of visit positions over list set `set` (its inverted list and records exist: build_lists +
+// run_quantize_list).  The flat work items are written here: their buffer is sized from the slot totals (setup_rounds).
+int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos hi, bool dense, size_t set = 0) {
     cudaStream_t st = ix->stream;
-    if (!lists_built) {
-        int rc = build_lists(ix, nb, P, sa.MS, lo, hi, set, st);
-        if (rc) return rc;
-    } else {
-        CU(cudaStreamWaitEvent(st, ix->lists[set].ready, 0));
-    }
+    const int K = (int)ix->K;
     ListSet& L = ix->lists[set];
-    sa.cl_items = L.cl_items.as<uint32_t>();
+    CU(L.work.ensure(ix->max_items * sizeof(ScanItem)));
+    work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(), L.cl_start.as<uint32_t>(), ix->offsets,
+                                                       ix->chunk_start, K, L.MS, L.ch_min, L.work.as<ScanItem>());
+    CU(cudaGetLastError()); ix->counts[5]++;
+    sa.cl_items = L.cl_items.as<uint2>();
     sa.work = L.work.as<ScanItem>();
     sa.work_ctl = L.work_ctl.as<uint32_t>();
+    sa.qrec = L.qrec.as<unsigned char>();
+    sa.MS = L.MS;
     if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
     sa.p_lo = lo.p; sa.ch_lo = lo.ch; sa.p_hi = hi.p; sa.ch_hi = hi.ch;
     int rc = dense ? launch_scan<true>(ix, sa) : launch_scan<false>(ix, sa);
@@ -1096,6 +1128,34 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
     return 0;
 }
 
+// round windows of visit positions (probe rank, 128-vector chunk): the first round covers only the first `first_chunks` chunks
+// of the nearest cluster, so that everything after it is filtered with a real threshold
+std::vector<Pos> round_bounds(const rabitq_index* ix, int P, bool dense) {
+    std::vector<Pos> bounds;
+    if (dense) return {{0, 0}, {P, 0}};
+    bounds.push_back({0, 0});
+    if (ix->first_chunks > 0) bounds.push_back({0, ix->first_chunks});
+    for (uint32_t r : ix->rounds)
+        if ((int)r > 0 && (int)r < P && (int)r > bounds.back().p) bounds.push_back({(int)r, 0});
+    bounds.push_back({P, 0});
+    return bounds;
+}
+
+// inverted lists of every round on the side stream (they depend on K2b only), K3 over each list on the main stream as soon as
+// the list exists
+int run_lists_and_quantize(rabitq_index* ix, size_t nb, int P, const std::vector<Pos>& bounds) {
+    const uint32_t MS = scan_ms(ix);
+    CU(cudaStreamWaitEvent(ix->aux_stream, ix->ev_fork, 0));
+    int rc;
+    for (size_t r = 0; r + 1 < bounds.size(); r++)
+        if ((rc = build_lists(ix, nb, P, MS, bounds[r], bounds[r + 1], r, ix->aux_stream))) return rc;
+    if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
+    for (size_t r = 0; r + 1 < bounds.size(); r++)
+        if ((rc = run_quantize_list(ix, P, r))) return rc;
+    if (tick(ix, ST_QUANT)) return RABITQ_ECUDA;
+    return 0;
+}
+
 // One sub-batch of nb queries, already on the device in ix->qraw (nb x len).  Runs up to `stop`.
 int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t topk, bool heuristic, StopAfter stop, BatchOut* bo) {
     const int P = (int)std::min(probe, ix->K);
@@ -1104,28 +1164,15 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     if (rc || stop == STOP_ROTATE) return rc;
     if ((rc = post_totals(ix, nb))) return rc;
     if (stop == STOP_PROBE) return wait_totals(ix, bo);
-    if ((rc = run_quantize(ix, nb, P))) return rc;
+    const std::vector<Pos> bounds = round_bounds(ix, P, stop == STOP_SCAN_DENSE);
+    if (bounds.size() > 17) return fail(RABITQ_EUNSUPPORTED, "more than 16 rerank rounds");
+    if ((rc = run_lists_and_quantize(ix, nb, P, bounds))) return rc;
     if ((rc = wait_totals(ix, bo)) || stop == STOP_QUANT) return rc;
     ScanArgs sa;
     RerankArgs ra;
     if ((rc = setup_rounds(ix, nb, P, topk, bo, &sa, &ra))) return rc;
-    // rounds: windows of visit positions (probe rank, 128-vector chunk).  The first round covers only the first
-    // `first_chunks` chunks of the nearest cluster, so that everything after it is filtered with a real threshold.
-    std::vector<Pos> bounds;
-    if (stop == STOP_SCAN_DENSE) bounds = {{0, 0}, {P, 0}};
-    else {
-        bounds.push_back({0, 0});
-        if (ix->first_chunks > 0) bounds.push_back({0, ix->first_chunks});
-        for (uint32_t r : ix->rounds)
-            if ((int)r > 0 && (int)r < P && (int)r > bounds.back().p) bounds.push_back({(int)r, 0});
-        bounds.push_back({P, 0});
-    }
-    // the lists of every round depend on K2b only: built on the side stream (forked after K2b) while K3 runs on the main one
-    CU(cudaStreamWaitEvent(ix->aux_stream, ix->ev_fork, 0));
-    for (size_t r = 0; r + 1 < bounds.size(); r++)
-        if ((rc = build_lists(ix, nb, P, sa.MS, bounds[r], bounds[r + 1], r, ix->aux_stream))) return rc;
     for (size_t r = 0; r + 1 < bounds.size(); r++) {
-        if ((rc = run_round_scan(ix, nb, P, sa, bounds[r], bounds[r + 1], stop == STOP_SCAN_DENSE, r, true))) return rc;
+        if ((rc = run_round_scan(ix, nb, P, sa, bounds[r], bounds[r + 1], stop == STOP_SCAN_DENSE, r))) return rc;
         if (stop == STOP_SCAN_DENSE) return 0;
         if ((rc = run_round_rerank(ix, nb, ra, bounds[r], bounds[r + 1], r == 0, r + 2 == bounds.size(), heuristic, ROUND_REPLAY))) return rc;
     }
@@ -1414,7 +1461,9 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a
     bo.P = P;
     int rc = post_totals(ix, nq);
     if (rc) return rc;
-    if ((rc = run_quantize(ix, nq, P))) return rc;
+    const int fc = (int)(d.r1cap / SCAN_THREADS);
+    // both rounds' inverted lists on the side stream (they depend on the unpacked probe lists only), K3 over each behind it
+    if ((rc = run_lists_and_quantize(ix, nq, P, {Pos{0, 0}, Pos{0, fc}, Pos{P, 0}}))) return rc;
     if ((rc = wait_totals(ix, &bo))) return rc;
     ix->counts[0] += bo.total_pairs;
     if ((rc = setup_rounds(ix, nq, P, d.topk, &bo, &d.sa, &d.ra))) return rc;
@@ -1426,12 +1475,7 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a
     d.ra.peers = d.peers_d;
     d.ra.off_r1cnt = d.off_r1cnt; d.ra.off_r1rec = d.off_r1rec;
     d.ra.world = d.world; d.ra.rank = d.rank; d.ra.nq_local = (int)d.nq_l; d.ra.r1cap = (int)d.r1cap;
-    const int fc = (int)(d.r1cap / SCAN_THREADS);
-    // both rounds' inverted lists on the side stream (they depend on the unpacked probe lists only), concurrently with K3
-    CU(cudaStreamWaitEvent(ix->aux_stream, ix->ev_fork, 0));
-    if ((rc = build_lists(ix, nq, P, d.sa.MS, Pos{0, 0}, Pos{0, fc}, 0, ix->aux_stream))) return rc;
-    if ((rc = build_lists(ix, nq, P, d.sa.MS, Pos{0, fc}, Pos{P, 0}, 1, ix->aux_stream))) return rc;
-    if ((rc = run_round_scan(ix, nq, P, d.sa, Pos{0, 0}, Pos{0, fc}, false, 0, true))) return rc;
+    if ((rc = run_round_scan(ix, nq, P, d.sa, Pos{0, 0}, Pos{0, fc}, false, 0))) return rc;
     if ((rc = run_round_rerank(ix, nq, d.ra, Pos{0, 0}, Pos{0, fc}, true, false, false, ROUND_SINK1))) return rc;
     d.phase = 2;
     return RABITQ_OK;
@@ -1450,7 +1494,7 @@ int dist_round2_impl(rabitq_index* ix, uint32_t* d_status) {
     const int P = d.P, fc = (int)(d.r1cap / SCAN_THREADS);
     if (tick(ix, -1)) return RABITQ_ECUDA;
     CU(cudaMemsetAsync(d_status, 0, 4, st));
-    int rc = run_round_scan(ix, nq, P, d.sa, Pos{0, fc}, Pos{P, 0}, false, 1, true);
+    int rc = run_round_scan(ix, nq, P, d.sa, Pos{0, fc}, Pos{P, 0}, false, 1);
     if (rc) return rc;
     r2_count_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(ix->bitmap.as<uint32_t>(), ix->q_wbase.as<uint32_t>(), ix->slot_local.as<uint32_t>(),
                                                               ix->q_p0.as<uint32_t>(), (int)nq, P, 0, fc, ix->r2_cnt.as<uint32_t>());
@@ -1744,6 +1788,7 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     else if (n == "debug_rerank") idx->debug_rerank = (int)value;
     else if (n == "scan_slices") idx->scan_slices = (int)std::max(1L, value);
     else if (n == "scan_stages") idx->scan_stages = (int)std::max(0L, value);
+    else if (n == "scan_sub") idx->scan_sub = (int)std::max(0L, value);
     else if (n == "prefilter") idx->prefilter = (int)value;
     else if (n == "prefilter_mode") { idx->pf_mode = (int)value; idx->pf_strikes = 0; }
     else if (n == "prefilter_cap") idx->prefilter_cap = (int)value;
@@ -1830,25 +1875,41 @@ int rabitq_stage_quantize(rabitq_index* idx, const float* queries, size_t nq, si
     BatchOut bo;
     int rc = stage_prefix(idx, queries, nq, len, probe, STOP_QUANT, &bo);
     if (rc) return rc;
-    const size_t D = idx->D, W32 = D / 32, RS = (D + REC_META_BYTES) / 4, items = nq * bo.P;
-    std::vector<uint32_t> rec(items * RS);
-    CU(cudaMemcpy(rec.data(), idx->qrec.p, items * RS * 4, cudaMemcpyDeviceToHost));
+    const size_t D = idx->D, W32 = D / 32, K = idx->K, items = nq * bo.P, pitch = (size_t)scan_rec_pitch((int)D);
+    const size_t n_lists = round_bounds(idx, (int)bo.P, false).size() - 1;
     std::vector<uint32_t> planes(4 * W32);
-    for (size_t i = 0; i < items; i++) {
-        const uint32_t* r = &rec[i * RS];
-        if (out_planes) {  // vector_binarize_query (src/simd.rs:83-107) of the record's 4-bit codes: [4][W64] u64 little-endian == [4][W32] u32
-            const unsigned char* cb = reinterpret_cast<const unsigned char*>(r);
-            std::fill(planes.begin(), planes.end(), 0u);
-            for (size_t d = 0; d < D; d++) {
-                const uint32_t q4 = (uint32_t)cb[rec_pos((int)d)] >> (3 - (d & 3));
-                for (size_t b = 0; b < 4; b++) planes[b * W32 + d / 32] |= ((q4 >> b) & 1u) << (d & 31);
-            }
-            std::memcpy(out_planes + i * 2 * W32, planes.data(), 4 * W32 * 4);
+    std::vector<char> seen(items, 0);
+    for (size_t l = 0; l < n_lists; l++) {  // every (q, p) record is in the list of the round(s) that visit it
+        ListSet& L = idx->lists[l];
+        uint32_t n_l = 0;
+        CU(cudaMemcpy(&n_l, L.cl_start.as<uint32_t>() + K, 4, cudaMemcpyDeviceToHost));
+        std::vector<uint2> ids(n_l);
+        std::vector<unsigned char> rec((size_t)n_l * pitch);
+        if (n_l) {
+            CU(cudaMemcpy(ids.data(), L.cl_items.p, (size_t)n_l * 8, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(rec.data(), L.qrec.p, (size_t)n_l * pitch, cudaMemcpyDeviceToHost));
         }
-        if (out_lo) std::memcpy(&out_lo[i], r + D / 4 + 0, 4);
-        if (out_delta) std::memcpy(&out_delta[i], r + D / 4 + 1, 4);
-        if (out_sum) out_sum[i] = r[D / 4 + 5];
+        for (size_t s = 0; s < n_l; s++) {
+            const size_t i = ids[s].x;
+            if (i >= items) return fail(RABITQ_ECUDA, "corrupt inverted list");
+            seen[i] = 1;
+            const unsigned char* cb = rec.data() + s * pitch;
+            const uint32_t* r = reinterpret_cast<const uint32_t*>(cb);
+            if (out_planes) {  // vector_binarize_query (src/simd.rs:83-107) of the record's 4-bit codes: [4][W64] u64 little-endian == [4][W32] u32
+                std::fill(planes.begin(), planes.end(), 0u);
+                for (size_t d = 0; d < D; d++) {
+                    const uint32_t q4 = (uint32_t)cb[rec_pos((int)d)] >> (3 - (d & 3));
+                    for (size_t b = 0; b < 4; b++) planes[b * W32 + d / 32] |= ((q4 >> b) & 1u) << (d & 31);
+                }
+                std::memcpy(out_planes + i * 2 * W32, planes.data(), 4 * W32 * 4);
+            }
+            if (out_lo) std::memcpy(&out_lo[i], r + D / 4 + 0, 4);
+            if (out_delta) std::memcpy(&out_delta[i], r + D / 4 + 1, 4);
+            if (out_sum) out_sum[i] = r[D / 4 + 5];
+        }
     }
+    for (size_t i = 0; i < items; i++)
+        if (!seen[i]) return fail(RABITQ_ECUDA, "a (query, probe) record is in no round's list");
     return RABITQ_OK;
 }
 
