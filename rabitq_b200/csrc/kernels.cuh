@@ -1301,6 +1301,41 @@ RQ_DEV float l2_quad_global(const float* __restrict__ row, const float* __restri
     return __fadd_rn(s, __shfl_xor_sync(FULL, s, 1));
 }
 
+// Latency-first variant for the rerank replay: EIGHT threads per candidate, thread l = AVX lane l of simd::l2_squared_distance as one
+// scalar chain (dependent FFMA latency 4 cycles; the packed f32x2 chain of l2_quad issues at half rate and the wave's critical path
+// was 2.4 k cycles at D = 960), NC candidates interleaved per thread for instruction-level parallelism.  Rows and query in shared
+// memory; the 8 lanes of a group read 32 contiguous bytes per step.  Every lane of a group returns the same bits.
+template <int NC>
+RQ_DEV void l2_oct(const float* const (&row)[NC], const float* __restrict__ qv, int D, int l, float (&out)[NC]) {
+    float acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = 0.0f;
+#pragma unroll 1
+    for (int s0 = 0; s0 < D; s0 += 64) {  // 8 steps of 8 elements per iteration (D is a multiple of 64)
+        float x[NC][8], q[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            q[u] = qv[s0 + 8 * u + l];
+#pragma unroll
+            for (int c = 0; c < NC; c++) x[c][u] = row[c][s0 + 8 * u + l];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const float d = __fsub_rn(x[c][u], q[u]);
+                acc[c] = fmaf(d, d, acc[c]);
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) {  // reduce_f32_256: c_i = s_i + s_{i+4}; (c0 + c1) + (c2 + c3)   (fp32 addition commutes: all lanes agree)
+        float a = acc[c];
+        a = __fadd_rn(a, __shfl_xor_sync(FULL, a, 4));
+        a = __fadd_rn(a, __shfl_xor_sync(FULL, a, 1));
+        out[c] = __fadd_rn(a, __shfl_xor_sync(FULL, a, 2));
+    }
+}
+
 // HEUR = false: HeapReRanker (src/rerank.rs:61-114).  HEUR = true: HeuristicReRanker (src/rerank.rs:117-176): the filter
 // threshold is the largest accepted distance of the last WINDOW_SIZE = 12 accepted candidates (src/consts.rs:12); every
 // accepted candidate is a result candidate and get_result keeps the topk smallest, which is what the k-slot buffer holds.
@@ -1396,10 +1431,22 @@ __global__ void __launch_bounds__(128, 5) rerank_kernel(RerankArgs a, int p_lo, 
         if (act) {
             const float* rw = rows + (size_t)w * R * pitch;
             float exact = 0.0f;
-            for (int g = 0; g < n; g += 8) {  // 8 candidates per pass: lanes 4c .. 4c+3 compute candidate g + c
-                const float d2 = l2_quad(rw + (size_t)min(g + (lane >> 2), R - 1) * pitch, qv, D, lane & 3);
-                const float res = __shfl_sync(FULL, d2, 4 * ((lane - g) & 7));
-                if (lane >= g && lane < g + 8) exact = res;
+            for (int g = 0; g < n; g += 8) {  // 8 candidates per pass: the 8 lanes of group c compute candidates g + c and g + 4 + c
+                const int grp = lane >> 3, l8 = lane & 7;
+                if (g + 4 < n) {
+                    const float* const rp[2] = {rw + (size_t)min(g + grp, R - 1) * pitch, rw + (size_t)min(g + 4 + grp, R - 1) * pitch};
+                    float d2[2];
+                    l2_oct<2>(rp, qv, D, l8, d2);
+                    const float r0 = __shfl_sync(FULL, d2[0], 8 * ((lane - g) & 3)), r1 = __shfl_sync(FULL, d2[1], 8 * ((lane - g) & 3));
+                    if (lane >= g && lane < g + 4) exact = r0;
+                    if (lane >= g + 4 && lane < g + 8) exact = r1;
+                } else {
+                    const float* const rp[1] = {rw + (size_t)min(g + grp, R - 1) * pitch};
+                    float d2[1];
+                    l2_oct<1>(rp, qv, D, l8, d2);
+                    const float r0 = __shfl_sync(FULL, d2[0], 8 * ((lane - g) & 3));
+                    if (lane >= g && lane < g + 4) exact = r0;
+                }
             }
             if (dbg_on) { const long long t = clock64(); dbg_l2 += (uint32_t)(t - dt0); dt0 = t; }
             // in-order replay (rerank.rs:83-101).  The threshold only moves when a candidate is ACCEPTED (rough < thr and
