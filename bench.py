@@ -372,10 +372,18 @@ def measure_ours(args, workload, device, rank, world, stream, main_leg=True):
     o_c = torch.empty((nq_l,), dtype=torch.int32).pin_memory()
     qh, od, oi, oc = q_host.numpy(), o_d.numpy(), o_i.numpy().view(np.uint32), o_c.numpy().view(np.uint32)
     q_stage = torch.empty_like(q_local)
+    # two pinned host batches, alternating: while batch i is answered the library uploads batch i+1 on its copy stream
+    # (rabitq_query_batch_pipelined); every timed step still contains one H2D of nq x len floats and one D2H of the results
+    q_host2 = torch.empty_like(q_host).pin_memory()
+    q_host2.copy_(q_host)
+    qh2 = q_host2.numpy()
+    flip = [0]
 
     def step_e2e():
         if world == 1:
-            g.query_batch_into(qh, probe, TOPK, od, oi, oc)  # H2D of queries + all kernels + D2H of results inside
+            cur, nxt = (qh, qh2) if flip[0] == 0 else (qh2, qh)
+            flip[0] ^= 1
+            g.query_batch_into(cur, probe, TOPK, od, oi, oc, next_q_host=nxt)  # H2D of queries + all kernels + D2H of results inside
             return
         # every rank: its slice of the batch from pinned host memory, the distributed step, its results back to the host
         q_stage.copy_(q_host, non_blocking=True)

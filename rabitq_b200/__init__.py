@@ -23,7 +23,7 @@ c_u64p = C.POINTER(C.c_uint64)
 ABI_SYMBOLS = [
     "rabitq_load_from_dir", "rabitq_load_from_dir_sharded", "rabitq_from_arrays", "rabitq_from_path", "rabitq_build",
     "rabitq_dump_to_dir", "rabitq_export_arrays", "rabitq_free", "rabitq_dim",
-    "rabitq_num_vectors", "rabitq_num_clusters", "rabitq_query", "rabitq_query_batch", "rabitq_query_batch_device",
+    "rabitq_num_vectors", "rabitq_num_clusters", "rabitq_query", "rabitq_query_batch", "rabitq_query_batch_pipelined", "rabitq_query_batch_device",
     "rabitq_shard_range", "rabitq_merge_topk_device", "rabitq_metrics", "rabitq_metrics_reset", "rabitq_last_error", "rabitq_set_rounds",
     "rabitq_set_option", "rabitq_set_stream", "rabitq_last_timings", "rabitq_stage_rotate", "rabitq_stage_probe", "rabitq_stage_quantize", "rabitq_stage_scan",
     "rabitq_dist_init", "rabitq_dist_ipc_handle", "rabitq_dist_inbox_ptr", "rabitq_dist_set_peer", "rabitq_dist_chunk_words", "rabitq_dist_front",
@@ -75,6 +75,7 @@ def lib():
     L.rabitq_query.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp, vp]
     L.rabitq_query_batch.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp, vp]
     L.rabitq_query_batch_device.argtypes = L.rabitq_query_batch.argtypes
+    L.rabitq_query_batch_pipelined.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, vp, vp]
     L.rabitq_merge_topk_device.argtypes = [C.c_int, vp, vp, C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp, vp]
     L.rabitq_dist_init.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]
     L.rabitq_dist_ipc_handle.argtypes = [vp, C.c_char_p]
@@ -298,10 +299,17 @@ class RaBitQ:
         _check(lib().rabitq_query_batch_device(self._h, C.c_void_p(queries.data_ptr()), nq, ln, probe, topk, int(heuristic_rank),
                                                C.c_void_p(d.data_ptr()), C.c_void_p(ids.data_ptr()), C.c_void_p(cnt.data_ptr())))
 
-    def query_batch_into(self, q_host: np.ndarray, probe: int, topk: int, d: np.ndarray, ids: np.ndarray, cnt: np.ndarray):
-        """Host-buffer call with caller-owned outputs (used by bench.py's end-to-end leg with pinned memory)."""
+    def query_batch_into(self, q_host: np.ndarray, probe: int, topk: int, d: np.ndarray, ids: np.ndarray, cnt: np.ndarray,
+                         next_q_host: np.ndarray | None = None):
+        """Host-buffer call with caller-owned outputs (used by bench.py's end-to-end leg with pinned memory).  `next_q_host`: the
+        NEXT batch (same shape), uploaded on a copy stream while this one is answered (`rabitq_query_batch_pipelined`)."""
         nq, ln = q_host.shape
-        _check(lib().rabitq_query_batch(self._h, _ptr(q_host), nq, ln, probe, topk, 0, _ptr(d), _ptr(ids), _ptr(cnt)))
+        if next_q_host is None:
+            _check(lib().rabitq_query_batch(self._h, _ptr(q_host), nq, ln, probe, topk, 0, _ptr(d), _ptr(ids), _ptr(cnt)))
+        else:
+            assert next_q_host.shape == q_host.shape and next_q_host.dtype == np.float32
+            _check(lib().rabitq_query_batch_pipelined(self._h, _ptr(q_host), _ptr(next_q_host), nq, ln, probe, topk, 0, _ptr(d), _ptr(ids),
+                                                      _ptr(cnt)))
 
     # ---- metrics ---------------------------------------------------------------------------------------------------
     def metrics(self) -> dict:

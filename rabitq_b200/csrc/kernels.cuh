@@ -692,6 +692,114 @@ __global__ void __launch_bounds__(128) quantize_kernel(const float* __restrict__
     }
 }
 
+// K3 for dim <= 256: EIGHT lanes per record, four records per warp side by side.  A lane owns the 16-byte chunks l8, l8 + 8, ... of
+// the rotated query row (dims 32 i + 4 l8 + e), so a group's loads are 128 contiguous bytes and its min / max / sum reductions are
+// three shuffle steps instead of five; the centroid row stays in registers across the consecutive slots of one cluster.  Same
+// arithmetic per element as quantize_kernel (the reductions are order-free: min, max, integer sum), same record.
+template <int W32T>
+__global__ void __launch_bounds__(128) quantize_small_kernel(const float* __restrict__ y, const float* __restrict__ cent,
+                                                             const uint2* __restrict__ cl_items, const uint32_t* __restrict__ n_items_ptr,
+                                                             const float* __restrict__ probe_dist, const uint32_t* __restrict__ slot_local,
+                                                             const uint32_t* __restrict__ q_wbase, const uint32_t* __restrict__ offsets,
+                                                             const float* __restrict__ bias, unsigned char* __restrict__ qrec, int rec_stride,
+                                                             int P, int pch) {
+    constexpr int D = 32 * W32T, RS = (D + REC_META_BYTES) / 4;
+    const int lane = threadIdx.x & 31, l8 = lane & 7, grp = lane >> 3;
+    const size_t gid = ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * 4 + grp;  // group index
+    const size_t n_items = *n_items_ptr;
+    const size_t i_begin = min(n_items, gid * (size_t)pch), i_end = min(n_items, i_begin + (size_t)pch);
+    // (groups past the end of the list keep running with an empty range: the shuffles below are warp-wide)
+    extern __shared__ __align__(16) uint32_t qz_smem[];
+    uint32_t* sr = qz_smem + (size_t)((threadIdx.x >> 5) * 4 + grp) * RS;
+    unsigned char* sb = reinterpret_cast<unsigned char*>(sr);
+    // element e of chunk i (dimension 32 i + 4 l8 + e) -> byte rec_pos: 64 (i >> 1) + 16 e + 8 (i & 1) + 4 (l8 & 1) + (l8 >> 1)
+    const int lane_pos = 4 * (l8 & 1) + (l8 >> 1);
+    float4 cv[W32T];
+    uint32_t c_held = 0xffffffffu;
+    uint2 my_item = make_uint2(0u, 0u);
+    float my_ycd = 0.f;
+    uint32_t my_wb = 0u, my_skip = 1u;
+    if (i_begin + l8 < i_end) {  // lane l8 fetches what slot i_begin + l8 needs besides the two rows (pch <= 8)
+        my_item = __ldg(&cl_items[i_begin + l8]);
+        my_ycd = probe_dist[my_item.x];
+        my_wb = q_wbase[my_item.x / (uint32_t)P] + slot_local[my_item.x];
+        my_skip = (offsets && offsets[my_item.y + 1] == offsets[my_item.y]) ? 1u : 0u;
+    }
+    for (int sl = 0; sl < pch; sl++) {
+        const size_t slot = i_begin + sl;
+        const bool live = slot < i_end;                         // uniform inside the group, not inside the warp
+        const uint32_t gw = __shfl_sync(FULL, my_item.x, sl, 8);
+        const uint32_t c = __shfl_sync(FULL, my_item.y, sl, 8);
+        const float ycd = __shfl_sync(FULL, my_ycd, sl, 8);
+        const uint32_t wb = __shfl_sync(FULL, my_wb, sl, 8);
+        const bool skip = __shfl_sync(FULL, my_skip, sl, 8) != 0u || !live;
+        const uint32_t q = gw / (uint32_t)P;
+        float4 rr[W32T];
+        float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+        if (!skip) {
+            const float4* yr = reinterpret_cast<const float4*>(y + (size_t)q * D);
+            const float4* cr = reinterpret_cast<const float4*>(cent + (size_t)c * D);
+            if (c != c_held) {
+#pragma unroll
+                for (int i = 0; i < W32T; i++) cv[i] = __ldg(&cr[8 * i + l8]);
+                c_held = c;
+            }
+#pragma unroll
+            for (int i = 0; i < W32T; i++) {
+                const float4 yv = __ldg(&yr[8 * i + l8]);
+                rr[i] = make_float4(__fsub_rn(yv.x, cv[i].x), __fsub_rn(yv.y, cv[i].y), __fsub_rn(yv.z, cv[i].z), __fsub_rn(yv.w, cv[i].w));
+                mn = fminf(fminf(fminf(mn, rr[i].x), fminf(rr[i].y, rr[i].z)), rr[i].w);
+                mx = fmaxf(fmaxf(fmaxf(mx, rr[i].x), fmaxf(rr[i].y, rr[i].z)), rr[i].w);
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+        }
+        const float delta = __fmul_rn(__fsub_rn(mx, mn), SCALAR_1_15);  // rabitq.rs:307
+        const float inv = __fdiv_rn(1.0f, delta);                       // :308 recip()
+        int sum = 0;
+        if (!skip) {
+#pragma unroll
+            for (int i = 0; i < W32T; i++) {
+                const float rv[4] = {rr[i].x, rr[i].y, rr[i].z, rr[i].w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    int qi;
+                    if (bias) {  // scalar_quantize_raw (src/utils.rs:194-209): truncate, saturate, NaN -> 0
+                        const float f = __fadd_rn(__fmul_rn(__fsub_rn(rv[e], mn), inv), __ldg(&bias[32 * i + 4 * l8 + e]));
+                        qi = (f != f) ? 0 : (f <= 0.0f ? 0 : (f >= 255.0f ? 255 : (int)f));
+                    } else {
+                        qi = cvtps_epi32(__fmul_rn(__fsub_rn(rv[e], mn), inv));
+                    }
+                    sum += qi;  // i32 lanes wrap like _mm256_add_epi32
+                    sb[64 * (i >> 1) + 16 * e + 8 * (i & 1) + lane_pos] = (unsigned char)((qi & 15) << (3 - e));
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        if (!skip && l8 == 0) {
+            float* rf = reinterpret_cast<float*>(sr + D / 4);
+            rf[0] = mn;
+            rf[1] = delta;
+            rf[2] = __uint2float_rn((uint32_t)sum);  // `scalar_sum as f32`, rabitq.rs:322
+            rf[3] = ycd;
+            rf[4] = __fsqrt_rn(ycd);                 // rabitq.rs:346
+            sr[D / 4 + 5] = (uint32_t)sum;
+            sr[D / 4 + 6] = wb;
+            sr[D / 4 + 7] = c;
+        }
+        __syncwarp();
+        if (!skip) {
+            uint4* rec = reinterpret_cast<uint4*>(qrec + slot * (size_t)rec_stride);
+            for (int i = l8; i < RS / 4; i += 8) rec[i] = reinterpret_cast<const uint4*>(sr)[i];
+        }
+        __syncwarp();  // the staging area is rewritten by the next record
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Inverted probe lists for one round of probe ranks [p_lo, p_hi): cluster -> the (q, p) items probing it, and
 // the scan work list (cluster, chunk of VT vectors).

@@ -173,6 +173,16 @@ struct rabitq_index {
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
         entries, counters, out_all, rr_dbg, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag;
     DistState dist;
+    const float* q_in = nullptr;   // the sub-batch's raw queries (nb x len) on the device: ix->qraw, or the caller's device pointer
+    const float* q_pad = nullptr;  // the same, zero-padded to D: ix->qpad, or q_in itself when len == D (nothing to pad, nothing copied)
+    // double-buffered upload (rabitq_query_batch_pipelined): the NEXT batch's queries travel on the copy stream while this one runs
+    DevBuf qstage;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_staged = nullptr;
+    const float* staged_src = nullptr;
+    size_t staged_nq = 0, staged_len = 0;
+    const float* stage_next = nullptr;  // upload still to be started for this call
+    size_t stage_bytes = 0;
     uint32_t* h_pin = nullptr;  // small pinned staging (totals, counters)
     float* ovr_dist = nullptr;  // device-pointer call answered in one sub-batch: K5 writes straight into the caller's tensors
     uint32_t *ovr_ids = nullptr, *ovr_count = nullptr;
@@ -214,6 +224,9 @@ struct rabitq_index {
         if (ev_totals) cudaEventDestroy(ev_totals);
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto& l : lists) l.release();
+        qstage.release();
+        if (ev_staged) cudaEventDestroy(ev_staged);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (aux_stream) cudaStreamDestroy(aux_stream);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
@@ -313,6 +326,8 @@ int finish_index(rabitq_index* ix) {
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     CU(cudaStreamCreateWithFlags(&ix->aux_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ix->ev_staged, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&ix->h_pin, 256));
     std::memset(ix->h_pin, 0, 256);
@@ -793,15 +808,19 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view);
 int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_rotate, bool global_view) {
     const int D = (int)ix->D;
     cudaStream_t st = ix->stream;
-    CU(ix->qpad.ensure(nb * D * 4));
     CU(ix->y.ensure(nb * D * 4));
-    {
+    if (!ix->q_in) ix->q_in = ix->qraw.as<float>();
+    if ((int)len == D) {
+        ix->q_pad = ix->q_in;  // src/rabitq.rs:277-280 pads only when the query is shorter than the index dimension
+    } else {
+        CU(ix->qpad.ensure(nb * D * 4));
         size_t tot = nb * (size_t)D;
-        pad_queries_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ix->qraw.as<float>(), ix->qpad.as<float>(), nb, (int)len, D);
+        pad_queries_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ix->q_in, ix->qpad.as<float>(), nb, (int)len, D);
         CU(cudaGetLastError()); ix->counts[5]++;
+        ix->q_pad = ix->qpad.as<float>();
     }
     if (tick(ix, ST_H2D)) return RABITQ_ECUDA;
-    if (launch_rotate(ix, ix->qpad.as<float>(), ix->y.as<float>(), nb, st)) return RABITQ_ECUDA;
+    if (launch_rotate(ix, ix->q_pad, ix->y.as<float>(), nb, st)) return RABITQ_ECUDA;
     ix->counts[5]++;
     if (tick(ix, ST_ROTATE)) return RABITQ_ECUDA;
     if (stop_after_rotate) return 0;
@@ -930,27 +949,32 @@ int run_quantize_list(rabitq_index* ix, int P, size_t set) {
     const int pitch = scan_rec_pitch(D);
     CU(L.qrec.ensure(std::max<size_t>(L.cap_items, 1) * (size_t)pitch));
     CU(cudaStreamWaitEvent(st, L.ready, 0));
-    // consecutive list slots per warp: 1 for the generic kernel; for D <= 256 (centroid in registers across the slots of one
-    // cluster) as many as keep >= ~64 warps per SM in the grid
-    int pch = 1;
-    if (W32 == 2 || W32 == 4 || W32 == 6 || W32 == 8)
-        while (pch < 8 && L.cap_items / (size_t)(2 * pch) >= (size_t)ix->sm_count * 64) pch *= 2;
-    const size_t warps = (L.cap_items + pch - 1) / pch;
-    if (warps == 0) return 0;
-    const unsigned qgrid = (unsigned)((warps + 3) / 4);
-    const size_t qsmem = (size_t)4 * RS * 4;  // one record per warp, staged for the coalesced store
     const uint32_t* skip = ix->shard_count > 1 ? ix->offsets : nullptr;
-#define QUANT_ARGS ix->y.as<float>(), ix->cent, L.cl_items.as<uint2>(), L.cl_start.as<uint32_t>() + ix->K,                                \
-                   ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), ix->q_wbase.as<uint32_t>(), skip, ix->quant_bias,           \
-                   L.qrec.as<unsigned char>(), pitch, P, D, pch
-    switch (W32) {
-        case 2: quantize_kernel<2><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
-        case 4: quantize_kernel<4><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
-        case 6: quantize_kernel<6><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
-        case 8: quantize_kernel<8><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
-        default: quantize_kernel<0><<<qgrid, 128, qsmem, st>>>(QUANT_ARGS); break;
+    if (L.cap_items == 0) return 0;
+#define QUANT_COMMON L.cl_items.as<uint2>(), L.cl_start.as<uint32_t>() + ix->K, ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), \
+                     ix->q_wbase.as<uint32_t>(), skip, ix->quant_bias, L.qrec.as<unsigned char>(), pitch, P
+    if (W32 == 2 || W32 == 4 || W32 == 6 || W32 == 8) {
+        // eight lanes per record; consecutive list slots per group (centroid in registers across the slots of one cluster): as
+        // many as keep >= ~48 warps per SM in the grid
+        int pch = 1;
+        while (pch < 8 && L.cap_items / (size_t)(8 * pch) >= (size_t)ix->sm_count * 48) pch *= 2;
+        const size_t groups = (L.cap_items + pch - 1) / pch;
+        const unsigned qgrid = (unsigned)((groups + 15) / 16);
+        const size_t qsmem = (size_t)16 * RS * 4;  // one record per group, staged for the coalesced store
+        switch (W32) {
+            case 2: quantize_small_kernel<2><<<qgrid, 128, qsmem, st>>>(ix->y.as<float>(), ix->cent, QUANT_COMMON, pch); break;
+            case 4: quantize_small_kernel<4><<<qgrid, 128, qsmem, st>>>(ix->y.as<float>(), ix->cent, QUANT_COMMON, pch); break;
+            case 6: quantize_small_kernel<6><<<qgrid, 128, qsmem, st>>>(ix->y.as<float>(), ix->cent, QUANT_COMMON, pch); break;
+            default: quantize_small_kernel<8><<<qgrid, 128, qsmem, st>>>(ix->y.as<float>(), ix->cent, QUANT_COMMON, pch); break;
+        }
+    } else {
+        const int pch = 1;
+        const size_t warps = L.cap_items;
+        const unsigned qgrid = (unsigned)((warps + 3) / 4);
+        const size_t qsmem = (size_t)4 * RS * 4;  // one record per warp, staged for the coalesced store
+        quantize_kernel<0><<<qgrid, 128, qsmem, st>>>(ix->y.as<float>(), ix->cent, QUANT_COMMON, D, pch);
     }
-#undef QUANT_ARGS
+#undef QUANT_COMMON
     CU(cudaGetLastError()); ix->counts[5]++;
     return 0;
 }
@@ -992,7 +1016,7 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
 
     RerankArgs ra;
     std::memset(&ra, 0, sizeof(ra));
-    ra.qpad = ix->qpad.as<float>();
+    ra.qpad = ix->q_pad;
     ra.base = ix->base;
     ra.map_ids = ix->map_ids;
     ra.q_wbase = ix->q_wbase.as<uint32_t>();
@@ -1128,6 +1152,17 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
     return 0;
 }
 
+// the next batch's queries (rabitq_query_batch_pipelined): on the copy stream, concurrent with this batch's kernels
+int start_staging(rabitq_index* ix) {
+    const float* src = ix->stage_next;
+    ix->stage_next = nullptr;
+    CU(ix->qstage.ensure(ix->stage_bytes));
+    CU(cudaMemcpyAsync(ix->qstage.p, src, ix->stage_bytes, cudaMemcpyHostToDevice, ix->copy_stream));
+    CU(cudaEventRecord(ix->ev_staged, ix->copy_stream));
+    ix->staged_src = src;
+    return 0;
+}
+
 // round windows of visit positions (probe rank, 128-vector chunk): the first round covers only the first `first_chunks` chunks
 // of the nearest cluster, so that everything after it is filtered with a real threshold
 std::vector<Pos> round_bounds(const rabitq_index* ix, int P, bool dense) {
@@ -1167,6 +1202,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     const std::vector<Pos> bounds = round_bounds(ix, P, stop == STOP_SCAN_DENSE);
     if (bounds.size() > 17) return fail(RABITQ_EUNSUPPORTED, "more than 16 rerank rounds");
     if ((rc = run_lists_and_quantize(ix, nb, P, bounds))) return rc;
+    if (ix->stage_next && (rc = start_staging(ix))) return rc;
     if ((rc = wait_totals(ix, bo)) || stop == STOP_QUANT) return rc;
     ScanArgs sa;
     RerankArgs ra;
@@ -1203,7 +1239,7 @@ size_t pick_sub_batch(const rabitq_index* ix, size_t nq, size_t probe) {
 }
 
 int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, size_t nq, size_t len, size_t probe, size_t topk,
-                     int heuristic, float* out_dist, uint32_t* out_ids, uint32_t* out_count) {
+                     int heuristic, float* out_dist, uint32_t* out_ids, uint32_t* out_count, const float* next_host = nullptr) {
     int rc = validate_query_args(ix, len, probe, topk, heuristic);
     if (rc) return rc;
     if (nq == 0) return RABITQ_OK;
@@ -1221,8 +1257,28 @@ int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, siz
     if (tick(ix, -1)) return RABITQ_ECUDA;
     for (size_t q0 = 0; q0 < nq; q0 += nbmax) {
         const size_t nb = std::min(nbmax, nq - q0);
-        CU(ix->qraw.ensure(nb * len * 4));
-        CU(cudaMemcpyAsync(ix->qraw.p, queries + q0 * len, nb * len * 4, kin, ix->stream));
+        if (on_device) {
+            ix->q_in = queries + q0 * len;  // read in place: nothing is copied
+        } else {
+            if (nb == nq && ix->staged_src == queries && ix->staged_nq == nq && ix->staged_len == len) {
+                // uploaded by the previous pipelined call while that batch was being answered
+                CU(cudaStreamWaitEvent(ix->stream, ix->ev_staged, 0));
+                std::swap(ix->qstage, ix->qraw);
+            } else {
+                CU(ix->qraw.ensure(nb * len * 4));
+                CU(cudaMemcpyAsync(ix->qraw.p, queries + q0 * len, nb * len * 4, kin, ix->stream));
+            }
+            ix->staged_src = nullptr;
+            ix->staged_nq = nq; ix->staged_len = len;
+            ix->q_in = ix->qraw.as<float>();
+            ix->stage_next = (next_host && nb == nq) ? next_host : nullptr;
+            ix->stage_bytes = nq * len * 4;
+            static const bool late = std::getenv("RABITQ_STAGE_LATE") != nullptr;
+            if (ix->stage_next && !late) {
+                int rc2 = start_staging(ix);
+                if (rc2) return rc2;
+            }
+        }
         BatchOut bo;
         const bool direct = on_device && nb == nq;
         if (direct) { ix->ovr_dist = out_dist; ix->ovr_ids = out_ids; ix->ovr_count = out_count; }
@@ -1280,6 +1336,7 @@ int stage_prefix(rabitq_index* ix, const float* queries, size_t nq, size_t len, 
     std::memset(ix->counts, 0, sizeof(ix->counts));
     CU(ix->qraw.ensure(nq * len * 4));
     CU(cudaMemcpyAsync(ix->qraw.p, queries, nq * len * 4, cudaMemcpyHostToDevice, ix->stream));
+    ix->q_in = ix->qraw.as<float>();
     if (tick(ix, -1)) return RABITQ_ECUDA;
     rc = run_sub_batch(ix, nq, len, probe, 1, false, stop, bo);
     if (rc) return rc;
@@ -1376,6 +1433,7 @@ int dist_front_rotate_impl(rabitq_index* ix, const float* d_queries, size_t len,
     CU(cudaMemsetAsync(d.inbox + d.off_r1cnt, 0, (size_t)d.world * nq_l * 4, st));  // before the all-gather = before any owner writes
     CU(ix->qraw.ensure(nq_l * len * 4));
     CU(cudaMemcpyAsync(ix->qraw.p, d_queries, nq_l * len * 4, cudaMemcpyDeviceToDevice, st));
+    ix->q_in = ix->qraw.as<float>();
     int rc = run_front(ix, nq_l, len, d.P, true, true);
     if (rc) return rc;
     uint32_t* send = static_cast<uint32_t*>(d_send_qy);
@@ -1444,6 +1502,7 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a
     CU(ix->r2_off.ensure(nq * 4));
     CU(ix->home_tot.ensure(32 * 4));
     CU(ix->cand.ensure((size_t)d.world * d.cap2 * sizeof(Cand)));
+    ix->q_pad = ix->qpad.as<float>();  // all ranks' queries, padded by the unpack below
     if (tick(ix, -1)) return RABITQ_ECUDA;  // the all-gather sits between the phases: not ours to time
     dist_unpack_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(static_cast<const uint32_t*>(d_gathered_a), stride_a,
                                                           static_cast<const uint32_t*>(d_gathered_b), stride_b, d.world, (int)d.nq_l, (int)d.len, (int)D, P,
@@ -1731,6 +1790,11 @@ int rabitq_query(rabitq_index* idx, const float* query, size_t len, size_t probe
 int rabitq_query_batch(rabitq_index* idx, const float* queries, size_t nq, size_t len, size_t probe, size_t topk,
                        int heuristic_rank, float* out_dist, uint32_t* out_ids, uint32_t* out_count) {
     return query_batch_impl(idx, queries, false, nq, len, probe, topk, heuristic_rank, out_dist, out_ids, out_count);
+}
+
+int rabitq_query_batch_pipelined(rabitq_index* idx, const float* queries, const float* next_queries, size_t nq, size_t len, size_t probe,
+                                 size_t topk, int heuristic_rank, float* out_dist, uint32_t* out_ids, uint32_t* out_count) {
+    return query_batch_impl(idx, queries, false, nq, len, probe, topk, heuristic_rank, out_dist, out_ids, out_count, next_queries);
 }
 
 int rabitq_query_batch_device(rabitq_index* idx, const float* d_queries, size_t nq, size_t len, size_t probe, size_t topk,
