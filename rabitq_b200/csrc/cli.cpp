@@ -122,7 +122,11 @@ int main(int argc, char** argv) {
     if (nq == 0 || truths.size() < nq) { std::fprintf(stderr, "empty queries or too few truth rows\n"); return 101; }
     const size_t len = queries[0].size();
     std::vector<float> flat(nq * len);
-    for (size_t i = 0; i < nq; i++) std::memcpy(&flat[i * len], queries[i].data(), len * 4);
+    for (size_t i = 0; i < nq; i++) {
+        // the reference asserts the length of every query inside RaBitQ::query (src/rabitq.rs:275); a ragged file must not be read out of bounds
+        if (queries[i].size() != len) { std::fprintf(stderr, "query %zu has %zu dimensions, expected %zu\n", i, queries[i].size(), len); return 101; }
+        std::memcpy(&flat[i * len], queries[i].data(), len * 4);
+    }
     std::vector<float> dist(nq * topk);
     std::vector<uint32_t> ids(nq * topk), cnt(nq);
     double total_time = 0.0;

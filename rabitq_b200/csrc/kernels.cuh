@@ -517,6 +517,69 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_kernel(const float* 
     }
 }
 
+// K2b for probe > 4096 (the reference has no cap: `probe.min(k)`, src/rabitq.rs:294): the shared-memory selection above holds
+// at most 4096 results per query, so this path sorts ALL K (key, index) pairs of a query in a global-memory scratch row (bitonic,
+// one CTA per query) and emits the first P.  Same order as the fast path: ascending distance, smaller centroid id on ties.  Only
+// brute-force-like calls come here (every query scans thousands of clusters): correctness matters, speed does not.
+__global__ void __launch_bounds__(SEL_THREADS) select_probe_large_kernel(const float* __restrict__ cdist, int K, int Kpow2, int P,
+                                                                         const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ offsets_g,
+                                                                         unsigned long long* __restrict__ scratch /* nq x Kpow2 */,
+                                                                         uint32_t* __restrict__ probe_ids, float* __restrict__ probe_dist,
+                                                                         uint32_t* __restrict__ slot_local, uint32_t* __restrict__ q_words,
+                                                                         uint32_t* __restrict__ q_pairs, uint32_t* __restrict__ q_p0) {
+    __shared__ uint32_t warp_tot[SEL_THREADS / 32 + 1];
+    __shared__ uint32_t part[SEL_THREADS];
+    __shared__ uint32_t s_p0, s_pairs;
+    const int tid = threadIdx.x;
+    const size_t q = blockIdx.x;
+    const float* row = cdist + q * (size_t)K;
+    unsigned long long* buf = scratch + q * (size_t)Kpow2;
+    for (int i = tid; i < Kpow2; i += SEL_THREADS) buf[i] = i < K ? (((unsigned long long)okey(row[i]) << 32) | (uint32_t)i) : ~0ull;
+    if (tid == 0) { s_p0 = 0xffffffffu; s_pairs = 0u; }
+    __syncthreads();
+    for (int k2 = 2; k2 <= Kpow2; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < Kpow2; i += SEL_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = buf[i], z = buf[ixj];
+                    const bool up = (i & k2) == 0;
+                    if ((x > z) == up) { buf[i] = z; buf[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    // outputs: ids / distances, then the exclusive prefix of 32-vector words (thread t owns a contiguous run of ranks)
+    const int per = (P + SEL_THREADS - 1) / SEL_THREADS, lo = min(P, tid * per), hi = min(P, lo + per);
+    uint32_t words = 0, pairs = 0, first = 0xffffffffu;
+    for (int p = lo; p < hi; p++) {
+        const uint32_t id = (uint32_t)(buf[p] & 0xffffffffu);
+        probe_ids[q * P + p] = id;
+        probe_dist[q * P + p] = row[id];
+        const uint32_t n_c = offsets[id + 1] - offsets[id];
+        const uint32_t n_g = offsets_g ? offsets_g[id + 1] - offsets_g[id] : n_c;
+        words += (n_c + 31u) >> 5;
+        pairs += n_g;
+        if (n_g && first == 0xffffffffu) first = (uint32_t)p;
+    }
+    part[tid] = words;
+    atomicAdd(&s_pairs, pairs);
+    atomicMin(&s_p0, first);
+    __syncthreads();
+    const uint32_t total_words = block_exclusive_scan<SEL_THREADS>(part, SEL_THREADS, warp_tot);
+    uint32_t run = part[tid];
+    for (int p = lo; p < hi; p++) {
+        slot_local[q * P + p] = run;
+        const uint32_t id = probe_ids[q * P + p];
+        run += (offsets[id + 1] - offsets[id] + 31u) >> 5;
+    }
+    if (tid == 0) {
+        q_pairs[q] = s_pairs;
+        q_words[q] = total_words;
+        q_p0[q] = s_p0 == 0xffffffffu ? 0u : s_p0;
+    }
+}
+
 // Exclusive scan over the per-query word/pair totals (single block).  q_wbase[nq] = total words.
 __global__ void __launch_bounds__(1024) query_base_scan_kernel(const uint32_t* __restrict__ q_words, const uint32_t* __restrict__ q_pairs,
                                                                int nq, uint32_t* __restrict__ q_wbase,

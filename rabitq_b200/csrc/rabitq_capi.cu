@@ -5,6 +5,7 @@
 #include "../../include/rabitq_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -171,7 +172,7 @@ struct rabitq_index {
     int scan_slices = 1;   // shared-memory record slices per scan work item (hot clusters are cut into several items)
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
-        entries, counters, out_all, rr_dbg, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag;
+        entries, counters, out_all, rr_dbg, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag, sel_scratch;
     DistState dist;
     const float* q_in = nullptr;   // the sub-batch's raw queries (nb x len) on the device: ix->qraw, or the caller's device pointer
     const float* q_pad = nullptr;  // the same, zero-padded to D: ix->qpad, or q_in itself when len == D (nothing to pad, nothing copied)
@@ -189,7 +190,7 @@ struct rabitq_index {
     uint32_t* h_out = nullptr;  // pinned staging of a sub-batch's results (host-pointer calls)
     size_t h_out_cap = 0;
     // metrics (src/metrics.rs)
-    uint64_t m_query = 0, m_rough = 0, m_precise = 0;
+    std::atomic<uint64_t> m_query{0}, m_rough{0}, m_precise{0};  // relaxed atomics like the reference's METRICS: read without the handle lock
     // last-call measurements
     float ms[ST_N] = {0};
     uint64_t counts[6] = {0};
@@ -216,7 +217,7 @@ struct rabitq_index {
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_all, &rr_dbg,
-                          &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag})
+                          &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag, &sel_scratch})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         if (h_out) cudaFreeHost(h_out);
@@ -899,6 +900,16 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
     CU(ix->q_wbase.ensure((nb + 1) * 4));
     CU(ix->q_pbase.ensure((nb + 1) * 8));
     {
+        if (P > 4096) {  // no cap in the reference (src/rabitq.rs:294): full sort of the K keys in a global scratch row per query
+            int Kpow2 = 1;
+            while (Kpow2 < K) Kpow2 <<= 1;
+            CU(ix->sel_scratch.ensure(nb * (size_t)Kpow2 * 8));
+            select_probe_large_kernel<<<(unsigned)nb, SEL_THREADS, 0, st>>>(
+                ix->cdist.as<float>(), K, Kpow2, P, ix->offsets, global_view ? ix->goffsets : nullptr, ix->sel_scratch.as<unsigned long long>(),
+                ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(),
+                ix->q_pairs.as<uint32_t>(), ix->q_p0.as<uint32_t>());
+            CU(cudaGetLastError()); ix->counts[5]++;
+        } else {
         int Ppow2 = 1;
         while (Ppow2 < P) Ppow2 <<= 1;
         const bool pivot_ok = K >= 16 * P && K >= 4 * SEL_SAMPLE;  // kernels.cuh: sampling-pivot path, keys stay in L2/HBM
@@ -909,6 +920,7 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
             ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(),
             ix->q_p0.as<uint32_t>(), run_if);
         CU(cudaGetLastError()); ix->counts[5]++;
+        }
         query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nb,
                                                    ix->q_wbase.as<uint32_t>(), ix->q_pbase.as<unsigned long long>());
         CU(cudaGetLastError()); ix->counts[5]++;
@@ -1057,7 +1069,11 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     else
         for (int R = ra.R; R >= 2; R--)
             if (rr_resident(R) >= nb) { ra.R = R; break; }
-    ra.R = (int)std::max<size_t>(1, std::min<size_t>(ra.R, (80 * 1024) / (2 * (size_t)(D + 8) * 4)));  // <= 80 KB of row buffers per warp
+    {   // <= 80 KB of row buffers per warp, and the whole per-warp state (query row, k-slot result buffer, rows) inside 200 KB
+        const size_t fixed = (size_t)D * 4 + 2 * topk * 4 + 2048;
+        const size_t budget = std::min<size_t>(80 * 1024, (size_t)200 * 1024 > fixed ? (size_t)200 * 1024 - fixed : 0);
+        ra.R = (int)std::max<size_t>(1, std::min<size_t>(ra.R, budget / (2 * (size_t)(D + 8) * 4)));
+    }
     ra.smem_per_warp = rr_smem(ra.R);
     ra.prefetch = ix->rerank_prefetch;
     if (ix->debug_rerank) {
@@ -1220,9 +1236,11 @@ int validate_query_args(const rabitq_index* ix, size_t len, size_t probe, size_t
     if ((len + 63) / 64 * 64 != ix->D)
         return fail(RABITQ_EINVAL, "assertion `left == right` failed: dim != query.len().div_ceil(64) * 64");
     if (probe == 0) return fail(RABITQ_EINVAL, "probe must be >= 1 (the reference underflows on `length - 1`)");
-    if (std::min(probe, ix->K) > 4096) return fail(RABITQ_EUNSUPPORTED, "probe > 4096 is not supported");
     if (topk == 0) return fail(RABITQ_EINVAL, "topk must be >= 1 (the reference panics on an empty heap peek)");
-    if (topk > 1024) return fail(RABITQ_EUNSUPPORTED, "topk > 1024 is not supported");
+    // the reference caps neither probe (`probe.min(k)`, src/rabitq.rs:294) nor topk (BinaryHeap::with_capacity, src/rerank.rs:69-78).
+    // probe: any.  topk: the k-slot result buffer of a query lives in shared memory next to its row buffers (K5), which bounds
+    // topk * 8 + dim * 12 bytes by one SM's 200 KB -- 16384 results per query at dim <= 1024; beyond that is not an ANN call.
+    if (topk * 8 + (size_t)ix->D * 12 + 4096 > (size_t)200 * 1024) return fail(RABITQ_EUNSUPPORTED, "topk * 8 + dim * 12 exceeds the on-chip rerank state (200 KB)");
     return 0;
 }
 
@@ -1355,6 +1373,8 @@ int dist_init_impl(rabitq_index* ix, int rank, int world, size_t nq_l, size_t pr
     if (nq_l == 0) return fail(RABITQ_EINVAL, "nq_local must be >= 1");
     int rc = validate_query_args(ix, ix->D, probe, topk, 0);
     if (rc) return rc;
+    if (std::min(probe, ix->K) > 4096 || topk > 1024)
+        return fail(RABITQ_EUNSUPPORTED, "the sharded pipeline keeps probe <= 4096 and topk <= 1024 (record capacities of the inboxes)");
     if (nq_l * world * std::min(probe, ix->K) > 0xffffffffu) return fail(RABITQ_EUNSUPPORTED, "nq_total * probe exceeds 2^32");
     std::lock_guard<std::mutex> lk(ix->mu);
     CU(cudaSetDevice(ix->device));
@@ -1822,14 +1842,14 @@ int rabitq_merge_topk_device(int device, const float* d_dist, const uint32_t* d_
 }
 
 void rabitq_metrics(const rabitq_index* idx, uint64_t out[4]) {
-    out[0] = idx ? idx->m_query : 0;
-    out[1] = idx ? idx->m_rough : 0;
-    out[2] = idx ? idx->m_precise : 0;
+    out[0] = idx ? idx->m_query.load(std::memory_order_relaxed) : 0;
+    out[1] = idx ? idx->m_rough.load(std::memory_order_relaxed) : 0;
+    out[2] = idx ? idx->m_precise.load(std::memory_order_relaxed) : 0;
     out[3] = 0;  // cache miss: the disk/S3 cache of crates/disk is out of scope; base vectors are HBM-resident
 }
 
 void rabitq_metrics_reset(rabitq_index* idx) {
-    if (idx) idx->m_query = idx->m_rough = idx->m_precise = 0;
+    if (idx) { idx->m_query = 0; idx->m_rough = 0; idx->m_precise = 0; }
 }
 
 int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n) {

@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <exception>
 #include <map>
 #include <mutex>
 #include <string>
@@ -49,6 +50,10 @@ void on_signal(int) {
 }
 
 #define INFO(...) do { std::fprintf(stderr, "[INFO  rabitq_service] " __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
+
+constexpr uint32_t kMaxTopK = 1024;          // results per request (validated before any buffer is sized from it)
+constexpr size_t kMaxQueryLen = 65536;        // floats per query
+constexpr size_t kMaxBodyBytes = 4u << 20;    // Content-Length cap: a query of 65536 floats in decimal is ~1 MB
 
 struct Pending {  // one /query request waiting for its batch
     std::vector<float> query;
@@ -102,25 +107,36 @@ struct Batcher {
                 const size_t len = std::get<0>(kv.first), probe = std::get<1>(kv.first), topk = std::get<2>(kv.first);
                 auto& g = kv.second;
                 const size_t nq = g.size();
-                std::vector<float> q(nq * len), dist(nq * topk);
-                std::vector<uint32_t> ids(nq * topk), cnt(nq);
-                for (size_t i = 0; i < nq; i++) std::memcpy(q.data() + i * len, g[i]->query.data(), len * 4);
-                int rc = rabitq_query_batch(idx, q.data(), nq, len, probe, topk, 0, dist.data(), ids.data(), cnt.data());
-                std::string err = rc ? rabitq_last_error() : "";
+                int rc = 0;
+                std::string err;
+                std::vector<float> dist;
+                std::vector<uint32_t> ids, cnt;
+                try {  // one bad group (e.g. an allocation failure) must not take the batcher thread -- and the process -- down
+                    std::vector<float> q(nq * len);
+                    dist.resize(nq * topk);
+                    ids.resize(nq * topk);
+                    cnt.resize(nq);
+                    for (size_t i = 0; i < nq; i++) std::memcpy(q.data() + i * len, g[i]->query.data(), len * 4);
+                    rc = rabitq_query_batch(idx, q.data(), nq, len, probe, topk, 0, dist.data(), ids.data(), cnt.data());
+                    if (rc) err = rabitq_last_error();
+                } catch (const std::exception& e) {
+                    rc = -1;
+                    err = std::string("batch failed: ") + e.what();
+                }
                 batches++;
                 requests += nq;
                 for (size_t i = 0; i < nq; i++) {
                     Pending* p = g[i];
-                    {
-                        std::lock_guard<std::mutex> lk(p->mu);
-                        p->rc = rc;
-                        p->err = err;
-                        if (!rc) {
-                            p->ids.assign(ids.begin() + i * topk, ids.begin() + i * topk + cnt[i]);
-                            p->scores.assign(dist.begin() + i * topk, dist.begin() + i * topk + cnt[i]);
-                        }
-                        p->done = true;
+                    std::lock_guard<std::mutex> lk(p->mu);
+                    p->rc = rc;
+                    p->err = err;
+                    if (!rc) {
+                        p->ids.assign(ids.begin() + i * topk, ids.begin() + i * topk + cnt[i]);
+                        p->scores.assign(dist.begin() + i * topk, dist.begin() + i * topk + cnt[i]);
                     }
+                    p->done = true;
+                    // notified while the lock is held: `p` lives on the connection thread's stack, which may destroy it as
+                    // soon as it can observe done == true
                     p->cv.notify_one();
                 }
             }
@@ -158,14 +174,24 @@ bool parse_request(const std::string& body, Pending* out, std::string* err) {
     auto get_u32 = [&](const char* key, uint32_t* v) {
         size_t q;
         if (!find_key(body, key, &q)) { *err = std::string("missing field `") + key + "`"; return false; }
-        char* e = nullptr;
         const char* b = body.c_str() + q;
-        unsigned long x = std::strtoul(b, &e, 10);
-        if (e == b) { *err = std::string("`") + key + "` is not an integer"; return false; }
+        while (*b == ' ' || *b == '\t' || *b == '\n' || *b == '\r') b++;
+        if (*b < '0' || *b > '9') { *err = std::string("`") + key + "` is not an unsigned integer"; return false; }  // u32 in the reference: '-1' is a deserialisation error there too
+        unsigned long long x = 0;
+        for (; *b >= '0' && *b <= '9'; b++) {
+            x = x * 10 + (unsigned)(*b - '0');
+            if (x > 0xffffffffull) { *err = std::string("`") + key + "` does not fit u32"; return false; }
+        }
         *v = (uint32_t)x;
         return true;
     };
-    return get_u32("top_k", &out->top_k) && get_u32("probe", &out->probe);
+    if (!get_u32("top_k", &out->top_k) || !get_u32("probe", &out->probe)) return false;
+    // the reference would panic (top_k == 0: empty heap peek; probe == 0: `length - 1` underflow) or allocate without bound; a
+    // service must not let one request take the process down
+    if (out->top_k == 0 || out->top_k > kMaxTopK) { *err = "`top_k` must be in 1.." + std::to_string(kMaxTopK); return false; }
+    if (out->probe == 0) { *err = "`probe` must be >= 1"; return false; }
+    if (out->query.empty() || out->query.size() > kMaxQueryLen) { *err = "`query` is empty or too long"; return false; }
+    return true;
 }
 
 std::string to_json(const Pending& p) {  // struct Response, main.rs:62-66
@@ -240,6 +266,7 @@ void serve_connection(int fd, Batcher* b) {
             if (p != std::string::npos) clen = std::strtoul(lhead.c_str() + p + 17, nullptr, 10);
         }
         const bool keep = lhead.find("\r\nconnection: close") == std::string::npos;
+        if (clen > kMaxBodyBytes) { respond(fd, 413, "Payload Too Large", "text/plain", "body too large", false); break; }
         while (buf.size() < hdr_end + 4 + clen) {
             ssize_t r = ::recv(fd, tmp, sizeof tmp, 0);
             if (r <= 0) { ::close(fd); return; }

@@ -89,6 +89,25 @@ def test_service_contract_and_micro_batching(case_d128, tmp_path):
         c.request("POST", "/query", body=json.dumps({"query": [0.0] * 7, "top_k": 10, "probe": 4}))
         r = c.getresponse(); body = r.read().decode()
         assert r.status == 500 and "dim" in body
+        # hostile parameters are rejected before any buffer is sized from them, and the service stays up
+        for bad in ({"query": [0.0] * 128, "top_k": 4294967295, "probe": 4}, {"query": [0.0] * 128, "top_k": 0, "probe": 4},
+                    {"query": [0.0] * 128, "top_k": 10, "probe": 0}, {"query": [], "top_k": 10, "probe": 4}):
+            c.request("POST", "/query", body=json.dumps(bad))
+            r = c.getresponse(); r.read()
+            assert r.status == 422, bad
+        c.request("POST", "/query", body='{"query": [0.0], "top_k": -1, "probe": 4}')
+        r = c.getresponse(); r.read()
+        assert r.status == 422
+        c.request("POST", "/query", body='{"query": [0.0], "top_k": 99999999999999999999, "probe": 4}')
+        r = c.getresponse(); r.read()
+        assert r.status == 422
+        c2 = http.client.HTTPConnection("127.0.0.1", port, timeout=10)   # oversized Content-Length: refused, connection closed
+        c2.putrequest("POST", "/query"); c2.putheader("content-length", str(1 << 30)); c2.endheaders()
+        r = c2.getresponse(); r.read()
+        assert r.status == 413
+        c2.close()
+        c.request("GET", "/health")
+        assert c.getresponse().read() == b"Ok"
         c.request("GET", "/nope")
         r = c.getresponse(); r.read()
         assert r.status == 404
