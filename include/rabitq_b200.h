@@ -150,6 +150,9 @@ int rabitq_dist_ipc_handle(rabitq_index* idx, unsigned char out_handle[64]);
 int rabitq_dist_inbox_ptr(rabitq_index* idx, void** out);
 /* Register the inbox of rank `peer_rank`: an IPC handle from that rank's process (opened here), or a raw pointer. */
 int rabitq_dist_set_peer(rabitq_index* idx, int peer_rank, const unsigned char* ipc_handle, void* raw_ptr);
+/* Unmaps every peer inbox this rank has open.  Before an inbox is re-created (rabitq_dist_init with other sizes) EVERY rank calls
+ * this, then a barrier, then rabitq_dist_init: an exported allocation must not be freed while a peer still maps it. */
+int rabitq_dist_close_peers(rabitq_index* idx);
 /* 4-byte words one rank contributes to the all-gather: nq_local x (len + dim + 2*probe + 1). */
 size_t rabitq_dist_chunk_words(const rabitq_index* idx, size_t len);
 int rabitq_dist_front(rabitq_index* idx, const float* d_queries, size_t len, void* d_send);
@@ -160,6 +163,10 @@ int rabitq_dist_round1(rabitq_index* idx, const void* d_gathered, float* d_thr /
  * (rabitq_dist_chunk_words_meta words), second all-gather, then `round1_split` takes the two gathered buffers. */
 size_t rabitq_dist_chunk_words_qy(const rabitq_index* idx, size_t len);
 size_t rabitq_dist_chunk_words_meta(const rabitq_index* idx, size_t len);
+/* d_send_qy == NULL (and d_gathered_qy == NULL in round1_split): PUSH mode -- instead of handing the [q | y] chunk to a
+ * collective, front_rotate copies it into slot `rank` of every peer's inbox with copy-engine transfers over NVLink on a side
+ * stream (no SM, no collective); front_select orders the main stream behind those copies, so the meta all-gather that follows
+ * tells every peer that its slot is complete. */
 int rabitq_dist_front_rotate(rabitq_index* idx, const float* d_queries, size_t len, void* d_send_qy);
 int rabitq_dist_front_select(rabitq_index* idx, void* d_send_meta);
 int rabitq_dist_round1_split(rabitq_index* idx, const void* d_gathered_qy, const void* d_gathered_meta, float* d_thr);

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "rabitq_num_vectors", "rabitq_num_clusters", "rabitq_query", "rabitq_query_batch", "rabitq_query_batch_pipelined", "rabitq_query_batch_device",
     "rabitq_shard_range", "rabitq_merge_topk_device", "rabitq_metrics", "rabitq_metrics_reset", "rabitq_last_error", "rabitq_set_rounds",
     "rabitq_set_option", "rabitq_set_stream", "rabitq_last_timings", "rabitq_stage_rotate", "rabitq_stage_probe", "rabitq_stage_quantize", "rabitq_stage_scan",
-    "rabitq_dist_init", "rabitq_dist_ipc_handle", "rabitq_dist_inbox_ptr", "rabitq_dist_set_peer", "rabitq_dist_chunk_words", "rabitq_dist_front",
+    "rabitq_dist_init", "rabitq_dist_ipc_handle", "rabitq_dist_inbox_ptr", "rabitq_dist_set_peer", "rabitq_dist_close_peers", "rabitq_dist_chunk_words", "rabitq_dist_front",
     "rabitq_dist_round1", "rabitq_dist_round2", "rabitq_dist_finish", "rabitq_min_f32_device", "rabitq_set_quantize_bias", "rabitq_reshard", "rabitq_debug_rerank_stats", "rabitq_dist_last_status", "rabitq_dist_chunk_words_qy", "rabitq_dist_chunk_words_meta",
     "rabitq_dist_front_rotate", "rabitq_dist_front_select", "rabitq_dist_round1_split",
 ]
@@ -81,6 +81,7 @@ def lib():
     L.rabitq_dist_ipc_handle.argtypes = [vp, C.c_char_p]
     L.rabitq_dist_inbox_ptr.argtypes = [vp, C.POINTER(vp)]
     L.rabitq_dist_set_peer.argtypes = [vp, C.c_int, C.c_char_p, vp]
+    L.rabitq_dist_close_peers.argtypes = [vp]
     L.rabitq_dist_chunk_words.argtypes = [vp, C.c_size_t]
     L.rabitq_dist_chunk_words.restype = C.c_size_t
     for f in (L.rabitq_dist_chunk_words_qy, L.rabitq_dist_chunk_words_meta):

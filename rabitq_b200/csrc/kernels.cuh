@@ -869,15 +869,18 @@ __global__ void __launch_bounds__(128) quantize_small_kernel(const float* __rest
 // Rounds are expressed in EFFECTIVE ranks pe = p - p0[q] (p0 = first probe rank with vectors on this shard), so that the
 // first round always sees the first candidates a query really visits here, also on a shard that does not own its
 // nearest cluster.
-__global__ void bucket_count_kernel(const uint32_t* __restrict__ probe_ids, const uint32_t* __restrict__ q_p0, size_t nq, int P,
-                                    int p_lo, int p_hi, uint32_t* __restrict__ cl_count) {
+// (`offsets` non-NULL on a shard: clusters held by another shard get no items, so K3 and K4 never see them.)
+__global__ void bucket_count_kernel(const uint32_t* __restrict__ probe_ids, const uint32_t* __restrict__ q_p0, const uint32_t* __restrict__ offsets,
+                                    size_t nq, int P, int p_lo, int p_hi, uint32_t* __restrict__ cl_count) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     int R = p_hi - p_lo;
     if (i >= nq * (size_t)R) return;
     size_t q = i / R;
     int p = p_lo + (int)(i % R) + (int)q_p0[q];
     if (p >= P) return;
-    atomicAdd(&cl_count[probe_ids[q * P + p]], 1u);
+    const uint32_t c = probe_ids[q * P + p];
+    if (offsets && offsets[c + 1] == offsets[c]) return;
+    atomicAdd(&cl_count[c], 1u);
 }
 
 // Work items of one cluster in one round: (chunks of VT vectors in the window) x (slices of at most MS of the m records
@@ -952,8 +955,8 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __res
     }
 }
 
-__global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, const uint32_t* __restrict__ q_p0, size_t nq, int P,
-                                   int p_lo, int p_hi, const uint32_t* __restrict__ cl_start, uint32_t* __restrict__ cl_cursor,
+__global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, const uint32_t* __restrict__ q_p0, const uint32_t* __restrict__ offsets,
+                                   size_t nq, int P, int p_lo, int p_hi, const uint32_t* __restrict__ cl_start, uint32_t* __restrict__ cl_cursor,
                                    uint2* __restrict__ cl_items /* (q*P+p, cluster) */) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     int R = p_hi - p_lo;
@@ -962,6 +965,7 @@ __global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, const
     int p = p_lo + (int)(i % R) + (int)q_p0[q];
     if (p >= P) return;
     uint32_t c = probe_ids[q * P + p];
+    if (offsets && offsets[c + 1] == offsets[c]) return;
     uint32_t pos = atomicAdd(&cl_cursor[c], 1u);
     cl_items[cl_start[c] + pos] = make_uint2((uint32_t)(q * P + p), c);
 }

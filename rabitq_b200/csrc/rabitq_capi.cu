@@ -102,6 +102,9 @@ struct DistState {
     uint32_t r1cap = 0, cap2 = 0;
     unsigned char* inbox = nullptr;
     size_t inbox_bytes = 0, off_r1cnt = 0, off_r1rec = 0, off_r2tab = 0, off_r2rec = 0;
+    size_t off_qy = 0, qy_stride_words = 0;  // region every rank's [q | y] chunk is PUSHED into by its owner (copy engine, no collective)
+    cudaEvent_t ev_rot = nullptr, ev_push = nullptr;
+    bool push_pending = false;
     std::vector<unsigned char*> peers_h;
     std::vector<char> opened;  // peers_h[r] came from cudaIpcOpenMemHandle
     unsigned char** peers_d = nullptr;
@@ -214,6 +217,8 @@ struct rabitq_index {
         for (size_t r = 0; r < dist.peers_h.size(); r++)
             if (dist.opened[r] && dist.peers_h[r]) cudaIpcCloseMemHandle(dist.peers_h[r]);
         if (dist.inbox) cudaFree(dist.inbox);
+        if (dist.ev_rot) cudaEventDestroy(dist.ev_rot);
+        if (dist.ev_push) cudaEventDestroy(dist.ev_push);
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_all, &rr_dbg,
@@ -297,15 +302,25 @@ int resolve_timings(rabitq_index* ix) {
     return 0;
 }
 
-// ---- shard geometry: contiguous cluster-id ranges balanced by vector count --------------------------------------
+// ---- shard geometry: contiguous cluster-id ranges balanced by EXPECTED SCAN WORK -------------------------------------------
+// The pairs a shard scans are sum_c n_c * (queries probing c).  Queries follow the data, so a big cluster is probed more often,
+// but with P probes per query most of a cluster's visitors come from its NEIGHBOURS, which averages the effect out: measured on
+// C2 at two shards, ranges balanced by n_c alone were 5.6 % off one way, ranges balanced by n_c * (n_c + mean) / 2 were 12 % off
+// the other way.  The weight n_c * (0.2 n_c + 0.8 mean) sits between; memory stays within a small factor of even.
 void shard_rows(const uint32_t* offsets, size_t K, int rank, int count, size_t* row_lo, size_t* row_hi) {
-    size_t N = offsets[K];
+    const size_t N = offsets[K];
+    const double mean = K ? (double)N / (double)K : 0.0;
+    std::vector<double> cum(K + 1, 0.0);
+    for (size_t c = 0; c < K; c++) {
+        const double n = (double)(offsets[c + 1] - offsets[c]);
+        cum[c + 1] = cum[c] + n * (0.2 * n + 0.8 * mean);
+    }
     auto bound = [&](int r) -> size_t {
         if (r <= 0) return 0;
         if (r >= count) return N;
-        size_t target = N * size_t(r) / size_t(count);
-        const uint32_t* it = std::lower_bound(offsets, offsets + K + 1, (uint32_t)target);
-        return *it;
+        const double target = cum[K] * (double)r / (double)count;
+        const size_t c = (size_t)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+        return offsets[std::min(c, K)];
     };
     *row_lo = bound(rank);
     *row_hi = bound(rank + 1);
@@ -1099,6 +1114,7 @@ int build_lists(rabitq_index* ix, size_t nb, int P, uint32_t MS, Pos lo, Pos hi,
     const uint32_t ch_min = single_rank ? (uint32_t)lo.ch : 0u;
     const uint32_t ch_max = (single_rank && hi.ch > 0) ? (uint32_t)hi.ch : 0xffffffffu;
     const size_t items = nb * (size_t)(p_hi_incl - p_lo);
+    const uint32_t* foreign = ix->shard_count > 1 ? ix->offsets : nullptr;  // on a shard, clusters that live elsewhere get no items
     L.cap_items = items;
     L.MS = MS;
     L.ch_min = ch_min;
@@ -1111,7 +1127,7 @@ int build_lists(rabitq_index* ix, size_t nb, int P, uint32_t MS, Pos lo, Pos hi,
     if (!L.ready) CU(cudaEventCreateWithFlags(&L.ready, cudaEventDisableTiming));
     CU(cudaMemsetAsync(L.cl_count.p, 0, (size_t)K * 4, st));
     if (items) {
-        bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
+        bucket_count_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), foreign, nb, P, p_lo, p_hi_incl,
                                                                               L.cl_count.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
     }
@@ -1120,7 +1136,7 @@ int build_lists(rabitq_index* ix, size_t nb, int P, uint32_t MS, Pos lo, Pos hi,
                                            L.work_ctl.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
     if (items) {
-        bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), nb, P, p_lo, p_hi_incl,
+        bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), foreign, nb, P, p_lo, p_hi_incl,
                                                                              L.cl_start.as<uint32_t>(), L.cl_cursor.as<uint32_t>(),
                                                                              L.cl_items.as<uint2>());
         CU(cudaGetLastError()); ix->counts[5]++;
@@ -1379,11 +1395,20 @@ int dist_init_impl(rabitq_index* ix, int rank, int world, size_t nq_l, size_t pr
     std::lock_guard<std::mutex> lk(ix->mu);
     CU(cudaSetDevice(ix->device));
     DistState& d = ix->dist;
+    // Peers' inboxes must be unmapped by every rank BEFORE their owners free them (CUDA IPC: freeing exported memory that a peer
+    // still has open is undefined).  The caller closes them first on every rank (rabitq_dist_close_peers), runs a barrier, and only
+    // then re-initialises; whatever is still open here is closed as a last resort.
     for (size_t r = 0; r < d.peers_h.size(); r++)
         if (d.opened[r] && d.peers_h[r]) cudaIpcCloseMemHandle(d.peers_h[r]);
+    CU(cudaStreamSynchronize(ix->stream));
+    if (ix->copy_stream) CU(cudaStreamSynchronize(ix->copy_stream));
     if (d.inbox) cudaFree(d.inbox);
     if (d.peers_d) cudaFree(d.peers_d);
+    if (d.ev_rot) cudaEventDestroy(d.ev_rot);
+    if (d.ev_push) cudaEventDestroy(d.ev_push);
     d = DistState();
+    CU(cudaEventCreateWithFlags(&d.ev_rot, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&d.ev_push, cudaEventDisableTiming));
     d.world = world; d.rank = rank; d.nq_l = nq_l; d.topk = topk;
     d.P = (int)std::min(probe, ix->K);
     d.r1cap = (uint32_t)(SCAN_THREADS * std::max(1, ix->first_chunks));
@@ -1395,7 +1420,9 @@ int dist_init_impl(rabitq_index* ix, int rank, int world, size_t nq_l, size_t pr
     d.off_r1rec = up(d.off_r1cnt + (size_t)world * nq_l * 4);
     d.off_r2tab = up(d.off_r1rec + (size_t)world * nq_l * d.r1cap * sizeof(SurvRec));
     d.off_r2rec = up(d.off_r2tab + (size_t)world * nq_l * 8);
-    d.inbox_bytes = up(d.off_r2rec + (size_t)world * d.cap2 * sizeof(SurvRec));
+    d.off_qy = up(d.off_r2rec + (size_t)world * d.cap2 * sizeof(SurvRec));
+    d.qy_stride_words = dist_chunk_layout(nq_l, ix->D, ix->D, (size_t)d.P).words_a;  // sized for len == dim, the longest a query can be
+    d.inbox_bytes = up(d.off_qy + (size_t)world * d.qy_stride_words * 4);
     CU(cudaMalloc((void**)&d.inbox, d.inbox_bytes));
     CU(cudaMemset(d.inbox, 0, d.off_r1rec));
     CU(cudaMalloc((void**)&d.peers_d, sizeof(void*) * world));
@@ -1437,7 +1464,10 @@ int dist_set_peer_impl(rabitq_index* ix, int r, const unsigned char* ipc_handle,
 //   1b  K2p / K2 / K2b        -> d_send_meta (words_b)
 int dist_front_rotate_impl(rabitq_index* ix, const float* d_queries, size_t len, void* d_send_qy) {
     if (!ix || !ix->dist.ready) return fail(RABITQ_EINVAL, "rabitq_dist_init first");
-    if (!d_queries || !d_send_qy) return fail(RABITQ_EINVAL, "null argument");
+    if (!d_queries) return fail(RABITQ_EINVAL, "null argument");
+    if (!d_send_qy)  // push mode: the chunk goes straight into every peer's inbox
+        for (int r = 0; r < ix->dist.world; r++)
+            if (!ix->dist.peers_h[r]) return fail(RABITQ_EINVAL, "peer inbox of rank " + std::to_string(r) + " not set (rabitq_dist_set_peer)");
     DistState& d = ix->dist;
     if ((len + 63) / 64 * 64 != ix->D) return fail(RABITQ_EINVAL, "assertion `left == right` failed: dim != query.len().div_ceil(64) * 64");
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -1456,10 +1486,28 @@ int dist_front_rotate_impl(rabitq_index* ix, const float* d_queries, size_t len,
     ix->q_in = ix->qraw.as<float>();
     int rc = run_front(ix, nq_l, len, d.P, true, true);
     if (rc) return rc;
-    uint32_t* send = static_cast<uint32_t*>(d_send_qy);
     const DistChunk L = dist_chunk_layout(nq_l, len, D, (size_t)d.P);
-    CU(cudaMemcpyAsync(send + L.a_q, ix->qraw.p, nq_l * len * 4, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(send + L.a_y, ix->y.p, nq_l * D * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_send_qy) {  // the caller all-gathers the chunk
+        uint32_t* send = static_cast<uint32_t*>(d_send_qy);
+        CU(cudaMemcpyAsync(send + L.a_q, ix->qraw.p, nq_l * len * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(send + L.a_y, ix->y.p, nq_l * D * 4, cudaMemcpyDeviceToDevice, st));
+        d.push_pending = false;
+    } else {
+        // PUSH: this rank's [q | y] into slot `rank` of every inbox (its own included) with copy-engine transfers over NVLink, on the
+        // copy stream: no collective and no SM is involved, so the centroid scan and the probe selection that follow on the main
+        // stream run undisturbed.  Peers may read their slot once they have seen this rank's part of the NEXT collective, which
+        // the main stream enters only after the pushes (front_select waits for ev_push).
+        CU(cudaEventRecord(d.ev_rot, st));
+        CU(cudaStreamWaitEvent(ix->copy_stream, d.ev_rot, 0));
+        for (int k = 0; k < d.world; k++) {
+            const int r = (d.rank + 1 + k) % d.world;  // stagger the targets: rank i starts with i+1, itself last
+            uint32_t* slot = reinterpret_cast<uint32_t*>(d.peers_h[r] + d.off_qy) + (size_t)d.rank * d.qy_stride_words;
+            CU(cudaMemcpyAsync(slot + L.a_q, ix->qraw.p, nq_l * len * 4, cudaMemcpyDeviceToDevice, ix->copy_stream));
+            CU(cudaMemcpyAsync(slot + L.a_y, ix->y.p, nq_l * D * 4, cudaMemcpyDeviceToDevice, ix->copy_stream));
+        }
+        CU(cudaEventRecord(d.ev_push, ix->copy_stream));
+        d.push_pending = true;
+    }
     if (tick(ix, ST_ROTATE)) return RABITQ_ECUDA;
     d.phase = 10;
     return RABITQ_OK;
@@ -1482,6 +1530,7 @@ int dist_front_select_impl(rabitq_index* ix, void* d_send_meta) {
     CU(cudaMemcpyAsync(send + L.b_ids, ix->probe_ids.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(send + L.b_dist, ix->probe_dist.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(send + L.b_p0, ix->q_p0.p, nq_l * 4, cudaMemcpyDeviceToDevice, st));
+    if (d.push_pending) CU(cudaStreamWaitEvent(st, d.ev_push, 0));  // the collective that follows carries the "my pushes are done" edge
     if (tick(ix, ST_SELECT)) return RABITQ_ECUDA;
     d.phase = 1;
     return RABITQ_OK;
@@ -1499,8 +1548,14 @@ int dist_front_impl(rabitq_index* ix, const float* d_queries, size_t len, void* 
 // cluster) on the shard that owns it; the round-1 threshold of every owned query lands in d_thr (others keep +FLT_MAX).
 int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a, const void* d_gathered_b, size_t stride_b, float* d_thr) {
     if (!ix || !ix->dist.ready || ix->dist.phase != 1) return fail(RABITQ_EINVAL, "rabitq_dist_front first");
-    if (!d_gathered_a || !d_gathered_b || !d_thr) return fail(RABITQ_EINVAL, "null argument");
+    if (!d_gathered_b || !d_thr) return fail(RABITQ_EINVAL, "null argument");
     DistState& d = ix->dist;
+    if (!d_gathered_a) {  // push mode: every rank's [q | y] already sits in this rank's inbox
+        if (!d.push_pending) return fail(RABITQ_EINVAL, "no gathered [q | y] buffer and nothing was pushed");
+        d_gathered_a = d.inbox + d.off_qy;
+        stride_a = d.qy_stride_words;
+        d.push_pending = false;
+    }
     for (int r = 0; r < d.world; r++)
         if (!d.peers_h[r]) return fail(RABITQ_EINVAL, "peer inbox of rank " + std::to_string(r) + " not set (rabitq_dist_set_peer)");
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -1665,6 +1720,21 @@ int rabitq_dist_inbox_ptr(rabitq_index* idx, void** out) {
     return RABITQ_OK;
 }
 
+int rabitq_dist_close_peers(rabitq_index* idx) {
+    if (!idx) return fail(RABITQ_EINVAL, "null index");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CU(cudaSetDevice(idx->device));
+    DistState& d = idx->dist;
+    CU(cudaStreamSynchronize(idx->stream));
+    if (idx->copy_stream) CU(cudaStreamSynchronize(idx->copy_stream));
+    for (size_t r = 0; r < d.peers_h.size(); r++) {
+        if (d.opened[r] && d.peers_h[r]) cudaIpcCloseMemHandle(d.peers_h[r]);
+        if ((int)r != d.rank) d.peers_h[r] = nullptr;
+        d.opened[r] = 0;
+    }
+    return RABITQ_OK;
+}
+
 int rabitq_dist_set_peer(rabitq_index* idx, int peer_rank, const unsigned char* ipc_handle, void* raw_ptr) {
     return dist_set_peer_impl(idx, peer_rank, ipc_handle, raw_ptr);
 }
@@ -1695,7 +1765,7 @@ int rabitq_dist_front_select(rabitq_index* idx, void* d_send_meta) { return dist
 int rabitq_dist_round1_split(rabitq_index* idx, const void* d_gathered_qy, const void* d_gathered_meta, float* d_thr) {
     if (!idx || !idx->dist.ready) return fail(RABITQ_EINVAL, "rabitq_dist_init first");
     const DistChunk L = dist_chunk_layout(idx->dist.nq_l, idx->dist.len, idx->D, (size_t)idx->dist.P);
-    return dist_round1_impl(idx, d_gathered_qy, L.words_a, d_gathered_meta, L.words_b, d_thr);
+    return dist_round1_impl(idx, d_gathered_qy /* NULL: pushed */, L.words_a, d_gathered_meta, L.words_b, d_thr);
 }
 int rabitq_dist_round2(rabitq_index* idx, uint32_t* d_status) { return dist_round2_impl(idx, d_status); }
 int rabitq_dist_finish(rabitq_index* idx, float* d_out_dist, uint32_t* d_out_ids, uint32_t* d_out_count, uint32_t* d_status) {
@@ -1993,7 +2063,7 @@ int rabitq_stage_quantize(rabitq_index* idx, const float* queries, size_t nq, si
         }
     }
     for (size_t i = 0; i < items; i++)
-        if (!seen[i]) return fail(RABITQ_ECUDA, "a (query, probe) record is in no round's list");
+        if (!seen[i] && idx->shard_count == 1) return fail(RABITQ_ECUDA, "a (query, probe) record is in no round's list");
     return RABITQ_OK;
 }
 

@@ -122,10 +122,11 @@ class ShardedRaBitQ:
 class _RankState:
     """Per-rank buffers of the distributed pipeline (torch CUDA tensors, so that the collectives can take them)."""
 
-    def __init__(self, shard: RaBitQ, rank: int, world: int, nq_local: int, length: int, probe: int, topk: int, records_per_query: int):
+    def __init__(self, shard: RaBitQ, rank: int, world: int, nq_local: int, length: int, probe: int, topk: int, records_per_query: int,
+                 push: bool = True):
         import torch
 
-        self.shard, self.rank, self.world = shard, rank, world
+        self.shard, self.rank, self.world, self.push = shard, rank, world, push
         self.nq_local, self.len, self.probe, self.topk, self.rpq = nq_local, length, probe, topk, records_per_query
         nbytes = C.c_size_t(0)
         _check(lib().rabitq_dist_init(shard._h, rank, world, nq_local, probe, topk, records_per_query, C.byref(nbytes)))
@@ -133,9 +134,10 @@ class _RankState:
         dev = torch.device("cuda", shard.device)
         wa = int(lib().rabitq_dist_chunk_words_qy(shard._h, length))     # [q | y]: the big part, gathered while K2 runs
         wb = int(lib().rabitq_dist_chunk_words_meta(shard._h, length))   # [probe ids | probe distances | first non-empty rank]
-        self.send_qy = torch.empty(wa, dtype=torch.int32, device=dev)
+        # push mode: the [q | y] chunks travel by copy-engine stores into the peers' inboxes, no tensors of ours are involved
+        self.send_qy = None if push else torch.empty(wa, dtype=torch.int32, device=dev)
+        self.gathered_qy = None if push else torch.empty(wa * world, dtype=torch.int32, device=dev)
         self.send_meta = torch.empty(wb, dtype=torch.int32, device=dev)
-        self.gathered_qy = torch.empty(wa * world, dtype=torch.int32, device=dev)
         self.gathered_meta = torch.empty(wb * world, dtype=torch.int32, device=dev)
         self.thr = torch.empty(nq_local * world, dtype=torch.float32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -156,14 +158,15 @@ class _RankState:
     # phases (everything asynchronous on the shard's stream, except the one host read that sizes the survivor slots)
     def front_rotate(self, q_dev):
         assert q_dev.is_cuda and q_dev.is_contiguous() and tuple(q_dev.shape) == (self.nq_local, self.len), tuple(q_dev.shape)
-        _check(lib().rabitq_dist_front_rotate(self.shard._h, C.c_void_p(q_dev.data_ptr()), self.len, C.c_void_p(self.send_qy.data_ptr())))
+        _check(lib().rabitq_dist_front_rotate(self.shard._h, C.c_void_p(q_dev.data_ptr()), self.len,
+                                              None if self.push else C.c_void_p(self.send_qy.data_ptr())))
 
     def front_select(self):
         _check(lib().rabitq_dist_front_select(self.shard._h, C.c_void_p(self.send_meta.data_ptr())))
 
     def round1(self):
-        _check(lib().rabitq_dist_round1_split(self.shard._h, C.c_void_p(self.gathered_qy.data_ptr()), C.c_void_p(self.gathered_meta.data_ptr()),
-                                              C.c_void_p(self.thr.data_ptr())))
+        _check(lib().rabitq_dist_round1_split(self.shard._h, None if self.push else C.c_void_p(self.gathered_qy.data_ptr()),
+                                              C.c_void_p(self.gathered_meta.data_ptr()), C.c_void_p(self.thr.data_ptr())))
 
     def round2(self):
         _check(lib().rabitq_dist_round2(self.shard._h, C.c_void_p(self.status.data_ptr())))
@@ -185,6 +188,8 @@ class DistributedRaBitQ:
         self.shard, self.comm = shard, comm or TorchComm()
         self.rpq = records_per_query
         self.overlap = os.environ.get("RABITQ_DIST_OVERLAP", "1") != "0"
+        # the [q | y] exchange: pushed into the peers' inboxes by the copy engines (default), or an NCCL all-gather (A/B switch)
+        self.push = os.environ.get("RABITQ_DIST_PUSH", "1") != "0"
         self._st: _RankState | None = None
 
     @classmethod
@@ -204,7 +209,12 @@ class DistributedRaBitQ:
         import torch
 
         torch.cuda.synchronize(self.shard.device)
-        st = _RankState(self.shard, self.comm.rank, self.comm.world, nq_local, length, probe, topk, self.rpq)
+        if st is not None:
+            # re-creating the inboxes: every rank unmaps its peers' inboxes FIRST, and only after a barrier does anybody free its
+            # own (CUDA IPC: an exported allocation must not be freed while a peer still has it open)
+            _check(lib().rabitq_dist_close_peers(self.shard._h))
+            self.comm.exchange_bytes(b"")
+        st = _RankState(self.shard, self.comm.rank, self.comm.world, nq_local, length, probe, topk, self.rpq, push=self.push)
         handles = self.comm.exchange_bytes(st.ipc_handle())  # also a barrier: nobody writes into a freed inbox
         for r, h in enumerate(handles):
             if r != self.comm.rank:
@@ -226,7 +236,10 @@ class DistributedRaBitQ:
         for _ in range(max_retries + 1):
             st = self._state(nq_local, length, probe, topk)
             st.front_rotate(queries_local)
-            if self.overlap:
+            if st.push:    # [q | y] is on its way into every inbox (copy engines); front_select orders this stream behind the pushes
+                st.front_select()
+                self.comm.all_gather(st.gathered_meta, st.send_meta)
+            elif self.overlap:
                 work = self.comm.all_gather_start(st.gathered_qy, st.send_qy)   # 7.7 KB per query: in flight during K2 / K2b
                 st.front_select()
                 self.comm.all_gather(st.gathered_meta, st.send_meta)
@@ -246,7 +259,8 @@ class DistributedRaBitQ:
         raise RabitqError(5, "survivor-record regions still overflow after growing; raise records_per_query")
 
 
-def run_virtual_ranks(shards: list[RaBitQ], queries, probe: int, topk: int, records_per_query: int = 256, states=None, grow: bool = True):
+def run_virtual_ranks(shards: list[RaBitQ], queries, probe: int, topk: int, records_per_query: int = 256, states=None, grow: bool = True,
+                      push: bool = True):
     """The distributed step for `len(shards)` ranks living in THIS process on one GPU: same phases, same kernels, the
     collectives replaced by device copies.  queries: CUDA tensor [world * nq_local, len].  Returns (dist, ids, count, states)."""
     import torch
@@ -260,7 +274,7 @@ def run_virtual_ranks(shards: list[RaBitQ], queries, probe: int, topk: int, reco
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            out = run_virtual_ranks(shards, queries, probe, topk, records_per_query, states, grow)
+            out = run_virtual_ranks(shards, queries, probe, topk, records_per_query, states, grow, push)
         torch.cuda.current_stream(dev).wait_stream(side)
         return out
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -269,7 +283,7 @@ def run_virtual_ranks(shards: list[RaBitQ], queries, probe: int, topk: int, reco
     while True:
         if states is None:
             torch.cuda.synchronize(dev)
-            states = [_RankState(s, r, world, nq_l, length, probe, topk, records_per_query) for r, s in enumerate(shards)]
+            states = [_RankState(s, r, world, nq_l, length, probe, topk, records_per_query, push=push) for r, s in enumerate(shards)]
             for a in states:
                 for b in states:
                     if a is not b:
@@ -277,10 +291,12 @@ def run_virtual_ranks(shards: list[RaBitQ], queries, probe: int, topk: int, reco
         for r, st in enumerate(states):
             st.front_rotate(queries[r * nq_l:(r + 1) * nq_l])
             st.front_select()
-        gathered_qy = torch.cat([st.send_qy for st in states])     # the two all-gathers
-        gathered_meta = torch.cat([st.send_meta for st in states])
+        gathered_meta = torch.cat([st.send_meta for st in states])  # the all-gather(s)
+        if not states[0].push:
+            gathered_qy = torch.cat([st.send_qy for st in states])
         for st in states:
-            st.gathered_qy.copy_(gathered_qy)
+            if not st.push:
+                st.gathered_qy.copy_(gathered_qy)
             st.gathered_meta.copy_(gathered_meta)
             st.round1()
         thr = states[0].thr.clone()                                 # all-reduce(min)
