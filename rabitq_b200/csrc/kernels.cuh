@@ -1048,23 +1048,29 @@ RQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
     // try_wait suspends the warp in hardware only briefly; a waiter that expects to wait long (the scan's producer, which runs
     // stages ahead) sleeps between attempts instead of burning issue slots.  A lost transaction must fail loudly, never hang
     // the GPU: trap after ~4 s.
-    uint32_t ok = 0;
     const uint32_t addr = smem_u32(bar);
-    long long t0 = 0;
-    for (uint32_t spin = 0; !ok; spin++) {
+    auto attempt = [&]() -> uint32_t {
+        uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok)
                      : "r"(addr), "r"(parity)
                      : "memory");
-        if (!ok) {
-            if constexpr (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
-            if ((spin & 63u) == 63u) {
-                const long long now = clock64();
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > 8000000000ll) __trap();
-            }
+        return ok;
+    };
+    if (attempt()) return;
+    if constexpr (SLEEP_NS > 0) {
+        for (uint32_t spin = 0; spin < 4000000000u / SLEEP_NS; spin++) {
+            __nanosleep(SLEEP_NS);
+            if (attempt()) return;
+        }
+    } else {
+        const long long t0 = clock64();
+        for (uint32_t spin = 1;; spin++) {
+            if (attempt()) return;
+            if ((spin & 1023u) == 0u && clock64() - t0 > 8000000000ll) break;
         }
     }
+    __trap();
 }
 
 // Scan-layout copy of the codes and Factors, built once per index: for every cluster, chunks of 128 vectors (the last one
@@ -1163,7 +1169,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, MINB) scan_mma_kernel(ScanArgs a) 
                 w.rec_begin = w0.x; w.nr = w0.y; w.chunk_g = w0.z; w.chunk = w0.w; w.jbase = w1.x; w.nv = w1.y;
                 if (lane == 0) next = atomicAdd(&a.work_ctl[0], 1u);  // in flight while this item is staged
             }
-            mbar_wait<400>(&empty[st], ph ^ 1u);  // the consumers released this stage (passes at once on its first use)
+            mbar_wait<1000>(&empty[st], ph ^ 1u);  // the consumers released this stage (passes at once on its first use)
             if (done) {
                 if (lane == 0) hdr[0] = -1;
                 mbar_arrive(&full[st]);
@@ -1216,7 +1222,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, MINB) scan_mma_kernel(ScanArgs a) 
         const int st = (int)(it % (uint32_t)S);
         const uint32_t ph = (it / (uint32_t)S) & 1u;
         unsigned char* sp = stage0 + (size_t)st * stage_bytes;
-        mbar_wait<100>(&full[st], ph);
+        mbar_wait<200>(&full[st], ph);
         const int4 hdr = *reinterpret_cast<const int4*>(sp + o_hdr);
         if (hdr.x < 0) break;
         const int nr_all = hdr.x;
@@ -1942,8 +1948,9 @@ __global__ void dist_unpack_kernel(const uint32_t* __restrict__ gathered_a, size
     if (gq >= (size_t)world * nq_l) return;
     const DistChunk L = dist_chunk_layout(nq_l, len, D, P);
     const int r = (int)(gq / nq_l), ql = (int)(gq % nq_l);
-    const uint32_t* ca = gathered_a + (size_t)r * stride_a;
     const uint32_t* cb = gathered_b + (size_t)r * stride_b;
+    if (qpad) {  // (NULL: the rows were pushed straight into their flat arrays, only the probe lists travel by collective)
+    const uint32_t* ca = gathered_a + (size_t)r * stride_a;
     {
         const uint4* src = reinterpret_cast<const uint4*>(ca + L.a_y + (size_t)ql * D);
         uint4* dst = reinterpret_cast<uint4*>(y + gq * D);
@@ -1956,6 +1963,7 @@ __global__ void dist_unpack_kernel(const uint32_t* __restrict__ gathered_a, size
     } else {
         const uint32_t* src = ca + L.a_q + (size_t)ql * len;
         for (int i = lane; i < D; i += 32) qpad[gq * D + i] = i < len ? __uint_as_float(src[i]) : 0.0f;
+    }
     }
     for (int i = lane; i < P; i += 32) {
         probe_ids[gq * P + i] = cb[L.b_ids + (size_t)ql * P + i];

@@ -102,9 +102,11 @@ struct DistState {
     uint32_t r1cap = 0, cap2 = 0;
     unsigned char* inbox = nullptr;
     size_t inbox_bytes = 0, off_r1cnt = 0, off_r1rec = 0, off_r2tab = 0, off_r2rec = 0;
-    size_t off_qy = 0, qy_stride_words = 0;  // region every rank's [q | y] chunk is PUSHED into by its owner (copy engine, no collective)
-    cudaEvent_t ev_rot = nullptr, ev_push = nullptr;
-    bool push_pending = false;
+    size_t off_q = 0, off_y = 0;  // flat [world * nq_l][D] regions: padded queries and rotated queries, PUSHED block by block by their owners
+    static constexpr int NCOPY = 3;
+    cudaEvent_t ev_rot = nullptr, ev_pushes[NCOPY] = {nullptr, nullptr, nullptr};
+    cudaStream_t copy_streams[NCOPY] = {nullptr, nullptr, nullptr};
+    bool push_pending = false, pushed = false;
     std::vector<unsigned char*> peers_h;
     std::vector<char> opened;  // peers_h[r] came from cudaIpcOpenMemHandle
     unsigned char** peers_d = nullptr;
@@ -178,6 +180,7 @@ struct rabitq_index {
         entries, counters, out_all, rr_dbg, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag, sel_scratch;
     DistState dist;
     const float* q_in = nullptr;   // the sub-batch's raw queries (nb x len) on the device: ix->qraw, or the caller's device pointer
+    const float* y_all = nullptr;  // rotated queries K3 reads: ix->y, or (distributed push mode) the inbox region every rank pushed its block into
     const float* q_pad = nullptr;  // the same, zero-padded to D: ix->qpad, or q_in itself when len == D (nothing to pad, nothing copied)
     // double-buffered upload (rabitq_query_batch_pipelined): the NEXT batch's queries travel on the copy stream while this one runs
     DevBuf qstage;
@@ -202,7 +205,7 @@ struct rabitq_index {
     size_t ev_used = 0;
     bool timings_pending = false;  // the last call's event chain has not been turned into ms[] yet
     int scan_blocks_per_sm = 0;
-    bool scan_attr_done[2][4] = {{false, false, false, false}, {false, false, false, false}};
+    bool scan_attr_done[2][5] = {{false, false, false, false, false}, {false, false, false, false, false}};
     int scan_stages = 0;   // ring depth of the scan (0 = by dimension)
     int scan_sub = 0;      // consumer passes per stage (0 = by dimension)
     size_t max_items = 0;  // capacity of a round's scan work list for the current sub-batch (setup_rounds)
@@ -218,7 +221,10 @@ struct rabitq_index {
             if (dist.opened[r] && dist.peers_h[r]) cudaIpcCloseMemHandle(dist.peers_h[r]);
         if (dist.inbox) cudaFree(dist.inbox);
         if (dist.ev_rot) cudaEventDestroy(dist.ev_rot);
-        if (dist.ev_push) cudaEventDestroy(dist.ev_push);
+        for (int c = 0; c < DistState::NCOPY; c++) {
+            if (dist.copy_streams[c]) cudaStreamDestroy(dist.copy_streams[c]);
+            if (dist.ev_pushes[c]) cudaEventDestroy(dist.ev_pushes[c]);
+        }
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_all, &rr_dbg,
@@ -774,7 +780,7 @@ int launch_scan_nt(rabitq_index* ix, ScanArgs& a, const ScanGeom& g) {
     const size_t smem = scan_smem_bytes((int)ix->D, 8 * NT * g.sub, g.stages);
     if (smem > (size_t)227 * 1024) return fail(RABITQ_EUNSUPPORTED, "dim too large for the code scan's shared-memory staging (dim <= 8192)");
     auto kern = scan_mma_kernel<NT, DENSE, MINB>;
-    bool& attr_done = ix->scan_attr_done[DENSE ? 1 : 0][MINB == 3 ? 3 : NT == 4 ? 2 : NT == 2 ? 1 : 0];
+    bool& attr_done = ix->scan_attr_done[DENSE ? 1 : 0][MINB == 4 ? 4 : MINB == 3 ? 3 : NT == 4 ? 2 : NT == 2 ? 1 : 0];
     if (!attr_done) {  // once per handle (= per device) and instantiation; always the maximum, other handles share the function
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
@@ -798,6 +804,7 @@ int launch_scan(rabitq_index* ix, ScanArgs& a) {
     a.sub = g.sub;
     if constexpr (!DENSE) {  // three CTAs per SM want <= 128 registers; where shared memory allows two anyway, the compiler gets 200
         if (g.nt == 4 && scan_smem_bytes(D, 8 * g.nt * g.sub, g.stages) <= (size_t)74 * 1024) return launch_scan_nt<4, false, 3>(ix, a, g);
+        if (g.nt == 2 && scan_smem_bytes(D, 8 * g.nt * g.sub, g.stages) <= (size_t)55 * 1024) return launch_scan_nt<2, false, 4>(ix, a, g);
     }
     switch (g.nt) {
         case 4: return launch_scan_nt<4, DENSE, 2>(ix, a, g);
@@ -836,6 +843,7 @@ int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_ro
         ix->q_pad = ix->qpad.as<float>();
     }
     if (tick(ix, ST_H2D)) return RABITQ_ECUDA;
+    ix->y_all = ix->y.as<float>();
     if (launch_rotate(ix, ix->q_pad, ix->y.as<float>(), nb, st)) return RABITQ_ECUDA;
     ix->counts[5]++;
     if (tick(ix, ST_ROTATE)) return RABITQ_ECUDA;
@@ -989,17 +997,23 @@ int run_quantize_list(rabitq_index* ix, int P, size_t set) {
         const unsigned qgrid = (unsigned)((groups + 15) / 16);
         const size_t qsmem = (size_t)16 * RS * 4;  // one record per group, staged for the coalesced store
         switch (W32) {
-            case 2: quantize_small_kernel<2><<<qgrid, 128, qsmem, st>>>(ix->y.as<float>(), ix->cent, QUANT_COMMON, pch); break;
-            case 4: quantize_small_kernel<4><<<qgrid, 128, qsmem, st>>>(ix->y.as<float>(), ix->cent, QUANT_COMMON, pch); break;
-            case 6: quantize_small_kernel<6><<<qgrid, 128, qsmem, st>>>(ix->y.as<float>(), ix->cent, QUANT_COMMON, pch); break;
-            default: quantize_small_kernel<8><<<qgrid, 128, qsmem, st>>>(ix->y.as<float>(), ix->cent, QUANT_COMMON, pch); break;
+            case 2: quantize_small_kernel<2><<<qgrid, 128, qsmem, st>>>(ix->y_all, ix->cent, QUANT_COMMON, pch); break;
+            case 4: quantize_small_kernel<4><<<qgrid, 128, qsmem, st>>>(ix->y_all, ix->cent, QUANT_COMMON, pch); break;
+            case 6: quantize_small_kernel<6><<<qgrid, 128, qsmem, st>>>(ix->y_all, ix->cent, QUANT_COMMON, pch); break;
+            default: quantize_small_kernel<8><<<qgrid, 128, qsmem, st>>>(ix->y_all, ix->cent, QUANT_COMMON, pch); break;
         }
     } else {
+        // a warp per record; up to dim 1536 the residual stays in registers (one pass over the two rows), beyond that two passes
         const int pch = 1;
         const size_t warps = L.cap_items;
         const unsigned qgrid = (unsigned)((warps + 3) / 4);
         const size_t qsmem = (size_t)4 * RS * 4;  // one record per warp, staged for the coalesced store
-        quantize_kernel<0><<<qgrid, 128, qsmem, st>>>(ix->y.as<float>(), ix->cent, QUANT_COMMON, D, pch);
+        switch (W32) {
+#define QK(w) case w: quantize_kernel<w><<<qgrid, 128, qsmem, st>>>(ix->y_all, ix->cent, QUANT_COMMON, D, pch); break;
+            QK(10) QK(12) QK(14) QK(16) QK(20) QK(24) QK(30) QK(32) QK(40) QK(48)
+#undef QK
+            default: quantize_kernel<0><<<qgrid, 128, qsmem, st>>>(ix->y_all, ix->cent, QUANT_COMMON, D, pch); break;
+        }
     }
 #undef QUANT_COMMON
     CU(cudaGetLastError()); ix->counts[5]++;
@@ -1405,10 +1419,16 @@ int dist_init_impl(rabitq_index* ix, int rank, int world, size_t nq_l, size_t pr
     if (d.inbox) cudaFree(d.inbox);
     if (d.peers_d) cudaFree(d.peers_d);
     if (d.ev_rot) cudaEventDestroy(d.ev_rot);
-    if (d.ev_push) cudaEventDestroy(d.ev_push);
+    for (int c = 0; c < DistState::NCOPY; c++) {
+        if (d.copy_streams[c]) { cudaStreamSynchronize(d.copy_streams[c]); cudaStreamDestroy(d.copy_streams[c]); }
+        if (d.ev_pushes[c]) cudaEventDestroy(d.ev_pushes[c]);
+    }
     d = DistState();
     CU(cudaEventCreateWithFlags(&d.ev_rot, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&d.ev_push, cudaEventDisableTiming));
+    for (int c = 0; c < DistState::NCOPY; c++) {
+        CU(cudaStreamCreateWithFlags(&d.copy_streams[c], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&d.ev_pushes[c], cudaEventDisableTiming));
+    }
     d.world = world; d.rank = rank; d.nq_l = nq_l; d.topk = topk;
     d.P = (int)std::min(probe, ix->K);
     d.r1cap = (uint32_t)(SCAN_THREADS * std::max(1, ix->first_chunks));
@@ -1420,9 +1440,9 @@ int dist_init_impl(rabitq_index* ix, int rank, int world, size_t nq_l, size_t pr
     d.off_r1rec = up(d.off_r1cnt + (size_t)world * nq_l * 4);
     d.off_r2tab = up(d.off_r1rec + (size_t)world * nq_l * d.r1cap * sizeof(SurvRec));
     d.off_r2rec = up(d.off_r2tab + (size_t)world * nq_l * 8);
-    d.off_qy = up(d.off_r2rec + (size_t)world * d.cap2 * sizeof(SurvRec));
-    d.qy_stride_words = dist_chunk_layout(nq_l, ix->D, ix->D, (size_t)d.P).words_a;  // sized for len == dim, the longest a query can be
-    d.inbox_bytes = up(d.off_qy + (size_t)world * d.qy_stride_words * 4);
+    d.off_q = up(d.off_r2rec + (size_t)world * d.cap2 * sizeof(SurvRec));
+    d.off_y = up(d.off_q + (size_t)world * nq_l * ix->D * 4);
+    d.inbox_bytes = up(d.off_y + (size_t)world * nq_l * ix->D * 4);
     CU(cudaMalloc((void**)&d.inbox, d.inbox_bytes));
     CU(cudaMemset(d.inbox, 0, d.off_r1rec));
     CU(cudaMalloc((void**)&d.peers_d, sizeof(void*) * world));
@@ -1493,19 +1513,21 @@ int dist_front_rotate_impl(rabitq_index* ix, const float* d_queries, size_t len,
         CU(cudaMemcpyAsync(send + L.a_y, ix->y.p, nq_l * D * 4, cudaMemcpyDeviceToDevice, st));
         d.push_pending = false;
     } else {
-        // PUSH: this rank's [q | y] into slot `rank` of every inbox (its own included) with copy-engine transfers over NVLink, on the
-        // copy stream: no collective and no SM is involved, so the centroid scan and the probe selection that follow on the main
-        // stream run undisturbed.  Peers may read their slot once they have seen this rank's part of the NEXT collective, which
-        // the main stream enters only after the pushes (front_select waits for ev_push).
+        // PUSH: this rank's block of padded queries and of rotated queries into rows [rank * nq_l, (rank + 1) * nq_l) of the flat
+        // Q and Y regions of every inbox (its own included) with copy-engine transfers over NVLink, spread over a few copy streams:
+        // no collective and no SM is involved, so the centroid scan and the probe selection that follow on the main stream run
+        // undisturbed, and nothing has to be unpacked afterwards.  Peers may read the rows once they have seen this rank's part of
+        // the NEXT collective, which the main stream enters only after the pushes (front_select waits for the push events).
         CU(cudaEventRecord(d.ev_rot, st));
-        CU(cudaStreamWaitEvent(ix->copy_stream, d.ev_rot, 0));
+        const size_t blk = nq_l * D * 4;
+        for (int c = 0; c < DistState::NCOPY; c++) CU(cudaStreamWaitEvent(d.copy_streams[c], d.ev_rot, 0));
         for (int k = 0; k < d.world; k++) {
             const int r = (d.rank + 1 + k) % d.world;  // stagger the targets: rank i starts with i+1, itself last
-            uint32_t* slot = reinterpret_cast<uint32_t*>(d.peers_h[r] + d.off_qy) + (size_t)d.rank * d.qy_stride_words;
-            CU(cudaMemcpyAsync(slot + L.a_q, ix->qraw.p, nq_l * len * 4, cudaMemcpyDeviceToDevice, ix->copy_stream));
-            CU(cudaMemcpyAsync(slot + L.a_y, ix->y.p, nq_l * D * 4, cudaMemcpyDeviceToDevice, ix->copy_stream));
+            cudaStream_t cs = d.copy_streams[k % DistState::NCOPY];
+            CU(cudaMemcpyAsync(d.peers_h[r] + d.off_q + (size_t)d.rank * blk, ix->q_pad, blk, cudaMemcpyDeviceToDevice, cs));
+            CU(cudaMemcpyAsync(d.peers_h[r] + d.off_y + (size_t)d.rank * blk, ix->y.p, blk, cudaMemcpyDeviceToDevice, cs));
         }
-        CU(cudaEventRecord(d.ev_push, ix->copy_stream));
+        for (int c = 0; c < DistState::NCOPY; c++) CU(cudaEventRecord(d.ev_pushes[c], d.copy_streams[c]));
         d.push_pending = true;
     }
     if (tick(ix, ST_ROTATE)) return RABITQ_ECUDA;
@@ -1530,7 +1552,8 @@ int dist_front_select_impl(rabitq_index* ix, void* d_send_meta) {
     CU(cudaMemcpyAsync(send + L.b_ids, ix->probe_ids.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(send + L.b_dist, ix->probe_dist.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(send + L.b_p0, ix->q_p0.p, nq_l * 4, cudaMemcpyDeviceToDevice, st));
-    if (d.push_pending) CU(cudaStreamWaitEvent(st, d.ev_push, 0));  // the collective that follows carries the "my pushes are done" edge
+    if (d.push_pending)  // the collective that follows carries the "my pushes are done" edge
+        for (int c = 0; c < DistState::NCOPY; c++) CU(cudaStreamWaitEvent(st, d.ev_pushes[c], 0));
     if (tick(ix, ST_SELECT)) return RABITQ_ECUDA;
     d.phase = 1;
     return RABITQ_OK;
@@ -1550,10 +1573,9 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a
     if (!ix || !ix->dist.ready || ix->dist.phase != 1) return fail(RABITQ_EINVAL, "rabitq_dist_front first");
     if (!d_gathered_b || !d_thr) return fail(RABITQ_EINVAL, "null argument");
     DistState& d = ix->dist;
-    if (!d_gathered_a) {  // push mode: every rank's [q | y] already sits in this rank's inbox
+    const bool pushed = !d_gathered_a;  // push mode: every rank's rows already sit in the flat Q / Y regions of this rank's inbox
+    if (pushed) {
         if (!d.push_pending) return fail(RABITQ_EINVAL, "no gathered [q | y] buffer and nothing was pushed");
-        d_gathered_a = d.inbox + d.off_qy;
-        stride_a = d.qy_stride_words;
         d.push_pending = false;
     }
     for (int r = 0; r < d.world; r++)
@@ -1563,8 +1585,10 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a
     cudaStream_t st = ix->stream;
     const size_t nq = d.nq_l * d.world, D = ix->D;
     const int P = d.P;
-    CU(ix->qpad.ensure(nq * D * 4));
-    CU(ix->y.ensure(nq * D * 4));
+    if (!pushed) {
+        CU(ix->qpad.ensure(nq * D * 4));
+        CU(ix->y.ensure(nq * D * 4));
+    }
     CU(ix->probe_ids.ensure(nq * P * 4));
     CU(ix->probe_dist.ensure(nq * P * 4));
     CU(ix->slot_local.ensure(nq * P * 4));
@@ -1577,11 +1601,13 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a
     CU(ix->r2_off.ensure(nq * 4));
     CU(ix->home_tot.ensure(32 * 4));
     CU(ix->cand.ensure((size_t)d.world * d.cap2 * sizeof(Cand)));
-    ix->q_pad = ix->qpad.as<float>();  // all ranks' queries, padded by the unpack below
+    // all ranks' queries: unpacked from the gathered chunks below, or already in place (pushed)
+    ix->q_pad = pushed ? reinterpret_cast<const float*>(d.inbox + d.off_q) : ix->qpad.as<float>();
+    ix->y_all = pushed ? reinterpret_cast<const float*>(d.inbox + d.off_y) : ix->y.as<float>();
     if (tick(ix, -1)) return RABITQ_ECUDA;  // the all-gather sits between the phases: not ours to time
     dist_unpack_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(static_cast<const uint32_t*>(d_gathered_a), stride_a,
                                                           static_cast<const uint32_t*>(d_gathered_b), stride_b, d.world, (int)d.nq_l, (int)d.len, (int)D, P,
-                                                          ix->qpad.as<float>(), ix->y.as<float>(), ix->probe_ids.as<uint32_t>(),
+                                                          pushed ? nullptr : ix->qpad.as<float>(), pushed ? nullptr : ix->y.as<float>(), ix->probe_ids.as<uint32_t>(),
                                                           ix->probe_dist.as<float>(), ix->q_p0.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
     if (tick(ix, ST_H2D)) return RABITQ_ECUDA;
@@ -1642,7 +1668,7 @@ int dist_round2_impl(rabitq_index* ix, uint32_t* d_status) {
                                                                 ix->cand.as<Cand>());
     CU(cudaGetLastError()); ix->counts[5]++;
     if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
-    r2_exact_kernel<<<ix->sm_count * 8, 256, 0, st>>>(ix->cand.as<Cand>(), ix->home_tot.as<uint32_t>(), d.world, ix->qpad.as<float>(), ix->base,
+    r2_exact_kernel<<<ix->sm_count * 8, 256, 0, st>>>(ix->cand.as<Cand>(), ix->home_tot.as<uint32_t>(), d.world, ix->q_pad, ix->base,
                                                       ix->map_ids, (int)ix->D, (int)d.nq_l, d.rank, d.cap2, d.peers_d, d.off_r2rec,
                                                       ix->counters.as<unsigned long long>());
     CU(cudaGetLastError()); ix->counts[5]++;
@@ -1726,7 +1752,8 @@ int rabitq_dist_close_peers(rabitq_index* idx) {
     CU(cudaSetDevice(idx->device));
     DistState& d = idx->dist;
     CU(cudaStreamSynchronize(idx->stream));
-    if (idx->copy_stream) CU(cudaStreamSynchronize(idx->copy_stream));
+    for (int c = 0; c < DistState::NCOPY; c++)
+        if (d.copy_streams[c]) CU(cudaStreamSynchronize(d.copy_streams[c]));
     for (size_t r = 0; r < d.peers_h.size(); r++) {
         if (d.opened[r] && d.peers_h[r]) cudaIpcCloseMemHandle(d.peers_h[r]);
         if ((int)r != d.rank) d.peers_h[r] = nullptr;

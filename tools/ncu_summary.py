@@ -1,12 +1,19 @@
 """Summarise ncu outputs (read here, without a GPU):
     python tools/ncu_summary.py launches gpurun_out/launches_c2.csv       # per-kernel share of the launch list
     python tools/ncu_summary.py full gpurun_out/prof_scan_c2.ncu-rep      # key metrics of a --set full capture
+    python tools/ncu_summary.py profile c2 gpurun_out/prof_scan_c2.ncu-rep profiles/scan_profile.json
+        # the facts bench.py's `roofline` block quotes for the dominant kernel (DRAM bytes per launch, pipe utilisation, the unit
+        # that binds), merged into profiles/scan_profile.json under the workload's key
 """
 import collections
 import csv
 import io
 import subprocess
 import sys
+
+KEYS_EXTRA_TENSOR = ["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                     "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active",
+                     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 KEYS = [
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -59,14 +66,58 @@ def full(path, extra=()):
     hdr, units = rows[0], rows[1]
     for row in rows[2:]:
         print("--", row[hdr.index("Kernel Name")][:100], "grid", row[hdr.index("Grid Size")] if "Grid Size" in hdr else "")
-        for k in list(KEYS) + list(extra):
+        for k in list(KEYS) + KEYS_EXTRA_TENSOR + list(extra):
             if k in hdr:
                 i = hdr.index(k)
                 print(f"   {k:90s} {row[i]:>16s} {units[i]}")
 
 
+def profile(workload, path, out_json):
+    import json
+    import os
+
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, row = rows[0], rows[-1]
+
+    def val(k):
+        return float(row[hdr.index(k)].replace(",", "")) if k in hdr and row[hdr.index(k)] not in ("", "n/a") else None
+
+    def byt(k):
+        v = val(k)
+        u = rows[1][hdr.index(k)] if k in hdr else ""
+        return None if v is None else v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+
+    pipes = {"alu": val("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+             "fma": val("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+             "xu": val("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+             "lsu": val("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+             "tensor_imma": val("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+             "issue_active": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+             "dram": val("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+             "warps_active": val("sm__warps_active.avg.pct_of_peak_sustained_active")}
+    units = {k: v for k, v in pipes.items() if k in ("alu", "fma", "xu", "lsu", "tensor_imma", "dram") and v is not None}
+    top = max(units, key=units.get)
+    entry = {"kernel": row[hdr.index("Kernel Name")].split("(")[0], "source": f"ncu --set full, {os.path.basename(path)} (one launch of the main scan round)",
+             "duration_us_under_ncu": val("gpu__time_duration.sum"),
+             "dram_bytes_per_launch": (byt("dram__bytes_read.sum") or 0) + (byt("dram__bytes_write.sum") or 0),
+             "pipes_pct": {k: (None if v is None else round(v, 1)) for k, v in pipes.items()},
+             "registers_per_thread": val("launch__registers_per_thread"),
+             "bound": {"alu": "alu (integer / logic pipe: A-fragment expansion + epilogue)", "fma": "fma", "xu": "xu",
+                       "lsu": "lsu (shared-memory fragment loads)", "tensor_imma": "tensor (IMMA)", "dram": "hbm"}[top] +
+                      f"; issue slots active {pipes['issue_active']:.0f} % -- latency-bound below every pipe's peak"}
+    data = {}
+    if os.path.exists(out_json):
+        data = json.load(open(out_json))
+    data[workload] = entry
+    json.dump(data, open(out_json, "w"), indent=1, sort_keys=True)
+    print(json.dumps(entry, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "profile":
+        profile(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
         full(sys.argv[2], sys.argv[3:])
