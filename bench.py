@@ -402,6 +402,45 @@ def measure_ours(args, workload, device, rank, world, stream, main_leg=True):
     e2e_ids = torch.from_numpy(oi.view(np.int32).copy()).to(device)
     recall_e2e = global_recall(e2e_ids)
 
+    # ---- optional sweeps the configs name (C2: nprobe 16-256; C5: query batch 1-65536); single GPU, after the main legs ----------
+    sweeps = {}
+    if world == 1 and main_leg and args.sweep_probe:
+        rows = []
+        for p in [int(x) for x in args.sweep_probe.split(",")]:
+            _, ids_p, _ = one_pass(p)
+            rec_p = global_recall(ids_p)
+            for _ in range(3):
+                g.query_batch_device_into(queries, p, TOPK, dev_d, dev_i, dev_c)
+            ms = timed(lambda: g.query_batch_device_into(queries, p, TOPK, dev_d, dev_i, dev_c), max(3, steps // 2))
+            tl = g.last_timings()
+            ms2 = timed(lambda: g.query_batch_into(qh, p, TOPK, od, oi, oc, next_q_host=qh), max(3, steps // 2))
+            rows.append({"nprobe": p, "recall_at_10": round(rec_p, 4), "qps": round(nq / (sum(ms) / len(ms) * 1e-3), 1),
+                         "qps_e2e": round(nq / (sum(ms2) / len(ms2) * 1e-3), 1), "ms_per_step": round(sum(ms) / len(ms), 4),
+                         "scan_ms": round(tl["ms_scan"], 4), "rerank_ms": round(tl["ms_rerank"], 4), "pairs": tl["pairs"],
+                         "scan_gpairs_per_s": round(tl["pairs"] / (tl["ms_scan"] * 1e-3) / 1e9, 1) if tl["ms_scan"] > 0 else None})
+            log(f"[bench] nprobe sweep: {rows[-1]}")
+        sweeps["probe_sweep"] = rows
+    if world == 1 and main_leg and args.sweep_batch:
+        rows = []
+        for nb in [int(x) for x in args.sweep_batch.split(",")]:
+            nb = min(nb, nq)
+            qb = queries[:nb].contiguous()
+            bd, bi, bc = dev_d[:nb], dev_i[:nb], dev_c[:nb]
+            qhb, odb, oib, ocb = qh[:nb], od[:nb], oi[:nb], oc[:nb]
+            reps = max(3, min(50, 4096 // nb))
+            for _ in range(3):
+                g.query_batch_device_into(qb, probe, TOPK, bd, bi, bc)
+            ms = timed(lambda: g.query_batch_device_into(qb, probe, TOPK, bd, bi, bc), reps)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                g.query_batch_into(qhb, probe, TOPK, odb, oib, ocb)
+            wall = (time.perf_counter() - t0) / reps * 1e3
+            rec_b = recall_at_k(bi[:min(nb, tq)], truth_local[:min(nb, tq)], TOPK)
+            rows.append({"batch": nb, "ms_device": round(sum(ms) / len(ms), 4), "qps_device": round(nb / (sum(ms) / len(ms) * 1e-3), 1),
+                         "ms_host_call": round(wall, 4), "qps_host_call": round(nb / (wall * 1e-3), 1), "recall_at_10": round(rec_b, 4)})
+            log(f"[bench] batch sweep: {rows[-1]}")
+        sweeps["batch_sweep"] = rows
+
     tot_dev, tot_e2e = sum(ms_dev), sum(ms_e2e)
     if world > 1:
         t = torch.tensor([tot_dev, tot_e2e], dtype=torch.float64, device=device)
@@ -466,6 +505,7 @@ def measure_ours(args, workload, device, rank, world, stream, main_leg=True):
         if per_rank:
             out["per_rank"] = {"pairs": [int(r[0]) for r in per_rank], "scan_ms": [round(r[1], 4) for r in per_rank],
                                "busy_ms": [round(r[2], 4) for r in per_rank]}
+        out.update(sweeps)
         if parity_check is not None:
             out["parity_check"] = parity_check
         if cpu is not None:
@@ -636,6 +676,8 @@ def main():
     ap.add_argument("--rounds", default=None, help="rerank round boundaries, e.g. 0,1,8")
     ap.add_argument("--builder", default="native", choices=["native", "torch"], help="index training: rabitq_build (CUDA) or the torch harness")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sweep-probe", default=None, help="comma list of nprobe values timed after the main legs (config 2: 16,32,64,128,256)")
+    ap.add_argument("--sweep-batch", default=None, help="comma list of query-batch sizes timed after the main legs (config 5: 1,8,...,65536)")
     ap.add_argument("--no-c1", action="store_true", help="skip the short north-star (C1) leg that rides in the N=1 line")
     ap.add_argument("--records-per-query", type=int, default=256, help="multi-GPU: survivor-record capacity per (home query, source shard)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")

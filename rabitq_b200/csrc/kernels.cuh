@@ -1059,12 +1059,14 @@ RQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
     };
     if (attempt()) return;
     if constexpr (SLEEP_NS > 0) {
+#pragma unroll 1
         for (uint32_t spin = 0; spin < 4000000000u / SLEEP_NS; spin++) {
             __nanosleep(SLEEP_NS);
             if (attempt()) return;
         }
     } else {
         const long long t0 = clock64();
+#pragma unroll 1
         for (uint32_t spin = 1;; spin++) {
             if (attempt()) return;
             if ((spin & 1023u) == 0u && clock64() - t0 > 8000000000ll) break;
