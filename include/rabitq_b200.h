@@ -203,6 +203,10 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
  * (the handle moves 1 -> 3 -> 0 by itself when batches cannot be certified). */
 int rabitq_set_option(rabitq_index* idx, const char* name, long value);
 
+/* Byte position of dimension d inside a K3 query record (the tensor-core fragment order K4 reads, kernels.cuh rec_pos); host-only,
+ * lets the CPU tests check the layout algebra without a GPU. */
+int rabitq_debug_rec_pos(int d);
+
 /* After a batch run with "debug_rerank" = 1: out[nq][2 rounds][8] = {SM cycles the query's warp spent in K5, waves, exact
  * distances computed, cycles inside enqueue (including the waves processed there), cycles waiting for gathered rows, in the exact distances, in the replay, staging
  * survivor words} of the last sub-batch.  Tuning aid; not part of the reference's surface. */

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "rabitq_shard_range", "rabitq_merge_topk_device", "rabitq_metrics", "rabitq_metrics_reset", "rabitq_last_error", "rabitq_set_rounds",
     "rabitq_set_option", "rabitq_set_stream", "rabitq_last_timings", "rabitq_stage_rotate", "rabitq_stage_probe", "rabitq_stage_quantize", "rabitq_stage_scan",
     "rabitq_dist_init", "rabitq_dist_ipc_handle", "rabitq_dist_inbox_ptr", "rabitq_dist_set_peer", "rabitq_dist_close_peers", "rabitq_dist_chunk_words", "rabitq_dist_front",
-    "rabitq_dist_round1", "rabitq_dist_round2", "rabitq_dist_finish", "rabitq_min_f32_device", "rabitq_set_quantize_bias", "rabitq_reshard", "rabitq_debug_rerank_stats", "rabitq_dist_last_status", "rabitq_dist_chunk_words_qy", "rabitq_dist_chunk_words_meta",
+    "rabitq_dist_round1", "rabitq_dist_round2", "rabitq_dist_finish", "rabitq_min_f32_device", "rabitq_set_quantize_bias", "rabitq_reshard", "rabitq_debug_rerank_stats", "rabitq_debug_rec_pos", "rabitq_dist_last_status", "rabitq_dist_chunk_words_qy", "rabitq_dist_chunk_words_meta",
     "rabitq_dist_front_rotate", "rabitq_dist_front_select", "rabitq_dist_round1_split",
 ]
 
@@ -106,6 +106,7 @@ def lib():
     L.rabitq_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.rabitq_set_quantize_bias.argtypes = [vp, vp]
     L.rabitq_debug_rerank_stats.argtypes = [vp, vp, C.c_size_t]
+    L.rabitq_debug_rec_pos.argtypes = [C.c_int]
     L.rabitq_stage_rotate.argtypes = [vp, vp, C.c_size_t, C.c_size_t, vp]
     L.rabitq_stage_probe.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp]
     L.rabitq_stage_quantize.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp, vp]

@@ -1276,13 +1276,29 @@ int validate_query_args(const rabitq_index* ix, size_t len, size_t probe, size_t
 
 size_t pick_sub_batch(const rabitq_index* ix, size_t nq, size_t probe) {
     const size_t K = ix->K, P = std::min(probe, K);
-    size_t nb = 65536;
-    nb = std::min(nb, ((size_t)1 << 31) / (K * 4) ? ((size_t)1 << 31) / (K * 4) : 1);  // centroid distances <= 2 GiB
-    // survivor slots: 260 B per 32-vector word; budget 12 GiB of slots (2x headroom on the average cluster size)
-    double words_per_q = double(P) * (double(ix->n) / double(K) / 32.0 + 1.0) * 2.0;
-    size_t by_slots = (size_t)std::max(1.0, (12.0 * 1073741824.0 / 260.0) / words_per_q);
-    nb = std::min(nb, by_slots);
-    nb = std::min(nb, (size_t)0xffffffffu / std::max<size_t>(P, 1));
+    // survivor slots: 260 B per 32-vector word (2x headroom on the average cluster size); centroid-distance matrix: 4 B per (query, centroid)
+    const double words_per_q = double(P) * (double(ix->n) / double(K) / 32.0 + 1.0) * 2.0;
+    auto fit = [&](double slot_bytes, double cdist_bytes) {
+        size_t nb = 65536;
+        nb = std::min(nb, std::max<size_t>(1, (size_t)(cdist_bytes / (double(K) * 4.0))));
+        nb = std::min(nb, (size_t)std::max(1.0, (slot_bytes / 260.0) / words_per_q));
+        nb = std::min(nb, (size_t)0xffffffffu / std::max<size_t>(P, 1));
+        return std::max<size_t>(1, nb);
+    };
+    // default budgets: 12 GiB of slots, 2 GiB of centroid distances -- enough for every batch the small configurations send
+    size_t nb = fit(12.0 * 1073741824.0, 2.0 * 1073741824.0);
+    if (nb < nq) {
+        // a big batch on a big index (config 5: 65536 queries x 65536 clusters): the more queries share a sub-batch, the more
+        // records each scanned cluster chunk serves (the scan's tiles fill up), so take what the part's free memory allows --
+        // half of it, counting the work buffers this handle already holds, for the slots and a sixth for the distance matrix
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const double avail = double(free_b) + double(ix->bitmap.cap) + double(ix->entries.cap) + double(ix->cdist.cap);
+            nb = std::max(nb, fit(std::min(64.0 * 1073741824.0, avail * 0.5), std::min(8.0 * 1073741824.0, avail / 6.0)));
+        } else {
+            cudaGetLastError();
+        }
+    }
     return std::max<size_t>(1, std::min(nb, nq));
 }
 
@@ -1815,6 +1831,8 @@ int rabitq_min_f32_device(int device, float* d_dst, const float* d_src, size_t n
 }
 
 const char* rabitq_last_error(void) { return g_err.c_str(); }
+
+int rabitq_debug_rec_pos(int d) { return rq::rec_pos(d); }
 
 int rabitq_load_from_dir(const char* dir, int device, rabitq_index** out) { return load_dir(dir, device, 0, 1, out); }
 
