@@ -1868,6 +1868,309 @@ __global__ void __launch_bounds__(128, 5) rerank_kernel(RerankArgs a, int p_lo, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K5 (single-GPU form): the same exact sequential replay as rerank_kernel, one CTA per query, warp-specialised.
+//
+// rerank_kernel gives a query ONE warp, which streams the survivors, issues the row gathers, computes the exact distances and
+// replays the reference's tests, one after the other: a launch lasts as long as its slowest query's chain of latencies (7 % of
+// the warp slots active).  Here the three jobs run concurrently on different warps of the query's CTA and
+// meet through mbarriers:
+//   * warp 0, the PRODUCER, streams the query's survivor words in visit order (bitmap words two blocks ahead, entries one block
+//     ahead), keeps the candidates whose estimate is below the threshold as it stands (a stale threshold is only LARGER: the
+//     queue is a superset of what the reference computes) and packs them into WAVES of R rows; every row is gathered with one TMA
+//     bulk copy into one of two row buffers, completion on the wave's `full` barrier;
+//   * warps 2.., the COMPUTE warps, turn a full wave into exact squared distances: eight lanes per candidate, lane l = AVX lane l
+//     of simd::l2_squared_distance (src/simd.rs:14-73) as one scalar FMA chain (l2_oct), NC candidates per group, all groups of
+//     all compute warps at once -- the dependent chain of D/8 FMAs is paid once per wave, not once per four rows;
+//   * warp 1, the REPLAY warp, owns the k-slot result buffer and the threshold: it walks the wave in order with the reference's
+//     two strict tests (src/rerank.rs:84,92), stretch by stretch, and publishes the threshold for the other two.
+// Row buffers are double-buffered between producer and compute warps, the (rough, position, exact) wave records live in a ring
+// of four between producer, compute and replay.  Heap contents, threshold trajectory and `precise` are exactly those of the
+// sequential loop; speculation costs extra gathers only.
+template <bool HEUR, int NC>
+__global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo, int ch_lo, int p_hi, int ch_hi, int first, int finalize) {
+    extern __shared__ __align__(16) unsigned char rc_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ncw = (int)(blockDim.x >> 5) - 2;
+    const int q = blockIdx.x;
+    const int D = a.D, k = a.topk, R = a.R, pitch = D + 8;
+    const uint32_t rowbytes = (uint32_t)D * 4u;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(rc_smem_raw);  // [2] rows of a wave landed (producer arrive + TMA bytes)
+    uint64_t* bar_rfree = bar_full + 2;                             // [2] every compute warp is done with the row buffer
+    uint64_t* bar_exact = bar_full + 4;                             // [4] every compute warp has written its exact distances
+    uint64_t* bar_mfree = bar_full + 8;                             // [4] the replay warp is done with the wave record
+    volatile float* thr_s = reinterpret_cast<volatile float*>(rc_smem_raw + 96);
+    volatile uint32_t* wn = reinterpret_cast<volatile uint32_t*>(rc_smem_raw + 100);  // [4] candidates of the wave
+    volatile uint32_t* wlast = wn + 4;                                               // [4] last wave of the query
+    float* qv = reinterpret_cast<float*>(rc_smem_raw + 144);
+    float* rows = qv + D;                                    // [2][R][pitch]
+    float* hd = rows + (size_t)2 * R * pitch;
+    uint32_t* hid = reinterpret_cast<uint32_t*>(hd + k);
+    float* qr = reinterpret_cast<float*>(hid + k);           // [4][32] rough
+    uint32_t* qj = reinterpret_cast<uint32_t*>(qr + 128);    // [4][32] position
+    float* ex = reinterpret_cast<float*>(qj + 128);          // [4][32] exact
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const long long dbg_t0 = a.dbg ? clock64() : 0ll;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
+        mbar_init(&bar_rfree[0], (uint32_t)ncw); mbar_init(&bar_rfree[1], (uint32_t)ncw);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { mbar_init(&bar_exact[i], (uint32_t)ncw); mbar_init(&bar_mfree[i], 1); }
+        *thr_s = first ? 3.402823466e+38f : a.thr[q];
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.qpad + (size_t)q * D);
+        float4* dst = reinterpret_cast<float4*>(qv);
+        for (int d = threadIdx.x; d < D / 4; d += blockDim.x) dst[d] = __ldg(&src[d]);
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------------- producer
+        const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
+        const int p0 = (int)a.q_p0[q];
+        auto word_at = [&](int pe, int ch) -> uint32_t {
+            const int p = pe + p0;
+            if (p >= a.P) return wend;
+            const uint32_t s0 = wb + a.slot_local[(size_t)q * a.P + p];
+            const uint32_t s1 = (p + 1 < a.P) ? wb + a.slot_local[(size_t)q * a.P + p + 1] : wend;
+            return min(s0 + (uint32_t)ch * (SCAN_THREADS / 32), s1);
+        };
+        const uint32_t wlo = word_at(p_lo, ch_lo), whi = word_at(p_hi, ch_hi);
+        uint32_t w = 0;
+        int fill = 0;
+        auto open_wave = [&]() {  // the wave's row buffer and record slot must have been drained
+            if (w >= 2) mbar_wait<32>(&bar_rfree[w & 1], ((w >> 1) + 1) & 1u);
+            if (w >= 4) mbar_wait<32>(&bar_mfree[w & 3], ((w >> 2) + 1) & 1u);
+        };
+        auto close_wave = [&](uint32_t last) {
+            if (fill == 0) open_wave();
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) {
+                wn[w & 3] = (uint32_t)fill;
+                wlast[w & 3] = last;
+                mbar_arrive(&bar_full[w & 1]);
+            }
+            w++;
+            fill = 0;
+        };
+        auto enqueue = [&](uint32_t pm, float rough, uint32_t j) {
+            while (pm) {
+                if (fill == 0) open_wave();
+                const uint32_t s = w & 1, m = w & 3;
+                const int space = R - fill;
+                const int rank = __popc(pm & lt_mask);
+                const bool take = ((pm >> lane) & 1u) && rank < space;
+                const uint32_t took = __ballot_sync(FULL, take);
+                if (lane == __ffs(took) - 1) mbar_expect_tx(&bar_full[s], rowbytes * (uint32_t)__popc(took));
+                __syncwarp();
+                if (take) {
+                    const int slot = fill + rank;
+                    qr[m * 32 + slot] = rough;
+                    qj[m * 32 + slot] = j;
+                    tma_bulk_g2s(rows + ((size_t)s * R + slot) * pitch, a.base + (size_t)j * D, rowbytes, &bar_full[s]);
+                }
+                pm &= ~took;
+                fill += __popc(took);
+                if (fill == R) close_wave(0u);
+            }
+        };
+        auto load_bitmap = [&](uint32_t w0) -> uint32_t {
+            const uint32_t idx = w0 + lane;
+            return (w0 < whi && idx < whi) ? a.bitmap[idx] : 0u;
+        };
+        auto prefix = [&](uint32_t m) -> uint32_t {  // inclusive prefix sum of the words' survivor counts
+            uint32_t x = __popc(m);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, x, o);
+                if (lane >= o) x += t;
+            }
+            return x;
+        };
+        auto load_chunk = [&](uint32_t w0, uint32_t incl, uint32_t exc, uint32_t T, uint32_t e0) -> float2 {  // survivor e0 + lane of the block
+            const uint32_t e = e0 + lane;
+            int pos = 0;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const uint32_t pv = __shfl_sync(FULL, incl, pos + s - 1);
+                if (pv <= e) pos += s;
+            }
+            pos = min(pos, 31);
+            const uint32_t src_excl = __shfl_sync(FULL, exc, pos);
+            float2 en = make_float2(3.402823466e+38f, 0.0f);
+            if (e < T) en = a.entries[(size_t)(w0 + pos) * 32 + (e - src_excl)];
+            return en;
+        };
+        // software pipeline over blocks of 32 words: bitmap words two blocks ahead, the first 32 entries one block ahead
+        uint32_t m1 = load_bitmap(wlo), m2 = load_bitmap(wlo + 32);
+        uint32_t incl1 = prefix(m1);
+        uint32_t T1 = __shfl_sync(FULL, incl1, 31);
+        float2 en1 = load_chunk(wlo, incl1, incl1 - __popc(m1), T1, 0u);
+        for (uint32_t w0 = wlo; w0 < whi; w0 += 32) {
+            const uint32_t m = m1, incl = incl1, T = T1;
+            float2 en = en1;
+            m1 = m2;
+            m2 = load_bitmap(w0 + 64);
+            incl1 = prefix(m1);
+            T1 = __shfl_sync(FULL, incl1, 31);
+            en1 = load_chunk(w0 + 32, incl1, incl1 - __popc(m1), T1, 0u);
+            if (T == 0) continue;  // uniform
+            const uint32_t exc = incl - __popc(m);
+            for (uint32_t e0 = 0; e0 < T; e0 += 32) {  // dense blocks (loose threshold): the next chunk's entries fly meanwhile
+                float2 nxt = make_float2(3.402823466e+38f, 0.0f);
+                if (e0 + 32 < T) nxt = load_chunk(w0, incl, exc, T, e0 + 32);
+                const uint32_t pm = __ballot_sync(FULL, e0 + lane < T && en.x < *thr_s);
+                if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
+                en = nxt;
+            }
+        }
+        close_wave(1u);
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------------- replay
+        int cnt = first ? 0 : (int)a.heap_cnt[q];
+        float thr = *thr_s;
+        float hmax = 3.402823466e+38f;
+        float recent = first ? -3.402823466e+38f : a.h_recent[q];
+        uint32_t wcount = first ? 0u : a.h_wcount[q];
+        int maxpos = 0;
+        for (int s = lane; s < cnt; s += 32) {
+            hd[s] = a.heap_dist[(size_t)q * k + s];
+            hid[s] = a.heap_ids[(size_t)q * k + s];
+        }
+        __syncwarp();
+        if (cnt == k) {
+            heap_recompute_max(hd, k, lane, maxpos, hmax);
+            if constexpr (!HEUR) thr = hmax;
+        }
+        uint32_t precise = 0, computed = 0, waves = 0;
+        for (uint32_t w = 0;; w++) {
+            const uint32_t m = w & 3;
+            mbar_wait(&bar_exact[m], (w >> 2) & 1u);
+            const int n = (int)wn[m];
+            const uint32_t last = wlast[m];
+            const bool mine = lane < n;
+            const float rough = mine ? qr[m * 32 + lane] : 0.0f;
+            const uint32_t j = mine ? qj[m * 32 + lane] : 0u;
+            const float exact = mine ? ex[m * 32 + lane] : 0.0f;
+            computed += (uint32_t)n;
+            waves += n ? 1u : 0u;
+            // in-order replay (rerank.rs:83-101).  The threshold only moves when a candidate is ACCEPTED (rough < thr and
+            // exact < thr), so the stretch up to the next accepted candidate is evaluated in one step: every lane of the
+            // stretch with rough < thr is a candidate the reference computes an exact distance for.
+            uint32_t rem = __ballot_sync(FULL, mine && rough < thr);
+            while (rem) {
+                const bool pass = ((rem >> lane) & 1u) && rough < thr;
+                const uint32_t pm = __ballot_sync(FULL, pass);
+                const uint32_t am = __ballot_sync(FULL, pass && exact < thr);
+                const int t = __ffs(am) - 1;                           // the next accepted candidate (-1: none)
+                const uint32_t upto = am ? ((2u << t) - 1u) : FULL;    // lanes 0..t
+                precise += __popc(pm & upto);
+                if (!am) break;
+                rem &= ~upto;
+                const float exa = __shfl_sync(FULL, exact, t);
+                if (!HEUR || cnt < k || exa < hmax) {
+                    const int slot = cnt < k ? cnt : maxpos;
+                    if (lane == t) { hd[slot] = exa; hid[slot] = j; }  // the POSITION; map_ids at finalize
+                    if (cnt < k) cnt++;
+                    __syncwarp();
+                    if (cnt == k) {
+                        heap_recompute_max(hd, k, lane, maxpos, hmax);
+                        if constexpr (!HEUR) thr = hmax;  // rerank.rs:98-100
+                    }
+                }
+                if constexpr (HEUR) {  // rerank.rs:155-162
+                    wcount++;
+                    recent = fmaxf(recent, exa);
+                    if (wcount >= 12u) {
+                        thr = recent;
+                        wcount = 0;
+                        recent = -3.402823466e+38f;
+                    }
+                }
+                if (lane == 0) *thr_s = thr;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_mfree[m]);
+            if (last) break;
+        }
+        if (a.dbg && lane == 0) {
+            uint32_t* o = a.dbg + ((size_t)q * 2 + (first ? 0 : 1)) * 8;
+            o[0] = (uint32_t)(clock64() - dbg_t0); o[1] = waves; o[2] = computed;
+        }
+        if (lane == 0) {
+            a.q_precise[q] = (first ? 0u : a.q_precise[q]) + precise;
+            atomicAdd(&a.counters[1], (unsigned long long)computed);
+            atomicAdd(&a.counters[2], (unsigned long long)precise);
+        }
+        if (!finalize) {
+            for (int s = lane; s < cnt; s += 32) {
+                a.heap_dist[(size_t)q * k + s] = hd[s];
+                a.heap_ids[(size_t)q * k + s] = hid[s];
+            }
+            if (lane == 0) { a.heap_cnt[q] = (uint32_t)cnt; a.thr[q] = thr; a.h_recent[q] = recent; a.h_wcount[q] = wcount; }
+        } else {
+            // ascending by (distance, id): rank by counting; the original ids (rerank.rs:94) are looked up here
+            __syncwarp();
+            for (int s = lane; s < cnt; s += 32) hid[s] = a.map_ids[hid[s]];
+            __syncwarp();
+            for (int s = lane; s < k; s += 32) {
+                if (s < cnt) {
+                    const uint32_t ks = okey(hd[s]), is = hid[s];
+                    int rank = 0;
+                    for (int t = 0; t < cnt; t++) {
+                        const uint32_t kt = okey(hd[t]), itt = hid[t];
+                        rank += (kt < ks) || (kt == ks && (itt < is || (itt == is && t < s)));
+                    }
+                    a.out_dist[(size_t)q * k + rank] = hd[s];
+                    a.out_ids[(size_t)q * k + rank] = is;
+                } else {
+                    a.out_dist[(size_t)q * k + s] = __int_as_float(0x7f800000);
+                    a.out_ids[(size_t)q * k + s] = 0xffffffffu;
+                }
+            }
+            if (lane == 0) a.out_count[q] = (uint32_t)cnt;
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------- compute
+        const int cw = warp - 2, grp = lane >> 3, l8 = lane & 7;
+        for (uint32_t w = 0;; w++) {
+            const uint32_t s = w & 1, m = w & 3;
+            mbar_wait(&bar_full[s], (w >> 1) & 1u);
+            const int n = (int)wn[m];
+            const uint32_t last = wlast[m];
+            const float thr = *thr_s;  // stale at worst = larger: whatever the replay will test has been computed
+            const float* rw = rows + (size_t)s * R * pitch;
+            int c[NC];
+            bool need = false;
+#pragma unroll
+            for (int i = 0; i < NC; i++) {
+                c[i] = (cw * NC + i) * 4 + grp;
+                need = need || (c[i] < n && qr[m * 32 + c[i]] < thr);
+            }
+            if (__any_sync(FULL, need)) {
+                float d2[NC];
+                if constexpr (NC == 2) {
+                    const float* const rp[2] = {rw + (size_t)min(c[0], R - 1) * pitch, rw + (size_t)min(c[1], R - 1) * pitch};
+                    l2_oct<2>(rp, qv, D, l8, d2);
+                } else {
+                    const float* const rp[1] = {rw + (size_t)min(c[0], R - 1) * pitch};
+                    l2_oct<1>(rp, qv, D, l8, d2);
+                }
+#pragma unroll
+                for (int i = 0; i < NC; i++)
+                    if (l8 == 0 && c[i] < n) ex[m * 32 + c[i]] = d2[i];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the rows of this buffer are rewritten by later bulk copies
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&bar_rfree[s]); mbar_arrive(&bar_exact[m]); }
+            if (last) break;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K6 (after the NCCL all-gather of per-shard results): k smallest of n_lists x topk candidates per query.
 __global__ void merge_topk_kernel(const float* __restrict__ dist, const uint32_t* __restrict__ ids, int n_lists, size_t nq, int topk,
                                   float* __restrict__ out_dist, uint32_t* __restrict__ out_ids, uint32_t* __restrict__ out_count) {

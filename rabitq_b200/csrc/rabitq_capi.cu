@@ -123,11 +123,14 @@ struct ListSet {
     DevBuf qrec;            // this round's records (K3), in list order: a cluster's records are contiguous
     size_t cap_items = 0;   // upper bound of the list's length (queries x ranks of the window)
     uint32_t MS = 0, ch_min = 0;
-    cudaEvent_t ready = nullptr;  // inverted list built (K3 and the work-item pass wait for it)
+    cudaEvent_t ready = nullptr;   // inverted list built (K3 and the work-item pass wait for it)
+    cudaEvent_t qready = nullptr;  // records written by K3 on the side stream (later rounds only; the scan of the round waits for it)
+    bool q_on_aux = false;
     void release() {
         for (DevBuf* b : {&cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &qrec}) b->release();
         if (ready) cudaEventDestroy(ready);
-        ready = nullptr;
+        if (qready) cudaEventDestroy(qready);
+        ready = qready = nullptr;
     }
 };
 
@@ -171,6 +174,8 @@ struct rabitq_index {
     std::mutex mu;
     std::vector<uint32_t> rounds{0};
     int rerank_rows = 0;   // rows per rerank wave; 0 = by dimension
+    int rerank_mode = 1;   // 1: one CTA per query, warp-specialised (rerank_cta_kernel); 0: one warp per query (rerank_kernel)
+    int rerank_nc = 0;     // candidates per eight-lane group of the CTA form (1 or 2; 0 = by wave size)
     int debug_rerank = 0;     // per-query rerank statistics (rabitq_debug_rerank_stats)
     int rerank_prefetch = 0;  // L2 prefetch of survivor rows in the rerank stream (rabitq_set_option("rerank_prefetch"))
     int first_chunks = 1;  // 128-vector chunks of the nearest cluster in the first round (0 = the whole cluster)
@@ -342,6 +347,8 @@ int finish_index(rabitq_index* ix) {
     if (const char* e = std::getenv("RABITQ_FIRST_CHUNKS")) ix->first_chunks = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("RABITQ_RR_ROWS")) ix->rerank_rows = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_RR_PREFETCH")) ix->rerank_prefetch = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_RR_MODE")) ix->rerank_mode = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_RR_NC")) ix->rerank_nc = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_SCAN_SLICES")) ix->scan_slices = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RABITQ_SCAN_STAGES")) ix->scan_stages = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("RABITQ_SCAN_SUB")) ix->scan_sub = std::max(0, std::atoi(e));
@@ -356,6 +363,10 @@ int finish_index(rabitq_index* ix) {
     CU(cudaFuncSetAttribute(rerank_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(rerank_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(rerank_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_cta_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_cta_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_cta_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_cta_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(approx_gemm_tf32_kernel<128, 128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * PF_PITCH * 4));
     if (const char* e = std::getenv("RABITQ_PREFILTER")) ix->prefilter = std::atoi(e);
@@ -977,15 +988,18 @@ uint32_t scan_ms(const rabitq_index* ix) { return (uint32_t)std::max(1, scan_qs(
 
 // K3 over the inverted list of round `set` (built on the side stream: the main stream waits for it here); on a shard, items
 // whose cluster lives elsewhere are skipped
-int run_quantize_list(rabitq_index* ix, int P, size_t set) {
+int run_quantize_list(rabitq_index* ix, int P, size_t set, bool on_aux) {
     const int D = (int)ix->D, W32 = D / 32, RS = (D + REC_META_BYTES) / 4;  // record words: D code bytes + scalars
-    cudaStream_t st = ix->stream;
+    // the first round's records on the main stream (its scan comes next); later rounds' on the side stream, right behind their
+    // list: they are written while the first round's scan and (latency-bound, SM-starved) replay run
+    cudaStream_t st = on_aux ? ix->aux_stream : ix->stream;
     ListSet& L = ix->lists[set];
     const int pitch = scan_rec_pitch(D);
     CU(L.qrec.ensure(std::max<size_t>(L.cap_items, 1) * (size_t)pitch));
-    CU(cudaStreamWaitEvent(st, L.ready, 0));
+    L.q_on_aux = on_aux;
+    if (!on_aux) CU(cudaStreamWaitEvent(st, L.ready, 0));
     const uint32_t* skip = ix->shard_count > 1 ? ix->offsets : nullptr;
-    if (L.cap_items == 0) return 0;
+    if (L.cap_items == 0) { L.q_on_aux = false; return 0; }
 #define QUANT_COMMON L.cl_items.as<uint2>(), L.cl_start.as<uint32_t>() + ix->K, ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), \
                      ix->q_wbase.as<uint32_t>(), skip, ix->quant_bias, L.qrec.as<unsigned char>(), pitch, P
     if (W32 == 2 || W32 == 4 || W32 == 6 || W32 == 8) {
@@ -1016,6 +1030,10 @@ int run_quantize_list(rabitq_index* ix, int P, size_t set) {
         }
     }
 #undef QUANT_COMMON
+    if (on_aux) {
+        if (!L.qready) CU(cudaEventCreateWithFlags(&L.qready, cudaEventDisableTiming));
+        CU(cudaEventRecord(L.qready, st));
+    }
     CU(cudaGetLastError()); ix->counts[5]++;
     return 0;
 }
@@ -1165,6 +1183,8 @@ int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos
     cudaStream_t st = ix->stream;
     const int K = (int)ix->K;
     ListSet& L = ix->lists[set];
+    CU(cudaStreamWaitEvent(st, L.ready, 0));
+    if (L.q_on_aux) CU(cudaStreamWaitEvent(st, L.qready, 0));
     CU(L.work.ensure(ix->max_items * sizeof(ScanItem)));
     work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(), L.cl_start.as<uint32_t>(), ix->offsets,
                                                        ix->chunk_start, K, L.MS, L.ch_min, L.work.as<ScanItem>());
@@ -1190,6 +1210,32 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
     const dim3 rgrid((unsigned)((nb + rr_wpb - 1) / rr_wpb)), rblock(rr_wpb * 32);
     const size_t rsmem = (size_t)rr_wpb * ra.smem_per_warp;
     const int f = is_first ? 1 : 0, l = is_last ? 1 : 0;
+    if (kind != ROUND_SINK1 && ix->rerank_mode == 1) {
+        // one CTA per query: producer + replay + compute warps (rerank_cta_kernel).  Wave size by dimension: 8 rows of a large
+        // dimension keep three queries per SM resident, short rows take 16 with two candidates per eight-lane group
+        const size_t D = (size_t)ra.D, fixed = 144 + D * 4 + 2 * (size_t)ra.topk * 4 + 3 * 128 * 4;
+        int R = ix->rerank_rows > 0 ? std::min(32, ix->rerank_rows) : (D <= 256 ? 16 : 8);
+        while (R > 1 && fixed + 2 * (size_t)R * (D + 8) * 4 > (size_t)200 * 1024) R--;
+        const size_t smem = fixed + 2 * (size_t)R * (D + 8) * 4;
+        if (smem <= (size_t)200 * 1024) {
+            int nc = ix->rerank_nc == 1 || ix->rerank_nc == 2 ? ix->rerank_nc : (R >= 16 ? 2 : 1);
+            if ((R + 4 * nc - 1) / (4 * nc) > 8) nc = 2;
+            const int ncw = (R + 4 * nc - 1) / (4 * nc);
+            RerankArgs rc = ra;
+            rc.R = R;
+            const dim3 grid((unsigned)nb), block((unsigned)(2 + ncw) * 32);
+            if (heuristic) {
+                if (nc == 2) rerank_cta_kernel<true, 2><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
+                else rerank_cta_kernel<true, 1><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
+            } else {
+                if (nc == 2) rerank_cta_kernel<false, 2><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
+                else rerank_cta_kernel<false, 1><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
+            }
+            CU(cudaGetLastError()); ix->counts[5]++;
+            if (tick(ix, ST_RERANK)) return RABITQ_ECUDA;
+            return 0;
+        }
+    }
     if (kind == ROUND_SINK1) rerank_kernel<false, 1><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
     else if (heuristic) rerank_kernel<true, 0><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
     else rerank_kernel<false, 0><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
@@ -1228,11 +1274,14 @@ int run_lists_and_quantize(rabitq_index* ix, size_t nb, int P, const std::vector
     const uint32_t MS = scan_ms(ix);
     CU(cudaStreamWaitEvent(ix->aux_stream, ix->ev_fork, 0));
     int rc;
-    for (size_t r = 0; r + 1 < bounds.size(); r++)
+    static const bool k3_aux = std::getenv("RABITQ_K3_MAIN") == nullptr;
+    for (size_t r = 0; r + 1 < bounds.size(); r++) {
         if ((rc = build_lists(ix, nb, P, MS, bounds[r], bounds[r + 1], r, ix->aux_stream))) return rc;
+        if (r > 0 && k3_aux && (rc = run_quantize_list(ix, P, r, true))) return rc;
+    }
     if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
     for (size_t r = 0; r + 1 < bounds.size(); r++)
-        if ((rc = run_quantize_list(ix, P, r))) return rc;
+        if ((r == 0 || !k3_aux) && (rc = run_quantize_list(ix, P, r, false))) return rc;
     if (tick(ix, ST_QUANT)) return RABITQ_ECUDA;
     return 0;
 }
@@ -1405,6 +1454,7 @@ int stage_prefix(rabitq_index* ix, const float* queries, size_t nq, size_t len, 
     rc = run_sub_batch(ix, nq, len, probe, 1, false, stop, bo);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaStreamSynchronize(ix->aux_stream));  // later rounds' records are written there
     return 0;
 }
 
@@ -1984,6 +2034,8 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     else if (n == "scan_mode") idx->scan_mode = (int)value;
     else if (n == "rerank_rows") idx->rerank_rows = (int)value;
     else if (n == "rerank_prefetch") idx->rerank_prefetch = (int)value;
+    else if (n == "rerank_mode") idx->rerank_mode = (int)value;
+    else if (n == "rerank_nc") idx->rerank_nc = (int)value;
     else if (n == "debug_rerank") idx->debug_rerank = (int)value;
     else if (n == "scan_slices") idx->scan_slices = (int)std::max(1L, value);
     else if (n == "scan_stages") idx->scan_stages = (int)std::max(0L, value);
