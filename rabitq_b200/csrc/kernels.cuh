@@ -1389,7 +1389,9 @@ struct RerankArgs {
     uint32_t* out_ids;
     uint32_t* out_count;
     int nq, P, D, topk;
-    int R;                        // rows per wave (<= 32)
+    int R;                        // rows per wave (<= 32; rerank_cta_kernel: <= 8)
+    int ns;                       // rerank_cta_kernel: row buffers in the ring
+    const uint2* win;             // rerank_cta_kernel: this round's (first word, end word) per query (round_windows_kernel), or NULL
     int smem_per_warp;            // bytes
     int prefetch;                 // L2 prefetch of the survivors' base rows at discovery time (0 = off)
     uint32_t* dbg;                // NULL, or nq x 2 rounds x {cycles, waves, computed, enqueue (incl. the waves processed inside), wait, l2, replay, stage} (rabitq_debug_rerank_stats)
@@ -1494,7 +1496,7 @@ RQ_DEV void l2_oct(const float* const (&row)[NC], const float* __restrict__ qv, 
 #pragma unroll
     for (int c = 0; c < NC; c++) acc[c] = 0.0f;
 #pragma unroll 1
-    for (int s0 = 0; s0 < D; s0 += 64) {  // 8 steps of 8 elements per iteration (D is a multiple of 64)
+    for (int s0 = 0; s0 < D; s0 += 64) {  // 8 steps of 8 elements per iteration (D is a multiple of 64); (a register-prefetched form was measured slower)
         float x[NC][8], q[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -1886,37 +1888,70 @@ __global__ void __launch_bounds__(128, 5) rerank_kernel(RerankArgs a, int p_lo, 
 // Row buffers are double-buffered between producer and compute warps, the (rough, position, exact) wave records live in a ring
 // of four between producer, compute and replay.  Heap contents, threshold trajectory and `precise` are exactly those of the
 // sequential loop; speculation costs extra gathers only.
+// Word windows [first, end) of every rerank round of every query in the survivor-slot space: the round bounds are visit positions
+// (effective probe rank, 128-vector chunk); turning them into words is a chain of three dependent loads (q_p0 -> slot_local ->
+// ...) that would otherwise open every query's replay -- done here, once, on the side stream.
+struct RoundBounds { int n; int p[17]; int ch[17]; };  // n positions = n - 1 rounds
+__global__ void round_windows_kernel(const uint32_t* __restrict__ q_wbase, const uint32_t* __restrict__ slot_local, const uint32_t* __restrict__ q_p0,
+                                     int nq, int P, RoundBounds b, uint2* __restrict__ win /* (n - 1) x nq */) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint32_t wb = q_wbase[q], wend = q_wbase[q + 1];
+    const int p0 = (int)q_p0[q];
+    uint32_t prev = 0;
+    for (int i = 0; i < b.n; i++) {
+        const int p = b.p[i] + p0;
+        uint32_t w = wend;
+        if (p < P) {
+            const uint32_t s0 = wb + slot_local[(size_t)q * P + p];
+            const uint32_t s1 = (p + 1 < P) ? wb + slot_local[(size_t)q * P + p + 1] : wend;
+            w = min(s0 + (uint32_t)b.ch[i] * (SCAN_THREADS / 32), s1);
+        }
+        if (i > 0) win[(size_t)(i - 1) * nq + q] = make_uint2(prev, w);
+        prev = w;
+    }
+}
+
+// blocks of 32 survivor words per super-block of the producer's stream: 8 for long rows (few queries per SM anyway), 2 for short rows
+// (NC = 2), where registers and shared memory per CTA decide how many queries an SM keeps in flight
+__host__ __device__ constexpr int rerank_cta_sb(int nc) { return nc == 2 ? 2 : 8; }
+__host__ __device__ __forceinline__ size_t rerank_cta_smem(int D, int topk, int R, int ns, int nc) {
+    const int sb = rerank_cta_sb(nc);
+    return 528 + (size_t)D * 4 + (size_t)ns * R * (D + 8) * 4 + 2 * (size_t)topk * 4 + 3 * 16 * 8 * 4 + (size_t)sb * 32 * 16 + sb * 4 + 16;
+}
 template <bool HEUR, int NC>
 __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo, int ch_lo, int p_hi, int ch_hi, int first, int finalize) {
     extern __shared__ __align__(16) unsigned char rc_smem_raw[];
+    constexpr int RC_SB = rerank_cta_sb(NC);
+    constexpr uint32_t NM = 16, RW = 8;  // wave records in the ring, candidates per record (R <= 4 NC <= 8)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ncw = (int)(blockDim.x >> 5) - 2;
     const int q = blockIdx.x;
     const int D = a.D, k = a.topk, R = a.R, pitch = D + 8;
+    const uint32_t NS = (uint32_t)a.ns;  // row buffers in the ring (<= 8)
     const uint32_t rowbytes = (uint32_t)D * 4u;
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(rc_smem_raw);  // [2] rows of a wave landed (producer arrive + TMA bytes)
-    uint64_t* bar_rfree = bar_full + 2;                             // [2] every compute warp is done with the row buffer
-    uint64_t* bar_exact = bar_full + 4;                             // [4] every compute warp has written its exact distances
-    uint64_t* bar_mfree = bar_full + 8;                             // [4] the replay warp is done with the wave record
-    volatile float* thr_s = reinterpret_cast<volatile float*>(rc_smem_raw + 96);
-    volatile uint32_t* wn = reinterpret_cast<volatile uint32_t*>(rc_smem_raw + 100);  // [4] candidates of the wave
-    volatile uint32_t* wlast = wn + 4;                                               // [4] last wave of the query
-    float* qv = reinterpret_cast<float*>(rc_smem_raw + 144);
-    float* rows = qv + D;                                    // [2][R][pitch]
-    float* hd = rows + (size_t)2 * R * pitch;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(rc_smem_raw);  // [8]  rows of a wave landed (producer arrive + TMA bytes)
+    uint64_t* bar_rfree = bar_full + 8;                             // [8]  the wave's compute warp is done with the row buffer
+    uint64_t* bar_exact = bar_full + 16;                            // [16] the wave's exact distances are written
+    uint64_t* bar_mfree = bar_full + 32;                            // [16] the replay warp is done with the wave record
+    volatile float* thr_s = reinterpret_cast<volatile float*>(rc_smem_raw + 384);
+    volatile uint32_t* wn = reinterpret_cast<volatile uint32_t*>(rc_smem_raw + 388);  // [16] candidates of the wave
+    volatile uint32_t* wlast = wn + NM;                                              // [16] 1: last wave of the query, 2: terminator
+    float* qv = reinterpret_cast<float*>(rc_smem_raw + 528);
+    float* rows = qv + D;                                    // [NS][R][pitch]
+    float* hd = rows + (size_t)NS * R * pitch;
     uint32_t* hid = reinterpret_cast<uint32_t*>(hd + k);
-    float* qr = reinterpret_cast<float*>(hid + k);           // [4][32] rough
-    uint32_t* qj = reinterpret_cast<uint32_t*>(qr + 128);    // [4][32] position
-    float* ex = reinterpret_cast<float*>(qj + 128);          // [4][32] exact
+    float* qr = reinterpret_cast<float*>(hid + k);           // [NM][RW] rough
+    uint32_t* qj = reinterpret_cast<uint32_t*>(qr + NM * RW);  // [NM][RW] position
+    float* ex = reinterpret_cast<float*>(qj + NM * RW);      // [NM][RW] exact
+    float2* s_en = reinterpret_cast<float2*>(ex + NM * RW);  // [RC_SB][32] the producer's stash of one super-block's first entries
+    uint32_t* s_incl = reinterpret_cast<uint32_t*>(s_en + RC_SB * 32);  // [RC_SB][32] inclusive prefix of the words' survivor counts
+    uint32_t* s_m = s_incl + RC_SB * 32;                                // [RC_SB][32] the bitmap words
+    uint32_t* s_T = s_m + RC_SB * 32;                                   // [RC_SB] survivors per block
     const uint32_t lt_mask = (1u << lane) - 1u;
     const long long dbg_t0 = a.dbg ? clock64() : 0ll;
 
-    if (threadIdx.x == 0) {
-        mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
-        mbar_init(&bar_rfree[0], (uint32_t)ncw); mbar_init(&bar_rfree[1], (uint32_t)ncw);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { mbar_init(&bar_exact[i], (uint32_t)ncw); mbar_init(&bar_mfree[i], 1); }
-        *thr_s = first ? 3.402823466e+38f : a.thr[q];
-    }
+    if (threadIdx.x < 48) mbar_init(&bar_full[threadIdx.x], 1);
+    if (threadIdx.x == 0) *thr_s = first ? 3.402823466e+38f : a.thr[q];
     {
         const float4* src = reinterpret_cast<const float4*>(a.qpad + (size_t)q * D);
         float4* dst = reinterpret_cast<float4*>(qv);
@@ -1926,30 +1961,39 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------- producer
-        const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
-        const int p0 = (int)a.q_p0[q];
-        auto word_at = [&](int pe, int ch) -> uint32_t {
-            const int p = pe + p0;
-            if (p >= a.P) return wend;
-            const uint32_t s0 = wb + a.slot_local[(size_t)q * a.P + p];
-            const uint32_t s1 = (p + 1 < a.P) ? wb + a.slot_local[(size_t)q * a.P + p + 1] : wend;
-            return min(s0 + (uint32_t)ch * (SCAN_THREADS / 32), s1);
-        };
-        const uint32_t wlo = word_at(p_lo, ch_lo), whi = word_at(p_hi, ch_hi);
+        uint32_t wlo, whi;
+        if (a.win) {
+            const uint2 ww = a.win[q];
+            wlo = ww.x; whi = ww.y;
+        } else {
+            const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
+            const int p0 = (int)a.q_p0[q];
+            auto word_at = [&](int pe, int ch) -> uint32_t {
+                const int p = pe + p0;
+                if (p >= a.P) return wend;
+                const uint32_t s0 = wb + a.slot_local[(size_t)q * a.P + p];
+                const uint32_t s1 = (p + 1 < a.P) ? wb + a.slot_local[(size_t)q * a.P + p + 1] : wend;
+                return min(s0 + (uint32_t)ch * (SCAN_THREADS / 32), s1);
+            };
+            wlo = word_at(p_lo, ch_lo); whi = word_at(p_hi, ch_hi);
+        }
         uint32_t w = 0;
         int fill = 0;
+        uint32_t dbg_blocked = 0;
         auto open_wave = [&]() {  // the wave's row buffer and record slot must have been drained
-            if (w >= 2) mbar_wait<32>(&bar_rfree[w & 1], ((w >> 1) + 1) & 1u);
-            if (w >= 4) mbar_wait<32>(&bar_mfree[w & 3], ((w >> 2) + 1) & 1u);
+            const long long t0 = a.dbg ? clock64() : 0ll;
+            if (w >= NS) mbar_wait<32>(&bar_rfree[w % NS], ((w / NS) + 1) & 1u);
+            if (w >= NM) mbar_wait<32>(&bar_mfree[w % NM], ((w / NM) + 1) & 1u);
+            if (a.dbg) dbg_blocked += (uint32_t)(clock64() - t0);
         };
         auto close_wave = [&](uint32_t last) {
             if (fill == 0) open_wave();
             __threadfence_block();
             __syncwarp();
             if (lane == 0) {
-                wn[w & 3] = (uint32_t)fill;
-                wlast[w & 3] = last;
-                mbar_arrive(&bar_full[w & 1]);
+                wn[w % NM] = (uint32_t)fill;
+                wlast[w % NM] = last;
+                mbar_arrive(&bar_full[w % NS]);
             }
             w++;
             fill = 0;
@@ -1957,7 +2001,7 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
         auto enqueue = [&](uint32_t pm, float rough, uint32_t j) {
             while (pm) {
                 if (fill == 0) open_wave();
-                const uint32_t s = w & 1, m = w & 3;
+                const uint32_t s = w % NS, m = w % NM;
                 const int space = R - fill;
                 const int rank = __popc(pm & lt_mask);
                 const bool take = ((pm >> lane) & 1u) && rank < space;
@@ -1966,18 +2010,14 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
                 __syncwarp();
                 if (take) {
                     const int slot = fill + rank;
-                    qr[m * 32 + slot] = rough;
-                    qj[m * 32 + slot] = j;
+                    qr[m * RW + slot] = rough;
+                    qj[m * RW + slot] = j;
                     tma_bulk_g2s(rows + ((size_t)s * R + slot) * pitch, a.base + (size_t)j * D, rowbytes, &bar_full[s]);
                 }
                 pm &= ~took;
                 fill += __popc(took);
                 if (fill == R) close_wave(0u);
             }
-        };
-        auto load_bitmap = [&](uint32_t w0) -> uint32_t {
-            const uint32_t idx = w0 + lane;
-            return (w0 < whi && idx < whi) ? a.bitmap[idx] : 0u;
         };
         auto prefix = [&](uint32_t m) -> uint32_t {  // inclusive prefix sum of the words' survivor counts
             uint32_t x = __popc(m);
@@ -2002,30 +2042,75 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             if (e < T) en = a.entries[(size_t)(w0 + pos) * 32 + (e - src_excl)];
             return en;
         };
-        // software pipeline over blocks of 32 words: bitmap words two blocks ahead, the first 32 entries one block ahead
-        uint32_t m1 = load_bitmap(wlo), m2 = load_bitmap(wlo + 32);
-        uint32_t incl1 = prefix(m1);
-        uint32_t T1 = __shfl_sync(FULL, incl1, 31);
-        float2 en1 = load_chunk(wlo, incl1, incl1 - __popc(m1), T1, 0u);
-        for (uint32_t w0 = wlo; w0 < whi; w0 += 32) {
-            const uint32_t m = m1, incl = incl1, T = T1;
-            float2 en = en1;
-            m1 = m2;
-            m2 = load_bitmap(w0 + 64);
-            incl1 = prefix(m1);
-            T1 = __shfl_sync(FULL, incl1, 31);
-            en1 = load_chunk(w0 + 32, incl1, incl1 - __popc(m1), T1, 0u);
-            if (T == 0) continue;  // uniform
-            const uint32_t exc = incl - __popc(m);
-            for (uint32_t e0 = 0; e0 < T; e0 += 32) {  // dense blocks (loose threshold): the next chunk's entries fly meanwhile
-                float2 nxt = make_float2(3.402823466e+38f, 0.0f);
-                if (e0 + 32 < T) nxt = load_chunk(w0, incl, exc, T, e0 + 32);
-                const uint32_t pm = __ballot_sync(FULL, e0 + lane < T && en.x < *thr_s);
-                if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
-                en = nxt;
+        // Super-blocks of SB x 32 words.  The stream is a chain of dependent DRAM accesses (bitmap word -> entries -> row), about a
+        // microsecond each under load, so it runs two super-blocks ahead: bitmap words of super-block i+2 and the first 32 entries
+        // of every block of super-block i+1 are in flight while super-block i is filtered and queued (from a shared-memory stash,
+        // so that the processing loop stays rolled).
+        constexpr int SB = RC_SB;
+        uint32_t mB[SB], mC[SB], inclB[SB];
+        float2 enB[SB];
+        auto load_bm = [&](uint32_t wbase, uint32_t (&m)[SB]) {
+#pragma unroll
+            for (int u = 0; u < SB; u++) {
+                const uint32_t idx = wbase + u * 32 + lane;
+                m[u] = idx < whi ? a.bitmap[idx] : 0u;
             }
+        };
+        auto load_entries = [&](uint32_t wbase) {  // needs mB
+#pragma unroll
+            for (int u = 0; u < SB; u++) inclB[u] = prefix(mB[u]);
+#pragma unroll
+            for (int u = 0; u < SB; u++)
+                enB[u] = load_chunk(wbase + u * 32, inclB[u], inclB[u] - __popc(mB[u]), __shfl_sync(FULL, inclB[u], 31), 0u);
+        };
+        load_bm(wlo, mB);
+        load_bm(wlo + 32 * SB, mC);
+        load_entries(wlo);
+        for (uint32_t w0 = wlo; w0 < whi; w0 += 32 * SB) {
+#pragma unroll
+            for (int u = 0; u < SB; u++) {
+                s_en[u * 32 + lane] = enB[u];
+                s_incl[u * 32 + lane] = inclB[u];
+                s_m[u * 32 + lane] = mB[u];
+                if (lane == 31) s_T[u] = inclB[u];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < SB; u++) mB[u] = mC[u];
+            load_bm(w0 + 2 * 32 * SB, mC);
+            load_entries(w0 + 32 * SB);
+#pragma unroll 1
+            for (int u = 0; u < SB; u++) {
+                const uint32_t T = s_T[u];
+                if (T == 0) continue;  // uniform
+                {
+                    const float2 en = s_en[u * 32 + lane];
+                    const uint32_t pm = __ballot_sync(FULL, (uint32_t)lane < T && en.x < *thr_s);
+                    if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
+                }
+                if (T > 32) {  // dense block (loose threshold, e.g. the first probed cluster): further chunks, three at a time in flight
+                    const uint32_t wblk = w0 + u * 32;
+                    const uint32_t inc = s_incl[u * 32 + lane], exc = inc - __popc(s_m[u * 32 + lane]);
+                    for (uint32_t e0 = 32; e0 < T; e0 += 96) {
+                        float2 en[3];
+#pragma unroll
+                        for (int c = 0; c < 3; c++) en[c] = load_chunk(wblk, inc, exc, T, e0 + 32 * c);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const uint32_t pm = __ballot_sync(FULL, e0 + 32 * c + lane < T && en[c].x < *thr_s);
+                            if (pm) enqueue(pm, en[c].x, __float_as_uint(en[c].y));
+                        }
+                    }
+                }
+            }
+            __syncwarp();
         }
         close_wave(1u);
+        for (int i = 1; i < ncw; i++) close_wave(2u);  // one terminator for each of the other compute warps (waves go round-robin)
+        if (a.dbg && lane == 0) {
+            uint32_t* o = a.dbg + ((size_t)q * 2 + (first ? 0 : 1)) * 8;
+            o[3] = dbg_blocked; o[7] = (uint32_t)(clock64() - dbg_t0);
+        }
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------------------- replay
         int cnt = first ? 0 : (int)a.heap_cnt[q];
@@ -2043,16 +2128,18 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             heap_recompute_max(hd, k, lane, maxpos, hmax);
             if constexpr (!HEUR) thr = hmax;
         }
-        uint32_t precise = 0, computed = 0, waves = 0;
+        uint32_t precise = 0, computed = 0, waves = 0, dbg_rwait = 0;
         for (uint32_t w = 0;; w++) {
-            const uint32_t m = w & 3;
-            mbar_wait(&bar_exact[m], (w >> 2) & 1u);
+            const uint32_t m = w % NM;
+            const long long tw0 = a.dbg ? clock64() : 0ll;
+            mbar_wait(&bar_exact[m], (w / NM) & 1u);
+            if (a.dbg) dbg_rwait += (uint32_t)(clock64() - tw0);
             const int n = (int)wn[m];
             const uint32_t last = wlast[m];
             const bool mine = lane < n;
-            const float rough = mine ? qr[m * 32 + lane] : 0.0f;
-            const uint32_t j = mine ? qj[m * 32 + lane] : 0u;
-            const float exact = mine ? ex[m * 32 + lane] : 0.0f;
+            const float rough = mine ? qr[m * RW + lane] : 0.0f;
+            const uint32_t j = mine ? qj[m * RW + lane] : 0u;
+            const float exact = mine ? ex[m * RW + lane] : 0.0f;
             computed += (uint32_t)n;
             waves += n ? 1u : 0u;
             // in-order replay (rerank.rs:83-101).  The threshold only moves when a candidate is ACCEPTED (rough < thr and
@@ -2096,7 +2183,7 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
         }
         if (a.dbg && lane == 0) {
             uint32_t* o = a.dbg + ((size_t)q * 2 + (first ? 0 : 1)) * 8;
-            o[0] = (uint32_t)(clock64() - dbg_t0); o[1] = waves; o[2] = computed;
+            o[0] = (uint32_t)(clock64() - dbg_t0); o[1] = waves; o[2] = computed; o[6] = dbg_rwait;
         }
         if (lane == 0) {
             a.q_precise[q] = (first ? 0u : a.q_precise[q]) + precise;
@@ -2133,10 +2220,15 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
         }
     } else {
         // ------------------------------------------------------------------------------------------- compute
+        // waves go round-robin over the compute warps: a wave (<= 4 NC rows) is one warp's job, several waves are computed at once
         const int cw = warp - 2, grp = lane >> 3, l8 = lane & 7;
-        for (uint32_t w = 0;; w++) {
-            const uint32_t s = w & 1, m = w & 3;
-            mbar_wait(&bar_full[s], (w >> 1) & 1u);
+        uint32_t dbg_cwait = 0, dbg_cl2 = 0;
+        for (uint32_t w = (uint32_t)cw;; w += (uint32_t)ncw) {
+            const uint32_t s = w % NS, m = w % NM;
+            const long long tc0 = a.dbg ? clock64() : 0ll;
+            mbar_wait(&bar_full[s], (w / NS) & 1u);
+            const long long tc1 = a.dbg ? clock64() : 0ll;
+            dbg_cwait += (uint32_t)(tc1 - tc0);
             const int n = (int)wn[m];
             const uint32_t last = wlast[m];
             const float thr = *thr_s;  // stale at worst = larger: whatever the replay will test has been computed
@@ -2145,8 +2237,8 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             bool need = false;
 #pragma unroll
             for (int i = 0; i < NC; i++) {
-                c[i] = (cw * NC + i) * 4 + grp;
-                need = need || (c[i] < n && qr[m * 32 + c[i]] < thr);
+                c[i] = i * 4 + grp;
+                need = need || (c[i] < n && qr[m * RW + c[i]] < thr);
             }
             if (__any_sync(FULL, need)) {
                 float d2[NC];
@@ -2159,13 +2251,18 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
                 }
 #pragma unroll
                 for (int i = 0; i < NC; i++)
-                    if (l8 == 0 && c[i] < n) ex[m * 32 + c[i]] = d2[i];
+                    if (l8 == 0 && c[i] < n) ex[m * RW + c[i]] = d2[i];
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the rows of this buffer are rewritten by later bulk copies
             __threadfence_block();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&bar_rfree[s]); mbar_arrive(&bar_exact[m]); }
+            if (a.dbg) dbg_cl2 += (uint32_t)(clock64() - tc1);
             if (last) break;
+        }
+        if (a.dbg && cw == 0 && lane == 0) {
+            uint32_t* o = a.dbg + ((size_t)q * 2 + (first ? 0 : 1)) * 8;
+            o[4] = dbg_cwait; o[5] = dbg_cl2;
         }
     }
 }

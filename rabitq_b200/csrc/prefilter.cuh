@@ -209,53 +209,58 @@ RQ_DEV float margin(float yn, float cn, float a, float alpha, float gamma) {
     return __fadd_ru(__fadd_ru(__fmul_ru(__fmul_ru(yn, cn), alpha), __fmul_ru(__fmul_ru(s, s), 4.76837158203125e-07f)), __fmul_ru(e, gamma));
 }
 
-__global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
+template <int PST>  // threads per query: 256, or 128 when the batch has several waves of CTAs (twice the queries per SM: the kernel is a chain of latencies)
+__global__ void __launch_bounds__(PST) prefilter_select_kernel(
     const float* __restrict__ A, const float* __restrict__ ynorm, const float* __restrict__ cnorm, const float* __restrict__ cnorm_max,
     const float* __restrict__ y, const float* __restrict__ cent, int K, int P, int D, const uint32_t* __restrict__ offsets,
     const uint32_t* __restrict__ offsets_g, uint32_t* __restrict__ probe_ids, float* __restrict__ probe_dist,
     uint32_t* __restrict__ slot_local, uint32_t* __restrict__ q_words, uint32_t* __restrict__ q_pairs, uint32_t* __restrict__ q_p0,
-    uint32_t* __restrict__ fallback_flag, int cap /* <= PS_CAP; tests lower it to exercise the fallback */, float alpha, float gamma) {
+    uint32_t* __restrict__ fallback_flag, int cap /* candidate capacity (even, <= PS_CAP; sizes the shared-memory arrays); tests lower it to exercise the fallback */, float alpha, float gamma) {
     extern __shared__ __align__(16) unsigned char ps_smem_raw[];
     float* sy = reinterpret_cast<float*>(ps_smem_raw);                            // D
-    uint32_t* cid = reinterpret_cast<uint32_t*>(sy + D);                          // PS_CAP candidate ids
-    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(cid + PS_CAP);  // PS_CAP (okey(exact) << 32 | id)
-    uint32_t* words = reinterpret_cast<uint32_t*>(ckey + PS_CAP);                 // P
+    uint32_t* cid = reinterpret_cast<uint32_t*>(sy + D);                          // cap candidate ids
+    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(cid + cap);  // cap (okey(exact) << 32 | id)   (cap is even: 8-byte aligned)
+    uint32_t* words = reinterpret_cast<uint32_t*>(ckey + cap);                    // P
     __shared__ uint32_t hist[256];
-    __shared__ float s_red[2 * (PS_THREADS / 32)];
+    __shared__ float s_red[2 * (PST / 32)];
     __shared__ uint32_t s_ncand, s_nle, s_p0, s_pairs;
-    __shared__ uint32_t warp_tot[PS_THREADS / 32 + 1];
+    __shared__ uint32_t warp_tot[PST / 32 + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t q = blockIdx.x;
     const float* row = A + q * (size_t)K;
     const float yn = ynorm[q], cn_max = cnorm_max[0];
 
-    for (int d = tid; d < D; d += PS_THREADS) sy[d] = y[q * (size_t)D + d];
+    for (int d = tid; d < D; d += PST) sy[d] = y[q * (size_t)D + d];
     // sample: 256 strided keys.  base = their minimum; hi = the largest of the minima of groups of G samples, i.e. roughly
     // the (ln(256/G) + 0.6) / G quantile of the keys -- a little above the P/K quantile the threshold has to reach, so that
     // only a small fraction of the keys enters the histogram (no hot bins) and the 255 bins below `hi` are narrow.
     int G = 64;
     while (G > 2 && (size_t)G * 4 * P > (size_t)K) G >>= 1;  // G ~ K / (4 P), a power of two in [2, 64]
-    float gmin = __ldg(&row[(size_t)tid * K / PS_THREADS]);
-    for (int o = 1; o < min(G, 32); o <<= 1) gmin = fminf(gmin, __shfl_xor_sync(FULL, gmin, o));
+    constexpr int SPT = 256 / PST;  // samples per thread
+    float gmin = __ldg(&row[(size_t)(tid * SPT) * K / 256]);
+#pragma unroll
+    for (int i = 1; i < SPT; i++) gmin = fminf(gmin, __ldg(&row[(size_t)(tid * SPT + i) * K / 256]));
+    const int Gt = max(1, G / SPT);  // group size in threads
+    for (int o = 1; o < min(Gt, 32); o <<= 1) gmin = fminf(gmin, __shfl_xor_sync(FULL, gmin, o));
     float wmin = gmin, wmaxmin = gmin;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         wmin = fminf(wmin, __shfl_xor_sync(FULL, wmin, o));
         wmaxmin = fmaxf(wmaxmin, __shfl_xor_sync(FULL, wmaxmin, o));
     }
-    if (lane == 0) { s_red[warp] = wmin; s_red[PS_THREADS / 32 + warp] = wmaxmin; }
-    hist[tid] = 0;
+    if (lane == 0) { s_red[warp] = wmin; s_red[PST / 32 + warp] = wmaxmin; }
+    for (int i = tid; i < 256; i += PST) hist[i] = 0;
     if (tid == 0) { s_p0 = 0xffffffffu; s_pairs = 0; s_ncand = 0; s_nle = 0; }
     __syncthreads();
     float base = s_red[0], hi = -3.402823466e+38f;
 #pragma unroll
-    for (int w = 1; w < PS_THREADS / 32; w++) base = fminf(base, s_red[w]);
-    if (G == 64) {  // groups of two warps
+    for (int w = 1; w < PST / 32; w++) base = fminf(base, s_red[w]);
+    if (Gt == 64) {  // groups of two warps
 #pragma unroll
-        for (int w = 0; w < PS_THREADS / 32; w += 2) hi = fmaxf(hi, fminf(s_red[w], s_red[w + 1]));
+        for (int w = 0; w < PST / 32; w += 2) hi = fmaxf(hi, fminf(s_red[w], s_red[w + 1]));
     } else {
 #pragma unroll
-        for (int w = 0; w < PS_THREADS / 32; w++) hi = fmaxf(hi, s_red[PS_THREADS / 32 + w]);
+        for (int w = 0; w < PST / 32; w++) hi = fmaxf(hi, s_red[PST / 32 + w]);
     }
     const bool vec4 = (K & 3) == 0;
     __shared__ float s_tau;
@@ -273,12 +278,12 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
         if (vec4) {  // 128-bit loads, several in flight per thread: the pass is a stream over K keys
             const float4* row4 = reinterpret_cast<const float4*>(row);
 #pragma unroll 4
-            for (int i4 = tid; i4 < K / 4; i4 += PS_THREADS) {
+            for (int i4 = tid; i4 < K / 4; i4 += PST) {
                 const float4 v = __ldg(&row4[i4]);
                 hadd(v.x); hadd(v.y); hadd(v.z); hadd(v.w);
             }
         } else {
-            for (int i = tid; i < K; i += PS_THREADS) hadd(__ldg(&row[i]));
+            for (int i = tid; i < K; i += PST) hadd(__ldg(&row[i]));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(FULL, vmin, o));
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
         __syncthreads();
         kmin_true = s_red[0];
 #pragma unroll
-        for (int w = 1; w < PS_THREADS / 32; w++) kmin_true = fminf(kmin_true, s_red[w]);
+        for (int w = 1; w < PST / 32; w++) kmin_true = fminf(kmin_true, s_red[w]);
         if (warp == 0) {  // first bin whose cumulative count reaches P -> tau = its upper edge (hi itself if none does)
             uint32_t c[8], s = 0;
 #pragma unroll
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
             hi = tau;
             base = kmin_true;
             __syncthreads();
-            hist[tid] = 0;
+            for (int i = tid; i < 256; i += PST) hist[i] = 0;
             __syncthreads();
             continue;
         }
@@ -335,18 +340,18 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
             nle += v <= tau;
             if (v <= Uq && __fsub_rd(v, margin(yn, __ldg(&cnorm[i]), v, alpha, gamma)) <= U) {  // (quick reject first)
                 const uint32_t pos = atomicAdd(&s_ncand, 1u);
-                if (pos < (uint32_t)PS_CAP) cid[pos] = (uint32_t)i;
+                if (pos < (uint32_t)cap) cid[pos] = (uint32_t)i;
             }
         };
         if (vec4) {
             const float4* row4 = reinterpret_cast<const float4*>(row);
 #pragma unroll 4
-            for (int i4 = tid; i4 < K / 4; i4 += PS_THREADS) {
+            for (int i4 = tid; i4 < K / 4; i4 += PST) {
                 const float4 v = __ldg(&row4[i4]);
                 consider(v.x, 4 * i4); consider(v.y, 4 * i4 + 1); consider(v.z, 4 * i4 + 2); consider(v.w, 4 * i4 + 3);
             }
         } else {
-            for (int i = tid; i < K; i += PS_THREADS) consider(__ldg(&row[i]), i);
+            for (int i = tid; i < K; i += PST) consider(__ldg(&row[i]), i);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nle += __shfl_xor_sync(FULL, nle, o);
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
         if (s_nle >= (uint32_t)P) break;
         // fewer than P keys below hi (the sample was unlucky) or a bin edge a hair too low: widen and repeat (rare)
         __syncthreads();
-        hist[tid] = 0;
+        for (int i = tid; i < 256; i += PST) hist[i] = 0;
         if (tid == 0) { s_ncand = 0; s_nle = 0; }
         hi = attempt == 0 ? base + (hi - base) * 4.0f + 1e-30f : 3.402823466e+38f;
         attempt++;
@@ -369,8 +374,8 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
     // exact distances of the candidates, order of simd::l2_squared_distance: four threads per candidate, two AVX lanes each
     // (packed f32x2, 64-bit loads of the centroid row; kernels.cuh l2_quad_global)
     {
-        const int v4 = lane & 3, sub = tid >> 2;  // PS_THREADS / 4 = 64 candidates per sweep
-        for (uint32_t c0 = 0; c0 < nc; c0 += PS_THREADS / 4) {
+        const int v4 = lane & 3, sub = tid >> 2;  // PST / 4 candidates per sweep
+        for (uint32_t c0 = 0; c0 < nc; c0 += PST / 4) {
             const uint32_t ci = c0 + sub;
             const bool act = ci < nc;
             const uint32_t id = cid[act ? ci : 0];
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
     }
     __syncthreads();
     // the P smallest (key, id): rank by counting (candidates are few)
-    for (uint32_t ci = tid; ci < nc; ci += PS_THREADS) {
+    for (uint32_t ci = tid; ci < nc; ci += PST) {
         const unsigned long long me = ckey[ci];
         uint32_t rank = 0;
         for (uint32_t j = 0; j < nc; j++) rank += ckey[j] < me;
@@ -395,8 +400,8 @@ __global__ void __launch_bounds__(PS_THREADS) prefilter_select_kernel(
         }
     }
     __syncthreads();
-    const uint32_t total_words = block_exclusive_scan<PS_THREADS>(words, P, warp_tot);
-    for (int p = tid; p < P; p += PS_THREADS) slot_local[q * P + p] = words[p];
+    const uint32_t total_words = block_exclusive_scan<PST>(words, P, warp_tot);
+    for (int p = tid; p < P; p += PST) slot_local[q * P + p] = words[p];
     if (tid == 0) {
         q_pairs[q] = s_pairs;
         q_words[q] = total_words;

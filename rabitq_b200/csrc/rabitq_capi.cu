@@ -176,13 +176,16 @@ struct rabitq_index {
     int rerank_rows = 0;   // rows per rerank wave; 0 = by dimension
     int rerank_mode = 1;   // 1: one CTA per query, warp-specialised (rerank_cta_kernel); 0: one warp per query (rerank_kernel)
     int rerank_nc = 0;     // candidates per eight-lane group of the CTA form (1 or 2; 0 = by wave size)
+    int pf_threads = 0;    // 256: always 256 threads per query in prefilter_select_kernel (A/B switch)
+    int rerank_stages = 0; // row buffers in the CTA form's ring (0 = 4)
+    int rerank_warps = 0;  // compute warps of the CTA form (0 = 3)
     int debug_rerank = 0;     // per-query rerank statistics (rabitq_debug_rerank_stats)
     int rerank_prefetch = 0;  // L2 prefetch of survivor rows in the rerank stream (rabitq_set_option("rerank_prefetch"))
     int first_chunks = 1;  // 128-vector chunks of the nearest cluster in the first round (0 = the whole cluster)
     int scan_slices = 1;   // shared-memory record slices per scan work item (hot clusters are cut into several items)
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
-        entries, counters, out_all, rr_dbg, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag, sel_scratch;
+        entries, counters, out_all, rr_dbg, round_win, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag, sel_scratch;
     DistState dist;
     const float* q_in = nullptr;   // the sub-batch's raw queries (nb x len) on the device: ix->qraw, or the caller's device pointer
     const float* y_all = nullptr;  // rotated queries K3 reads: ix->y, or (distributed push mode) the inbox region every rank pushed its block into
@@ -232,7 +235,7 @@ struct rabitq_index {
         }
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &thr, &heap_dist,
-                          &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_all, &rr_dbg,
+                          &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_all, &rr_dbg, &round_win,
                           &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag, &sel_scratch})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
@@ -349,6 +352,9 @@ int finish_index(rabitq_index* ix) {
     if (const char* e = std::getenv("RABITQ_RR_PREFETCH")) ix->rerank_prefetch = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_RR_MODE")) ix->rerank_mode = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_RR_NC")) ix->rerank_nc = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_PF_THREADS")) ix->pf_threads = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_RR_STAGES")) ix->rerank_stages = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_RR_WARPS")) ix->rerank_warps = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_SCAN_SLICES")) ix->scan_slices = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RABITQ_SCAN_STAGES")) ix->scan_stages = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("RABITQ_SCAN_SUB")) ix->scan_sub = std::max(0, std::atoi(e));
@@ -906,13 +912,19 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
         }
         CU(cudaGetLastError());
         if (tick(ix, ST_CDIST)) return RABITQ_ECUDA;
-        const size_t ps_smem = (size_t)D * 4 + PS_CAP * 12 + (size_t)P * 4;
-        prefilter_select_kernel<<<(unsigned)nb, PS_THREADS, ps_smem, st>>>(
-            ix->cdist.as<float>(), ix->pf_ynorm.as<float>(), ix->pf_cnorm, ix->pf_cnorm_max, ix->y.as<float>(), ix->cent, K, P, D, ix->offsets,
-            global_view ? ix->goffsets : nullptr, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(),
-            ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), ix->q_p0.as<uint32_t>(), ix->pf_flag.as<uint32_t>(),
-            std::max(1, std::min(ix->prefilter_cap, PS_CAP)), split ? (float)(2 * D + 64) * 4.76837158203125e-07f : 0.00390625f,
-            (float)(D / 8 + 8) * 1.1920928955078125e-07f);
+        // candidate capacity: 8 per probe (at least 512); the arrays live in shared memory, and a smaller CTA footprint means
+        // more queries per SM in flight
+        const int ps_cap = std::max(2, std::min(std::min(ix->prefilter_cap, PS_CAP), std::max(K >= 32768 ? 1024 : 512, 8 * P)) & ~1);
+        const size_t ps_smem = (size_t)D * 4 + (size_t)ps_cap * 12 + (size_t)P * 4;
+#define PS_ARGS ix->cdist.as<float>(), ix->pf_ynorm.as<float>(), ix->pf_cnorm, ix->pf_cnorm_max, ix->y.as<float>(), ix->cent, K, P, D, ix->offsets, \
+            global_view ? ix->goffsets : nullptr, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), \
+            ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), ix->q_p0.as<uint32_t>(), ix->pf_flag.as<uint32_t>(), ps_cap, \
+            split ? (float)(2 * D + 64) * 4.76837158203125e-07f : 0.00390625f, (float)(D / 8 + 8) * 1.1920928955078125e-07f
+        // one CTA per query; 128 threads instead of 256 when 256-thread CTAs would need several waves (the kernel is a chain of
+        // latencies: twice the queries in flight per SM beat twice the threads per query)
+        if (nb > (size_t)ix->sm_count * 8 && ix->pf_threads != 256) prefilter_select_kernel<128><<<(unsigned)nb, 128, ps_smem, st>>>(PS_ARGS);
+        else prefilter_select_kernel<256><<<(unsigned)nb, 256, ps_smem, st>>>(PS_ARGS);
+#undef PS_ARGS
         CU(cudaMemcpyAsync(ix->h_pin + 6, ix->pf_flag.p, 4, cudaMemcpyDeviceToHost, st));
         ix->pf_pending = true;
         CU(cudaGetLastError()); ix->counts[5]++;
@@ -1123,6 +1135,8 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     }
     ra.smem_per_warp = rr_smem(ra.R);
     ra.prefetch = ix->rerank_prefetch;
+    ra.win = nullptr;
+    ra.ns = 2;
     if (ix->debug_rerank) {
         CU(ix->rr_dbg.ensure(nb * 16 * 4));
         CU(cudaMemsetAsync(ix->rr_dbg.p, 0, nb * 16 * 4, st));
@@ -1211,18 +1225,28 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
     const size_t rsmem = (size_t)rr_wpb * ra.smem_per_warp;
     const int f = is_first ? 1 : 0, l = is_last ? 1 : 0;
     if (kind != ROUND_SINK1 && ix->rerank_mode == 1) {
-        // one CTA per query: producer + replay + compute warps (rerank_cta_kernel).  Wave size by dimension: 8 rows of a large
-        // dimension keep three queries per SM resident, short rows take 16 with two candidates per eight-lane group
-        const size_t D = (size_t)ra.D, fixed = 144 + D * 4 + 2 * (size_t)ra.topk * 4 + 3 * 128 * 4;
-        int R = ix->rerank_rows > 0 ? std::min(32, ix->rerank_rows) : (D <= 256 ? 16 : 8);
-        while (R > 1 && fixed + 2 * (size_t)R * (D + 8) * 4 > (size_t)200 * 1024) R--;
-        const size_t smem = fixed + 2 * (size_t)R * (D + 8) * 4;
+        // one CTA per query: producer + replay + compute warps (rerank_cta_kernel).  A wave is one compute warp's job (4 rows, or 8
+        // with two candidates per eight-lane group for short rows); `ns` row buffers keep that many gathers in flight
+        const size_t D = (size_t)ra.D;
+        int R = ix->rerank_rows > 0 ? std::min(8, ix->rerank_rows) : (D <= 256 ? 8 : 4);
+        if (ix->rerank_nc == 1) R = std::min(R, 4);
+        const int nc = R > 4 || ix->rerank_nc == 2 ? 2 : 1;
+        // a row buffer is always consumed by the same compute warp (waves go round-robin over the warps, buffers round-robin over
+        // the waves: ns must be a multiple of ncw, or a warp would wait on a barrier whose phases it has not followed)
+        int ncw = std::max(1, std::min(8, ix->rerank_warps > 0 ? ix->rerank_warps : (nc == 2 ? 1 : 3)));
+        int bpw = std::max(1, (std::min(8, ix->rerank_stages > 0 ? ix->rerank_stages : (nc == 2 ? 2 : 3)) + ncw - 1) / ncw);  // buffers per warp
+        while (ncw * bpw > 8) bpw--;
+        if (bpw < 1) { bpw = 1; ncw = 8; }
+        int ns = ncw * bpw;
+        auto need = [&]() { return rerank_cta_smem((int)D, ra.topk, R, ns, nc); };
+        while (need() > (size_t)200 * 1024 && bpw > 1) { bpw--; ns = ncw * bpw; }
+        while (need() > (size_t)200 * 1024 && ncw > 1) { ncw--; ns = ncw * bpw; }
+        while (need() > (size_t)200 * 1024 && R > 1) R--;
+        const size_t smem = need();
         if (smem <= (size_t)200 * 1024) {
-            int nc = ix->rerank_nc == 1 || ix->rerank_nc == 2 ? ix->rerank_nc : (R >= 16 ? 2 : 1);
-            if ((R + 4 * nc - 1) / (4 * nc) > 8) nc = 2;
-            const int ncw = (R + 4 * nc - 1) / (4 * nc);
             RerankArgs rc = ra;
             rc.R = R;
+            rc.ns = ns;
             const dim3 grid((unsigned)nb), block((unsigned)(2 + ncw) * 32);
             if (heuristic) {
                 if (nc == 2) rerank_cta_kernel<true, 2><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
@@ -1273,6 +1297,16 @@ std::vector<Pos> round_bounds(const rabitq_index* ix, int P, bool dense) {
 int run_lists_and_quantize(rabitq_index* ix, size_t nb, int P, const std::vector<Pos>& bounds) {
     const uint32_t MS = scan_ms(ix);
     CU(cudaStreamWaitEvent(ix->aux_stream, ix->ev_fork, 0));
+    {   // word windows of every round (K5 reads one pair per query instead of resolving the bounds through three dependent loads);
+        // first on the side stream: the first list's `ready` event, which the main stream waits for, covers it
+        RoundBounds rb;
+        rb.n = (int)bounds.size();
+        for (int i = 0; i < rb.n; i++) { rb.p[i] = bounds[i].p; rb.ch[i] = bounds[i].ch; }
+        CU(ix->round_win.ensure((size_t)(rb.n - 1) * nb * 8));
+        round_windows_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ix->aux_stream>>>(ix->q_wbase.as<uint32_t>(), ix->slot_local.as<uint32_t>(),
+                                                                                       ix->q_p0.as<uint32_t>(), (int)nb, P, rb, ix->round_win.as<uint2>());
+        CU(cudaGetLastError()); ix->counts[5]++;
+    }
     int rc;
     static const bool k3_aux = std::getenv("RABITQ_K3_MAIN") == nullptr;
     for (size_t r = 0; r + 1 < bounds.size(); r++) {
@@ -1305,6 +1339,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     for (size_t r = 0; r + 1 < bounds.size(); r++) {
         if ((rc = run_round_scan(ix, nb, P, sa, bounds[r], bounds[r + 1], stop == STOP_SCAN_DENSE, r))) return rc;
         if (stop == STOP_SCAN_DENSE) return 0;
+        ra.win = ix->round_win.as<uint2>() + r * nb;
         if ((rc = run_round_rerank(ix, nb, ra, bounds[r], bounds[r + 1], r == 0, r + 2 == bounds.size(), heuristic, ROUND_REPLAY))) return rc;
     }
     return 0;
@@ -2036,6 +2071,8 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     else if (n == "rerank_prefetch") idx->rerank_prefetch = (int)value;
     else if (n == "rerank_mode") idx->rerank_mode = (int)value;
     else if (n == "rerank_nc") idx->rerank_nc = (int)value;
+    else if (n == "rerank_stages") idx->rerank_stages = (int)value;
+    else if (n == "rerank_warps") idx->rerank_warps = (int)value;
     else if (n == "debug_rerank") idx->debug_rerank = (int)value;
     else if (n == "scan_slices") idx->scan_slices = (int)std::max(1L, value);
     else if (n == "scan_stages") idx->scan_stages = (int)std::max(0L, value);

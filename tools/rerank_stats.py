@@ -29,9 +29,9 @@ def main():
     print(f"{wl_name} {opts}: rerank {t['ms_rerank']:.4f} ms scan {t['ms_scan']:.4f} total {t['ms_total']:.4f} exact {t['exact_computed']} precise {t['precise']}")
     pct = [50, 90, 99, 100]
     for r in range(2):
-        for i, name in enumerate(["cycles", "waves", "computed", "enqueue", "wait", "l2", "replay", "stage"]):
+        for i, name in enumerate(["cycles", "waves", "computed", "enq|pblock", "wait|cwait", "l2|cbusy", "replay|rwait", "stage|ptotal"]):
             v = st[:, r, i]
-            print(f"  round {r + 1} {name:9s} mean {v.mean():10.1f}  " + "  ".join(f"p{p}={np.percentile(v, p):9.0f}" for p in pct))
+            print(f"  round {r + 1} {name:13s} mean {v.mean():10.1f}  " + "  ".join(f"p{p}={np.percentile(v, p):9.0f}" for p in pct))
         c, w = st[:, r, 0], np.maximum(st[:, r, 1], 1)
         print(f"  round {r + 1} cycles/wave: mean {np.mean(c / w):.0f}; corr(cycles, waves) {np.corrcoef(c, st[:, r, 1])[0, 1]:.3f}")
 
