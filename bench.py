@@ -113,6 +113,80 @@ def workload_string(wl, probe):
             f"{wl['k']} IVF centroids, nprobe={probe}, top-{TOPK}")
 
 
+def _bcast_chunked(t, src=0, max_elems=1 << 28):
+    """NCCL broadcast of a big contiguous tensor in slices (element counts stay below 2^31)."""
+    import torch.distributed as dist
+
+    flat = t.view(-1)
+    for s in range(0, flat.numel(), max_elems):
+        dist.broadcast(flat[s:s + max_elems], src)
+
+
+def _index_fingerprint(g):
+    """Position-weighted integer checksums of every array of an unsharded handle (device side, chunked): two handles hold the same
+    index iff the fingerprints match."""
+    import torch
+
+    a = g.export_arrays(device_tensors=True)
+    dev = a["base"].device
+    w = (torch.arange(1 << 24, device=dev, dtype=torch.int64) % 65521) + 1
+    out = []
+    for key in ("base", "orthogonal", "centroids", "offsets", "map_ids", "codes", "factors"):
+        flat = a[key].contiguous().view(-1).view(torch.int32)
+        acc = torch.zeros((), dtype=torch.int64, device=dev)
+        for s in range(0, flat.numel(), 1 << 24):
+            c = flat[s:s + (1 << 24)].to(torch.int64)
+            acc += (c * w[:c.numel()]).sum() + (s >> 24)
+        out.append(acc)
+    del a
+    torch.cuda.empty_cache()
+    return torch.stack(out)
+
+
+def _same_index_everywhere(g0, device, rank, world, log_fn):
+    """world > 1: every rank trains the whole index from the same inputs and keeps its cluster range, which is only a valid sharding
+    if the trained copies are bit-identical.  They are checked (fingerprints, all-reduced); ranks whose copy differs from rank 0's
+    (not observed up to 10M vectors; at 100M the torch data generator is not bit-reproducible from run to run) adopt rank 0's
+    arrays.  Returns (handle, identical_before_fix)."""
+    import torch
+    import torch.distributed as dist
+
+    import rabitq_b200 as rb
+
+    fp = _index_fingerprint(g0)
+    ref = fp.clone()
+    dist.broadcast(ref, 0)
+    same = torch.tensor([int(bool((fp == ref).all()))], device=device)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if int(same.item()) == 1:
+        return g0, True
+    if rank == 0:
+        log_fn("[bench] trained index copies differ between ranks: every rank adopts rank 0's arrays")
+    keys = ("base", "orthogonal", "centroids", "offsets", "map_ids", "codes", "factors")
+    if rank == 0:
+        a = g0.export_arrays(device_tensors=True)
+    else:
+        D, n, k = g0.dim, g0.num_vectors, g0.num_clusters
+        g0.close()
+        torch.cuda.empty_cache()
+        a = dict(dim=D, base=torch.empty((n, D), dtype=torch.float32, device=device),
+                 orthogonal=torch.empty((D, D), dtype=torch.float32, device=device),
+                 centroids=torch.empty((k, D), dtype=torch.float32, device=device),
+                 offsets=torch.empty((k + 1,), dtype=torch.int32, device=device),
+                 map_ids=torch.empty((n,), dtype=torch.int32, device=device),
+                 codes=torch.empty((n, D // 64), dtype=torch.int64, device=device),
+                 factors=torch.empty((n, 4), dtype=torch.float32, device=device))
+    for key in keys:
+        _bcast_chunked(a[key], 0)
+    torch.cuda.synchronize(device)
+    if rank != 0:
+        g0 = rb.RaBitQ.from_arrays(a["dim"], a["base"], a["orthogonal"], a["centroids"], a["offsets"], a["map_ids"], a["codes"], a["factors"],
+                                   device=device.index)
+    del a
+    torch.cuda.empty_cache()
+    return g0, False
+
+
 def build_workload(args, device, rank, world, builder=None, keep_single=True):
     """Synthetic data + index on the device; returns dict with torch tensors.
 
@@ -137,6 +211,10 @@ def build_workload(args, device, rank, world, builder=None, keep_single=True):
     base = mix.draw(n, seed)
     queries = mix.draw(nq * world, seed + 1)  # weak scaling: the query batch grows with the number of GPUs
     cent = mix.centroids()
+    if world > 1:  # one copy of the synthetic inputs: rank 0's (the generator's matmul / rounding is not bit-reproducible at 100M vectors)
+        base, queries, cent = base.contiguous(), queries.contiguous(), cent.contiguous()
+        for t in (base, queries, cent):
+            _bcast_chunked(t, 0)
     torch.cuda.synchronize()
     t1 = time.time()
     builder = builder or getattr(args, "builder", "native")
@@ -168,13 +246,16 @@ def build_workload(args, device, rank, world, builder=None, keep_single=True):
     del base
     torch.cuda.empty_cache()
     g = g0
-    if world > 1 and g0 is not None:  # every rank trained the whole index (same seeds, same result) and keeps its cluster range
+    identical = None
+    if world > 1 and g0 is not None:  # every rank trained the whole index from the same inputs and keeps its cluster range
+        g0, identical = _same_index_everywhere(g0, device, rank, world, log)
         g = g0.reshard(rank, world)
         if not keep_single:
             g0.close()
             g0 = None
     return dict(name=name, n=n, dim=dim, nq=nq * world, nq_rank=nq, truth_queries=tq, k=k, flavour=flavour, queries=queries.contiguous(),
-                truth=truth, handle=g, single=g0, arrays=arrays, D=(g.dim if g is not None else arrays["dim"]))
+                truth=truth, handle=g, single=g0, arrays=arrays, D=(g.dim if g is not None else arrays["dim"]),
+                index_identical_across_ranks=identical)
 
 
 def oracle_from_index(g=None, arrays=None):
@@ -507,6 +588,7 @@ def measure_ours(args, workload, device, rank, world, stream, main_leg=True):
                                "busy_ms": [round(r[2], 4) for r in per_rank]}
         out.update(sweeps)
         if parity_check is not None:
+            parity_check["trained_index_identical_across_ranks"] = wl.get("index_identical_across_ranks")
             out["parity_check"] = parity_check
         if cpu is not None:
             out["parity"] = cpu.pop("parity")

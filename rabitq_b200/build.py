@@ -45,10 +45,12 @@ def sources() -> list[str]:
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = sources()
     if force or _stale(LIB, srcs):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "rabitq_capi.cu")]
+        tmp = LIB + ".tmp"  # built aside and renamed: a repo snapshot never sees a half-written library
+        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", tmp, os.path.join(CSRC, "rabitq_capi.cu")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd, cwd=ROOT)
+        os.replace(tmp, LIB)
     cli_src = os.path.join(CSRC, "cli.cpp")
     if os.path.exists(cli_src) and (force or _stale(CLI, srcs + [LIB])):
         gxx = shutil.which("g++") or "g++"

@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "build_index.cuh"
 #include "prefilter.cuh"
+#include "tc5_gemm.cuh"
 #include <sys/stat.h>
 
 namespace {
@@ -125,12 +126,15 @@ struct ListSet {
     uint32_t MS = 0, ch_min = 0;
     cudaEvent_t ready = nullptr;   // inverted list built (K3 and the work-item pass wait for it)
     cudaEvent_t qready = nullptr;  // records written by K3 on the side stream (later rounds only; the scan of the round waits for it)
+    cudaEvent_t wready = nullptr;  // flat work items written on the second side stream
+    bool w_on_aux = false;
     bool q_on_aux = false;
     void release() {
         for (DevBuf* b : {&cl_count, &cl_start, &item_start, &cl_cursor, &cl_items, &work, &work_ctl, &qrec}) b->release();
         if (ready) cudaEventDestroy(ready);
         if (qready) cudaEventDestroy(qready);
-        ready = qready = nullptr;
+        if (wready) cudaEventDestroy(wready);
+        ready = qready = wready = nullptr;
     }
 };
 
@@ -153,6 +157,9 @@ struct rabitq_index {
     int pf_mode = 1;              // 1 = plain TF32 keys, 3 = 3xTF32 split (tighter bound), 0 = gave up (exact path); adapts to the data
     int pf_strikes = 0;           // batches the current mode could not certify
     bool pf_pending = false;      // a fallback flag is on its way to h_pin[6]
+    int pf_gemm = 1;              // 1 = tcgen05 / TMEM / TMA key GEMM (tc5_gemm.cuh), 0 = mma.sync key GEMM (prefilter.cuh)
+    CUtensorMap tm_chat, tm_chat_lo, tm_yhat, tm_yhat_lo;
+    bool tm_c_ready = false;
     int prefilter_cap = 1024;     // candidates per query the prefilter may certify (tests lower it to force the fallback)
     float* quant_bias = nullptr;  // D: non-NULL switches K3 to the reference's non-AVX2 quantiser (rabitq_set_quantize_bias)
     uint32_t* goffsets = nullptr; // K+1, rows of the WHOLE index (equal to offsets on an unsharded handle)
@@ -169,6 +176,10 @@ struct rabitq_index {
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_totals = nullptr;  // marks the arrival of the slot totals in h_pin
     cudaStream_t aux_stream = nullptr;  // side stream: the rounds' inverted lists are built here, concurrently with K3
+    cudaStream_t aux2_stream = nullptr; // second side stream: round windows and the scan's flat work items (off the main stream's chain of tiny launches)
+    cudaEvent_t ev_win = nullptr;       // round windows written (the first replay waits for it)
+    bool use_aux2 = true;               // (A/B switch RABITQ_AUX2=0: the same work on the main stream)
+    bool state_reset_done = false;      // thresholds / counters of this batch were reset on the side stream already
     cudaEvent_t ev_fork = nullptr;      // recorded on `stream` after K2b: everything the lists depend on is done
     std::vector<ListSet> lists;
     std::mutex mu;
@@ -248,6 +259,8 @@ struct rabitq_index {
         if (ev_staged) cudaEventDestroy(ev_staged);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (aux_stream) cudaStreamDestroy(aux_stream);
+        if (aux2_stream) cudaStreamDestroy(aux2_stream);
+        if (ev_win) cudaEventDestroy(ev_win);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 };
@@ -353,6 +366,9 @@ int finish_index(rabitq_index* ix) {
     if (const char* e = std::getenv("RABITQ_RR_MODE")) ix->rerank_mode = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_RR_NC")) ix->rerank_nc = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_PF_THREADS")) ix->pf_threads = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_PF_GEMM")) ix->pf_gemm = std::atoi(e);
+    if (const char* e = std::getenv("RABITQ_AUX2")) ix->use_aux2 = std::atoi(e) != 0;
+    CU(cudaFuncSetAttribute(approx_gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC5_SMEM_BYTES));
     if (const char* e = std::getenv("RABITQ_RR_STAGES")) ix->rerank_stages = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_RR_WARPS")) ix->rerank_warps = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_SCAN_SLICES")) ix->scan_slices = std::max(1, std::atoi(e));
@@ -361,6 +377,8 @@ int finish_index(rabitq_index* ix) {
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     CU(cudaStreamCreateWithFlags(&ix->aux_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ix->aux2_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ix->ev_win, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ix->ev_staged, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
@@ -848,6 +866,7 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view);
 int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_rotate, bool global_view) {
     const int D = (int)ix->D;
     cudaStream_t st = ix->stream;
+    ix->state_reset_done = false;
     CU(ix->y.ensure(nb * D * 4));
     if (!ix->q_in) ix->q_in = ix->qraw.as<float>();
     if ((int)len == D) {
@@ -893,8 +912,28 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
                                                                       split ? ix->pf_yhat_lo.as<float>() : nullptr, ix->pf_ynorm.as<float>());
         CU(cudaGetLastError()); ix->counts[5]++;
         const size_t tiles128 = ((nb + 127) / 128) * (size_t)((K + 127) / 128);
+        // tcgen05 form: tensor maps of the operands (centroid side once per index, query side per batch: a host-side encode)
+        bool tc5 = ix->pf_gemm == 1;
+        if (tc5 && !ix->tm_c_ready) {
+            if (tc5_make_tmap(&ix->tm_chat, ix->pf_chat, (size_t)K, (size_t)D, TC5_BN) || tc5_make_tmap(&ix->tm_chat_lo, ix->pf_chat_lo, (size_t)K, (size_t)D, TC5_BN)) {
+                ix->pf_gemm = 0;  // no tensor-map encoder in this driver: the mma.sync form computes the same keys
+                tc5 = false;
+            } else {
+                ix->tm_c_ready = true;
+            }
+        }
+        if (tc5) {
+            if (tc5_make_tmap(&ix->tm_yhat, ix->pf_yhat.as<float>(), nb, (size_t)D, TC5_BM) ||
+                (split && tc5_make_tmap(&ix->tm_yhat_lo, ix->pf_yhat_lo.as<float>(), nb, (size_t)D, TC5_BM)))
+                return fail(RABITQ_ECUDA, "cuTensorMapEncodeTiled failed for the query operand");
+        }
         auto gemm = [&](const float* ya, const float* cb, int accumulate) {
-            if (tiles128 >= (size_t)ix->sm_count) {
+            if (tc5) {
+                dim3 grid((K + TC5_BN - 1) / TC5_BN, (unsigned)((nb + TC5_BM - 1) / TC5_BM));
+                approx_gemm_tc5_kernel<<<grid, TC5_THREADS, TC5_SMEM_BYTES, st>>>(ya == ix->pf_yhat.as<float>() ? ix->tm_yhat : ix->tm_yhat_lo,
+                                                                                  cb == ix->pf_chat ? ix->tm_chat : ix->tm_chat_lo, ix->pf_cnorm2,
+                                                                                  (int)nb, K, D, ix->cdist.as<float>(), accumulate);
+            } else if (tiles128 >= (size_t)ix->sm_count) {
                 dim3 grid((K + 127) / 128, (unsigned)((nb + 127) / 128));
                 approx_gemm_tf32_kernel<128, 128, 2, 4><<<grid, 256, 2 * 256 * PF_PITCH * 4, st>>>(ya, cb, ix->pf_cnorm2, (int)nb, K, D,
                                                                                                     ix->cdist.as<float>(), accumulate);
@@ -1069,9 +1108,12 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     CU(ix->h_wcount.ensure(nb * 4));
     CU(ix->counters.ensure(64));
     CU(ix->out_all.ensure(nb * topk * 8 + nb * 4));  // [dist nb x topk | ids nb x topk | count nb]: one D2H for the three results
-    CU(cudaMemsetAsync(ix->counters.p, 0, 64, st));
-    fill_f32_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(ix->thr.as<float>(), nb, 3.402823466e+38f);
-    CU(cudaGetLastError()); ix->counts[5]++;
+    if (!ix->state_reset_done) {
+        CU(cudaMemsetAsync(ix->counters.p, 0, 64, st));
+        fill_f32_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(ix->thr.as<float>(), nb, 3.402823466e+38f);
+        CU(cudaGetLastError()); ix->counts[5]++;
+    }
+    ix->state_reset_done = false;
 
     ScanArgs sa;
     sa.scan_codes = ix->scan_codes;
@@ -1199,10 +1241,15 @@ int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos
     ListSet& L = ix->lists[set];
     CU(cudaStreamWaitEvent(st, L.ready, 0));
     if (L.q_on_aux) CU(cudaStreamWaitEvent(st, L.qready, 0));
-    CU(L.work.ensure(ix->max_items * sizeof(ScanItem)));
-    work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(), L.cl_start.as<uint32_t>(), ix->offsets,
-                                                       ix->chunk_start, K, L.MS, L.ch_min, L.work.as<ScanItem>());
-    CU(cudaGetLastError()); ix->counts[5]++;
+    if (L.w_on_aux) {
+        CU(cudaStreamWaitEvent(st, L.wready, 0));
+        L.w_on_aux = false;
+    } else {
+        CU(L.work.ensure(ix->max_items * sizeof(ScanItem)));
+        work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(), L.cl_start.as<uint32_t>(), ix->offsets,
+                                                           ix->chunk_start, K, L.MS, L.ch_min, L.work.as<ScanItem>());
+        CU(cudaGetLastError()); ix->counts[5]++;
+    }
     sa.cl_items = L.cl_items.as<uint2>();
     sa.work = L.work.as<ScanItem>();
     sa.work_ctl = L.work_ctl.as<uint32_t>();
@@ -1297,15 +1344,24 @@ std::vector<Pos> round_bounds(const rabitq_index* ix, int P, bool dense) {
 int run_lists_and_quantize(rabitq_index* ix, size_t nb, int P, const std::vector<Pos>& bounds) {
     const uint32_t MS = scan_ms(ix);
     CU(cudaStreamWaitEvent(ix->aux_stream, ix->ev_fork, 0));
-    {   // word windows of every round (K5 reads one pair per query instead of resolving the bounds through three dependent loads);
-        // first on the side stream: the first list's `ready` event, which the main stream waits for, covers it
+    {   // second side stream: the batch's thresholds / counters are reset and the word windows of every round written (K5 reads one
+        // pair per query instead of resolving the bounds through three dependent loads) -- none of it in the main stream's chain
+        cudaStream_t a2 = ix->use_aux2 ? ix->aux2_stream : ix->stream;
+        CU(cudaStreamWaitEvent(a2, ix->ev_fork, 0));
+        CU(ix->thr.ensure(nb * 4));
+        CU(ix->counters.ensure(64));
+        CU(cudaMemsetAsync(ix->counters.p, 0, 64, a2));
+        fill_f32_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, a2>>>(ix->thr.as<float>(), nb, 3.402823466e+38f);
+        CU(cudaGetLastError()); ix->counts[5]++;
+        ix->state_reset_done = true;
         RoundBounds rb;
         rb.n = (int)bounds.size();
         for (int i = 0; i < rb.n; i++) { rb.p[i] = bounds[i].p; rb.ch[i] = bounds[i].ch; }
         CU(ix->round_win.ensure((size_t)(rb.n - 1) * nb * 8));
-        round_windows_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ix->aux_stream>>>(ix->q_wbase.as<uint32_t>(), ix->slot_local.as<uint32_t>(),
-                                                                                       ix->q_p0.as<uint32_t>(), (int)nb, P, rb, ix->round_win.as<uint2>());
+        round_windows_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, a2>>>(ix->q_wbase.as<uint32_t>(), ix->slot_local.as<uint32_t>(),
+                                                                                        ix->q_p0.as<uint32_t>(), (int)nb, P, rb, ix->round_win.as<uint2>());
         CU(cudaGetLastError()); ix->counts[5]++;
+        CU(cudaEventRecord(ix->ev_win, a2));
     }
     int rc;
     static const bool k3_aux = std::getenv("RABITQ_K3_MAIN") == nullptr;
@@ -1336,6 +1392,23 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     ScanArgs sa;
     RerankArgs ra;
     if ((rc = setup_rounds(ix, nb, P, topk, bo, &sa, &ra))) return rc;
+    if (stop != STOP_SCAN_DENSE) {
+        // the flat work items of every round on the second side stream (their buffers are sized now; the lists were built long ago)
+        cudaStream_t a2 = ix->use_aux2 ? ix->aux2_stream : ix->stream;
+        for (size_t r = 0; r + 1 < bounds.size(); r++) {
+            ListSet& L = ix->lists[r];
+            CU(L.work.ensure(ix->max_items * sizeof(ScanItem)));
+            CU(cudaStreamWaitEvent(a2, L.ready, 0));
+            work_items_kernel<<<((int)ix->K + 255) / 256, 256, 0, a2>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(),
+                                                                                       L.cl_start.as<uint32_t>(), ix->offsets, ix->chunk_start, (int)ix->K,
+                                                                                       L.MS, L.ch_min, L.work.as<ScanItem>());
+            CU(cudaGetLastError()); ix->counts[5]++;
+            if (!L.wready) CU(cudaEventCreateWithFlags(&L.wready, cudaEventDisableTiming));
+            CU(cudaEventRecord(L.wready, a2));
+            L.w_on_aux = true;
+        }
+    }
+    CU(cudaStreamWaitEvent(ix->stream, ix->ev_win, 0));
     for (size_t r = 0; r + 1 < bounds.size(); r++) {
         if ((rc = run_round_scan(ix, nb, P, sa, bounds[r], bounds[r + 1], stop == STOP_SCAN_DENSE, r))) return rc;
         if (stop == STOP_SCAN_DENSE) return 0;
@@ -1490,6 +1563,7 @@ int stage_prefix(rabitq_index* ix, const float* queries, size_t nq, size_t len, 
     if (rc) return rc;
     CU(cudaStreamSynchronize(ix->stream));
     CU(cudaStreamSynchronize(ix->aux_stream));  // later rounds' records are written there
+    CU(cudaStreamSynchronize(ix->aux2_stream));
     return 0;
 }
 
@@ -2080,6 +2154,7 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     else if (n == "prefilter") idx->prefilter = (int)value;
     else if (n == "prefilter_mode") { idx->pf_mode = (int)value; idx->pf_strikes = 0; }
     else if (n == "prefilter_cap") idx->prefilter_cap = (int)value;
+    else if (n == "prefilter_gemm") idx->pf_gemm = (int)value;
     else return fail(RABITQ_EINVAL, "unknown option: " + n);
     return RABITQ_OK;
 }
