@@ -583,7 +583,8 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_large_kernel(const f
 // Exclusive scan over the per-query word/pair totals (single block).  q_wbase[nq] = total words.
 __global__ void __launch_bounds__(1024) query_base_scan_kernel(const uint32_t* __restrict__ q_words, const uint32_t* __restrict__ q_pairs,
                                                                int nq, uint32_t* __restrict__ q_wbase,
-                                                               unsigned long long* __restrict__ q_pbase) {
+                                                               unsigned long long* __restrict__ q_pbase, uint32_t cap_words = 0u,
+                                                               uint32_t* __restrict__ spec_fail = nullptr) {
     __shared__ unsigned long long wtot[33], ptot[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (nq + 1023) / 1024;
@@ -616,7 +617,13 @@ __global__ void __launch_bounds__(1024) query_base_scan_kernel(const uint32_t* _
         rw += q_words[i];
         rp += q_pairs[i];
     }
-    if (tid == 0) { q_wbase[nq] = (uint32_t)wtot[32]; q_pbase[nq] = ptot[32]; }
+    if (tid == 0) {
+        q_wbase[nq] = (uint32_t)wtot[32];
+        q_pbase[nq] = ptot[32];
+        // speculative slot sizing (no host round trip in the middle of the batch): the survivor slots were sized from earlier batches;
+        // a batch that needs more raises the flag, its scan gets no work and its replay empty windows, and the host repeats it
+        if (spec_fail && wtot[32] > (unsigned long long)cap_words) *spec_fail = 1u;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -908,7 +915,8 @@ struct __align__(16) ScanItem {
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __restrict__ cl_count, const uint32_t* __restrict__ offsets,
                                                            int K, int VT, uint32_t MS, uint32_t ch_min, uint32_t ch_max, uint32_t* __restrict__ cl_start,
                                                            uint32_t* __restrict__ item_start, uint32_t* __restrict__ cl_cursor,
-                                                           uint32_t* __restrict__ work_ctl /* [0] counter, [1] n_work */) {
+                                                           uint32_t* __restrict__ work_ctl /* [0] counter, [1] n_work */,
+                                                           const uint32_t* __restrict__ spec_fail = nullptr) {
     __shared__ uint32_t wa[33], wb[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (K + 1023) / 1024;
@@ -951,7 +959,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const uint32_t* __res
         cl_start[K] = wa[32];
         item_start[K] = wb[32];
         work_ctl[0] = 0;
-        work_ctl[1] = wb[32];
+        work_ctl[1] = (spec_fail && *spec_fail) ? 0u : wb[32];
     }
 }
 
@@ -972,9 +980,10 @@ __global__ void bucket_fill_kernel(const uint32_t* __restrict__ probe_ids, const
 
 __global__ void work_items_kernel(const uint32_t* __restrict__ item_start, const uint32_t* __restrict__ cl_count,
                                   const uint32_t* __restrict__ cl_start, const uint32_t* __restrict__ offsets,
-                                  const uint32_t* __restrict__ chunk_start, int K, uint32_t MS, uint32_t ch_min, ScanItem* __restrict__ work) {
+                                  const uint32_t* __restrict__ chunk_start, int K, uint32_t MS, uint32_t ch_min, ScanItem* __restrict__ work,
+                                  const uint32_t* __restrict__ spec_fail = nullptr) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= K) return;
+    if (c >= K || (spec_fail && *spec_fail)) return;
     const uint32_t s = item_start[c], e = item_start[c + 1];
     if (s == e) return;
     const uint32_t m = cl_count[c], nsl = slice_count(m, MS), off = offsets[c], n_c = offsets[c + 1] - off;
@@ -1893,9 +1902,14 @@ __global__ void __launch_bounds__(128, 5) rerank_kernel(RerankArgs a, int p_lo, 
 // ...) that would otherwise open every query's replay -- done here, once, on the side stream.
 struct RoundBounds { int n; int p[17]; int ch[17]; };  // n positions = n - 1 rounds
 __global__ void round_windows_kernel(const uint32_t* __restrict__ q_wbase, const uint32_t* __restrict__ slot_local, const uint32_t* __restrict__ q_p0,
-                                     int nq, int P, RoundBounds b, uint2* __restrict__ win /* (n - 1) x nq */) {
+                                     int nq, int P, RoundBounds b, uint2* __restrict__ win /* (n - 1) x nq */,
+                                     const uint32_t* __restrict__ spec_fail = nullptr) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
+    if (spec_fail && *spec_fail) {  // the batch is going to be repeated: nothing to replay
+        for (int i = 1; i < b.n; i++) win[(size_t)(i - 1) * nq + q] = make_uint2(0u, 0u);
+        return;
+    }
     const uint32_t wb = q_wbase[q], wend = q_wbase[q + 1];
     const int p0 = (int)q_p0[q];
     uint32_t prev = 0;

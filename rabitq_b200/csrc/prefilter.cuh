@@ -371,6 +371,7 @@ __global__ void __launch_bounds__(PST) prefilter_select_kernel(
         if (tid == 0) atomicOr(fallback_flag, nc > (uint32_t)cap ? 1u : 2u);  // bit 0: too many candidates, bit 1: no valid threshold
         return;
     }
+    if (tid == 0) atomicAdd(fallback_flag + 1, nc);  // statistics: candidates rechecked exactly (RABITQ_TRACE prints the mean)
     // exact distances of the candidates, order of simd::l2_squared_distance: four threads per candidate, two AVX lanes each
     // (packed f32x2, 64-bit loads of the centroid row; kernels.cuh l2_quad_global)
     {

@@ -157,6 +157,7 @@ struct rabitq_index {
     int pf_mode = 1;              // 1 = plain TF32 keys, 3 = 3xTF32 split (tighter bound), 0 = gave up (exact path); adapts to the data
     int pf_strikes = 0;           // batches the current mode could not certify
     bool pf_pending = false;      // a fallback flag is on its way to h_pin[6]
+    size_t pf_last_nb = 0;
     int pf_gemm = 1;              // 1 = tcgen05 / TMEM / TMA key GEMM (tc5_gemm.cuh), 0 = mma.sync key GEMM (prefilter.cuh)
     CUtensorMap tm_chat, tm_chat_lo, tm_yhat, tm_yhat_lo;
     bool tm_c_ready = false;
@@ -178,6 +179,11 @@ struct rabitq_index {
     cudaStream_t aux_stream = nullptr;  // side stream: the rounds' inverted lists are built here, concurrently with K3
     cudaStream_t aux2_stream = nullptr; // second side stream: round windows and the scan's flat work items (off the main stream's chain of tiny launches)
     cudaEvent_t ev_win = nullptr;       // round windows written (the first replay waits for it)
+    // speculative survivor-slot sizing: slots sized from the largest words-per-query seen so far, verified on the device
+    bool spec_enabled = true;           // (RABITQ_SPEC=0: always read the totals back in the middle of the batch)
+    bool spec_on = false;               // this sub-batch runs speculatively
+    uint32_t spec_cap = 0;              // slot words it may use
+    double hw_wpq = 0.0;                // high-water mark of slot words per query
     bool use_aux2 = true;               // (A/B switch RABITQ_AUX2=0: the same work on the main stream)
     bool state_reset_done = false;      // thresholds / counters of this batch were reset on the side stream already
     cudaEvent_t ev_fork = nullptr;      // recorded on `stream` after K2b: everything the lists depend on is done
@@ -196,7 +202,7 @@ struct rabitq_index {
     int scan_slices = 1;   // shared-memory record slices per scan work item (hot clusters are cut into several items)
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
-        entries, counters, out_all, rr_dbg, round_win, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag, sel_scratch;
+        entries, counters, out_all, rr_dbg, round_win, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag, sel_scratch, spec_flag;
     DistState dist;
     const float* q_in = nullptr;   // the sub-batch's raw queries (nb x len) on the device: ix->qraw, or the caller's device pointer
     const float* y_all = nullptr;  // rotated queries K3 reads: ix->y, or (distributed push mode) the inbox region every rank pushed its block into
@@ -247,7 +253,7 @@ struct rabitq_index {
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_all, &rr_dbg, &round_win,
-                          &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag, &sel_scratch})
+                          &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag, &sel_scratch, &spec_flag})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         if (h_out) cudaFreeHost(h_out);
@@ -368,6 +374,7 @@ int finish_index(rabitq_index* ix) {
     if (const char* e = std::getenv("RABITQ_PF_THREADS")) ix->pf_threads = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_PF_GEMM")) ix->pf_gemm = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_AUX2")) ix->use_aux2 = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RABITQ_SPEC")) ix->spec_enabled = std::atoi(e) != 0;
     CU(cudaFuncSetAttribute(approx_gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC5_SMEM_BYTES));
     if (const char* e = std::getenv("RABITQ_RR_STAGES")) ix->rerank_stages = std::atoi(e);
     if (const char* e = std::getenv("RABITQ_RR_WARPS")) ix->rerank_warps = std::atoi(e);
@@ -445,6 +452,8 @@ bool use_prefilter(const rabitq_index* ix, int P) {
 void prefilter_adapt(rabitq_index* ix) {
     if (!ix->pf_pending) return;
     ix->pf_pending = false;
+    static const bool pf_trace = std::getenv("RABITQ_TRACE") != nullptr;
+    if (pf_trace && ix->pf_last_nb) std::fprintf(stderr, "[rabitq trace] prefilter mode %d: %.1f candidates rechecked per query\n", ix->pf_mode, (double)ix->h_pin[7] / (double)ix->pf_last_nb);
     if (ix->h_pin[6] == 0u) return;
     if (std::getenv("RABITQ_TRACE")) std::fprintf(stderr, "[rabitq trace] prefilter mode %d could not certify a batch (reason bits %u)\n", ix->pf_mode, ix->h_pin[6]);
     ix->h_pin[6] = 0u;
@@ -854,6 +863,7 @@ struct BatchOut {  // device pointers of the sub-batch products
     uint32_t P = 0;
     uint32_t total_words = 0;
     uint64_t total_pairs = 0;
+    bool speculative = false;  // total_words is the speculative capacity: the real totals arrive with the batch's final synchronisation
 };
 
 // ---- pieces of the batch pipeline (shared by the single-GPU path and the distributed phases) ------------------------------
@@ -904,8 +914,8 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
         // tensor-core prefilter (prefilter.cuh): approximate keys for all K, exact distances for the few candidates
         CU(ix->pf_yhat.ensure(nb * (size_t)D * 4));
         CU(ix->pf_ynorm.ensure(nb * 4));
-        CU(ix->pf_flag.ensure(4));
-        CU(cudaMemsetAsync(ix->pf_flag.p, 0, 4, st));
+        CU(ix->pf_flag.ensure(8));  // [0] fallback flag, [1] candidates rechecked (statistics)
+        CU(cudaMemsetAsync(ix->pf_flag.p, 0, 8, st));
         const bool split = ix->pf_mode == 3;
         if (split) CU(ix->pf_yhat_lo.ensure(nb * (size_t)D * 4));
         query_center_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, st>>>(ix->y.as<float>(), ix->pf_mu, (int)nb, D, ix->pf_yhat.as<float>(),
@@ -964,7 +974,8 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
         if (nb > (size_t)ix->sm_count * 8 && ix->pf_threads != 256) prefilter_select_kernel<128><<<(unsigned)nb, 128, ps_smem, st>>>(PS_ARGS);
         else prefilter_select_kernel<256><<<(unsigned)nb, 256, ps_smem, st>>>(PS_ARGS);
 #undef PS_ARGS
-        CU(cudaMemcpyAsync(ix->h_pin + 6, ix->pf_flag.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ix->h_pin + 6, ix->pf_flag.p, 8, cudaMemcpyDeviceToHost, st));
+        ix->pf_last_nb = nb;
         ix->pf_pending = true;
         CU(cudaGetLastError()); ix->counts[5]++;
         run_if = ix->pf_flag.as<uint32_t>();  // the classic kernels below run only if some query could not be certified
@@ -1006,8 +1017,13 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
             ix->q_p0.as<uint32_t>(), run_if);
         CU(cudaGetLastError()); ix->counts[5]++;
         }
+        if (ix->spec_on) {
+            CU(ix->spec_flag.ensure(4));
+            CU(cudaMemsetAsync(ix->spec_flag.p, 0, 4, st));
+        }
         query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nb,
-                                                   ix->q_wbase.as<uint32_t>(), ix->q_pbase.as<unsigned long long>());
+                                                   ix->q_wbase.as<uint32_t>(), ix->q_pbase.as<unsigned long long>(),
+                                                   ix->spec_on ? ix->spec_cap : 0u, ix->spec_on ? ix->spec_flag.as<uint32_t>() : nullptr);
         CU(cudaGetLastError()); ix->counts[5]++;
     }
     return 0;
@@ -1019,6 +1035,7 @@ int post_totals(rabitq_index* ix, size_t nb) {
     cudaStream_t st = ix->stream;
     CU(cudaMemcpyAsync(ix->h_pin, ix->q_wbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ix->h_pin + 2, ix->q_pbase.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
+    if (ix->spec_on) CU(cudaMemcpyAsync(ix->h_pin + 4, ix->spec_flag.p, 4, cudaMemcpyDeviceToHost, st));
     if (!ix->ev_totals) CU(cudaEventCreateWithFlags(&ix->ev_totals, cudaEventDisableTiming));
     CU(cudaEventRecord(ix->ev_totals, st));
     CU(cudaEventRecord(ix->ev_fork, st));
@@ -1221,7 +1238,7 @@ int build_lists(rabitq_index* ix, size_t nb, int P, uint32_t MS, Pos lo, Pos hi,
     }
     bucket_scan_kernel<<<1, 1024, 0, st>>>(L.cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, MS, ch_min, ch_max,
                                            L.cl_start.as<uint32_t>(), L.item_start.as<uint32_t>(), L.cl_cursor.as<uint32_t>(),
-                                           L.work_ctl.as<uint32_t>());
+                                           L.work_ctl.as<uint32_t>(), ix->spec_on ? ix->spec_flag.as<uint32_t>() : nullptr);
     CU(cudaGetLastError()); ix->counts[5]++;
     if (items) {
         bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), foreign, nb, P, p_lo, p_hi_incl,
@@ -1247,7 +1264,8 @@ int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos
     } else {
         CU(L.work.ensure(ix->max_items * sizeof(ScanItem)));
         work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(), L.cl_start.as<uint32_t>(), ix->offsets,
-                                                           ix->chunk_start, K, L.MS, L.ch_min, L.work.as<ScanItem>());
+                                                           ix->chunk_start, K, L.MS, L.ch_min, L.work.as<ScanItem>(),
+                                                           ix->spec_on ? ix->spec_flag.as<uint32_t>() : nullptr);
         CU(cudaGetLastError()); ix->counts[5]++;
     }
     sa.cl_items = L.cl_items.as<uint2>();
@@ -1359,7 +1377,8 @@ int run_lists_and_quantize(rabitq_index* ix, size_t nb, int P, const std::vector
         for (int i = 0; i < rb.n; i++) { rb.p[i] = bounds[i].p; rb.ch[i] = bounds[i].ch; }
         CU(ix->round_win.ensure((size_t)(rb.n - 1) * nb * 8));
         round_windows_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, a2>>>(ix->q_wbase.as<uint32_t>(), ix->slot_local.as<uint32_t>(),
-                                                                                        ix->q_p0.as<uint32_t>(), (int)nb, P, rb, ix->round_win.as<uint2>());
+                                                                                        ix->q_p0.as<uint32_t>(), (int)nb, P, rb, ix->round_win.as<uint2>(),
+                                                               ix->spec_on ? ix->spec_flag.as<uint32_t>() : nullptr);
         CU(cudaGetLastError()); ix->counts[5]++;
         CU(cudaEventRecord(ix->ev_win, a2));
     }
@@ -1377,9 +1396,22 @@ int run_lists_and_quantize(rabitq_index* ix, size_t nb, int P, const std::vector
 }
 
 // One sub-batch of nb queries, already on the device in ix->qraw (nb x len).  Runs up to `stop`.
-int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t topk, bool heuristic, StopAfter stop, BatchOut* bo) {
+int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t topk, bool heuristic, StopAfter stop, BatchOut* bo,
+                  bool allow_spec = false) {
     const int P = (int)std::min(probe, ix->K);
     bo->P = P;
+    // Speculative slot sizing: the survivor slots (one bitmap word + 32 entries per 32 vectors of every probed cluster) are sized from
+    // the largest words-per-query any earlier batch needed (+25 %), so the host does not wait for this batch's totals between the
+    // probe selection and the scan; the device checks the real total against the capacity (query_base_scan_kernel) and a batch that
+    // does not fit is neutralised on the device and repeated by the caller with the exact sizes.
+    ix->spec_on = false;
+    if (allow_spec && stop == STOP_NONE && ix->spec_enabled && ix->rerank_mode == 1 && ix->hw_wpq > 0.0 && ix->shard_count == 1) {
+        const double cap = ix->hw_wpq * (double)nb * 1.25 + 4096.0;
+        if (cap * 260.0 <= 16.0 * 1073741824.0 && cap < 4.0e9) {
+            ix->spec_on = true;
+            ix->spec_cap = (uint32_t)cap;
+        }
+    }
     int rc = run_front(ix, nb, len, P, stop == STOP_ROTATE, false);
     if (rc || stop == STOP_ROTATE) return rc;
     if ((rc = post_totals(ix, nb))) return rc;
@@ -1388,7 +1420,13 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
     if (bounds.size() > 17) return fail(RABITQ_EUNSUPPORTED, "more than 16 rerank rounds");
     if ((rc = run_lists_and_quantize(ix, nb, P, bounds))) return rc;
     if (ix->stage_next && (rc = start_staging(ix))) return rc;
-    if ((rc = wait_totals(ix, bo)) || stop == STOP_QUANT) return rc;
+    if (ix->spec_on) {
+        bo->speculative = true;
+        bo->total_words = ix->spec_cap;
+        bo->total_pairs = 0;
+    } else if ((rc = wait_totals(ix, bo)) || stop == STOP_QUANT) {
+        return rc;
+    }
     ScanArgs sa;
     RerankArgs ra;
     if ((rc = setup_rounds(ix, nb, P, topk, bo, &sa, &ra))) return rc;
@@ -1401,7 +1439,8 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
             CU(cudaStreamWaitEvent(a2, L.ready, 0));
             work_items_kernel<<<((int)ix->K + 255) / 256, 256, 0, a2>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(),
                                                                                        L.cl_start.as<uint32_t>(), ix->offsets, ix->chunk_start, (int)ix->K,
-                                                                                       L.MS, L.ch_min, L.work.as<ScanItem>());
+                                                                                       L.MS, L.ch_min, L.work.as<ScanItem>(),
+                                                                                       ix->spec_on ? ix->spec_flag.as<uint32_t>() : nullptr);
             CU(cudaGetLastError()); ix->counts[5]++;
             if (!L.wready) CU(cudaEventCreateWithFlags(&L.wready, cudaEventDisableTiming));
             CU(cudaEventRecord(L.wready, a2));
@@ -1502,8 +1541,10 @@ int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, siz
         }
         BatchOut bo;
         const bool direct = on_device && nb == nq;
+        for (int attempt = 0;; attempt++) {  // (a second pass only when a speculatively sized batch did not fit)
+        bo = BatchOut();
         if (direct) { ix->ovr_dist = out_dist; ix->ovr_ids = out_ids; ix->ovr_count = out_count; }
-        rc = run_sub_batch(ix, nb, len, probe, topk, heuristic != 0, STOP_NONE, &bo);
+        rc = run_sub_batch(ix, nb, len, probe, topk, heuristic != 0, STOP_NONE, &bo, attempt == 0);
         ix->ovr_dist = nullptr; ix->ovr_ids = nullptr; ix->ovr_count = nullptr;
         if (rc) return rc;
         const uint32_t* oa = ix->out_all.as<uint32_t>();
@@ -1526,6 +1567,18 @@ int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, siz
         CU(cudaMemcpyAsync(ix->h_pin + 8, ix->counters.p, 32, cudaMemcpyDeviceToHost, ix->stream));
         if (tick(ix, ST_D2H)) return RABITQ_ECUDA;
         CU(cudaStreamSynchronize(ix->stream));
+        if (bo.speculative) {  // the totals (and the prefilter's verdict) arrived with everything else
+            prefilter_adapt(ix);
+            const uint32_t real_words = ix->h_pin[0];
+            std::memcpy(&bo.total_pairs, ix->h_pin + 2, 8);
+            ix->hw_wpq = std::max(ix->hw_wpq, (double)real_words / (double)nb);
+            ix->spec_on = false;
+            if (ix->h_pin[4] != 0u) continue;  // did not fit: neutralised on the device, repeated with the exact sizes
+        } else {
+            ix->hw_wpq = std::max(ix->hw_wpq, (double)bo.total_words / (double)nb);
+        }
+        break;
+        }
         if (!on_device) {
             std::memcpy(out_dist + q0 * topk, ix->h_out, nb * topk * 4);
             std::memcpy(out_ids + q0 * topk, ix->h_out + nb * topk, nb * topk * 4);
@@ -1802,6 +1855,7 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a
     if ((rc = wait_totals(ix, &bo))) return rc;
     ix->counts[0] += bo.total_pairs;
     if ((rc = setup_rounds(ix, nq, P, d.topk, &bo, &d.sa, &d.ra))) return rc;
+    CU(cudaStreamWaitEvent(st, ix->ev_win, 0));  // the batch's counters were reset on the second side stream (run_lists_and_quantize)
     fill_f32_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(d_thr, nq, 3.402823466e+38f);
     CU(cudaGetLastError()); ix->counts[5]++;
     d.d_thr = d_thr;
@@ -2155,6 +2209,8 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     else if (n == "prefilter_mode") { idx->pf_mode = (int)value; idx->pf_strikes = 0; }
     else if (n == "prefilter_cap") idx->prefilter_cap = (int)value;
     else if (n == "prefilter_gemm") idx->pf_gemm = (int)value;
+    else if (n == "speculative_sizing") idx->spec_enabled = value != 0;
+    else if (n == "spec_words_per_query_milli") idx->hw_wpq = (double)value / 1000.0;  // (tests: a tiny value makes the next batch overflow its speculative slots)
     else return fail(RABITQ_EINVAL, "unknown option: " + n);
     return RABITQ_OK;
 }

@@ -183,3 +183,32 @@ def test_property_random_shapes():
         o.close()
 
     run()
+
+
+def test_speculative_slot_sizing_and_its_overflow_path():
+    """The survivor slots of a batch are sized from earlier batches (no host round trip in the middle of the batch); a batch that
+    needs more is neutralised on the device and repeated with the exact sizes.  Results never depend on which path ran."""
+    from tools import synth
+
+    base, queries, cent = synth.make_numpy(6000, 128, 48, 24, "sift", seed=21)
+    o, g, a = _pair(base, cent, seed=5)
+    ref = o.query_batch(queries, 6, 10)
+
+    def same(res):
+        d, _, c = res
+        for i in range(queries.shape[0]):
+            n = int(ref["count"][i])
+            assert int(c[i]) == n
+            assert np.array_equal(np.sort(d[i, :n]).view(np.uint32), np.sort(ref["dist"][i, :n]).view(np.uint32)), i
+
+    same(g.query_batch(queries, 6, 10))           # first batch: exact sizes (nothing to speculate from)
+    same(g.query_batch(queries, 6, 10))           # second batch: speculative, fits
+    g.set_option("spec_words_per_query_milli", 1)  # pretend earlier batches were tiny: the next one overflows and is repeated
+    g.metrics_reset()
+    same(g.query_batch(queries, 6, 10))
+    assert g.metrics()["precise"] == ref["precise"] and g.metrics()["rough"] == ref["rough"]
+    same(g.query_batch(queries, 6, 10))           # high-water mark now real again: speculative, fits
+    g.set_option("speculative_sizing", 0)
+    same(g.query_batch(queries, 6, 10))
+    g.close()
+    o.close()
