@@ -192,15 +192,25 @@ const char* rabitq_last_error(void); /* thread-local */
  * the last round always extends to `probe`.  Default {0, 1}. */
 int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
 
-/* Integer tuning knobs (results never depend on them; tests sweep them): "first_chunks" = 128-vector chunks of the nearest
- * cluster that form the first rerank round (default 1, 0 = whole cluster); "scan_mode" = carry-save depth of the scan's
- * popcount (0 plain, 1 = 3->2, 2 = 7->3 compressors, 3 = half the words by 7->3 and the rest by 3->2, -1 = by dimension); "rerank_rows" = rows per rerank wave (0 = auto); "rerank_prefetch" = L2 prefetch of survivor rows ahead of the
- * gather (default 0: measured slower on B200); "debug_rerank" = 1 keeps per-query rerank statistics for rabitq_debug_rerank_stats; "scan_slices" = shared-memory record slices per scan
- * work item (default 1; hot clusters are cut into several items); "prefilter" = 1 (default) lets the centroid scan run as a
- * TF32 tensor-core prefilter + exact recheck of the candidates when k >= 512 and probe <= k/8 (probe lists stay bit-identical),
- * 0 = always all k exact distances; "prefilter_cap" = candidates per query the prefilter may certify (<= 1024; a query
- * above it sends its batch to the exact path on the device); "prefilter_mode" = 1 plain TF32 keys, 3 = 3xTF32 split, 0 = off
- * (the handle moves 1 -> 3 -> 0 by itself when batches cannot be certified). */
+/* Integer tuning knobs (results never depend on them; tests sweep them):
+ *   "first_chunks"     128-vector chunks of the nearest cluster that form the first rerank round (default 1, 0 = whole cluster);
+ *   "scan_slices"      shared-memory record slices per scan work item (default 1; hot clusters are cut into several items);
+ *   "scan_stages" / "scan_sub"  ring depth / record passes per stage of the scan (0 = by dimension); "scan_mode" 0..2 forces 1, 2, 4
+ *                      record tiles (n8) per consumer warp (-1 = by dimension; the tests run every instantiation);
+ *   "rerank_mode"      1 (default) = one warp-specialised CTA per query (rerank_cta_kernel), 0 = one warp per query (rerank_kernel);
+ *   "rerank_rows"      rows per rerank wave (0 = by dimension; CTA form: <= 8); "rerank_stages" / "rerank_warps" / "rerank_nc" = row
+ *                      buffers, compute warps and candidates per eight-lane group of the CTA form (0 = by dimension);
+ *   "rerank_prefetch"  L2 prefetch of survivor rows ahead of the gather, warp form (default 0: measured slower on B200);
+ *   "debug_rerank"     1 keeps per-query rerank statistics for rabitq_debug_rerank_stats;
+ *   "prefilter"        1 (default) lets the centroid scan run as a TF32 tensor-core prefilter + exact recheck of the candidates when
+ *                      k >= 512 and probe <= k/8 (probe lists stay bit-identical), 0 = always all k exact distances;
+ *   "prefilter_gemm"   1 (default) = the key GEMM on tcgen05 / TMEM / TMA (tc5_gemm.cuh), 0 = the mma.sync form;
+ *   "prefilter_cap"    candidates per query the prefilter may certify (<= 1024; a query above it sends its batch to the exact path on
+ *                      the device); "prefilter_mode" = 1 plain TF32 keys, 3 = 3xTF32 split, 0 = off (the handle moves 1 -> 3 -> 0 by
+ *                      itself when batches cannot be certified);
+ *   "speculative_sizing"  1 (default) sizes a batch's survivor slots from earlier batches and checks the capacity on the device (no host
+ *                      round trip in the middle of the batch; a batch that does not fit is repeated with exact sizes), 0 = always read
+ *                      the totals back first; "spec_words_per_query_milli" overrides the high-water mark (tests). */
 int rabitq_set_option(rabitq_index* idx, const char* name, long value);
 
 /* Byte position of dimension d inside a K3 query record (the tensor-core fragment order K4 reads, kernels.cuh rec_pos); host-only,
