@@ -1926,9 +1926,12 @@ __global__ void round_windows_kernel(const uint32_t* __restrict__ q_wbase, const
     }
 }
 
+#ifndef RQ_RC_SB1
+#define RQ_RC_SB1 8
+#endif
 // blocks of 32 survivor words per super-block of the producer's stream: 8 for long rows (few queries per SM anyway), 2 for short rows
 // (NC = 2), where registers and shared memory per CTA decide how many queries an SM keeps in flight
-__host__ __device__ constexpr int rerank_cta_sb(int nc) { return nc == 2 ? 2 : 8; }
+__host__ __device__ constexpr int rerank_cta_sb(int nc) { return nc == 2 ? 2 : RQ_RC_SB1; }
 __host__ __device__ __forceinline__ size_t rerank_cta_smem(int D, int topk, int R, int ns, int nc) {
     const int sb = rerank_cta_sb(nc);
     return 528 + (size_t)D * 4 + (size_t)ns * R * (D + 8) * 4 + 2 * (size_t)topk * 4 + 3 * 16 * 8 * 4 + (size_t)sb * 32 * 16 + sb * 4 + 16;

@@ -1298,8 +1298,8 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
         const int nc = R > 4 || ix->rerank_nc == 2 ? 2 : 1;
         // a row buffer is always consumed by the same compute warp (waves go round-robin over the warps, buffers round-robin over
         // the waves: ns must be a multiple of ncw, or a warp would wait on a barrier whose phases it has not followed)
-        int ncw = std::max(1, std::min(8, ix->rerank_warps > 0 ? ix->rerank_warps : (nc == 2 ? 1 : 3)));
-        int bpw = std::max(1, (std::min(8, ix->rerank_stages > 0 ? ix->rerank_stages : (nc == 2 ? 2 : 3)) + ncw - 1) / ncw);  // buffers per warp
+        int ncw = std::max(1, std::min(8, ix->rerank_warps > 0 ? ix->rerank_warps : (nc == 2 ? 1 : (D > 1024 ? 2 : 3))));  // (three CTAs per SM stay resident)
+        int bpw = std::max(1, (std::min(8, ix->rerank_stages > 0 ? ix->rerank_stages : (nc == 2 || D > 1024 ? 2 : 3)) + ncw - 1) / ncw);  // buffers per warp
         while (ncw * bpw > 8) bpw--;
         if (bpw < 1) { bpw = 1; ncw = 8; }
         int ns = ncw * bpw;
