@@ -114,3 +114,27 @@ def test_shard_range_edge_cases():
         assert rows[0][0] == 0 and rows[-1][1] == 20
         assert all(rows[r][1] == rows[r + 1][0] for r in range(world - 1))
         assert all(lo <= hi for lo, hi in rows)
+
+
+def _bcast_worker(rank, world, port, ret):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+
+    # every rank "generates" slightly different inputs (what happened at 100M vectors); after the chunked broadcast all hold rank 0's
+    t = torch.arange(1000, dtype=torch.float32).reshape(100, 10) + float(rank)
+    bench._bcast_chunked(t, 0, max_elems=96)  # forces several slices, the last one partial
+    ret[rank] = bool(torch.equal(t, torch.arange(1000, dtype=torch.float32).reshape(100, 10)))
+    dist.destroy_process_group()
+
+
+def test_bench_broadcasts_identical_inputs_to_every_rank():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bcast_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
