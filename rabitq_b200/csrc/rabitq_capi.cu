@@ -1811,6 +1811,7 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a
     std::lock_guard<std::mutex> lk(ix->mu);
     CU(cudaSetDevice(ix->device));
     cudaStream_t st = ix->stream;
+    ix->spec_on = false;  // (the distributed phases always read the slot totals back: a repeat would be a collective act)
     const size_t nq = d.nq_l * d.world, D = ix->D;
     const int P = d.P;
     if (!pushed) {
