@@ -1934,9 +1934,11 @@ __global__ void round_windows_kernel(const uint32_t* __restrict__ q_wbase, const
 __host__ __device__ constexpr int rerank_cta_sb(int nc) { return nc == 2 ? 2 : RQ_RC_SB1; }
 __host__ __device__ __forceinline__ size_t rerank_cta_smem(int D, int topk, int R, int ns, int nc) {
     const int sb = rerank_cta_sb(nc);
-    return 528 + (size_t)D * 4 + (size_t)ns * R * (D + 8) * 4 + 2 * (size_t)topk * 4 + 3 * 16 * 8 * 4 + (size_t)sb * 32 * 16 + sb * 4 + 16;
+    return 528 + (size_t)D * 4 + (size_t)ns * R * (D + 8) * 4 + 2 * (size_t)topk * 4 + 4 * 16 * 8 * 4 + (size_t)sb * 32 * 16 + sb * 4 + 16;
 }
-template <bool HEUR, int NC>
+// SINK = 1 (distributed round 1, run by the shard that owns the query's nearest non-empty cluster): the same replay, and every candidate
+// the reference computes an exact distance for is also written to the home rank's inbox (peer memory over NVLink), as in rerank_kernel.
+template <bool HEUR, int NC, int SINK = 0>
 __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo, int ch_lo, int p_hi, int ch_hi, int first, int finalize) {
     extern __shared__ __align__(16) unsigned char rc_smem_raw[];
     constexpr int RC_SB = rerank_cta_sb(NC);
@@ -1960,13 +1962,36 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
     float* qr = reinterpret_cast<float*>(hid + k);           // [NM][RW] rough
     uint32_t* qj = reinterpret_cast<uint32_t*>(qr + NM * RW);  // [NM][RW] position
     float* ex = reinterpret_cast<float*>(qj + NM * RW);      // [NM][RW] exact
-    float2* s_en = reinterpret_cast<float2*>(ex + NM * RW);  // [RC_SB][32] the producer's stash of one super-block's first entries
+    uint32_t* smid = reinterpret_cast<uint32_t*>(ex + NM * RW);  // [NM][RW] original id (SINK: looked up by the compute warps)
+    float2* s_en = reinterpret_cast<float2*>(smid + NM * RW);  // [RC_SB][32] the producer's stash of one super-block's first entries
     uint32_t* s_incl = reinterpret_cast<uint32_t*>(s_en + RC_SB * 32);  // [RC_SB][32] inclusive prefix of the words' survivor counts
     uint32_t* s_m = s_incl + RC_SB * 32;                                // [RC_SB][32] the bitmap words
     uint32_t* s_T = s_m + RC_SB * 32;                                   // [RC_SB] survivors per block
     const uint32_t lt_mask = (1u << lane) - 1u;
     const long long dbg_t0 = a.dbg ? clock64() : 0ll;
 
+    auto window = [&](uint32_t& wlo, uint32_t& whi) {  // word window of this round from the bounds (when no precomputed pair exists)
+        const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
+        const int p0 = (int)a.q_p0[q];
+        auto word_at = [&](int pe, int ch) -> uint32_t {
+            const int p = pe + p0;
+            if (p >= a.P) return wend;
+            const uint32_t s0 = wb + a.slot_local[(size_t)q * a.P + p];
+            const uint32_t s1 = (p + 1 < a.P) ? wb + a.slot_local[(size_t)q * a.P + p + 1] : wend;
+            return min(s0 + (uint32_t)ch * (SCAN_THREADS / 32), s1);
+        };
+        wlo = word_at(p_lo, ch_lo); whi = word_at(p_hi, ch_hi);
+    };
+    volatile uint32_t* s_win = reinterpret_cast<volatile uint32_t*>(rc_smem_raw + 520);  // [2]
+    if constexpr (SINK == 1) {  // most queries have no candidates in this shard's round-1 window: find out before anything else is loaded
+        if (threadIdx.x == 0) {
+            uint32_t wlo, whi;
+            window(wlo, whi);
+            s_win[0] = wlo; s_win[1] = whi;
+        }
+        __syncthreads();
+        if (s_win[0] >= s_win[1]) return;
+    }
     if (threadIdx.x < 48) mbar_init(&bar_full[threadIdx.x], 1);
     if (threadIdx.x == 0) *thr_s = first ? 3.402823466e+38f : a.thr[q];
     {
@@ -1979,20 +2004,13 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------- producer
         uint32_t wlo, whi;
-        if (a.win) {
+        if constexpr (SINK == 1) {
+            wlo = s_win[0]; whi = s_win[1];
+        } else if (a.win) {
             const uint2 ww = a.win[q];
             wlo = ww.x; whi = ww.y;
         } else {
-            const uint32_t wb = a.q_wbase[q], wend = a.q_wbase[q + 1];
-            const int p0 = (int)a.q_p0[q];
-            auto word_at = [&](int pe, int ch) -> uint32_t {
-                const int p = pe + p0;
-                if (p >= a.P) return wend;
-                const uint32_t s0 = wb + a.slot_local[(size_t)q * a.P + p];
-                const uint32_t s1 = (p + 1 < a.P) ? wb + a.slot_local[(size_t)q * a.P + p + 1] : wend;
-                return min(s0 + (uint32_t)ch * (SCAN_THREADS / 32), s1);
-            };
-            wlo = word_at(p_lo, ch_lo); whi = word_at(p_hi, ch_hi);
+            window(wlo, whi);
         }
         uint32_t w = 0;
         int fill = 0;
@@ -2146,6 +2164,14 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             if constexpr (!HEUR) thr = hmax;
         }
         uint32_t precise = 0, computed = 0, waves = 0, dbg_rwait = 0;
+        // record sink (SINK = 1): the candidates the reference computes, in order, into this shard's region of the home rank's inbox
+        const int home = SINK ? q / a.nq_local : 0, ql = SINK ? q - home * a.nq_local : 0;
+        SurvRec* rdst = nullptr;
+        uint32_t nrec = 0, prank = 0;
+        if constexpr (SINK == 1) {
+            rdst = reinterpret_cast<SurvRec*>(a.peers[home] + a.off_r1rec) + ((size_t)a.rank * a.nq_local + ql) * a.r1cap;
+            prank = a.q_p0[q] + (uint32_t)p_lo;
+        }
         for (uint32_t w = 0;; w++) {
             const uint32_t m = w % NM;
             const long long tw0 = a.dbg ? clock64() : 0ll;
@@ -2157,6 +2183,8 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             const float rough = mine ? qr[m * RW + lane] : 0.0f;
             const uint32_t j = mine ? qj[m * RW + lane] : 0u;
             const float exact = mine ? ex[m * RW + lane] : 0.0f;
+            uint32_t mid = 0;
+            if constexpr (SINK == 1) mid = mine ? smid[m * RW + lane] : 0u;
             computed += (uint32_t)n;
             waves += n ? 1u : 0u;
             // in-order replay (rerank.rs:83-101).  The threshold only moves when a candidate is ACCEPTED (rough < thr and
@@ -2169,13 +2197,23 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
                 const uint32_t am = __ballot_sync(FULL, pass && exact < thr);
                 const int t = __ffs(am) - 1;                           // the next accepted candidate (-1: none)
                 const uint32_t upto = am ? ((2u << t) - 1u) : FULL;    // lanes 0..t
-                precise += __popc(pm & upto);
+                const uint32_t cm = pm & upto;
+                precise += __popc(cm);
+                if constexpr (SINK == 1) {
+                    const uint32_t pos = nrec + __popc(cm & lt_mask);
+                    if (((cm >> lane) & 1u) && pos < (uint32_t)a.r1cap) {
+                        SurvRec rec;
+                        rec.rough = rough; rec.exact = exact; rec.id = mid; rec.p = prank;
+                        rdst[pos] = rec;
+                    }
+                    nrec += __popc(cm);
+                }
                 if (!am) break;
                 rem &= ~upto;
                 const float exa = __shfl_sync(FULL, exact, t);
                 if (!HEUR || cnt < k || exa < hmax) {
                     const int slot = cnt < k ? cnt : maxpos;
-                    if (lane == t) { hd[slot] = exa; hid[slot] = j; }  // the POSITION; map_ids at finalize
+                    if (lane == t) { hd[slot] = exa; hid[slot] = SINK == 1 ? mid : j; }  // SINK = 0: the POSITION; map_ids at finalize
                     if (cnt < k) cnt++;
                     __syncwarp();
                     if (cnt == k) {
@@ -2198,6 +2236,9 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             if (lane == 0) mbar_arrive(&bar_mfree[m]);
             if (last) break;
         }
+        if constexpr (SINK == 1) {  // the owner of the window tells the home rank how many records to replay
+            if (lane == 0) reinterpret_cast<uint32_t*>(a.peers[home] + a.off_r1cnt)[(size_t)a.rank * a.nq_local + ql] = min(nrec, (uint32_t)a.r1cap);
+        }
         if (a.dbg && lane == 0) {
             uint32_t* o = a.dbg + ((size_t)q * 2 + (first ? 0 : 1)) * 8;
             o[0] = (uint32_t)(clock64() - dbg_t0); o[1] = waves; o[2] = computed; o[6] = dbg_rwait;
@@ -2216,8 +2257,10 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
         } else {
             // ascending by (distance, id): rank by counting; the original ids (rerank.rs:94) are looked up here
             __syncwarp();
-            for (int s = lane; s < cnt; s += 32) hid[s] = a.map_ids[hid[s]];
-            __syncwarp();
+            if constexpr (SINK == 0) {
+                for (int s = lane; s < cnt; s += 32) hid[s] = a.map_ids[hid[s]];
+                __syncwarp();
+            }
             for (int s = lane; s < k; s += 32) {
                 if (s < cnt) {
                     const uint32_t ks = okey(hd[s]), is = hid[s];
@@ -2258,6 +2301,11 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
                 need = need || (c[i] < n && qr[m * RW + c[i]] < thr);
             }
             if (__any_sync(FULL, need)) {
+                uint32_t midv[NC];
+                if constexpr (SINK == 1) {  // in flight while the distances are computed
+#pragma unroll
+                    for (int i = 0; i < NC; i++) midv[i] = (l8 == 0 && c[i] < n) ? a.map_ids[qj[m * RW + c[i]]] : 0u;
+                }
                 float d2[NC];
                 if constexpr (NC == 2) {
                     const float* const rp[2] = {rw + (size_t)min(c[0], R - 1) * pitch, rw + (size_t)min(c[1], R - 1) * pitch};
@@ -2268,7 +2316,10 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
                 }
 #pragma unroll
                 for (int i = 0; i < NC; i++)
-                    if (l8 == 0 && c[i] < n) ex[m * RW + c[i]] = d2[i];
+                    if (l8 == 0 && c[i] < n) {
+                        ex[m * RW + c[i]] = d2[i];
+                        if constexpr (SINK == 1) smid[m * RW + c[i]] = midv[i];
+                    }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the rows of this buffer are rewritten by later bulk copies
             __threadfence_block();

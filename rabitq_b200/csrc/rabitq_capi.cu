@@ -192,6 +192,7 @@ struct rabitq_index {
     std::vector<uint32_t> rounds{0};
     int rerank_rows = 0;   // rows per rerank wave; 0 = by dimension
     int rerank_mode = 1;   // 1: one CTA per query, warp-specialised (rerank_cta_kernel); 0: one warp per query (rerank_kernel)
+    bool dist_sink_cta = true; // distributed round 1 on the CTA form of K5 (RABITQ_DIST_SINK_CTA=0: the warp form)
     int rerank_nc = 0;     // candidates per eight-lane group of the CTA form (1 or 2; 0 = by wave size)
     int pf_threads = 0;    // 256: always 256 threads per query in prefilter_select_kernel (A/B switch)
     int rerank_stages = 0; // row buffers in the CTA form's ring (0 = 4)
@@ -398,6 +399,9 @@ int finish_index(rabitq_index* ix) {
     CU(cudaFuncSetAttribute(rerank_cta_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(rerank_cta_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(rerank_cta_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_cta_kernel<false, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_cta_kernel<false, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (const char* e = std::getenv("RABITQ_DIST_SINK_CTA")) ix->dist_sink_cta = std::atoi(e) != 0;
     CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(approx_gemm_tf32_kernel<128, 128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * PF_PITCH * 4));
     if (const char* e = std::getenv("RABITQ_PREFILTER")) ix->prefilter = std::atoi(e);
@@ -1289,7 +1293,7 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
     const dim3 rgrid((unsigned)((nb + rr_wpb - 1) / rr_wpb)), rblock(rr_wpb * 32);
     const size_t rsmem = (size_t)rr_wpb * ra.smem_per_warp;
     const int f = is_first ? 1 : 0, l = is_last ? 1 : 0;
-    if (kind != ROUND_SINK1 && ix->rerank_mode == 1) {
+    if (ix->rerank_mode == 1 && (kind != ROUND_SINK1 || ix->dist_sink_cta)) {
         // one CTA per query: producer + replay + compute warps (rerank_cta_kernel).  A wave is one compute warp's job (4 rows, or 8
         // with two candidates per eight-lane group for short rows); `ns` row buffers keep that many gathers in flight
         const size_t D = (size_t)ra.D;
@@ -1313,7 +1317,10 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
             rc.R = R;
             rc.ns = ns;
             const dim3 grid((unsigned)nb), block((unsigned)(2 + ncw) * 32);
-            if (heuristic) {
+            if (kind == ROUND_SINK1) {  // distributed round 1: records go to the home ranks' inboxes
+                if (nc == 2) rerank_cta_kernel<false, 2, 1><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
+                else rerank_cta_kernel<false, 1, 1><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
+            } else if (heuristic) {
                 if (nc == 2) rerank_cta_kernel<true, 2><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
                 else rerank_cta_kernel<true, 1><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
             } else {
