@@ -1401,6 +1401,12 @@ struct RerankArgs {
     int R;                        // rows per wave (<= 32; rerank_cta_kernel: <= 8)
     int ns;                       // rerank_cta_kernel: row buffers in the ring
     const uint2* win;             // rerank_cta_kernel: this round's (first word, end word) per query (round_windows_kernel), or NULL
+    // rerank_cta_kernel<.., SINK = 2> (distributed frozen round, source side): per query the survivor count of the round (upper bound
+    // of the records; 0xffffffff = region overflow, flagged) and the offset of its records inside this shard's region of the home inbox
+    const uint32_t* r2_cnt;
+    const uint32_t* r2_off;
+    size_t off_r2rec, off_r2tab;
+    uint32_t cap2;
     int smem_per_warp;            // bytes
     int prefetch;                 // L2 prefetch of the survivors' base rows at discovery time (0 = off)
     uint32_t* dbg;                // NULL, or nq x 2 rounds x {cycles, waves, computed, enqueue (incl. the waves processed inside), wait, l2, replay, stage} (rabitq_debug_rerank_stats)
@@ -1934,7 +1940,7 @@ __global__ void round_windows_kernel(const uint32_t* __restrict__ q_wbase, const
 __host__ __device__ constexpr int rerank_cta_sb(int nc) { return nc == 2 ? 2 : RQ_RC_SB1; }
 __host__ __device__ __forceinline__ size_t rerank_cta_smem(int D, int topk, int R, int ns, int nc) {
     const int sb = rerank_cta_sb(nc);
-    return 528 + (size_t)D * 4 + (size_t)ns * R * (D + 8) * 4 + 2 * (size_t)topk * 4 + 4 * 16 * 8 * 4 + (size_t)sb * 32 * 16 + sb * 4 + 16;
+    return 528 + (size_t)D * 4 + (size_t)ns * R * (D + 8) * 4 + 2 * (size_t)topk * 4 + 5 * 16 * 8 * 4 + (size_t)sb * 32 * 16 + sb * 4 + 16;
 }
 // SINK = 1 (distributed round 1, run by the shard that owns the query's nearest non-empty cluster): the same replay, and every candidate
 // the reference computes an exact distance for is also written to the home rank's inbox (peer memory over NVLink), as in rerank_kernel.
@@ -1963,10 +1969,12 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
     uint32_t* qj = reinterpret_cast<uint32_t*>(qr + NM * RW);  // [NM][RW] position
     float* ex = reinterpret_cast<float*>(qj + NM * RW);      // [NM][RW] exact
     uint32_t* smid = reinterpret_cast<uint32_t*>(ex + NM * RW);  // [NM][RW] original id (SINK: looked up by the compute warps)
-    float2* s_en = reinterpret_cast<float2*>(smid + NM * RW);  // [RC_SB][32] the producer's stash of one super-block's first entries
+    uint32_t* sqw = smid + NM * RW;                              // [NM][RW] SINK = 2: slot word of the candidate -> its probe rank
+    float2* s_en = reinterpret_cast<float2*>(sqw + NM * RW);   // [RC_SB][32] the producer's stash of one super-block's first entries
     uint32_t* s_incl = reinterpret_cast<uint32_t*>(s_en + RC_SB * 32);  // [RC_SB][32] inclusive prefix of the words' survivor counts
     uint32_t* s_m = s_incl + RC_SB * 32;                                // [RC_SB][32] the bitmap words
     uint32_t* s_T = s_m + RC_SB * 32;                                   // [RC_SB] survivors per block
+    uint32_t* s_sl = s_T + RC_SB + 2;                                   // [P] SINK = 2: the query's slot_local row (word -> probe rank)
     const uint32_t lt_mask = (1u << lane) - 1u;
     const long long dbg_t0 = a.dbg ? clock64() : 0ll;
 
@@ -1982,18 +1990,26 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
         };
         wlo = word_at(p_lo, ch_lo); whi = word_at(p_hi, ch_hi);
     };
-    volatile uint32_t* s_win = reinterpret_cast<volatile uint32_t*>(rc_smem_raw + 520);  // [2]
-    if constexpr (SINK == 1) {  // most queries have no candidates in this shard's round-1 window: find out before anything else is loaded
+    volatile uint32_t* s_win = reinterpret_cast<volatile uint32_t*>(rc_smem_raw + 516);  // [3] first word, end word, (SINK = 2) the query's slot base
+    if constexpr (SINK != 0) {  // most queries have no candidates in this shard's window: find out before anything else is loaded
         if (threadIdx.x == 0) {
             uint32_t wlo, whi;
             window(wlo, whi);
+            if constexpr (SINK == 2) {  // nothing survived the frozen threshold, or the region overflowed (flagged by r2_offsets_kernel)
+                const uint32_t c2 = a.r2_cnt[q];
+                if (c2 == 0u || c2 == 0xffffffffu) whi = wlo;
+            }
             s_win[0] = wlo; s_win[1] = whi;
+            if constexpr (SINK == 2) s_win[2] = a.q_wbase[q];
         }
         __syncthreads();
         if (s_win[0] >= s_win[1]) return;
     }
     if (threadIdx.x < 48) mbar_init(&bar_full[threadIdx.x], 1);
-    if (threadIdx.x == 0) *thr_s = first ? 3.402823466e+38f : a.thr[q];
+    if (threadIdx.x == 0) *thr_s = (first && SINK != 2) ? 3.402823466e+38f : a.thr[q];  // SINK = 2: the frozen threshold of round 1
+    if constexpr (SINK == 2) {
+        for (int p = threadIdx.x; p < a.P; p += blockDim.x) s_sl[p] = a.slot_local[(size_t)q * a.P + p];
+    }
     {
         const float4* src = reinterpret_cast<const float4*>(a.qpad + (size_t)q * D);
         float4* dst = reinterpret_cast<float4*>(qv);
@@ -2004,7 +2020,7 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------- producer
         uint32_t wlo, whi;
-        if constexpr (SINK == 1) {
+        if constexpr (SINK != 0) {
             wlo = s_win[0]; whi = s_win[1];
         } else if (a.win) {
             const uint2 ww = a.win[q];
@@ -2033,7 +2049,7 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             w++;
             fill = 0;
         };
-        auto enqueue = [&](uint32_t pm, float rough, uint32_t j) {
+        auto enqueue = [&](uint32_t pm, float rough, uint32_t j, uint32_t word) {
             while (pm) {
                 if (fill == 0) open_wave();
                 const uint32_t s = w % NS, m = w % NM;
@@ -2047,6 +2063,7 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
                     const int slot = fill + rank;
                     qr[m * RW + slot] = rough;
                     qj[m * RW + slot] = j;
+                    if constexpr (SINK == 2) sqw[m * RW + slot] = word;
                     tma_bulk_g2s(rows + ((size_t)s * R + slot) * pitch, a.base + (size_t)j * D, rowbytes, &bar_full[s]);
                 }
                 pm &= ~took;
@@ -2063,6 +2080,7 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             }
             return x;
         };
+        int pos_last = 0;  // word (inside its block) of the survivor the last load_chunk gave this lane
         auto load_chunk = [&](uint32_t w0, uint32_t incl, uint32_t exc, uint32_t T, uint32_t e0) -> float2 {  // survivor e0 + lane of the block
             const uint32_t e = e0 + lane;
             int pos = 0;
@@ -2075,6 +2093,7 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             const uint32_t src_excl = __shfl_sync(FULL, exc, pos);
             float2 en = make_float2(3.402823466e+38f, 0.0f);
             if (e < T) en = a.entries[(size_t)(w0 + pos) * 32 + (e - src_excl)];
+            pos_last = pos;
             return en;
         };
         // Super-blocks of SB x 32 words.  The stream is a chain of dependent DRAM accesses (bitmap word -> entries -> row), about a
@@ -2120,20 +2139,35 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
                 if (T == 0) continue;  // uniform
                 {
                     const float2 en = s_en[u * 32 + lane];
+                    uint32_t word = 0;
+                    if constexpr (SINK == 2) {  // the word of survivor `lane` of the block: first word whose inclusive prefix exceeds it
+                        const uint32_t inc = s_incl[u * 32 + lane];
+                        int pos = 0;
+#pragma unroll
+                        for (int sft = 16; sft > 0; sft >>= 1) {
+                            const uint32_t pv = __shfl_sync(FULL, inc, pos + sft - 1);
+                            if (pv <= (uint32_t)lane) pos += sft;
+                        }
+                        word = w0 + u * 32 + min(pos, 31);
+                    }
                     const uint32_t pm = __ballot_sync(FULL, (uint32_t)lane < T && en.x < *thr_s);
-                    if (pm) enqueue(pm, en.x, __float_as_uint(en.y));
+                    if (pm) enqueue(pm, en.x, __float_as_uint(en.y), word);
                 }
                 if (T > 32) {  // dense block (loose threshold, e.g. the first probed cluster): further chunks, three at a time in flight
                     const uint32_t wblk = w0 + u * 32;
                     const uint32_t inc = s_incl[u * 32 + lane], exc = inc - __popc(s_m[u * 32 + lane]);
                     for (uint32_t e0 = 32; e0 < T; e0 += 96) {
                         float2 en[3];
+                        uint32_t wd[3];
 #pragma unroll
-                        for (int c = 0; c < 3; c++) en[c] = load_chunk(wblk, inc, exc, T, e0 + 32 * c);
+                        for (int c = 0; c < 3; c++) {
+                            en[c] = load_chunk(wblk, inc, exc, T, e0 + 32 * c);
+                            wd[c] = wblk + (uint32_t)pos_last;
+                        }
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
                             const uint32_t pm = __ballot_sync(FULL, e0 + 32 * c + lane < T && en[c].x < *thr_s);
-                            if (pm) enqueue(pm, en[c].x, __float_as_uint(en[c].y));
+                            if (pm) enqueue(pm, en[c].x, __float_as_uint(en[c].y), wd[c]);
                         }
                     }
                 }
@@ -2172,6 +2206,15 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             rdst = reinterpret_cast<SurvRec*>(a.peers[home] + a.off_r1rec) + ((size_t)a.rank * a.nq_local + ql) * a.r1cap;
             prank = a.q_p0[q] + (uint32_t)p_lo;
         }
+        // SINK = 2 (distributed frozen round, source side): this shard replays ITS candidates of the query in visit order against a
+        // LOCAL threshold -- min(frozen threshold, k-th smallest max(exact, rough) among the shard's own computed candidates) -- and
+        // ships every candidate it computes.  That threshold never drops below the one the reference holds at the same candidate:
+        // k local keys below the reference's threshold would be k candidates the reference has computed as well (rough <= key <
+        // its threshold, which only falls) with exact distances below its threshold, i.e. below its own k-th smallest.  So the
+        // shipped set is a superset of what the reference reranks on this shard, far smaller than the frozen round's survivors.
+        const float thr_cap = SINK == 2 ? thr : 3.402823466e+38f;
+        if constexpr (SINK == 2)
+            rdst = reinterpret_cast<SurvRec*>(a.peers[home] + a.off_r2rec) + (size_t)a.rank * a.cap2 + a.r2_off[q];
         for (uint32_t w = 0;; w++) {
             const uint32_t m = w % NM;
             const long long tw0 = a.dbg ? clock64() : 0ll;
@@ -2184,7 +2227,10 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             const uint32_t j = mine ? qj[m * RW + lane] : 0u;
             const float exact = mine ? ex[m * RW + lane] : 0.0f;
             uint32_t mid = 0;
-            if constexpr (SINK == 1) mid = mine ? smid[m * RW + lane] : 0u;
+            if constexpr (SINK != 0) mid = mine ? smid[m * RW + lane] : 0u;
+            if constexpr (SINK == 2) prank = mine ? sqw[m * RW + lane] : 0u;
+            // the key the heap keeps: the exact distance; SINK = 2: max(exact, rough) (a NaN distance is never kept, as in the reference)
+            const float key = SINK == 2 ? (exact == exact ? fmaxf(exact, rough) : 3.402823466e+38f) : exact;
             computed += (uint32_t)n;
             waves += n ? 1u : 0u;
             // in-order replay (rerank.rs:83-101).  The threshold only moves when a candidate is ACCEPTED (rough < thr and
@@ -2194,14 +2240,14 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             while (rem) {
                 const bool pass = ((rem >> lane) & 1u) && rough < thr;
                 const uint32_t pm = __ballot_sync(FULL, pass);
-                const uint32_t am = __ballot_sync(FULL, pass && exact < thr);
+                const uint32_t am = __ballot_sync(FULL, pass && key < thr);
                 const int t = __ffs(am) - 1;                           // the next accepted candidate (-1: none)
                 const uint32_t upto = am ? ((2u << t) - 1u) : FULL;    // lanes 0..t
                 const uint32_t cm = pm & upto;
                 precise += __popc(cm);
-                if constexpr (SINK == 1) {
+                if constexpr (SINK != 0) {
                     const uint32_t pos = nrec + __popc(cm & lt_mask);
-                    if (((cm >> lane) & 1u) && pos < (uint32_t)a.r1cap) {
+                    if (((cm >> lane) & 1u) && (SINK == 2 || pos < (uint32_t)a.r1cap)) {  // (SINK = 2: at most the round's survivors, which the region holds)
                         SurvRec rec;
                         rec.rough = rough; rec.exact = exact; rec.id = mid; rec.p = prank;
                         rdst[pos] = rec;
@@ -2210,7 +2256,7 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
                 }
                 if (!am) break;
                 rem &= ~upto;
-                const float exa = __shfl_sync(FULL, exact, t);
+                const float exa = __shfl_sync(FULL, key, t);
                 if (!HEUR || cnt < k || exa < hmax) {
                     const int slot = cnt < k ? cnt : maxpos;
                     if (lane == t) { hd[slot] = exa; hid[slot] = SINK == 1 ? mid : j; }  // SINK = 0: the POSITION; map_ids at finalize
@@ -2218,7 +2264,7 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
                     __syncwarp();
                     if (cnt == k) {
                         heap_recompute_max(hd, k, lane, maxpos, hmax);
-                        if constexpr (!HEUR) thr = hmax;  // rerank.rs:98-100
+                        if constexpr (!HEUR) thr = SINK == 2 ? fminf(thr_cap, hmax) : hmax;  // rerank.rs:98-100
                     }
                 }
                 if constexpr (HEUR) {  // rerank.rs:155-162
@@ -2239,6 +2285,9 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
         if constexpr (SINK == 1) {  // the owner of the window tells the home rank how many records to replay
             if (lane == 0) reinterpret_cast<uint32_t*>(a.peers[home] + a.off_r1cnt)[(size_t)a.rank * a.nq_local + ql] = min(nrec, (uint32_t)a.r1cap);
         }
+        if constexpr (SINK == 2) {  // (offset, count) of the query's run: r2_offsets_kernel wrote the survivor count, this is what was shipped
+            if (lane == 0) reinterpret_cast<uint2*>(a.peers[home] + a.off_r2tab)[(size_t)a.rank * a.nq_local + ql] = make_uint2(a.r2_off[q], nrec);
+        }
         if (a.dbg && lane == 0) {
             uint32_t* o = a.dbg + ((size_t)q * 2 + (first ? 0 : 1)) * 8;
             o[0] = (uint32_t)(clock64() - dbg_t0); o[1] = waves; o[2] = computed; o[6] = dbg_rwait;
@@ -2246,9 +2295,11 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
         if (lane == 0) {
             a.q_precise[q] = (first ? 0u : a.q_precise[q]) + precise;
             atomicAdd(&a.counters[1], (unsigned long long)computed);
-            atomicAdd(&a.counters[2], (unsigned long long)precise);
+            if (SINK != 2) atomicAdd(&a.counters[2], (unsigned long long)precise);
         }
-        if (!finalize) {
+        if (SINK == 2) {
+            // (the local heap dies with the CTA: the home rank replays the records against the real threshold)
+        } else if (!finalize) {
             for (int s = lane; s < cnt; s += 32) {
                 a.heap_dist[(size_t)q * k + s] = hd[s];
                 a.heap_ids[(size_t)q * k + s] = hid[s];
@@ -2302,9 +2353,22 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
             }
             if (__any_sync(FULL, need)) {
                 uint32_t midv[NC];
-                if constexpr (SINK == 1) {  // in flight while the distances are computed
+                if constexpr (SINK != 0) {  // in flight while the distances are computed
 #pragma unroll
                     for (int i = 0; i < NC; i++) midv[i] = (l8 == 0 && c[i] < n) ? a.map_ids[qj[m * RW + c[i]]] : 0u;
+                }
+                if constexpr (SINK == 2) {  // probe rank of the slot holding the candidate's word: the last p with slot_local[p] <= word - base
+#pragma unroll
+                    for (int i = 0; i < NC; i++)
+                        if (l8 == 0 && c[i] < n) {
+                            const uint32_t rel = sqw[m * RW + c[i]] - s_win[2];
+                            int lo = 0, hi = a.P;
+                            while (hi - lo > 1) {
+                                const int md = (lo + hi) >> 1;
+                                if (s_sl[md] <= rel) lo = md; else hi = md;
+                            }
+                            sqw[m * RW + c[i]] = (uint32_t)lo;
+                        }
                 }
                 float d2[NC];
                 if constexpr (NC == 2) {
@@ -2318,7 +2382,7 @@ __global__ void __launch_bounds__(320) rerank_cta_kernel(RerankArgs a, int p_lo,
                 for (int i = 0; i < NC; i++)
                     if (l8 == 0 && c[i] < n) {
                         ex[m * RW + c[i]] = d2[i];
-                        if constexpr (SINK == 1) smid[m * RW + c[i]] = midv[i];
+                        if constexpr (SINK != 0) smid[m * RW + c[i]] = midv[i];
                     }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the rows of this buffer are rewritten by later bulk copies

@@ -193,6 +193,7 @@ struct rabitq_index {
     int rerank_rows = 0;   // rows per rerank wave; 0 = by dimension
     int rerank_mode = 1;   // 1: one CTA per query, warp-specialised (rerank_cta_kernel); 0: one warp per query (rerank_kernel)
     bool dist_sink_cta = true; // distributed round 1 on the CTA form of K5 (RABITQ_DIST_SINK_CTA=0: the warp form)
+    bool dist_r2_seq = true;   // distributed frozen round: source-side sequential filter (rerank_cta_kernel<.., 2>) instead of the flat exact pass (RABITQ_DIST_R2_SEQ=0)
     int rerank_nc = 0;     // candidates per eight-lane group of the CTA form (1 or 2; 0 = by wave size)
     int pf_threads = 0;    // 256: always 256 threads per query in prefilter_select_kernel (A/B switch)
     int rerank_stages = 0; // row buffers in the CTA form's ring (0 = 4)
@@ -402,6 +403,9 @@ int finish_index(rabitq_index* ix) {
     CU(cudaFuncSetAttribute(rerank_cta_kernel<false, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(rerank_cta_kernel<false, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (const char* e = std::getenv("RABITQ_DIST_SINK_CTA")) ix->dist_sink_cta = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RABITQ_DIST_R2_SEQ")) ix->dist_r2_seq = std::atoi(e) != 0;
+    CU(cudaFuncSetAttribute(rerank_cta_kernel<false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(rerank_cta_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(select_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(approx_gemm_tf32_kernel<128, 128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * PF_PITCH * 4));
     if (const char* e = std::getenv("RABITQ_PREFILTER")) ix->prefilter = std::atoi(e);
@@ -1210,7 +1214,7 @@ int setup_rounds(rabitq_index* ix, size_t nb, int P, size_t topk, const BatchOut
     return 0;
 }
 
-enum RoundKind { ROUND_REPLAY, ROUND_SINK1 };
+enum RoundKind { ROUND_REPLAY, ROUND_SINK1, ROUND_SINK2 };
 
 // inverted probe list (cluster -> records) of one window [lo, hi) of visit positions into list set `set`, on stream `st`;
 // also counts the window's scan work items.  Needs nothing but K2b's products: built for every round before K3.
@@ -1293,7 +1297,7 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
     const dim3 rgrid((unsigned)((nb + rr_wpb - 1) / rr_wpb)), rblock(rr_wpb * 32);
     const size_t rsmem = (size_t)rr_wpb * ra.smem_per_warp;
     const int f = is_first ? 1 : 0, l = is_last ? 1 : 0;
-    if (ix->rerank_mode == 1 && (kind != ROUND_SINK1 || ix->dist_sink_cta)) {
+    if ((ix->rerank_mode == 1 && (kind != ROUND_SINK1 || ix->dist_sink_cta)) || kind == ROUND_SINK2) {
         // one CTA per query: producer + replay + compute warps (rerank_cta_kernel).  A wave is one compute warp's job (4 rows, or 8
         // with two candidates per eight-lane group for short rows); `ns` row buffers keep that many gathers in flight
         const size_t D = (size_t)ra.D;
@@ -1307,7 +1311,7 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
         while (ncw * bpw > 8) bpw--;
         if (bpw < 1) { bpw = 1; ncw = 8; }
         int ns = ncw * bpw;
-        auto need = [&]() { return rerank_cta_smem((int)D, ra.topk, R, ns, nc); };
+        auto need = [&]() { return rerank_cta_smem((int)D, ra.topk, R, ns, nc) + (kind == ROUND_SINK2 ? (size_t)ra.P * 4 : 0); };
         while (need() > (size_t)200 * 1024 && bpw > 1) { bpw--; ns = ncw * bpw; }
         while (need() > (size_t)200 * 1024 && ncw > 1) { ncw--; ns = ncw * bpw; }
         while (need() > (size_t)200 * 1024 && R > 1) R--;
@@ -1317,7 +1321,10 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
             rc.R = R;
             rc.ns = ns;
             const dim3 grid((unsigned)nb), block((unsigned)(2 + ncw) * 32);
-            if (kind == ROUND_SINK1) {  // distributed round 1: records go to the home ranks' inboxes
+            if (kind == ROUND_SINK2) {  // distributed frozen round, source side: sequential local filter, records to the home ranks' inboxes
+                if (nc == 2) rerank_cta_kernel<false, 2, 2><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
+                else rerank_cta_kernel<false, 1, 2><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
+            } else if (kind == ROUND_SINK1) {  // distributed round 1: records go to the home ranks' inboxes
                 if (nc == 2) rerank_cta_kernel<false, 2, 1><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
                 else rerank_cta_kernel<false, 1, 1><<<grid, block, smem, st>>>(rc, lo.p, lo.ch, hi.p, hi.ch, f, l);
             } else if (heuristic) {
@@ -1332,6 +1339,7 @@ int run_round_rerank(rabitq_index* ix, size_t nb, const RerankArgs& ra, Pos lo, 
             return 0;
         }
     }
+    if (kind == ROUND_SINK2) return fail(RABITQ_EUNSUPPORTED, "the source-side sequential filter does not fit shared memory at this dim / topk / probe");
     if (kind == ROUND_SINK1) rerank_kernel<false, 1><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
     else if (heuristic) rerank_kernel<true, 0><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
     else rerank_kernel<false, 0><<<rgrid, rblock, rsmem, st>>>(ra, lo.p, lo.ch, hi.p, hi.ch, f, l);
@@ -1899,6 +1907,23 @@ int dist_round2_impl(rabitq_index* ix, uint32_t* d_status) {
     r2_offsets_kernel<<<d.world, 1024, 0, st>>>(ix->r2_cnt.as<uint32_t>(), ix->r2_off.as<uint32_t>(), (int)d.nq_l, d.cap2, d.peers_d, d.off_r2tab,
                                                  d.rank, d_status, ix->home_tot.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
+    const bool r2_seq = ix->dist_r2_seq && P <= 4096 &&
+                        rerank_cta_smem((int)ix->D, (int)d.topk, 1, 2, 1) + (size_t)P * 4 <= (size_t)200 * 1024;
+    if (r2_seq) {
+        // source-side sequential filter: every query's candidates on this shard replayed against a local threshold that is never
+        // below the reference's (rerank_cta_kernel<.., 2>); only what it computes is shipped, exact distances included
+        if (tick(ix, ST_BUCKET)) return RABITQ_ECUDA;
+        RerankArgs ra2 = d.ra;
+        ra2.win = nullptr;
+        ra2.r2_cnt = ix->r2_cnt.as<uint32_t>();
+        ra2.r2_off = ix->r2_off.as<uint32_t>();
+        ra2.off_r2rec = d.off_r2rec;
+        ra2.off_r2tab = d.off_r2tab;
+        ra2.cap2 = d.cap2;
+        if ((rc = run_round_rerank(ix, nq, ra2, Pos{0, fc}, Pos{P, 0}, true, false, false, ROUND_SINK2))) return rc;
+        d.phase = 3;
+        return RABITQ_OK;
+    }
     r2_compact_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(ix->bitmap.as<uint32_t>(), ix->entries.as<float2>(), ix->q_wbase.as<uint32_t>(),
                                                                 ix->slot_local.as<uint32_t>(), ix->q_p0.as<uint32_t>(), ix->r2_cnt.as<uint32_t>(),
                                                                 ix->r2_off.as<uint32_t>(), ix->home_tot.as<uint32_t>(), (int)nq, (int)d.nq_l, P, 0, fc,
@@ -2218,6 +2243,7 @@ int rabitq_set_option(rabitq_index* idx, const char* name, long value) {
     else if (n == "prefilter_cap") idx->prefilter_cap = (int)value;
     else if (n == "prefilter_gemm") idx->pf_gemm = (int)value;
     else if (n == "speculative_sizing") idx->spec_enabled = value != 0;
+    else if (n == "dist_r2_seq") idx->dist_r2_seq = value != 0;
     else if (n == "spec_words_per_query_milli") idx->hw_wpq = (double)value / 1000.0;  // (tests: a tiny value makes the next batch overflow its speculative slots)
     else return fail(RABITQ_EINVAL, "unknown option: " + n);
     return RABITQ_OK;
