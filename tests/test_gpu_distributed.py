@@ -32,8 +32,9 @@ def case(request):
     return request.getfixturevalue(request.param)
 
 
+@pytest.mark.parametrize("r2_seq,sink_mode", [(1, 1), (0, 0)])   # (source-side sequential filter, CTA form of K5) / (flat round 2, warp form)
 @pytest.mark.parametrize("world,probe,topk", [(2, 8, 10), (3, 32, 10), (4, 64, 1), (8, 24, 100), (5, 1, 10)])
-def test_virtual_ranks_identical_to_unsharded_oracle(case, world, probe, topk):
+def test_virtual_ranks_identical_to_unsharded_oracle(case, world, probe, topk, r2_seq, sink_mode):
     import torch
 
     from rabitq_b200 import distributed as rd
@@ -43,6 +44,9 @@ def test_virtual_ranks_identical_to_unsharded_oracle(case, world, probe, topk):
     q = np.ascontiguousarray(q[:nq])
     shards = _shards(case, world)
     try:
+        for s in shards:
+            s.set_option("dist_r2_seq", r2_seq)
+            s.set_option("rerank_mode", sink_mode)
         qd = torch.from_numpy(q).cuda()
         _, _, _, st = rd.run_virtual_ranks(shards, qd, probe, topk)   # sizes the inboxes (a too-small region grows and repeats)
         for s in shards:
