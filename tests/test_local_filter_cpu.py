@@ -109,3 +109,32 @@ def test_exact_distance_alone_is_not_a_safe_local_key():
         if any(c and not s for s, c in zip(shipped, ref_computed)):
             return
     pytest.fail("no counter-example found: the generator no longer produces bound failures that matter")
+
+
+def test_stale_thresholds_only_widen_the_queue():
+    """The single-GPU replay (rerank_cta_kernel): the scan filters a round with the threshold FROZEN at the round's start, the producer
+    filters with a threshold that is some waves old, the compute warps skip with another stale copy -- every one of them is >= the
+    live threshold (it only falls), so each stage passes a superset on to the next and the replay warp's exact tests see every
+    candidate the reference computes.  Model: any non-increasing sequence of stale thresholds."""
+    rng = random.Random(99)
+    for trial in range(400):
+        k = rng.choice([1, 5, 10])
+        stream = make_stream(rng, rng.randint(1, 20), k, fail_rate=rng.choice([0.0, 0.01, 0.2]))
+        ref_res, ref_precise, ref_computed = reference(stream, k)
+        bounds = sorted(rng.sample(range(len(stream) + 1), min(len(stream) + 1, rng.randint(1, 3))))  # round starts
+        live = Heap(k)
+        history = [INF]  # the live threshold after every candidate
+        frozen = INF
+        queued = []
+        for i, (_, rough, exact) in enumerate(stream):
+            if i in bounds:
+                frozen = history[-1]                                 # K4 of the round: the threshold the previous round left
+            lag = rng.randint(0, 16)
+            stale = history[max(0, len(history) - 1 - lag)]          # what the producer / compute warps happen to read
+            passed = rough < frozen and rough < stale
+            queued.append(passed)
+            if passed:
+                live.offer(rough, exact)                             # the replay warp: exact tests on the live threshold
+            history.append(live.thr)
+        assert all(qd or not c for qd, c in zip(queued, ref_computed)), f"trial {trial}"
+        assert live.result() == ref_res and live.precise == ref_precise, f"trial {trial}"
