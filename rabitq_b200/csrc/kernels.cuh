@@ -584,7 +584,8 @@ __global__ void __launch_bounds__(SEL_THREADS) select_probe_large_kernel(const f
 __global__ void __launch_bounds__(1024) query_base_scan_kernel(const uint32_t* __restrict__ q_words, const uint32_t* __restrict__ q_pairs,
                                                                int nq, uint32_t* __restrict__ q_wbase,
                                                                unsigned long long* __restrict__ q_pbase, uint32_t cap_words = 0u,
-                                                               uint32_t* __restrict__ spec_fail = nullptr) {
+                                                               uint32_t* __restrict__ spec_fail = nullptr,
+                                                               uint32_t* __restrict__ tot = nullptr /* [0] words, [2..3] pairs: the block the host reads */) {
     __shared__ unsigned long long wtot[33], ptot[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (nq + 1023) / 1024;
@@ -620,6 +621,10 @@ __global__ void __launch_bounds__(1024) query_base_scan_kernel(const uint32_t* _
     if (tid == 0) {
         q_wbase[nq] = (uint32_t)wtot[32];
         q_pbase[nq] = ptot[32];
+        if (tot) {
+            tot[0] = (uint32_t)wtot[32];
+            *reinterpret_cast<unsigned long long*>(tot + 2) = ptot[32];
+        }
         // speculative slot sizing (no host round trip in the middle of the batch): the survivor slots were sized from earlier batches;
         // a batch that needs more raises the flag, its scan gets no work and its replay empty windows, and the host repeats it
         if (spec_fail && wtot[32] > (unsigned long long)cap_words) *spec_fail = 1u;

@@ -157,6 +157,8 @@ struct rabitq_index {
     int pf_mode = 1;              // 1 = plain TF32 keys, 3 = 3xTF32 split (tighter bound), 0 = gave up (exact path); adapts to the data
     int pf_strikes = 0;           // batches the current mode could not certify
     bool pf_pending = false;      // a fallback flag is on its way to h_pin[6]
+    // tot_blk (device, 8 words) mirrors h_pin[0..8): [0] slot words of the batch, [1] speculative-sizing overflow flag, [2..3] pairs,
+    // [6] prefilter fallback flag, [7] prefilter candidates (statistics): ONE small copy brings all of it to the host
     size_t pf_last_nb = 0;
     int pf_gemm = 1;              // 1 = tcgen05 / TMEM / TMA key GEMM (tc5_gemm.cuh), 0 = mma.sync key GEMM (prefilter.cuh)
     CUtensorMap tm_chat, tm_chat_lo, tm_yhat, tm_yhat_lo;
@@ -204,7 +206,7 @@ struct rabitq_index {
     int scan_slices = 1;   // shared-memory record slices per scan work item (hot clusters are cut into several items)
     // work buffers
     DevBuf qraw, qpad, y, cdist, probe_ids, probe_dist, slot_local, q_words, q_pairs, q_p0, q_wbase, q_pbase, thr, heap_dist, heap_ids, heap_cnt, q_precise, h_recent, h_wcount, bitmap,
-        entries, counters, out_all, rr_dbg, round_win, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, pf_flag, sel_scratch, spec_flag;
+        entries, counters, out_all, rr_dbg, round_win, r2_cnt, r2_off, home_tot, cand, pf_yhat, pf_yhat_lo, pf_ynorm, sel_scratch, tot_blk;
     DistState dist;
     const float* q_in = nullptr;   // the sub-batch's raw queries (nb x len) on the device: ix->qraw, or the caller's device pointer
     const float* y_all = nullptr;  // rotated queries K3 reads: ix->y, or (distributed push mode) the inbox region every rank pushed its block into
@@ -255,7 +257,7 @@ struct rabitq_index {
         for (DevBuf* b : {&qraw, &qpad, &y, &cdist, &probe_ids, &probe_dist, &slot_local, &q_words, &q_pairs, &q_p0, &q_wbase, &q_pbase,
                           &thr, &heap_dist,
                           &heap_ids, &heap_cnt, &q_precise, &h_recent, &h_wcount, &bitmap, &entries, &counters, &out_all, &rr_dbg, &round_win,
-                          &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &pf_flag, &sel_scratch, &spec_flag})
+                          &r2_cnt, &r2_off, &home_tot, &cand, &pf_yhat, &pf_yhat_lo, &pf_ynorm, &sel_scratch, &tot_blk})
             b->release();
         if (h_pin) cudaFreeHost(h_pin);
         if (h_out) cudaFreeHost(h_out);
@@ -909,6 +911,8 @@ int run_front(rabitq_index* ix, size_t nb, size_t len, int P, bool stop_after_ro
 int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
     const int D = (int)ix->D, K = (int)ix->K;
     cudaStream_t st = ix->stream;
+    CU(ix->tot_blk.ensure(32));
+    CU(cudaMemsetAsync(ix->tot_blk.p, 0, 32, st));  // totals, speculative-sizing flag, prefilter flag + statistic of this batch
     CU(ix->cdist.ensure(nb * (size_t)K * 4));
     CU(ix->probe_ids.ensure(nb * P * 4));
     CU(ix->probe_dist.ensure(nb * P * 4));
@@ -922,8 +926,7 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
         // tensor-core prefilter (prefilter.cuh): approximate keys for all K, exact distances for the few candidates
         CU(ix->pf_yhat.ensure(nb * (size_t)D * 4));
         CU(ix->pf_ynorm.ensure(nb * 4));
-        CU(ix->pf_flag.ensure(8));  // [0] fallback flag, [1] candidates rechecked (statistics)
-        CU(cudaMemsetAsync(ix->pf_flag.p, 0, 8, st));
+
         const bool split = ix->pf_mode == 3;
         if (split) CU(ix->pf_yhat_lo.ensure(nb * (size_t)D * 4));
         query_center_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, st>>>(ix->y.as<float>(), ix->pf_mu, (int)nb, D, ix->pf_yhat.as<float>(),
@@ -975,18 +978,17 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
         const size_t ps_smem = (size_t)D * 4 + (size_t)ps_cap * 12 + (size_t)P * 4;
 #define PS_ARGS ix->cdist.as<float>(), ix->pf_ynorm.as<float>(), ix->pf_cnorm, ix->pf_cnorm_max, ix->y.as<float>(), ix->cent, K, P, D, ix->offsets, \
             global_view ? ix->goffsets : nullptr, ix->probe_ids.as<uint32_t>(), ix->probe_dist.as<float>(), ix->slot_local.as<uint32_t>(), \
-            ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), ix->q_p0.as<uint32_t>(), ix->pf_flag.as<uint32_t>(), ps_cap, \
+            ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), ix->q_p0.as<uint32_t>(), ix->tot_blk.as<uint32_t>() + 6, ps_cap, \
             split ? (float)(2 * D + 64) * 4.76837158203125e-07f : 0.00390625f, (float)(D / 8 + 8) * 1.1920928955078125e-07f
         // one CTA per query; 128 threads instead of 256 when 256-thread CTAs would need several waves (the kernel is a chain of
         // latencies: twice the queries in flight per SM beat twice the threads per query)
         if (nb > (size_t)ix->sm_count * 8 && ix->pf_threads != 256) prefilter_select_kernel<128><<<(unsigned)nb, 128, ps_smem, st>>>(PS_ARGS);
         else prefilter_select_kernel<256><<<(unsigned)nb, 256, ps_smem, st>>>(PS_ARGS);
 #undef PS_ARGS
-        CU(cudaMemcpyAsync(ix->h_pin + 6, ix->pf_flag.p, 8, cudaMemcpyDeviceToHost, st));
         ix->pf_last_nb = nb;
         ix->pf_pending = true;
         CU(cudaGetLastError()); ix->counts[5]++;
-        run_if = ix->pf_flag.as<uint32_t>();  // the classic kernels below run only if some query could not be certified
+        run_if = ix->tot_blk.as<uint32_t>() + 6;  // the classic kernels below run only if some query could not be certified
     }
     {
         const size_t tiles = (size_t)((K + CD_TC - 1) / CD_TC) * ((nb + CD_QG * CD_TQ - 1) / (CD_QG * CD_TQ));
@@ -1025,13 +1027,10 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
             ix->q_p0.as<uint32_t>(), run_if);
         CU(cudaGetLastError()); ix->counts[5]++;
         }
-        if (ix->spec_on) {
-            CU(ix->spec_flag.ensure(4));
-            CU(cudaMemsetAsync(ix->spec_flag.p, 0, 4, st));
-        }
         query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nb,
                                                    ix->q_wbase.as<uint32_t>(), ix->q_pbase.as<unsigned long long>(),
-                                                   ix->spec_on ? ix->spec_cap : 0u, ix->spec_on ? ix->spec_flag.as<uint32_t>() : nullptr);
+                                                   ix->spec_on ? ix->spec_cap : 0u, ix->spec_on ? ix->tot_blk.as<uint32_t>() + 1 : nullptr,
+                                                   ix->tot_blk.as<uint32_t>());
         CU(cudaGetLastError()); ix->counts[5]++;
     }
     return 0;
@@ -1041,9 +1040,9 @@ int run_front_select(rabitq_index* ix, size_t nb, int P, bool global_view) {
 // the host until it has landed: the caller launches K3 in between, so the GPU is never idle while the host sleeps.
 int post_totals(rabitq_index* ix, size_t nb) {
     cudaStream_t st = ix->stream;
-    CU(cudaMemcpyAsync(ix->h_pin, ix->q_wbase.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(ix->h_pin + 2, ix->q_pbase.as<unsigned long long>() + nb, 8, cudaMemcpyDeviceToHost, st));
-    if (ix->spec_on) CU(cudaMemcpyAsync(ix->h_pin + 4, ix->spec_flag.p, 4, cudaMemcpyDeviceToHost, st));
+    // one 32-byte copy of the totals block; a speculatively sized batch does not need it before its end (query_batch_impl copies it
+    // with the results), so nothing sits between the probe selection and K3 on the main stream
+    if (!ix->spec_on) CU(cudaMemcpyAsync(ix->h_pin, ix->tot_blk.p, 32, cudaMemcpyDeviceToHost, st));
     if (!ix->ev_totals) CU(cudaEventCreateWithFlags(&ix->ev_totals, cudaEventDisableTiming));
     CU(cudaEventRecord(ix->ev_totals, st));
     CU(cudaEventRecord(ix->ev_fork, st));
@@ -1246,7 +1245,7 @@ int build_lists(rabitq_index* ix, size_t nb, int P, uint32_t MS, Pos lo, Pos hi,
     }
     bucket_scan_kernel<<<1, 1024, 0, st>>>(L.cl_count.as<uint32_t>(), ix->offsets, K, SCAN_THREADS, MS, ch_min, ch_max,
                                            L.cl_start.as<uint32_t>(), L.item_start.as<uint32_t>(), L.cl_cursor.as<uint32_t>(),
-                                           L.work_ctl.as<uint32_t>(), ix->spec_on ? ix->spec_flag.as<uint32_t>() : nullptr);
+                                           L.work_ctl.as<uint32_t>(), ix->spec_on ? ix->tot_blk.as<uint32_t>() + 1 : nullptr);
     CU(cudaGetLastError()); ix->counts[5]++;
     if (items) {
         bucket_fill_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(ix->probe_ids.as<uint32_t>(), ix->q_p0.as<uint32_t>(), foreign, nb, P, p_lo, p_hi_incl,
@@ -1273,7 +1272,7 @@ int run_round_scan(rabitq_index* ix, size_t nb, int P, ScanArgs& sa, Pos lo, Pos
         CU(L.work.ensure(ix->max_items * sizeof(ScanItem)));
         work_items_kernel<<<(K + 255) / 256, 256, 0, st>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(), L.cl_start.as<uint32_t>(), ix->offsets,
                                                            ix->chunk_start, K, L.MS, L.ch_min, L.work.as<ScanItem>(),
-                                                           ix->spec_on ? ix->spec_flag.as<uint32_t>() : nullptr);
+                                                           ix->spec_on ? ix->tot_blk.as<uint32_t>() + 1 : nullptr);
         CU(cudaGetLastError()); ix->counts[5]++;
     }
     sa.cl_items = L.cl_items.as<uint2>();
@@ -1393,7 +1392,7 @@ int run_lists_and_quantize(rabitq_index* ix, size_t nb, int P, const std::vector
         CU(ix->round_win.ensure((size_t)(rb.n - 1) * nb * 8));
         round_windows_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, a2>>>(ix->q_wbase.as<uint32_t>(), ix->slot_local.as<uint32_t>(),
                                                                                         ix->q_p0.as<uint32_t>(), (int)nb, P, rb, ix->round_win.as<uint2>(),
-                                                               ix->spec_on ? ix->spec_flag.as<uint32_t>() : nullptr);
+                                                               ix->spec_on ? ix->tot_blk.as<uint32_t>() + 1 : nullptr);
         CU(cudaGetLastError()); ix->counts[5]++;
         CU(cudaEventRecord(ix->ev_win, a2));
     }
@@ -1455,7 +1454,7 @@ int run_sub_batch(rabitq_index* ix, size_t nb, size_t len, size_t probe, size_t 
             work_items_kernel<<<((int)ix->K + 255) / 256, 256, 0, a2>>>(L.item_start.as<uint32_t>(), L.cl_count.as<uint32_t>(),
                                                                                        L.cl_start.as<uint32_t>(), ix->offsets, ix->chunk_start, (int)ix->K,
                                                                                        L.MS, L.ch_min, L.work.as<ScanItem>(),
-                                                                                       ix->spec_on ? ix->spec_flag.as<uint32_t>() : nullptr);
+                                                                                       ix->spec_on ? ix->tot_blk.as<uint32_t>() + 1 : nullptr);
             CU(cudaGetLastError()); ix->counts[5]++;
             if (!L.wready) CU(cudaEventCreateWithFlags(&L.wready, cudaEventDisableTiming));
             CU(cudaEventRecord(L.wready, a2));
@@ -1579,6 +1578,7 @@ int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, siz
             }
             CU(cudaMemcpyAsync(ix->h_out, oa, out_words * 4, cudaMemcpyDeviceToHost, ix->stream));
         }
+        if (bo.speculative) CU(cudaMemcpyAsync(ix->h_pin, ix->tot_blk.p, 32, cudaMemcpyDeviceToHost, ix->stream));
         CU(cudaMemcpyAsync(ix->h_pin + 8, ix->counters.p, 32, cudaMemcpyDeviceToHost, ix->stream));
         if (tick(ix, ST_D2H)) return RABITQ_ECUDA;
         CU(cudaStreamSynchronize(ix->stream));
@@ -1588,7 +1588,7 @@ int query_batch_impl(rabitq_index* ix, const float* queries, bool on_device, siz
             std::memcpy(&bo.total_pairs, ix->h_pin + 2, 8);
             ix->hw_wpq = std::max(ix->hw_wpq, (double)real_words / (double)nb);
             ix->spec_on = false;
-            if (ix->h_pin[4] != 0u) continue;  // did not fit: neutralised on the device, repeated with the exact sizes
+            if (ix->h_pin[1] != 0u) continue;  // did not fit: neutralised on the device, repeated with the exact sizes
         } else {
             ix->hw_wpq = std::max(ix->hw_wpq, (double)bo.total_words / (double)nb);
         }
@@ -1789,7 +1789,7 @@ int dist_front_select_impl(rabitq_index* ix, void* d_send_meta) {
     cudaStream_t st = ix->stream;
     int rc = run_front_select(ix, nq_l, P, true);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(ix->h_pin + 4, ix->q_pbase.as<unsigned long long>() + nq_l, 8, cudaMemcpyDeviceToHost, st));  // `rough` of the home queries
+    CU(cudaMemcpyAsync(ix->h_pin + 18, ix->q_pbase.as<unsigned long long>() + nq_l, 8, cudaMemcpyDeviceToHost, st));  // `rough` of the home queries
     uint32_t* send = static_cast<uint32_t*>(d_send_meta);
     const DistChunk L = dist_chunk_layout(nq_l, d.len, D, (size_t)P);
     CU(cudaMemcpyAsync(send + L.b_ids, ix->probe_ids.p, nq_l * P * 4, cudaMemcpyDeviceToDevice, st));
@@ -1859,7 +1859,7 @@ int dist_round1_impl(rabitq_index* ix, const void* d_gathered_a, size_t stride_a
                                                                           ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
     query_base_scan_kernel<<<1, 1024, 0, st>>>(ix->q_words.as<uint32_t>(), ix->q_pairs.as<uint32_t>(), (int)nq, ix->q_wbase.as<uint32_t>(),
-                                               ix->q_pbase.as<unsigned long long>());
+                                               ix->q_pbase.as<unsigned long long>(), 0u, nullptr, ix->tot_blk.as<uint32_t>());
     CU(cudaGetLastError()); ix->counts[5]++;
     BatchOut bo;
     bo.P = P;
@@ -1969,7 +1969,7 @@ int dist_finish_impl(rabitq_index* ix, float* d_out_dist, uint32_t* d_out_ids, u
     prefilter_adapt(ix);
     unsigned long long c[4], rough_home;
     std::memcpy(c, ix->h_pin + 8, 32);
-    std::memcpy(&rough_home, ix->h_pin + 4, 8);
+    std::memcpy(&rough_home, ix->h_pin + 18, 8);
     ix->counts[1] += c[0];
     ix->counts[2] += c[1];
     ix->counts[3] += c[2];
