@@ -210,7 +210,9 @@ int rabitq_set_rounds(rabitq_index* idx, const uint32_t* rounds, int n);
  *                      itself when batches cannot be certified);
  *   "speculative_sizing"  1 (default) sizes a batch's survivor slots from earlier batches and checks the capacity on the device (no host
  *                      round trip in the middle of the batch; a batch that does not fit is repeated with exact sizes), 0 = always read
- *                      the totals back first; "spec_words_per_query_milli" overrides the high-water mark (tests). */
+ *                      the totals back first; "spec_words_per_query_milli" overrides the high-water mark (tests);
+ *   "dist_r2_seq"      1 (default) = the frozen round of the distributed pipeline runs the source-side sequential filter
+ *                      (rerank_cta_kernel<.., SINK = 2>), 0 = compaction + flat exact distances for every survivor. */
 int rabitq_set_option(rabitq_index* idx, const char* name, long value);
 
 /* Byte position of dimension d inside a K3 query record (the tensor-core fragment order K4 reads, kernels.cuh rec_pos); host-only,

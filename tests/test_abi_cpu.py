@@ -76,3 +76,19 @@ def test_service_and_cli_twins_fail_loudly_without_an_index():
     assert r.returncode != 0 and "orthogonal.fvecs" in r.stderr
     r = subprocess.run([bld.SERVICE], capture_output=True, text=True, timeout=30)
     assert r.returncode == 2 and "--dir is required" in r.stderr
+
+
+def test_every_option_is_documented_in_the_header():
+    """`rabitq_set_option` names (rabitq_capi.cu) <-> the option list in include/rabitq_b200.h: a knob nobody can find is not an API."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "rabitq_b200", "csrc", "rabitq_capi.cu")).read()
+    body = src[src.index("int rabitq_set_option("):]
+    body = body[:body.index("return RABITQ_OK;")]
+    names = set(re.findall(r'n == "([a-z0-9_]+)"', body))
+    assert len(names) >= 15
+    header = open(os.path.join(root, "include", "rabitq_b200.h")).read()
+    missing = sorted(n for n in names if f'"{n}"' not in header)
+    assert not missing, f"options without documentation in the header: {missing}"
